@@ -1,0 +1,265 @@
+#!/usr/bin/env python3
+"""Generate golden fixtures by running the UNMODIFIED reference (ManipulaPy v1.4.1).
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container, where the reference is
+mounted read-only at /root/reference (it does not exist on the GPU box, so the
+vectors are committed):
+
+    python oracle/gen_golden.py
+
+Writes
+  manipulapy_b200/robots/<robot>.npz   constant packs (S_list, M, Glist, Mlist_per_link,
+                                       joint_limits) extracted by the reference's own
+                                       URDFToSerialManipulator -- shipped as robot data.
+  tests/golden/dynamics_<robot>.npz    per-point float64 vectors: the reference's own
+                                       golden file replayed verbatim (ur5, panda:
+                                       tests/data/dynamics_golden_*.npz) plus FK / Jacobian /
+                                       forward_dynamics outputs computed here by the reference.
+  tests/golden/trajectory.npz          joint_trajectory / batch_joint_trajectory (float32).
+  tests/golden/id_trajectory.npz       inverse_dynamics_trajectory (float32, clipped).
+  tests/golden/fd_trajectory.npz       forward_dynamics_trajectory rollouts (float32).
+
+The reference needs a 2-file matplotlib stub (its only missing hard import,
+planning/_kernels.py:27); the stub is created in a temp dir, not in the repo.
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import sys
+import tempfile
+import warnings
+from pathlib import Path
+
+REPO = Path(__file__).resolve().parents[1]
+REF = Path(os.environ.get("MANIPULAPY_REFERENCE", "/root/reference"))
+
+
+def _bootstrap_reference() -> None:
+    stub = Path(tempfile.mkdtemp(prefix="mpl_stub_")) / "matplotlib"
+    stub.mkdir(parents=True)
+    (stub / "__init__.py").write_text("def use(*a, **k):\n    pass\n")
+    (stub / "pyplot.py").write_text("def __getattr__(name):\n    raise AttributeError(name)\n")
+    sys.path[:0] = [str(REF), str(stub.parent)]
+    os.environ.setdefault("MANIPULAPY_QUIET", "1")
+    os.environ.setdefault("NUMBA_DISABLE_CUDA", "1")
+    os.environ.setdefault("NUMBA_CACHE_DIR", tempfile.mkdtemp(prefix="numba_cache_"))
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    sys.dont_write_bytecode = True
+    warnings.filterwarnings("ignore")
+    logging.disable(logging.CRITICAL)
+
+
+_bootstrap_reference()
+
+import numpy as np  # noqa: E402
+
+from ManipulaPy.ManipulaPy_data import get_robot_urdf  # noqa: E402
+from ManipulaPy.path_planning import OptimizedTrajectoryPlanning  # noqa: E402
+from ManipulaPy.urdf_processor import URDFToSerialManipulator  # noqa: E402
+
+G_VEC = np.array([0.0, 0.0, -9.81])
+ROBOT_DIR = REPO / "manipulapy_b200" / "robots"
+GOLD_DIR = REPO / "tests" / "golden"
+
+
+def load(robot: str):
+    proc = URDFToSerialManipulator(get_robot_urdf(robot), load_meshes=False)
+    return proc, proc.serial_manipulator, proc.dynamics
+
+
+def limits_array(proc, n: int) -> np.ndarray:
+    lims = np.empty((n, 2))
+    for i, (lo, hi) in enumerate(proc.robot_data["joint_limits"]):
+        lims[i] = (-np.pi if lo is None else lo, np.pi if hi is None else hi)
+    return lims
+
+
+def clear_caches(dyn) -> None:
+    dyn._mass_matrix_cache.clear()
+    dyn._mass_matrix_derivative_cache.clear()
+
+
+def export_robot(robot: str) -> None:
+    proc, sm, dyn = load(robot)
+    n = dyn.S_list.shape[1]
+    np.savez(
+        ROBOT_DIR / f"{robot}.npz",
+        S_list=np.asarray(dyn.S_list, np.float64),
+        M=np.asarray(dyn.M_list, np.float64),
+        Glist=np.asarray(dyn.Glist, np.float64),
+        Mlist_per_link=np.asarray(dyn.Mlist_per_link, np.float64),
+        joint_limits=limits_array(proc, n),
+    )
+    print(f"robot pack {robot}: n={n}")
+
+
+def dynamics_golden(robot: str, n_cfg: int = 12, n_fd: int = 6) -> None:
+    proc, sm, dyn = load(robot)
+    n = dyn.S_list.shape[1]
+    ref_npz = REF / "tests" / "data" / f"dynamics_golden_{robot}.npz"
+    out = {}
+    if ref_npz.exists():
+        # the reference's own golden vectors, replayed verbatim
+        with np.load(ref_npz) as d:
+            for k in d.files:
+                out[k] = d[k]
+        out["source"] = np.array("reference tests/data/dynamics_golden_%s.npz" % robot)
+    else:
+        rng = np.random.default_rng(20260705)
+        lims = limits_array(proc, n)
+        th = rng.uniform(lims[:, 0], lims[:, 1], size=(n_cfg, n))
+        th[0] = 0.0
+        dth = rng.uniform(-1, 1, size=(n_cfg, n))
+        ddth = rng.uniform(-1, 1, size=(n_cfg, n))
+        dth[0] = ddth[0] = 0.0
+        ft = np.zeros((n_cfg, 6))
+        ft[min(5, n_cfg - 1)] = [1.0, -2.0, 0.5, 3.0, -1.5, 0.75]
+        out.update(thetas=th, dthetas=dth, ddthetas=ddth, g=G_VEC.copy(), ftips=ft)
+        M, ID, GF, C = [], [], [], []
+        for i in range(n_cfg):
+            clear_caches(dyn)
+            M.append(np.asarray(dyn.mass_matrix(th[i])))
+            ID.append(np.asarray(dyn.inverse_dynamics(th[i], dth[i], ddth[i], G_VEC, ft[i])))
+            GF.append(np.asarray(dyn.gravity_forces(th[i], G_VEC)))
+            C.append(np.asarray(dyn.velocity_quadratic_forces(th[i], dth[i])))
+        out.update(mass_matrix=np.array(M), inverse_dynamics=np.array(ID),
+                   gravity_forces=np.array(GF), velocity_quadratic_forces=np.array(C))
+        out["source"] = np.array("reference run by oracle/gen_golden.py")
+    th = out["thetas"]
+    # FK / Jacobian have no golden in the reference: computed by the reference here.
+    out["forward_kinematics"] = np.array([np.asarray(sm.forward_kinematics(t)) for t in th])
+    out["jacobian"] = np.array([np.asarray(sm.jacobian(t)) for t in th])
+    # forward_dynamics: a few rows (each call is 60-130 ms)
+    rng = np.random.default_rng(7)
+    idx = np.arange(min(n_fd, th.shape[0]))
+    tau = rng.uniform(-20, 20, size=(idx.size, n))
+    fd = []
+    for r, i in enumerate(idx):
+        clear_caches(dyn)
+        fd.append(np.asarray(dyn.forward_dynamics(th[i], out["dthetas"][i], tau[r], G_VEC, out["ftips"][i])))
+    out.update(fd_index=idx, fd_tau=tau, forward_dynamics=np.array(fd))
+    np.savez(GOLD_DIR / f"dynamics_{robot}.npz", **out)
+    print(f"dynamics golden {robot}: {th.shape[0]} configs, {idx.size} FD rows")
+
+
+def make_planner(robot: str, torque_limits=None):
+    proc, sm, dyn = load(robot)
+    n = dyn.S_list.shape[1]
+    lims = limits_array(proc, n)
+    planner = OptimizedTrajectoryPlanning(
+        sm, get_robot_urdf(robot), dyn, lims, torque_limits, use_cuda=False)
+    return planner, dyn, lims
+
+
+def trajectory_golden() -> None:
+    planner, dyn, lims = make_planner("ur5")
+    n = 6
+    out = {"joint_limits": lims}
+    rng = np.random.default_rng(1)
+    cases = {
+        # BASELINE config 1: seed 1, U(-1,1)^6, Tf=2, N=1000, quintic
+        "cfg1": (rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 2.0, 1000, 5),
+        "cubic50": (rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 1.5, 50, 3),
+        "two": (rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), 0.7, 2, 5),
+        # beyond the +-2pi / +-pi limits: exercises the position clip
+        "clipped": (np.full(n, -7.0), np.full(n, 7.0), 3.0, 101, 5),
+        "odd_tf": (rng.uniform(-3, 3, n), rng.uniform(-3, 3, n), 0.37, 257, 3),
+    }
+    for name, (s, e, Tf, N, method) in cases.items():
+        r = planner.joint_trajectory(s, e, Tf, N, method)
+        out[f"{name}_start"] = s
+        out[f"{name}_end"] = e
+        out[f"{name}_args"] = np.array([Tf, N, method], np.float64)
+        for k in ("positions", "velocities", "accelerations"):
+            a = np.asarray(r[k])
+            assert a.dtype == np.float32
+            out[f"{name}_{k}"] = a
+    sb = rng.uniform(-3.5, 3.5, (5, n))
+    eb = rng.uniform(-3.5, 3.5, (5, n))
+    r = planner.batch_joint_trajectory(sb, eb, 2.0, 33, 5)
+    out.update(batch_start=sb, batch_end=eb, batch_args=np.array([2.0, 33, 5], np.float64))
+    for k in ("positions", "velocities", "accelerations"):
+        out[f"batch_{k}"] = np.asarray(r[k])
+    np.savez(GOLD_DIR / "trajectory.npz", **out)
+    print("trajectory golden written")
+
+
+def id_trajectory_golden() -> None:
+    out = {}
+    for robot, npts in (("ur5", 24), ("iiwa14", 10)):
+        proc, sm, dyn = load(robot)
+        n = dyn.S_list.shape[1]
+        lims = limits_array(proc, n)
+        tl = np.tile(np.array([[-40.0, 35.0]]), (n, 1))  # finite: exercises the torque clip
+        planner = OptimizedTrajectoryPlanning(sm, get_robot_urdf(robot), dyn, lims, tl, use_cuda=False)
+        rng = np.random.default_rng(1)
+        s, e = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)
+        tr = planner.joint_trajectory(s, e, 2.0, 1000, 5)
+        sel = np.linspace(0, 999, npts).astype(int)
+        # float64 inputs (float32 arrays would make the reference run sin/cos in float32)
+        th = np.asarray(tr["positions"], np.float64)[sel]
+        dth = np.asarray(tr["velocities"], np.float64)[sel] * 3.0
+        ddth = np.asarray(tr["accelerations"], np.float64)[sel] * 3.0
+        ftip = np.array([0.5, -1.0, 0.25, 2.0, -1.5, 1.0])
+        clear_caches(dyn)
+        tau0 = np.asarray(planner.inverse_dynamics_trajectory(th, dth, ddth))
+        clear_caches(dyn)
+        tau1 = np.asarray(planner.inverse_dynamics_trajectory(th, dth, ddth, np.array([0.0, -9.81, 0.0]), ftip))
+        assert tau0.dtype == np.float32
+        out.update({f"{robot}_theta": th, f"{robot}_dtheta": dth, f"{robot}_ddtheta": ddth,
+                    f"{robot}_torque_limits": tl, f"{robot}_tau_default": tau0,
+                    f"{robot}_g1": np.array([0.0, -9.81, 0.0]), f"{robot}_ftip1": ftip,
+                    f"{robot}_tau_g1_ftip1": tau1})
+    np.savez(GOLD_DIR / "id_trajectory.npz", **out)
+    print("id trajectory golden written")
+
+
+def fd_trajectory_golden() -> None:
+    out = {}
+    for robot, N in (("iiwa14", 24), ("ur5", 16)):
+        planner, dyn, lims = make_planner(robot)
+        n = dyn.S_list.shape[1]
+        rng = np.random.default_rng(4)
+        th0 = rng.uniform(0.5 * lims[:, 0], 0.5 * lims[:, 1])
+        dth0 = rng.uniform(-0.5, 0.5, n)
+        tau = rng.uniform(-20, 20, (N, n))
+        clear_caches(dyn)
+        r = planner.forward_dynamics_trajectory(th0, dth0, tau, G_VEC, np.zeros((N, 6)), 1e-3, 1)
+        out.update({f"{robot}_a_theta0": th0, f"{robot}_a_dtheta0": dth0, f"{robot}_a_tau": tau,
+                    f"{robot}_a_args": np.array([1e-3, 1.0])})
+        for k in ("positions", "velocities", "accelerations"):
+            out[f"{robot}_a_{k}"] = np.asarray(r[k])
+        # case b: intRes=2, non-zero wrench, start next to a joint limit with a hard push
+        N2 = 8
+        th0b = lims[:, 1] - 1e-4
+        dth0b = np.full(n, 0.8)
+        taub = rng.uniform(0, 40, (N2, n))
+        ftb = rng.uniform(-2, 2, (N2, 6))
+        clear_caches(dyn)
+        r = planner.forward_dynamics_trajectory(th0b, dth0b, taub, np.array([0.0, -9.81, 0.0]), ftb, 5e-3, 2)
+        out.update({f"{robot}_b_theta0": th0b, f"{robot}_b_dtheta0": dth0b, f"{robot}_b_tau": taub,
+                    f"{robot}_b_ftip": ftb, f"{robot}_b_g": np.array([0.0, -9.81, 0.0]),
+                    f"{robot}_b_args": np.array([5e-3, 2.0])})
+        for k in ("positions", "velocities", "accelerations"):
+            out[f"{robot}_b_{k}"] = np.asarray(r[k])
+        out[f"{robot}_joint_limits"] = lims
+    np.savez(GOLD_DIR / "fd_trajectory.npz", **out)
+    print("fd trajectory golden written")
+
+
+def main() -> None:
+    ROBOT_DIR.mkdir(parents=True, exist_ok=True)
+    GOLD_DIR.mkdir(parents=True, exist_ok=True)
+    for robot in ("ur5", "iiwa14", "panda", "xarm6"):
+        export_robot(robot)
+    for robot in ("ur5", "panda", "iiwa14"):
+        dynamics_golden(robot)
+    trajectory_golden()
+    id_trajectory_golden()
+    fd_trajectory_golden()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,260 @@
+"""ctypes binding of ``oracle.c`` (the CPU restatement of the reference path).
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "_build" / "liboracle.so"
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+
+
+class _Robot(C.Structure):
+    _fields_ = [("n", C.c_int), ("S", _dp), ("M", _dp), ("G", _dp), ("Mcom", _dp)]
+
+
+def build_oracle(force: bool = False) -> Path:
+    """Compile ``oracle.c`` into ``oracle/_build/liboracle.so`` (gcc)."""
+    src = _HERE / "oracle.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-s", "-B", "all"], check=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def load_oracle():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            build_oracle()
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.orc_forward_dynamics.restype = C.c_int
+        _lib.orc_forward_dynamics_analytic.restype = C.c_int
+        _lib.orc_forward_dynamics_trajectory.restype = C.c_int
+        _lib.orc_forward_dynamics_rollout_batch.restype = C.c_int
+        _lib.orc_max_dof.restype = C.c_int
+    return _lib
+
+
+def _d(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _f(a) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+
+
+def _p(a: Optional[np.ndarray], ty=_dp):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+_THREADS = 1
+
+
+def set_threads(n: int) -> None:
+    """Host threads used by the batched oracle loops (ctypes releases the GIL)."""
+    global _THREADS
+    _THREADS = max(1, int(n))
+
+
+def _parallel(count: int, fn) -> None:
+    """Run ``fn(lo, hi)`` over contiguous slices of ``range(count)`` on ``_THREADS`` threads."""
+    if _THREADS == 1 or count < 2 * _THREADS:
+        fn(0, count)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    step = -(-count // _THREADS)
+    with ThreadPoolExecutor(_THREADS) as ex:
+        futs = [ex.submit(fn, lo, min(count, lo + step)) for lo in range(0, count, step)]
+        for f in futs:
+            f.result()
+
+
+class Oracle:
+    """The reference algorithm for one robot, float64, on the host.
+
+    Parameters mirror the reference's constant pack
+    (``dynamics/manipulator_dynamics.py:46-75``): ``S_list (6, n)``, ``M (4, 4)``,
+    ``Glist (n, 6, 6)``, ``Mlist_per_link (n, 4, 4)``.
+    """
+
+    def __init__(self, S_list, M, Glist, Mlist_per_link):
+        self.lib = load_oracle()
+        self.S = _d(S_list)
+        self.M = _d(M)
+        self.G = _d(Glist)
+        self.Mcom = _d(Mlist_per_link)
+        self.n = int(self.S.shape[1])
+        assert self.S.shape == (6, self.n) and self.M.shape == (4, 4)
+        assert self.G.shape == (self.n, 6, 6) and self.Mcom.shape == (self.n, 4, 4)
+        assert self.n <= self.lib.orc_max_dof()
+        self._rb = _Robot(self.n, _p(self.S), _p(self.M), _p(self.G), _p(self.Mcom))
+        self._r = C.byref(self._rb)
+
+    # -- per-point float64 API (batched over the leading axis) -------------------
+    def forward_kinematics(self, theta):
+        th = _d(theta).reshape(-1, self.n)
+        T = np.empty((th.shape[0], 4, 4))
+        _parallel(th.shape[0], lambda lo, hi: self.lib.orc_fk_jacobian_batch(
+            self._r, C.c_int64(hi - lo), _p(th[lo:hi]), _p(T[lo:hi]), None))
+        return T
+
+    def jacobian(self, theta):
+        th = _d(theta).reshape(-1, self.n)
+        J = np.empty((th.shape[0], 6, self.n))
+        _parallel(th.shape[0], lambda lo, hi: self.lib.orc_fk_jacobian_batch(
+            self._r, C.c_int64(hi - lo), _p(th[lo:hi]), None, _p(J[lo:hi])))
+        return J
+
+    def mass_matrix(self, theta, analytic=False):
+        th = _d(theta).reshape(-1, self.n)
+        M = np.empty((th.shape[0], self.n, self.n))
+        _parallel(th.shape[0], lambda lo, hi: self.lib.orc_mass_matrix_batch(
+            self._r, C.c_int64(hi - lo), _p(th[lo:hi]), C.c_int(int(analytic)), _p(M[lo:hi])))
+        return M
+
+    def inverse_dynamics(self, theta, dtheta, ddtheta, g=(0.0, 0.0, -9.81), Ftip=None, analytic=False):
+        th = _d(theta).reshape(-1, self.n)
+        P = th.shape[0]
+        dth = _d(dtheta).reshape(P, self.n)
+        ddth = _d(ddtheta).reshape(P, self.n)
+        g = _d(g)
+        if Ftip is None:
+            F, stride = None, 0
+        else:
+            F = _d(Ftip)
+            stride = 0 if F.ndim == 1 else 6
+        out = np.empty((P, self.n))
+        def run(lo, hi):
+            Fs = None if F is None else (F if stride == 0 else F[lo:hi])
+            self.lib.orc_inverse_dynamics_batch(
+                self._r, C.c_int64(hi - lo), _p(th[lo:hi]), _p(dth[lo:hi]), _p(ddth[lo:hi]), _p(g),
+                _p(Fs), C.c_int64(stride), C.c_int(int(analytic)), _p(out[lo:hi]))
+
+        _parallel(P, run)
+        return out
+
+    def gravity_forces(self, theta, g=(0.0, 0.0, -9.81), analytic=False):
+        th = _d(theta).reshape(-1, self.n)
+        if analytic:
+            z = np.zeros_like(th)
+            return self.inverse_dynamics(th, z, z, g, None, analytic=True)
+        out = np.empty_like(th)
+        g = _d(g)
+        for p in range(th.shape[0]):
+            self.lib.orc_gravity_forces(self._r, _p(th[p]), _p(g), _p(out[p]))
+        return out
+
+    def velocity_quadratic_forces(self, theta, dtheta, analytic=False):
+        th = _d(theta).reshape(-1, self.n)
+        dth = _d(dtheta).reshape(-1, self.n)
+        if analytic:
+            return self.inverse_dynamics(th, dth, np.zeros_like(th), (0.0, 0.0, 0.0), None, analytic=True)
+        out = np.empty_like(th)
+        for p in range(th.shape[0]):
+            self.lib.orc_velocity_quadratic_forces(self._r, _p(th[p]), _p(dth[p]), _p(out[p]))
+        return out
+
+    def forward_dynamics(self, theta, dtheta, tau, g=(0.0, 0.0, -9.81), Ftip=None, analytic=False):
+        th = _d(theta).reshape(-1, self.n)
+        P = th.shape[0]
+        dth = _d(dtheta).reshape(P, self.n)
+        ta = _d(tau).reshape(P, self.n)
+        g = _d(g)
+        F = np.zeros((P, 6)) if Ftip is None else np.broadcast_to(_d(Ftip), (P, 6)).copy()
+        out = np.empty((P, self.n))
+        fn = self.lib.orc_forward_dynamics_analytic if analytic else self.lib.orc_forward_dynamics
+        for p in range(P):
+            rc = fn(self._r, _p(th[p]), _p(dth[p]), _p(ta[p]), _p(g), _p(F[p]), _p(out[p]))
+            if rc:
+                raise np.linalg.LinAlgError("singular mass matrix")
+        return out
+
+    # -- trajectory-level float32 API --------------------------------------------
+    @staticmethod
+    def joint_trajectory(start, end, Tf, N, method, joint_limits=None, inputs_f32=None):
+        """``joint_trajectory`` (1-D start/end, float32-cast inputs) or
+        ``batch_joint_trajectory`` ((B, n) start/end, input dtype preserved)."""
+        lib = load_oracle()
+        s = np.asarray(start)
+        single = s.ndim == 1
+        if inputs_f32 is None:
+            inputs_f32 = single or s.dtype == np.float32
+        s = _d(s).reshape(-1, s.shape[-1])
+        e = _d(end).reshape(s.shape)
+        B, n = s.shape
+        lim = None if joint_limits is None else _f(joint_limits).reshape(n, 2)
+        pos = np.empty((B, N, n), np.float32)
+        vel = np.empty_like(pos)
+        acc = np.empty_like(pos)
+        for b in range(B):
+            lib.orc_joint_trajectory(
+                C.c_int(n), _p(s[b]), _p(e[b]), C.c_int(int(inputs_f32)), C.c_double(float(Tf)),
+                C.c_int64(int(N)), C.c_int(int(method)), _p(lim, _fp), _p(pos[b], _fp),
+                _p(vel[b], _fp), _p(acc[b], _fp))
+        if single:
+            pos, vel, acc = pos[0], vel[0], acc[0]
+        return {"positions": pos, "velocities": vel, "accelerations": acc}
+
+    def inverse_dynamics_trajectory(self, theta, dtheta, ddtheta, g=(0.0, 0.0, -9.81), Ftip=None,
+                                    torque_limits=None, analytic=False):
+        th = _d(theta).reshape(-1, self.n)
+        P = th.shape[0]
+        dth = _d(dtheta).reshape(P, self.n)
+        ddth = _d(ddtheta).reshape(P, self.n)
+        g = _d(g)
+        F = np.zeros(6) if Ftip is None else _d(Ftip)
+        lim = None if torque_limits is None else _f(torque_limits).reshape(self.n, 2)
+        out = np.empty((P, self.n), np.float32)
+        _parallel(P, lambda lo, hi: self.lib.orc_inverse_dynamics_trajectory(
+            self._r, C.c_int64(hi - lo), _p(th[lo:hi]), _p(dth[lo:hi]), _p(ddth[lo:hi]), _p(g), _p(F),
+            _p(lim, _fp), C.c_int(int(analytic)), _p(out[lo:hi], _fp)))
+        return out
+
+    def forward_dynamics_trajectory(self, theta0, dtheta0, taumat, g, Ftipmat, dt, intRes,
+                                    joint_limits=None, analytic=False):
+        """Single ``(n,)`` start or batched ``(B, n)`` starts with ``taumat (B, N, n)``."""
+        th0 = _d(theta0)
+        single = th0.ndim == 1
+        th0 = th0.reshape(-1, self.n)
+        B = th0.shape[0]
+        dth0 = _d(dtheta0).reshape(B, self.n)
+        tm = _d(taumat).reshape(B, -1, self.n)
+        N = tm.shape[1]
+        if N == 0:
+            raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+        g = _d(g)
+        Fm = None if Ftipmat is None else _d(Ftipmat).reshape(B, N, 6)
+        lim = None if joint_limits is None else _f(joint_limits).reshape(self.n, 2)
+        pos = np.empty((B, N, self.n), np.float32)
+        vel = np.empty_like(pos)
+        acc = np.empty_like(pos)
+        rcs = []
+
+        def run(lo, hi):
+            rcs.append(self.lib.orc_forward_dynamics_rollout_batch(
+                self._r, C.c_int64(hi - lo), _p(th0[lo:hi]), _p(dth0[lo:hi]), C.c_int64(N),
+                _p(tm[lo:hi]), _p(g), None if Fm is None else _p(Fm[lo:hi]), C.c_double(float(dt)),
+                C.c_int(int(intRes)), _p(lim, _fp), C.c_int(int(analytic)), _p(pos[lo:hi], _fp),
+                _p(vel[lo:hi], _fp), _p(acc[lo:hi], _fp)))
+
+        _parallel(B, run)
+        if any(rcs):
+            raise np.linalg.LinAlgError("singular mass matrix during rollout")
+        if single:
+            pos, vel, acc = pos[0], vel[0], acc[0]
+        return {"positions": pos, "velocities": vel, "accelerations": acc}

@@ -1,0 +1,160 @@
+"""Pin the CPU oracle (oracle/oracle.c) against the reference.
+
+* the reference's own golden vectors (tests/data/dynamics_golden_{ur5,panda}.npz, replayed
+  verbatim inside tests/golden/dynamics_*.npz) at the reference's own tolerances
+  (tests/test_dynamics_golden.py:77-83: rtol 1e-7, atol 1e-9 for M/g, 1e-8 for c/ID);
+* outputs of the unmodified reference run by oracle/gen_golden.py (FK, Jacobian, forward
+  dynamics, joint/batch trajectories, inverse/forward dynamics trajectories);
+* the analytic known answers the reference tests use (2R planar arm).
+"""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, load_pack, planar_2r_pack
+
+RTOL = 1e-7
+ATOL = {"mass_matrix": 1e-9, "gravity_forces": 1e-9,
+        "velocity_quadratic_forces": 1e-8, "inverse_dynamics": 1e-8}
+ROBOTS = ["ur5", "panda", "iiwa14"]
+
+
+@pytest.mark.parametrize("analytic", [False, True], ids=["literal", "analytic"])
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_dynamics_golden(oracle_factory, robot, analytic):
+    o = oracle_factory(robot)
+    g = load_golden(f"dynamics_{robot}")
+    th, dth, ddth, ft = g["thetas"], g["dthetas"], g["ddthetas"], g["ftips"]
+    got = {
+        "mass_matrix": o.mass_matrix(th, analytic),
+        "gravity_forces": o.gravity_forces(th, g["g"], analytic),
+        "velocity_quadratic_forces": o.velocity_quadratic_forces(th, dth, analytic),
+        "inverse_dynamics": o.inverse_dynamics(th, dth, ddth, g["g"], ft, analytic),
+    }
+    for k, v in got.items():
+        np.testing.assert_allclose(v, g[k], rtol=RTOL, atol=ATOL[k], err_msg=k)
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_kinematics_vs_reference(oracle_factory, robot):
+    o = oracle_factory(robot)
+    g = load_golden(f"dynamics_{robot}")
+    np.testing.assert_allclose(o.forward_kinematics(g["thetas"]), g["forward_kinematics"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(o.jacobian(g["thetas"]), g["jacobian"], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("analytic", [False, True], ids=["literal", "analytic"])
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_forward_dynamics_vs_reference(oracle_factory, robot, analytic):
+    o = oracle_factory(robot)
+    g = load_golden(f"dynamics_{robot}")
+    i = g["fd_index"]
+    got = o.forward_dynamics(g["thetas"][i], g["dthetas"][i], g["fd_tau"], g["g"], g["ftips"][i], analytic)
+    ref = g["forward_dynamics"]
+    # accelerations reach 1e5 rad/s^2 (lambda_min(M) ~ 1e-4): per-vector inf-norm relative
+    scale = np.maximum(1.0, np.abs(ref).max(axis=1, keepdims=True))
+    assert np.max(np.abs(got - ref) / scale) < 1e-9
+
+
+def _assert_traj_equal(got, ref, tag):
+    """Bit-exact float32, except at exact-cancellation points (tau = 0.5 or 1) where the
+    reference's Numba ``fastmath=True`` kernel (planning/trajectory.py:14) contracts the
+    polynomial into FMAs and leaves O(1e-16) residues instead of the IEEE zero."""
+    assert got.dtype == np.float32 and got.shape == ref.shape, tag
+    neq = got.view(np.uint32) != ref.view(np.uint32)
+    assert neq.mean() <= 0.5 and np.all(np.abs(got[neq].astype(np.float64) - ref[neq]) <= 1e-12), tag
+    assert np.all(got[neq] == 0), tag
+
+
+def test_joint_trajectory_bit_exact_vs_reference():
+    from oracle import Oracle
+
+    g = load_golden("trajectory")
+    lim = g["joint_limits"]
+    for name in ("cfg1", "cubic50", "two", "clipped", "odd_tf"):
+        Tf, N, method = g[f"{name}_args"]
+        r = Oracle.joint_trajectory(g[f"{name}_start"], g[f"{name}_end"], Tf, int(N), int(method), lim)
+        for k in ("positions", "velocities", "accelerations"):
+            _assert_traj_equal(r[k], g[f"{name}_{k}"], (name, k))
+        if name in ("cfg1", "odd_tf"):  # no exact-cancellation rows: every bit equal
+            assert all(np.array_equal(r[k].view(np.uint32), g[f"{name}_{k}"].view(np.uint32)) for k in r)
+    Tf, N, method = g["batch_args"]
+    r = Oracle.joint_trajectory(g["batch_start"], g["batch_end"], Tf, int(N), int(method), lim)
+    for k in ("positions", "velocities", "accelerations"):
+        _assert_traj_equal(r[k], g[f"batch_{k}"], ("batch", k))
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_dynamics_trajectory_vs_reference(oracle_factory, robot):
+    o = oracle_factory(robot)
+    g = load_golden("id_trajectory")
+    th, dth, ddth = g[f"{robot}_theta"], g[f"{robot}_dtheta"], g[f"{robot}_ddtheta"]
+    tl = g[f"{robot}_torque_limits"]
+    for analytic in (False, True):
+        t0 = o.inverse_dynamics_trajectory(th, dth, ddth, torque_limits=tl, analytic=analytic)
+        t1 = o.inverse_dynamics_trajectory(th, dth, ddth, g[f"{robot}_g1"], g[f"{robot}_ftip1"], tl, analytic)
+        for got, ref in ((t0, g[f"{robot}_tau_default"]), (t1, g[f"{robot}_tau_g1_ftip1"])):
+            assert got.dtype == np.float32
+            # float32 outputs: equal up to the last float32 ulp (finite-difference noise ~1e-9
+            # can flip a rounding); clipped entries must be exactly the limit
+            np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)
+            assert np.array_equal(got == tl[:, 0].astype(np.float32), ref == tl[:, 0].astype(np.float32))
+            assert np.array_equal(got == tl[:, 1].astype(np.float32), ref == tl[:, 1].astype(np.float32))
+        if robot == "ur5":  # the finite torque limits really clip on this fixture
+            assert (t0 == np.float32(35.0)).any() or (t0 == np.float32(-40.0)).any()
+
+
+@pytest.mark.parametrize("analytic", [False, True], ids=["literal", "analytic"])
+@pytest.mark.parametrize("robot", ["iiwa14", "ur5"])
+def test_forward_dynamics_trajectory_vs_reference(oracle_factory, robot, analytic):
+    o = oracle_factory(robot)
+    g = load_golden("fd_trajectory")
+    lim = g[f"{robot}_joint_limits"]
+    dt, intres = g[f"{robot}_a_args"]
+    r = o.forward_dynamics_trajectory(g[f"{robot}_a_theta0"], g[f"{robot}_a_dtheta0"], g[f"{robot}_a_tau"],
+                                      [0, 0, -9.81], None, dt, int(intres), lim, analytic)
+    for k in ("positions", "velocities", "accelerations"):
+        np.testing.assert_allclose(r[k], g[f"{robot}_a_{k}"], rtol=2e-6, atol=1e-6, err_msg=k)
+    dt, intres = g[f"{robot}_b_args"]
+    r = o.forward_dynamics_trajectory(g[f"{robot}_b_theta0"], g[f"{robot}_b_dtheta0"], g[f"{robot}_b_tau"],
+                                      g[f"{robot}_b_g"], g[f"{robot}_b_ftip"], dt, int(intres), lim, analytic)
+    ref_pos = g[f"{robot}_b_positions"]
+    for k in ("positions", "velocities", "accelerations"):
+        np.testing.assert_allclose(r[k], g[f"{robot}_b_{k}"], rtol=2e-6, atol=1e-6, err_msg=k)
+    # the joint-limit clip was exercised and lands exactly on the float32 limit
+    hi32 = lim[:, 1].astype(np.float32)
+    assert (ref_pos[1:] == hi32).any()
+    assert np.array_equal(r["positions"] == hi32, ref_pos == hi32)
+
+
+def test_forward_dynamics_trajectory_zero_steps(oracle_factory):
+    o = oracle_factory("ur5")
+    with pytest.raises(IndexError):
+        o.forward_dynamics_trajectory(np.zeros(6), np.zeros(6), np.zeros((0, 6)), [0, 0, -9.81], None, 1e-3, 1)
+
+
+def test_planar_2r_known_answers():
+    """Murray-Li-Sastry Ex. 4.3 mass matrix and hand-derived holding torques
+    (reference tests/test_v132_regressions.py:126-192, 229-286)."""
+    from oracle import Oracle
+
+    p = planar_2r_pack()
+    o = Oracle(p["S_list"], p["M"], p["Glist"], p["Mlist_per_link"])
+    th = np.array([0.0, np.pi / 2])
+    c2 = np.cos(th[1])
+    Mexp = np.array([[1 + (1 + 1 + 2 * c2), 1 + c2], [1 + c2, 1.0]])
+    for analytic in (False, True):
+        np.testing.assert_allclose(o.mass_matrix(th, analytic)[0], Mexp, atol=1e-12)
+        np.testing.assert_allclose(o.gravity_forces(th, [-9.81, 0, 0], analytic)[0], [-9.81, -9.81], atol=1e-12)
+        np.testing.assert_allclose(o.gravity_forces(th, [0, -9.81, 0], analytic)[0], [19.62, 0.0], atol=1e-12)
+        np.testing.assert_allclose(o.gravity_forces(th, [0, 0, -9.81], analytic)[0], [0.0, 0.0], atol=1e-12)
+
+
+def test_quintic_endpoints_and_linear_contract():
+    """Endpoint accelerations vanish for quintic (reference tests/test_v132_regressions.py:516-541)."""
+    from oracle import Oracle
+
+    r = Oracle.joint_trajectory(np.zeros(3), np.ones(3), 2.0, 11, 5)
+    assert np.all(r["accelerations"][0] == 0) and np.allclose(r["accelerations"][-1], 0, atol=1e-6)
+    assert np.all(r["positions"][0] == 0) and np.allclose(r["positions"][-1], 1.0)
+    assert np.all(r["velocities"][0] == 0)
