@@ -104,6 +104,14 @@ def test_inverse_dynamics_trajectory_vs_reference(oracle_factory, robot):
             assert (t0 == np.float32(35.0)).any() or (t0 == np.float32(-40.0)).any()
 
 
+def _assert_rows_close(got, ref, tol, tag):
+    """Per-row inf-norm relative: |d| <= tol * max(1, ||ref_row||_inf).  Accelerations reach
+    3e5 rad/s^2 on these fixtures (lambda_min(M) ~ 1e-4), so element-wise relative is meaningless."""
+    assert got.dtype == ref.dtype and got.shape == ref.shape, tag
+    scale = np.maximum(1.0, np.abs(ref).max(axis=-1, keepdims=True))
+    assert np.max(np.abs(got.astype(np.float64) - ref) / scale) <= tol, tag
+
+
 @pytest.mark.parametrize("analytic", [False, True], ids=["literal", "analytic"])
 @pytest.mark.parametrize("robot", ["iiwa14", "ur5"])
 def test_forward_dynamics_trajectory_vs_reference(oracle_factory, robot, analytic):
@@ -114,13 +122,13 @@ def test_forward_dynamics_trajectory_vs_reference(oracle_factory, robot, analyti
     r = o.forward_dynamics_trajectory(g[f"{robot}_a_theta0"], g[f"{robot}_a_dtheta0"], g[f"{robot}_a_tau"],
                                       [0, 0, -9.81], None, dt, int(intres), lim, analytic)
     for k in ("positions", "velocities", "accelerations"):
-        np.testing.assert_allclose(r[k], g[f"{robot}_a_{k}"], rtol=2e-6, atol=1e-6, err_msg=k)
+        _assert_rows_close(r[k], g[f"{robot}_a_{k}"], 1e-6, k)
     dt, intres = g[f"{robot}_b_args"]
     r = o.forward_dynamics_trajectory(g[f"{robot}_b_theta0"], g[f"{robot}_b_dtheta0"], g[f"{robot}_b_tau"],
                                       g[f"{robot}_b_g"], g[f"{robot}_b_ftip"], dt, int(intres), lim, analytic)
     ref_pos = g[f"{robot}_b_positions"]
     for k in ("positions", "velocities", "accelerations"):
-        np.testing.assert_allclose(r[k], g[f"{robot}_b_{k}"], rtol=2e-6, atol=1e-6, err_msg=k)
+        _assert_rows_close(r[k], g[f"{robot}_b_{k}"], 1e-6, k)
     # the joint-limit clip was exercised and lands exactly on the float32 limit
     hi32 = lim[:, 1].astype(np.float32)
     assert (ref_pos[1:] == hi32).any()
