@@ -1,0 +1,148 @@
+/*
+ * mpk.h -- C ABI of the B200-native batched trajectory-and-dynamics path.
+ *
+ * This is the drop-in boundary.  ManipulaPy has no FFI of its
+ * own: the seams are its Python methods, so every entry point below names the
+ * reference method (file:line, relative to the ManipulaPy v1.4.1 checkout) it
+ * replaces.  The Python host (manipulapy_b200/) and the PyTorch custom ops
+ * (torch.ops.mpk.*) are thin callers of exactly these symbols; a maintainer of
+ * the reference binds them with the ctypes stubs shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (a stream is
+ *     passed as `void*` holding a cudaStream_t; NULL = legacy default stream).
+ *   - "dev" pointers are device memory on the CURRENT CUDA device, row-major,
+ *     densely packed; "host" pointers are small host arrays read before the
+ *     call returns.  No hidden allocation, no synchronisation: every launcher
+ *     enqueues on `stream` and returns.
+ *   - return value: MPK_OK (0) or a negative MPK_E* code; nothing throws.
+ *     mpk_last_error() returns a human-readable reason for the last failure
+ *     on the calling thread.
+ *   - twists are [omega; v], wrenches [moment; force], S_list is (6, n) with
+ *     one column per joint -- the reference's conventions (utils/se3.py:45-52).
+ *   - element types: MPK_F64 / MPK_F32 select the STORAGE type of an array;
+ *     arithmetic is float64 throughout unless a launcher says otherwise.
+ */
+#ifndef MPK_H
+#define MPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPK_OK 0
+#define MPK_EINVAL (-1)      /* bad argument (NULL pointer, negative size, bad dtype)   */
+#define MPK_EUNSUPPORTED (-2) /* robot outside the supported class (see mpk_robot_create) */
+#define MPK_ECUDA (-3)       /* CUDA launch/runtime error                                */
+
+#define MPK_F64 0
+#define MPK_F32 1
+
+#define MPK_MAX_DOF 8
+
+/* mpk_robot_create flags */
+#define MPK_ROBOT_FORCE_GENERAL 1 /* route a rigid-body robot through the general-inertia kernels (tests) */
+
+typedef struct mpk_robot mpk_robot; /* opaque; host-resident constant pack (< 4 KB) */
+
+int mpk_version(void);
+const char *mpk_last_error(void);
+
+/* Constant pack of ManipulatorDynamics / SerialManipulator
+ * (dynamics/manipulator_dynamics.py:46-75; built by urdf/core.py:670-769).
+ *   S_list (6, n)   space screws, unit omega or omega = 0 (utils/se3.py:33-42 assumes this)
+ *   M      (4, 4)   end-effector home pose
+ *   Glist  (n,6,6)  spatial inertias in the link-CoM frames (NULL: kinematics only)
+ *   Mcom   (n,4,4)  Mlist_per_link (NULL with Glist NULL)
+ * All host, float64.  1 <= n <= MPK_MAX_DOF.  The pack is re-expressed in
+ * joint-aligned link frames on the host and later passed to every kernel as a
+ * __grid_constant__ parameter (constant bank), so there is no device allocation. */
+int mpk_robot_create(int n, const double *S_list, const double *M, const double *Glist,
+                     const double *Mcom, int flags, mpk_robot **out);
+void mpk_robot_destroy(mpk_robot *rb);
+int mpk_robot_dof(const mpk_robot *rb);
+/* 1 if every link inertia is a rigid body expressed at its centre of mass
+ * (block-diagonal [I, m*1]); 0 if the general symmetric-6x6 kernels are used. */
+int mpk_robot_is_rigid(const mpk_robot *rb);
+
+/* joint_trajectory / batch_joint_trajectory
+ * (planning/trajectory.py:103-169, 276-333, 335-502; kernel :15-75; clip :311-313).
+ *   start, end   dev (B, n) float64
+ *   inputs_f32   1: round start/end to float32 first and subtract in float32
+ *                (joint_trajectory, :147-153); 0: keep float64 (batch path, :474-476)
+ *   method       3 cubic, 5 quintic, anything else zero scaling (planner CPU contract :67-68)
+ *   limits       host (n, 2) float32 joint limits or NULL (no clip)
+ *   pos/vel/acc  dev (B, N, n) float32; any may be NULL (not written)
+ * Time scaling runs in float64 with the reference's operation order and one
+ * rounding to float32, so outputs are bit-identical to the reference's. */
+int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const double *end,
+                         int inputs_f32, double Tf, int method, const float *limits, float *pos,
+                         float *vel, float *acc, void *stream);
+
+/* SerialManipulator.forward_kinematics(theta, "space") (kinematics/fk.py:39-86) and
+ * SerialManipulator.jacobian(theta, "space") (kinematics/jacobian.py:39-93), batched.
+ *   theta dev (P, n) theta_dtype;  T dev (P, 4, 4) float64 or NULL;  J dev (P, 6, n) float64 or NULL */
+int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
+                          double *T, double *J, void *stream);
+
+/* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
+ * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).
+ *   theta/dtheta/ddtheta  dev (P, n) in_dtype; dtheta / ddtheta may be NULL (= 0), which gives
+ *                         gravity_forces (dynamics/forces.py:61-133) and
+ *                         velocity_quadratic_forces (:26-59, with g = 0)
+ *   g             host (3) float64
+ *   Ftip          host (6) float64 space-frame wrench for every point, or NULL
+ *   Ftip_rows     dev (P, 6) float64 per-point wrench (overrides Ftip), or NULL
+ *   tau_limits    host (n, 2) float32 or NULL; applied only when out_dtype = MPK_F32
+ *                 (row cast to float32, then clipped: trajectory_dynamics.py:354, 369-373)
+ *   tau           dev (P, n) out_dtype */
+int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *theta, const void *dtheta,
+                         const void *ddtheta, int in_dtype, const double *g, const double *Ftip,
+                         const double *Ftip_rows, const float *tau_limits, void *tau, int out_dtype,
+                         void *stream);
+
+/* joint_trajectory + inverse_dynamics_trajectory fused: the trajectory rows are
+ * produced in registers, rounded to float32 and clipped exactly as the two-call
+ * sequence would, and fed to the inverse dynamics without touching HBM.
+ *   start, end dev (B, n) float64;  tau dev (B, N, n) float32
+ *   pos/vel/acc dev (B, N, n) float32 or NULL (optional materialisation) */
+int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, int64_t N, const double *start,
+                                    const double *end, int inputs_f32, double Tf, int method,
+                                    const float *joint_limits, const double *g, const double *Ftip,
+                                    const float *tau_limits, float *tau, float *pos, float *vel,
+                                    float *acc, void *stream);
+
+/* ManipulatorDynamics.mass_matrix (dynamics/mass_matrix.py:16-99), batched.
+ *   theta dev (P, n) theta_dtype;  Mout dev (P, n, n) float64 (symmetric) */
+int mpk_mass_matrix(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
+                    double *Mout, void *stream);
+
+/* ManipulatorDynamics.forward_dynamics (dynamics/id_fd.py:50-83), batched.
+ *   theta/dtheta/tau dev (P, n) float64; Ftip_rows dev (P, 6) or NULL; ddtheta dev (P, n) float64 */
+int mpk_forward_dynamics(const mpk_robot *rb, int64_t P, const double *theta, const double *dtheta,
+                         const double *tau, const double *g, const double *Ftip,
+                         const double *Ftip_rows, double *ddtheta, void *stream);
+
+/* forward_dynamics_trajectory (planning/trajectory_dynamics.py:580-708) for B
+ * independent rollouts (B = 1 is the reference call).
+ *   theta0/dtheta0 dev (B, n) float64;  taumat dev (B, N, n) tau_dtype
+ *   Ftipmat dev (B, N, 6) float64 or NULL;  limits host (n, 2) float32 or NULL
+ *   pos/vel/acc dev (B, N, n) float32: row 0 = initial state with zero acceleration,
+ *   row i = state after intRes semi-implicit Euler sub-steps driven by taumat[i]. */
+int mpk_forward_dynamics_trajectory(const mpk_robot *rb, int64_t B, int64_t N, const double *theta0,
+                                    const double *dtheta0, const void *taumat, int tau_dtype,
+                                    const double *g, const double *Ftipmat, double dt, int intRes,
+                                    const float *limits, float *pos, float *vel, float *acc,
+                                    void *stream);
+
+/* Register-resident FMA micro-benchmark used by bench.py to measure the fp64 /
+ * fp32 CUDA-core peak the roofline fractions are quoted against.
+ * Runs `iters` dependent-chain FMAs x 8 chains per thread; flops = grid*block*iters*8*2. */
+int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, double *sink_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPK_H */

@@ -1,0 +1,92 @@
+"""Host <-> device plumbing shared by the API mirrors.
+
+Callers pass host arrays (NumPy, lists) and get fresh NumPy arrays back, exactly like the
+reference.  As an extension, ``torch`` CUDA tensors are accepted and then
+results stay on the device as ``torch`` tensors (no copies, current stream).
+"""
+
+from __future__ import annotations
+
+from typing import Any, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+
+
+def is_device_tensor(x: Any) -> bool:
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def any_device(*xs: Any) -> bool:
+    return any(is_device_tensor(x) for x in xs)
+
+
+def default_device(device: Optional[Any] = None) -> torch.device:
+    _native.require_cuda()
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise RuntimeError("manipulapy_b200 runs on CUDA devices only (no CPU fallback)")
+    return d if d.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(x: Any, device: torch.device, dtype: Optional[torch.dtype] = torch.float64,
+              keep_f32: bool = False) -> torch.Tensor:
+    """Host array / tensor -> contiguous CUDA tensor.
+
+    ``keep_f32``: float32 inputs stay float32 in HBM (the kernels upcast exactly in
+    registers); everything else becomes ``dtype``.
+    """
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        a = np.asarray(x)
+        if not (a.dtype == np.float32 and keep_f32) and a.dtype != np.float64:
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if keep_f32 and t.dtype == torch.float32:
+        want = torch.float32
+    else:
+        want = dtype if dtype is not None else t.dtype
+    if t.is_cuda:
+        return t.to(device=device, dtype=want).contiguous()
+    if t.numel() >= (1 << 16):
+        # large host arrays: stage through pinned memory so the copy runs at PCIe speed
+        pinned = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        pinned.copy_(t)
+        return pinned.to(device, non_blocking=True).to(want).contiguous()
+    return t.to(device).to(want).contiguous()
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """CUDA tensor -> fresh NumPy array (through pinned memory for large results)."""
+    if t.numel() >= (1 << 16):
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return out.numpy()
+    return t.cpu().numpy()
+
+
+def limits_tensor(limits: Any) -> Optional[torch.Tensor]:
+    """(n, 2) float32 host tensor, or None when every bound is infinite (clip is a no-op)."""
+    if limits is None:
+        return None
+    a = np.asarray(limits, dtype=np.float32)
+    if a.size == 0 or (np.isneginf(a[:, 0]).all() and np.isposinf(a[:, 1]).all()):
+        return None
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def vec(x: Any, n: int, name: str) -> list:
+    a = np.asarray(x.detach().cpu() if isinstance(x, torch.Tensor) else x, dtype=np.float64).reshape(-1)
+    if a.size != n:
+        raise ValueError(f"{name} must have {n} entries, got {a.size}")
+    return [float(v) for v in a]
+
+
+def gravity(g: Any) -> list:
+    return [0.0, 0.0, -9.81] if g is None else vec(g, 3, "gravity vector")

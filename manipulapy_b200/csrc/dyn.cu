@@ -1,0 +1,375 @@
+// dyn.cu -- batched inverse dynamics, fused trajectory + inverse dynamics, mass matrix
+// and per-point forward dynamics.
+//
+// Replace the per-point Python loops of the reference:
+//   inverse dynamics            dynamics/id_fd.py:16-48 and planning/trajectory_dynamics.py:308-380
+//   gravity / Coriolis forces   dynamics/forces.py:26-133 (ddtheta = 0 / g = 0 calls)
+//   mass matrix                 dynamics/mass_matrix.py:16-99
+//   forward dynamics            dynamics/id_fd.py:50-83
+// One thread owns one point; all link state lives in registers (mpk_device.cuh); robot
+// constants are constant-bank operands.  fp64 FMA-pipe bound.
+#include "mpk_common.cuh"
+
+namespace mpk {
+
+constexpr int kDynThreads = 128;
+
+struct TipArgs {
+    double g[3];
+    double ftip[6];
+    int has_ftip;
+    const double *ftip_rows;  // (P, 6) or nullptr
+};
+
+struct RneaArgs {
+    int64_t P;
+    const void *th, *dth, *ddth;
+    int in_dtype, vec_in;
+    TipArgs tip;
+    Limits lim;
+    void *out;
+    int out_dtype, vec_out;
+};
+
+template <int N>
+__device__ __forceinline__ void store_tau(void *out, int out_dtype, bool vec, int64_t p,
+                                          const double (&tau)[N], const Limits &lim) {
+    if (out_dtype == MPK_F64) {
+        store_row_f64<N>(static_cast<double *>(out), vec, p, tau);
+    } else {
+        float t32[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            t32[j] = (float)tau[j];
+            if (lim.on) t32[j] = clip_f32(t32[j], lim.lo[j], lim.hi[j]);
+        }
+        store_row_f32<N>(static_cast<float *>(out), vec, p, t32);
+    }
+}
+
+template <int N, bool GEN>
+__global__ void __launch_bounds__(kDynThreads)
+    rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    if (p >= a.P) return;
+    double th[N], dth[N], ddth[N];
+    load_row<N>(a.th, a.in_dtype, a.vec_in, p, th);
+    if (a.dth) load_row<N>(a.dth, a.in_dtype, a.vec_in, p, dth);
+    else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) dth[j] = 0.0;
+    }
+    if (a.ddth) load_row<N>(a.ddth, a.in_dtype, a.vec_in, p, ddth);
+    else {
+#pragma unroll
+        for (int j = 0; j < N; ++j) ddth[j] = 0.0;
+    }
+    double ft[6];
+    const double *ftp = nullptr;
+    if (a.tip.ftip_rows) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[k] = __ldg(a.tip.ftip_rows + p * 6 + k);
+        ftp = ft;
+    } else if (a.tip.has_ftip) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
+        ftp = ft;
+    }
+    JointCS<double, N> q;
+    joint_cs(rb, th, q);
+    double tau[N];
+    rnea<double, N, GEN>(rb, q, dth, ddth, a.tip.g, ftp, tau);
+    store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
+}
+
+// ---- fused trajectory + inverse dynamics ----------------------------------------
+struct TrajRneaArgs {
+    int64_t B, N, P;
+    const double *start, *end;
+    int inputs_f32;
+    double Tf;
+    int method;
+    Limits jlim, tlim;
+    TipArgs tip;
+    float *tau, *pos, *vel, *acc;
+};
+
+template <int N, bool GEN>
+__global__ void __launch_bounds__(kDynThreads)
+    traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
+    __shared__ __align__(16) float sm[kDynThreads * N];
+    int64_t b, t;
+    point_coords(a.N, b, t);
+    const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
+    const bool live = p0 + threadIdx.x < a.P;
+    const int64_t rem = a.P - p0;
+    const int cnt = (int)(rem < kDynThreads ? rem : kDynThreads) * N;
+    const int64_t off = p0 * N;
+    float pf[N], vf[N], af[N];
+    if (live) {
+        const TimeScale ts = time_scaling(t, a.N, a.Tf, a.method);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double st, dth;
+            endpoint(a.start, a.end, a.inputs_f32, b * N + j, st, dth);
+            traj_point(ts, st, dth, a.jlim.lo[j], a.jlim.hi[j], a.jlim.on, pf[j], vf[j], af[j]);
+        }
+    }
+    // optional materialisation of the trajectory rows (coalesced through shared memory)
+    float *outs[3] = {a.pos, a.vel, a.acc};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!outs[k]) continue;  // uniform
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                sm[threadIdx.x * N + j] = k == 0 ? pf[j] : (k == 1 ? vf[j] : af[j]);
+        }
+        __syncthreads();
+        tile_store(outs[k] + off, sm, cnt);
+        __syncthreads();
+    }
+    if (live) {
+        double th[N], dth[N], ddth[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            th[j] = (double)pf[j];
+            dth[j] = (double)vf[j];
+            ddth[j] = (double)af[j];
+        }
+        double ft[6];
+        const double *ftp = nullptr;
+        if (a.tip.has_ftip) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
+            ftp = ft;
+        }
+        JointCS<double, N> q;
+        joint_cs(rb, th, q);
+        double tau[N];
+        rnea<double, N, GEN>(rb, q, dth, ddth, a.tip.g, ftp, tau);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float x = (float)tau[j];
+            if (a.tlim.on) x = clip_f32(x, a.tlim.lo[j], a.tlim.hi[j]);
+            sm[threadIdx.x * N + j] = x;
+        }
+    }
+    __syncthreads();
+    tile_store(a.tau + off, sm, cnt);
+}
+
+// ---- mass matrix -------------------------------------------------------------------
+struct MassArgs {
+    int64_t P;
+    const void *th;
+    int th_dtype, vec_in, vec_out;
+    double *out;
+};
+
+template <int N, bool GEN>
+__global__ void __launch_bounds__(kDynThreads)
+    mass_matrix_kernel(const __grid_constant__ RobotPack<double, N> rb, const MassArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    if (p >= a.P) return;
+    double th[N];
+    load_row<N>(a.th, a.th_dtype, a.vec_in, p, th);
+    JointCS<double, N> q;
+    joint_cs(rb, th, q);
+    double Mm[N][N];
+    mass_matrix<double, N, GEN>(rb, q, Mm);
+    double flat[N * N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+#pragma unroll
+        for (int j = 0; j < N; ++j) flat[i * N + j] = Mm[i][j];
+    store_row_f64<N * N>(a.out, a.vec_out, p, flat);
+}
+
+// ---- per-point forward dynamics --------------------------------------------------------
+struct FdArgs {
+    int64_t P;
+    const double *th, *dth, *tau;
+    int vec;
+    TipArgs tip;
+    double *out;
+};
+
+template <int N, bool GEN>
+__global__ void __launch_bounds__(kDynThreads)
+    forward_dynamics_kernel(const __grid_constant__ RobotPack<double, N> rb, const FdArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    if (p >= a.P) return;
+    double th[N], dth[N], tau[N], dd[N];
+    load_row<N>(a.th, MPK_F64, a.vec, p, th);
+    load_row<N>(a.dth, MPK_F64, a.vec, p, dth);
+    load_row<N>(a.tau, MPK_F64, a.vec, p, tau);
+    double ft[6];
+    const double *ftp = nullptr;
+    if (a.tip.ftip_rows) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[k] = __ldg(a.tip.ftip_rows + p * 6 + k);
+        ftp = ft;
+    } else if (a.tip.has_ftip) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
+        ftp = ft;
+    }
+    forward_dynamics<double, N, GEN>(rb, th, dth, tau, a.tip.g, ftp, dd);
+    store_row_f64<N>(a.out, a.vec, p, dd);
+}
+
+static TipArgs make_tip(const double *g, const double *Ftip, const double *Ftip_rows) {
+    TipArgs t;
+    for (int k = 0; k < 3; ++k) t.g[k] = g ? g[k] : 0.0;
+    t.has_ftip = 0;
+    for (int k = 0; k < 6; ++k) {
+        t.ftip[k] = Ftip ? Ftip[k] : 0.0;
+        if (t.ftip[k] != 0.0) t.has_ftip = 1;
+    }
+    t.ftip_rows = Ftip_rows;
+    return t;
+}
+
+static int grid_for(int64_t P, unsigned &grid) {
+    const int64_t blocks = (P + kDynThreads - 1) / kDynThreads;
+    if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "point count exceeds the grid limit");
+    grid = (unsigned)blocks;
+    return MPK_OK;
+}
+
+}  // namespace mpk
+
+using namespace mpk;
+
+#define MPK_REQUIRE_DYN(rb)                                                      \
+    if (!(rb)) return fail(MPK_EINVAL, "robot is NULL");                         \
+    if (!(rb)->has_dynamics)                                                     \
+        return fail(MPK_EINVAL, "robot was created without Glist / Mlist_per_link")
+
+extern "C" int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *theta,
+                                    const void *dtheta, const void *ddtheta, int in_dtype,
+                                    const double *g, const double *Ftip, const double *Ftip_rows,
+                                    const float *tau_limits, void *tau, int out_dtype,
+                                    void *stream) {
+    MPK_REQUIRE_DYN(rb);
+    if (P < 0) return fail(MPK_EINVAL, "negative size");
+    if (P == 0) return MPK_OK;
+    if (!theta || !tau || !g) return fail(MPK_EINVAL, "theta, g and tau are required");
+    if ((in_dtype != MPK_F64 && in_dtype != MPK_F32) || (out_dtype != MPK_F64 && out_dtype != MPK_F32))
+        return fail(MPK_EINVAL, "bad dtype");
+    RneaArgs a;
+    a.P = P;
+    a.th = theta;
+    a.dth = dtheta;
+    a.ddth = ddtheta;
+    a.in_dtype = in_dtype;
+    a.vec_in = aligned16(theta) && (!dtheta || aligned16(dtheta)) && (!ddtheta || aligned16(ddtheta));
+    a.tip = make_tip(g, Ftip, Ftip_rows);
+    a.lim = make_limits(out_dtype == MPK_F32 ? tau_limits : nullptr, rb->n);
+    a.out = tau;
+    a.out_dtype = out_dtype;
+    a.vec_out = aligned16(tau);
+    unsigned grid;
+    if (int rc = grid_for(P, grid)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (rb->rigid) {
+        MPK_DISPATCH_DOF(rb->n, (rnea_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    } else {
+        MPK_DISPATCH_DOF(rb->n, (rnea_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    }
+    return check_launch("inverse_dynamics");
+}
+
+extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, int64_t N,
+                                               const double *start, const double *end,
+                                               int inputs_f32, double Tf, int method,
+                                               const float *joint_limits, const double *g,
+                                               const double *Ftip, const float *tau_limits,
+                                               float *tau, float *pos, float *vel, float *acc,
+                                               void *stream) {
+    MPK_REQUIRE_DYN(rb);
+    if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
+    if (B == 0 || N == 0) return MPK_OK;
+    if (!start || !end || !tau || !g) return fail(MPK_EINVAL, "start, end, g and tau are required");
+    for (float *o : {tau, pos, vel, acc})
+        if (o && !aligned16(o)) return fail(MPK_EINVAL, "outputs must be 16-byte aligned");
+    TrajRneaArgs a;
+    a.B = B;
+    a.N = N;
+    a.P = B * N;
+    a.start = start;
+    a.end = end;
+    a.inputs_f32 = inputs_f32;
+    a.Tf = Tf;
+    a.method = method;
+    a.jlim = make_limits(joint_limits, rb->n);
+    a.tlim = make_limits(tau_limits, rb->n);
+    a.tip = make_tip(g, Ftip, nullptr);
+    a.tau = tau;
+    a.pos = pos;
+    a.vel = vel;
+    a.acc = acc;
+    unsigned grid;
+    if (int rc = grid_for(a.P, grid)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (rb->rigid) {
+        MPK_DISPATCH_DOF(rb->n, (traj_rnea_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    } else {
+        MPK_DISPATCH_DOF(rb->n, (traj_rnea_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    }
+    return check_launch("trajectory_inverse_dynamics");
+}
+
+extern "C" int mpk_mass_matrix(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
+                               double *Mout, void *stream) {
+    MPK_REQUIRE_DYN(rb);
+    if (P < 0) return fail(MPK_EINVAL, "negative size");
+    if (P == 0) return MPK_OK;
+    if (!theta || !Mout) return fail(MPK_EINVAL, "theta and Mout are required");
+    if (theta_dtype != MPK_F64 && theta_dtype != MPK_F32) return fail(MPK_EINVAL, "bad dtype");
+    MassArgs a;
+    a.P = P;
+    a.th = theta;
+    a.th_dtype = theta_dtype;
+    a.vec_in = aligned16(theta);
+    a.vec_out = aligned16(Mout);
+    a.out = Mout;
+    unsigned grid;
+    if (int rc = grid_for(P, grid)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (rb->rigid) {
+        MPK_DISPATCH_DOF(rb->n, (mass_matrix_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    } else {
+        MPK_DISPATCH_DOF(rb->n, (mass_matrix_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    }
+    return check_launch("mass_matrix");
+}
+
+extern "C" int mpk_forward_dynamics(const mpk_robot *rb, int64_t P, const double *theta,
+                                    const double *dtheta, const double *tau, const double *g,
+                                    const double *Ftip, const double *Ftip_rows, double *ddtheta,
+                                    void *stream) {
+    MPK_REQUIRE_DYN(rb);
+    if (P < 0) return fail(MPK_EINVAL, "negative size");
+    if (P == 0) return MPK_OK;
+    if (!theta || !dtheta || !tau || !g || !ddtheta)
+        return fail(MPK_EINVAL, "theta, dtheta, tau, g and ddtheta are required");
+    FdArgs a;
+    a.P = P;
+    a.th = theta;
+    a.dth = dtheta;
+    a.tau = tau;
+    a.vec = aligned16(theta) && aligned16(dtheta) && aligned16(tau) && aligned16(ddtheta);
+    a.tip = make_tip(g, Ftip, Ftip_rows);
+    a.out = ddtheta;
+    unsigned grid;
+    if (int rc = grid_for(P, grid)) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (rb->rigid) {
+        MPK_DISPATCH_DOF(rb->n, (forward_dynamics_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    } else {
+        MPK_DISPATCH_DOF(rb->n, (forward_dynamics_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+    }
+    return check_launch("forward_dynamics");
+}

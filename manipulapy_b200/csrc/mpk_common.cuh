@@ -1,0 +1,201 @@
+// mpk_common.cuh -- host-side plumbing shared by the launcher translation units:
+// the opaque robot handle, error reporting, DOF dispatch and row load/store helpers.
+#pragma once
+#include <cstdio>
+#include <string>
+
+#include "../../include/mpk.h"
+#include "mpk_device.cuh"
+
+struct mpk_robot {
+    int n;
+    int rigid;
+    int has_dynamics;
+    mpk::RobotPack<double, MPK_MAX_DOF> pack;  // host copy, frames 0..n-1 valid
+};
+
+namespace mpk {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int check_launch(const char *what);
+
+// Narrow the max-DOF host pack to the N the kernel is instantiated for.
+template <int N>
+inline RobotPack<double, N> narrow(const mpk_robot *rb) {
+    RobotPack<double, N> o;
+    const auto &s = rb->pack;
+    for (int i = 0; i < N; ++i) {
+        for (int k = 0; k < 9; ++k) o.Rx[i][k] = s.Rx[i][k];
+        for (int k = 0; k < 3; ++k) {
+            o.px[i][k] = s.px[i][k];
+            o.h[i][k] = s.h[i][k];
+            o.cg[i][k] = s.cg[i][k];
+        }
+        for (int k = 0; k < 6; ++k) o.I[i][k] = s.I[i][k];
+        for (int k = 0; k < 21; ++k) o.G[i][k] = s.G[i][k];
+        o.sr[i] = s.sr[i];
+        o.st[i] = s.st[i];
+        o.m[i] = s.m[i];
+        o.mg[i] = s.mg[i];
+    }
+    for (int k = 0; k < 9; ++k) o.Ree[k] = s.Ree[k];
+    for (int k = 0; k < 3; ++k) o.pee[k] = s.pee[k];
+    return o;
+}
+
+#define MPK_DISPATCH_DOF(n, ...)                          \
+    switch (n) {                                          \
+        case 1: { constexpr int N_ = 1; __VA_ARGS__; } break;    \
+        case 2: { constexpr int N_ = 2; __VA_ARGS__; } break;    \
+        case 3: { constexpr int N_ = 3; __VA_ARGS__; } break;    \
+        case 4: { constexpr int N_ = 4; __VA_ARGS__; } break;    \
+        case 5: { constexpr int N_ = 5; __VA_ARGS__; } break;    \
+        case 6: { constexpr int N_ = 6; __VA_ARGS__; } break;    \
+        case 7: { constexpr int N_ = 7; __VA_ARGS__; } break;    \
+        case 8: { constexpr int N_ = 8; __VA_ARGS__; } break;    \
+        default: return mpk::fail(MPK_EUNSUPPORTED, "dof must be in 1..8"); \
+    }
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- per-thread row I/O -------------------------------------------------------
+// Row p of a dense (P, N) array of float64 / float32 -> N doubles in registers.
+// Each thread owns one contiguous row; rows of consecutive threads are adjacent, so a
+// warp touches one contiguous span and every fetched sector is fully used.  16-byte
+// vector loads are used when the row size allows (the launcher checks base alignment).
+template <int N>
+__device__ __forceinline__ void load_row(const void *base, int dtype, bool vec, int64_t p,
+                                         double (&out)[N]) {
+    if (dtype == MPK_F64) {
+        const double *r = static_cast<const double *>(base) + p * N;
+        if ((N % 2 == 0) && vec) {
+            const double2 *r2 = reinterpret_cast<const double2 *>(r);
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) {
+                const double2 v = __ldg(r2 + k);
+                out[2 * k] = v.x;
+                out[2 * k + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) out[k] = __ldg(r + k);
+        }
+    } else {
+        const float *r = static_cast<const float *>(base) + p * N;
+        if ((N % 4 == 0) && vec) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(r);
+#pragma unroll
+            for (int k = 0; k < N / 4; ++k) {
+                const float4 v = __ldg(r4 + k);
+                out[4 * k] = v.x;
+                out[4 * k + 1] = v.y;
+                out[4 * k + 2] = v.z;
+                out[4 * k + 3] = v.w;
+            }
+        } else if ((N % 2 == 0) && vec) {
+            const float2 *r2 = reinterpret_cast<const float2 *>(r);
+#pragma unroll
+            for (int k = 0; k < N / 2; ++k) {
+                const float2 v = __ldg(r2 + k);
+                out[2 * k] = v.x;
+                out[2 * k + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N; ++k) out[k] = __ldg(r + k);
+        }
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void store_row_f64(double *base, bool vec, int64_t p,
+                                              const double (&v)[K]) {
+    double *r = base + p * K;
+    if ((K % 2 == 0) && vec) {
+        double2 *r2 = reinterpret_cast<double2 *>(r);
+#pragma unroll
+        for (int k = 0; k < K / 2; ++k) r2[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = v[k];
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void store_row_f32(float *base, bool vec, int64_t p,
+                                              const float (&v)[K]) {
+    float *r = base + p * K;
+    if ((K % 4 == 0) && vec) {
+        float4 *r4 = reinterpret_cast<float4 *>(r);
+#pragma unroll
+        for (int k = 0; k < K / 4; ++k)
+            r4[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    } else if ((K % 2 == 0) && vec) {
+        float2 *r2 = reinterpret_cast<float2 *>(r);
+#pragma unroll
+        for (int k = 0; k < K / 2; ++k) r2[k] = make_float2(v[2 * k], v[2 * k + 1]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) r[k] = v[k];
+    }
+}
+
+struct Limits {
+    float lo[MPK_MAX_DOF], hi[MPK_MAX_DOF];
+    int on;
+};
+
+inline Limits make_limits(const float *lim, int n) {
+    Limits L;
+    L.on = lim != nullptr;
+    for (int j = 0; j < MPK_MAX_DOF; ++j) {
+        L.lo[j] = (lim && j < n) ? lim[2 * j] : 0.f;
+        L.hi[j] = (lim && j < n) ? lim[2 * j + 1] : 0.f;
+    }
+    return L;
+}
+
+// (trajectory, step) of the flattened point index blockIdx.x*128 + threadIdx.x: one
+// 64-bit division per block, plus one per warp that straddles a trajectory boundary.
+__device__ __forceinline__ void point_coords(int64_t N, int64_t &b, int64_t &t) {
+    __shared__ int64_t s_b0, s_t0;
+    if (threadIdx.x == 0) {
+        const int64_t p0 = (int64_t)blockIdx.x * blockDim.x;
+        s_b0 = p0 / N;
+        s_t0 = p0 - s_b0 * N;
+    }
+    __syncthreads();
+    b = s_b0;
+    t = s_t0 + threadIdx.x;
+    if (t >= N) {
+        const int64_t q = t / N;
+        b += q;
+        t -= q * N;
+    }
+}
+
+// start and (end - start) of joint j of trajectory b, in the precision the reference uses.
+__device__ __forceinline__ void endpoint(const double *start, const double *end, int inputs_f32,
+                                         int64_t idx, double &st, double &dth) {
+    const double s = __ldg(start + idx), e = __ldg(end + idx);
+    if (inputs_f32) {
+        const float s32 = (float)s, e32 = (float)e;
+        st = (double)s32;
+        dth = (double)rn_fsub(e32, s32);
+    } else {
+        st = s;
+        dth = rn_sub(e, s);
+    }
+}
+
+// Coalesced copy-out of a block's staged rows: cnt floats from shared memory to o.
+__device__ __forceinline__ void tile_store(float *o, const float *sm, int cnt) {
+    const int n4 = cnt >> 2;
+    const float4 *s4 = reinterpret_cast<const float4 *>(sm);
+    float4 *o4 = reinterpret_cast<float4 *>(o);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, s4[i]);
+    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) o[i] = sm[i];
+}
+
+}  // namespace mpk

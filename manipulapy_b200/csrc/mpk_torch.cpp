@@ -1,0 +1,301 @@
+// mpk_torch.cpp -- PyTorch custom-op extension: torch.ops.mpk.* are thin callers of the
+// C ABI in include/mpk.h.  PyTorch supplies device memory, the current stream and the
+// dispatcher; all arithmetic happens in libmpk.so's hand-written sm_100a kernels.  There
+// is no CPU implementation: every op requires CUDA tensors and raises otherwise.
+#include <ATen/ATen.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+#include <torch/library.h>
+
+#include <tuple>
+#include <vector>
+
+#include "mpk.h"
+
+namespace {
+
+using at::Tensor;
+using OptT = std::optional<Tensor>;
+
+void check(int rc, const char *what) {
+    TORCH_CHECK(rc == MPK_OK, "mpk::", what, " failed (", rc, "): ", mpk_last_error());
+}
+
+mpk_robot *robot(int64_t h) {
+    TORCH_CHECK(h != 0, "mpk: null robot handle");
+    return reinterpret_cast<mpk_robot *>(static_cast<intptr_t>(h));
+}
+
+void *stream_of(const Tensor &t) { return c10::cuda::getCurrentCUDAStream(t.get_device()).stream(); }
+
+Tensor dev_rows(const Tensor &t, int64_t n, const char *name, bool allow_f32) {
+    TORCH_CHECK(t.is_cuda(), "mpk: ", name, " must be a CUDA tensor (there is no CPU path)");
+    TORCH_CHECK(t.scalar_type() == at::kDouble || (allow_f32 && t.scalar_type() == at::kFloat),
+                "mpk: ", name, " must be float64", allow_f32 ? " or float32" : "");
+    TORCH_CHECK(t.dim() >= 1 && t.size(-1) == n, "mpk: ", name, " must have ", n, " columns");
+    return t.contiguous();
+}
+int dtype_of(const Tensor &t) { return t.scalar_type() == at::kDouble ? MPK_F64 : MPK_F32; }
+
+// small host constants -------------------------------------------------------------------
+std::vector<float> host_limits(const OptT &lim, int64_t n, const char *name) {
+    std::vector<float> v;
+    if (!lim.has_value()) return v;
+    Tensor l = lim->to(at::kCPU, at::kFloat).contiguous();
+    TORCH_CHECK(l.numel() == 2 * n, "mpk: ", name, " must be (", n, ", 2)");
+    v.assign(l.data_ptr<float>(), l.data_ptr<float>() + 2 * n);
+    return v;
+}
+const float *ptr_or_null(const std::vector<float> &v) { return v.empty() ? nullptr : v.data(); }
+
+std::vector<double> host_vec(c10::ArrayRef<double> a, size_t n, const char *name) {
+    TORCH_CHECK(a.size() == n, "mpk: ", name, " must have ", n, " entries");
+    return std::vector<double>(a.begin(), a.end());
+}
+
+// ops ---------------------------------------------------------------------------------------
+int64_t robot_create(const Tensor &S, const Tensor &M, const OptT &G, const OptT &Mcom, int64_t flags) {
+    Tensor s = S.to(at::kCPU, at::kDouble).contiguous();
+    Tensor m = M.to(at::kCPU, at::kDouble).contiguous();
+    TORCH_CHECK(s.dim() == 2 && s.size(0) == 6, "mpk: S_list must be (6, n)");
+    TORCH_CHECK(m.dim() == 2 && m.size(0) == 4 && m.size(1) == 4, "mpk: M must be (4, 4)");
+    const int64_t n = s.size(1);
+    Tensor g, mc;
+    const double *gp = nullptr, *mp = nullptr;
+    if (G.has_value()) {
+        TORCH_CHECK(Mcom.has_value(), "mpk: Glist needs Mlist_per_link");
+        g = G->to(at::kCPU, at::kDouble).contiguous();
+        mc = Mcom->to(at::kCPU, at::kDouble).contiguous();
+        TORCH_CHECK(g.numel() == n * 36, "mpk: Glist must be (n, 6, 6)");
+        TORCH_CHECK(mc.numel() == n * 16, "mpk: Mlist_per_link must be (n, 4, 4)");
+        gp = g.data_ptr<double>();
+        mp = mc.data_ptr<double>();
+    }
+    mpk_robot *rb = nullptr;
+    check(mpk_robot_create((int)n, s.data_ptr<double>(), m.data_ptr<double>(), gp, mp, (int)flags, &rb),
+          "robot_create");
+    return static_cast<int64_t>(reinterpret_cast<intptr_t>(rb));
+}
+
+void robot_destroy(int64_t h) { mpk_robot_destroy(robot(h)); }
+int64_t robot_dof(int64_t h) { return mpk_robot_dof(robot(h)); }
+bool robot_is_rigid(int64_t h) { return mpk_robot_is_rigid(robot(h)) == 1; }
+
+std::tuple<Tensor, Tensor, Tensor> joint_trajectory(const Tensor &start, const Tensor &end,
+                                                    bool inputs_f32, double Tf, int64_t N,
+                                                    int64_t method, const OptT &limits) {
+    TORCH_CHECK(start.dim() == 2, "mpk: start must be (B, n)");
+    const int64_t B = start.size(0), n = start.size(1);
+    Tensor s = dev_rows(start, n, "start", false), e = dev_rows(end, n, "end", false);
+    TORCH_CHECK(e.sizes() == s.sizes(), "mpk: start/end shape mismatch");
+    TORCH_CHECK(N >= 0, "mpk: N must be >= 0");
+    c10::cuda::CUDAGuard guard(s.device());
+    auto opt = s.options().dtype(at::kFloat);
+    Tensor pos = at::empty({B, N, n}, opt), vel = at::empty({B, N, n}, opt), acc = at::empty({B, N, n}, opt);
+    auto lim = host_limits(limits, n, "joint_limits");
+    check(mpk_joint_trajectory((int)n, B, N, s.data_ptr<double>(), e.data_ptr<double>(), inputs_f32, Tf,
+                               (int)method, ptr_or_null(lim), pos.data_ptr<float>(),
+                               vel.data_ptr<float>(), acc.data_ptr<float>(), stream_of(s)),
+          "joint_trajectory");
+    return {pos, vel, acc};
+}
+
+std::tuple<Tensor, Tensor> fk_jacobian(int64_t h, const Tensor &theta, bool want_T, bool want_J) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th = dev_rows(theta, n, "theta", true);
+    const int64_t P = th.numel() / n;
+    c10::cuda::CUDAGuard guard(th.device());
+    auto opt = th.options().dtype(at::kDouble);
+    Tensor T = want_T ? at::empty({P, 4, 4}, opt) : at::empty({0}, opt);
+    Tensor J = want_J ? at::empty({P, 6, n}, opt) : at::empty({0}, opt);
+    check(mpk_fk_jacobian_space(rb, P, th.data_ptr(), dtype_of(th), want_T ? T.data_ptr<double>() : nullptr,
+                                want_J ? J.data_ptr<double>() : nullptr, stream_of(th)),
+          "fk_jacobian_space");
+    return {T, J};
+}
+
+Tensor inverse_dynamics(int64_t h, const Tensor &theta, const OptT &dtheta, const OptT &ddtheta,
+                        c10::ArrayRef<double> g, std::optional<c10::ArrayRef<double>> ftip,
+                        const OptT &ftip_rows, const OptT &tau_limits, bool out_f32) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th = dev_rows(theta, n, "theta", true);
+    const int64_t P = th.numel() / n;
+    Tensor dth, ddth, fr;
+    const void *dp = nullptr, *ddp = nullptr;
+    const double *frp = nullptr;
+    if (dtheta.has_value()) {
+        dth = dev_rows(*dtheta, n, "dtheta", true).to(th.scalar_type());
+        TORCH_CHECK(dth.numel() == th.numel(), "mpk: dtheta shape mismatch");
+        dp = dth.data_ptr();
+    }
+    if (ddtheta.has_value()) {
+        ddth = dev_rows(*ddtheta, n, "ddtheta", true).to(th.scalar_type());
+        TORCH_CHECK(ddth.numel() == th.numel(), "mpk: ddtheta shape mismatch");
+        ddp = ddth.data_ptr();
+    }
+    if (ftip_rows.has_value()) {
+        fr = dev_rows(*ftip_rows, 6, "Ftip rows", false);
+        TORCH_CHECK(fr.numel() == P * 6, "mpk: Ftip rows must be (P, 6)");
+        frp = fr.data_ptr<double>();
+    }
+    auto gv = host_vec(g, 3, "g");
+    std::vector<double> fv;
+    if (ftip.has_value()) fv = host_vec(*ftip, 6, "Ftip");
+    auto lim = host_limits(tau_limits, n, "torque_limits");
+    c10::cuda::CUDAGuard guard(th.device());
+    Tensor tau = at::empty({P, n}, th.options().dtype(out_f32 ? at::kFloat : at::kDouble));
+    check(mpk_inverse_dynamics(rb, P, th.data_ptr(), dp, ddp, dtype_of(th), gv.data(),
+                               fv.empty() ? nullptr : fv.data(), frp, ptr_or_null(lim), tau.data_ptr(),
+                               out_f32 ? MPK_F32 : MPK_F64, stream_of(th)),
+          "inverse_dynamics");
+    return tau;
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
+    int64_t h, const Tensor &start, const Tensor &end, bool inputs_f32, double Tf, int64_t N,
+    int64_t method, const OptT &joint_limits, c10::ArrayRef<double> g,
+    std::optional<c10::ArrayRef<double>> ftip, const OptT &tau_limits, bool want_traj) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    TORCH_CHECK(start.dim() == 2, "mpk: start must be (B, n)");
+    Tensor s = dev_rows(start, n, "start", false), e = dev_rows(end, n, "end", false);
+    TORCH_CHECK(e.sizes() == s.sizes(), "mpk: start/end shape mismatch");
+    TORCH_CHECK(N >= 0, "mpk: N must be >= 0");
+    const int64_t B = s.size(0);
+    auto gv = host_vec(g, 3, "g");
+    std::vector<double> fv;
+    if (ftip.has_value()) fv = host_vec(*ftip, 6, "Ftip");
+    auto jl = host_limits(joint_limits, n, "joint_limits");
+    auto tl = host_limits(tau_limits, n, "torque_limits");
+    c10::cuda::CUDAGuard guard(s.device());
+    auto opt = s.options().dtype(at::kFloat);
+    Tensor tau = at::empty({B, N, n}, opt);
+    Tensor pos, vel, acc;
+    float *pp = nullptr, *vp = nullptr, *ap = nullptr;
+    if (want_traj) {
+        pos = at::empty({B, N, n}, opt);
+        vel = at::empty({B, N, n}, opt);
+        acc = at::empty({B, N, n}, opt);
+        pp = pos.data_ptr<float>();
+        vp = vel.data_ptr<float>();
+        ap = acc.data_ptr<float>();
+    } else {
+        pos = vel = acc = at::empty({0}, opt);
+    }
+    check(mpk_trajectory_inverse_dynamics(rb, B, N, s.data_ptr<double>(), e.data_ptr<double>(), inputs_f32,
+                                          Tf, (int)method, ptr_or_null(jl), gv.data(),
+                                          fv.empty() ? nullptr : fv.data(), ptr_or_null(tl),
+                                          tau.data_ptr<float>(), pp, vp, ap, stream_of(s)),
+          "trajectory_inverse_dynamics");
+    return {tau, pos, vel, acc};
+}
+
+Tensor mass_matrix(int64_t h, const Tensor &theta) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th = dev_rows(theta, n, "theta", true);
+    const int64_t P = th.numel() / n;
+    c10::cuda::CUDAGuard guard(th.device());
+    Tensor M = at::empty({P, n, n}, th.options().dtype(at::kDouble));
+    check(mpk_mass_matrix(rb, P, th.data_ptr(), dtype_of(th), M.data_ptr<double>(), stream_of(th)),
+          "mass_matrix");
+    return M;
+}
+
+Tensor forward_dynamics(int64_t h, const Tensor &theta, const Tensor &dtheta, const Tensor &tau,
+                        c10::ArrayRef<double> g, std::optional<c10::ArrayRef<double>> ftip,
+                        const OptT &ftip_rows) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th = dev_rows(theta, n, "theta", false), dth = dev_rows(dtheta, n, "dtheta", false),
+           ta = dev_rows(tau, n, "tau", false);
+    const int64_t P = th.numel() / n;
+    TORCH_CHECK(dth.numel() == th.numel() && ta.numel() == th.numel(), "mpk: shape mismatch");
+    Tensor fr;
+    const double *frp = nullptr;
+    if (ftip_rows.has_value()) {
+        fr = dev_rows(*ftip_rows, 6, "Ftip rows", false);
+        TORCH_CHECK(fr.numel() == P * 6, "mpk: Ftip rows must be (P, 6)");
+        frp = fr.data_ptr<double>();
+    }
+    auto gv = host_vec(g, 3, "g");
+    std::vector<double> fv;
+    if (ftip.has_value()) fv = host_vec(*ftip, 6, "Ftip");
+    c10::cuda::CUDAGuard guard(th.device());
+    Tensor dd = at::empty({P, n}, th.options());
+    check(mpk_forward_dynamics(rb, P, th.data_ptr<double>(), dth.data_ptr<double>(), ta.data_ptr<double>(),
+                               gv.data(), fv.empty() ? nullptr : fv.data(), frp, dd.data_ptr<double>(),
+                               stream_of(th)),
+          "forward_dynamics");
+    return dd;
+}
+
+std::tuple<Tensor, Tensor, Tensor> forward_dynamics_trajectory(
+    int64_t h, const Tensor &theta0, const Tensor &dtheta0, const Tensor &taumat, c10::ArrayRef<double> g,
+    const OptT &ftipmat, double dt, int64_t intRes, const OptT &limits) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    TORCH_CHECK(theta0.dim() == 2 && taumat.dim() == 3, "mpk: theta0 (B, n), taumat (B, N, n)");
+    Tensor th = dev_rows(theta0, n, "theta0", false), dth = dev_rows(dtheta0, n, "dtheta0", false);
+    Tensor tm = dev_rows(taumat, n, "taumat", true);
+    const int64_t B = th.size(0), N = tm.size(1);
+    TORCH_CHECK(dth.sizes() == th.sizes() && tm.size(0) == B, "mpk: batch mismatch");
+    TORCH_CHECK(intRes >= 1, "mpk: intRes must be >= 1");
+    Tensor fm;
+    const double *fmp = nullptr;
+    if (ftipmat.has_value()) {
+        fm = dev_rows(*ftipmat, 6, "Ftipmat", false);
+        TORCH_CHECK(fm.numel() == B * N * 6, "mpk: Ftipmat must be (B, N, 6)");
+        fmp = fm.data_ptr<double>();
+    }
+    auto gv = host_vec(g, 3, "g");
+    auto lim = host_limits(limits, n, "joint_limits");
+    c10::cuda::CUDAGuard guard(th.device());
+    auto opt = th.options().dtype(at::kFloat);
+    Tensor pos = at::empty({B, N, n}, opt), vel = at::empty({B, N, n}, opt), acc = at::empty({B, N, n}, opt);
+    check(mpk_forward_dynamics_trajectory(rb, B, N, th.data_ptr<double>(), dth.data_ptr<double>(),
+                                          tm.data_ptr(), dtype_of(tm), gv.data(), fmp, dt, (int)intRes,
+                                          ptr_or_null(lim), pos.data_ptr<float>(), vel.data_ptr<float>(),
+                                          acc.data_ptr<float>(), stream_of(th)),
+          "forward_dynamics_trajectory");
+    return {pos, vel, acc};
+}
+
+void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads, int64_t iters) {
+    TORCH_CHECK(sink.is_cuda() && sink.scalar_type() == at::kDouble && sink.numel() >= 1,
+                "mpk: sink must be a CUDA float64 tensor");
+    c10::cuda::CUDAGuard guard(sink.device());
+    check(mpk_fma_peak((int)dtype, (int)blocks, (int)threads, iters, sink.data_ptr<double>(), stream_of(sink)),
+          "fma_peak");
+}
+
+}  // namespace
+
+TORCH_LIBRARY(mpk, m) {
+    m.def("robot_create(Tensor S_list, Tensor M, Tensor? Glist, Tensor? Mlist_per_link, int flags) -> int",
+          &robot_create);
+    m.def("robot_destroy(int robot) -> ()", &robot_destroy);
+    m.def("robot_dof(int robot) -> int", &robot_dof);
+    m.def("robot_is_rigid(int robot) -> bool", &robot_is_rigid);
+    m.def("joint_trajectory(Tensor start, Tensor end, bool inputs_f32, float Tf, int N, int method, "
+          "Tensor? joint_limits) -> (Tensor, Tensor, Tensor)",
+          &joint_trajectory);
+    m.def("fk_jacobian(int robot, Tensor theta, bool want_T, bool want_J) -> (Tensor, Tensor)", &fk_jacobian);
+    m.def("inverse_dynamics(int robot, Tensor theta, Tensor? dtheta, Tensor? ddtheta, float[] g, "
+          "float[]? Ftip, Tensor? Ftip_rows, Tensor? torque_limits, bool out_f32) -> Tensor",
+          &inverse_dynamics);
+    m.def("trajectory_inverse_dynamics(int robot, Tensor start, Tensor end, bool inputs_f32, float Tf, "
+          "int N, int method, Tensor? joint_limits, float[] g, float[]? Ftip, Tensor? torque_limits, "
+          "bool want_traj) -> (Tensor, Tensor, Tensor, Tensor)",
+          &trajectory_inverse_dynamics);
+    m.def("mass_matrix(int robot, Tensor theta) -> Tensor", &mass_matrix);
+    m.def("forward_dynamics(int robot, Tensor theta, Tensor dtheta, Tensor tau, float[] g, float[]? Ftip, "
+          "Tensor? Ftip_rows) -> Tensor",
+          &forward_dynamics);
+    m.def("forward_dynamics_trajectory(int robot, Tensor theta0, Tensor dtheta0, Tensor taumat, float[] g, "
+          "Tensor? Ftipmat, float dt, int intRes, Tensor? joint_limits) -> (Tensor, Tensor, Tensor)",
+          &forward_dynamics_trajectory);
+    m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
+}

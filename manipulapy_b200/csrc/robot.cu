@@ -1,0 +1,281 @@
+// robot.cu -- host side of the C ABI: robot constant pack construction, error
+// reporting, and the FMA peak micro-benchmark.
+//
+// mpk_robot_create re-expresses the reference's constant pack (S_list, M, Glist,
+// Mlist_per_link; dynamics/manipulator_dynamics.py:46-75) in joint-aligned link
+// frames (see mpk_device.cuh).  For joint i with space screw S_i = (w, v) at the
+// home configuration:
+//   revolute (|w| = 1): frame origin q = w x v (the point of the axis closest to the
+//       space origin), z = w, pitch h = w.v (0 for URDF joints);
+//   prismatic (w = 0):  z = v/|v|, origin at the space origin, st = |v|.
+// With F_i that home pose,  e^{[S_i] th} F_i = F_i Jz(th), so
+//   prod_j e^{[S_j] th_j} = prod_j (X_j Jz(th_j)) F_n^{-1},   X_j = F_{j-1}^{-1} F_j,
+// which is the identity the kernels rely on.
+#include <cmath>
+#include <cstring>
+
+#include "mpk_common.cuh"
+
+namespace mpk {
+
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(MPK_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return MPK_OK;
+}
+
+namespace {
+
+struct SE3 {
+    double R[9];
+    double p[3];
+};
+
+SE3 from_mat4(const double *T) {
+    SE3 o;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) o.R[3 * r + c] = T[4 * r + c];
+        o.p[r] = T[4 * r + 3];
+    }
+    return o;
+}
+SE3 identity() {
+    SE3 o;
+    std::memset(&o, 0, sizeof o);
+    o.R[0] = o.R[4] = o.R[8] = 1.0;
+    return o;
+}
+SE3 inverse(const SE3 &a) {
+    SE3 o;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) o.R[3 * r + c] = a.R[3 * c + r];
+    for (int r = 0; r < 3; ++r)
+        o.p[r] = -(o.R[3 * r] * a.p[0] + o.R[3 * r + 1] * a.p[1] + o.R[3 * r + 2] * a.p[2]);
+    return o;
+}
+SE3 mul(const SE3 &a, const SE3 &b) {
+    SE3 o;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c)
+            o.R[3 * r + c] =
+                a.R[3 * r] * b.R[c] + a.R[3 * r + 1] * b.R[3 + c] + a.R[3 * r + 2] * b.R[6 + c];
+        o.p[r] = a.p[r] + a.R[3 * r] * b.p[0] + a.R[3 * r + 1] * b.p[1] + a.R[3 * r + 2] * b.p[2];
+    }
+    return o;
+}
+// 6x6 adjoint [[R,0],[[p]R,R]] (twists [w; v])
+void adjoint(const SE3 &T, double *Ad) {
+    const double *p = T.p;
+    const double P[9] = {0, -p[2], p[1], p[2], 0, -p[0], -p[1], p[0], 0};
+    std::memset(Ad, 0, 36 * sizeof(double));
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double s = 0;
+            for (int k = 0; k < 3; ++k) s += P[3 * r + k] * T.R[3 * k + c];
+            Ad[6 * r + c] = T.R[3 * r + c];
+            Ad[6 * (r + 3) + c + 3] = T.R[3 * r + c];
+            Ad[6 * (r + 3) + c] = s;
+        }
+}
+void cross(const double *a, const double *b, double *o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+double norm3(const double *a) { return std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); }
+
+// Right-handed frame with the given unit z; x is the world axis least aligned with z,
+// orthogonalised.  R columns = (x, y, z).
+void frame_from_z(const double *z, double *R) {
+    int k = 0;
+    if (std::fabs(z[1]) < std::fabs(z[k])) k = 1;
+    if (std::fabs(z[2]) < std::fabs(z[k])) k = 2;
+    double e[3] = {0, 0, 0};
+    e[k] = 1.0;
+    const double d = z[k];
+    double x[3] = {e[0] - d * z[0], e[1] - d * z[1], e[2] - d * z[2]};
+    const double nx = norm3(x);
+    for (double &c : x) c /= nx;
+    double y[3];
+    cross(z, x, y);
+    for (int r = 0; r < 3; ++r) {
+        R[3 * r] = x[r];
+        R[3 * r + 1] = y[r];
+        R[3 * r + 2] = z[r];
+    }
+}
+
+}  // namespace
+}  // namespace mpk
+
+using namespace mpk;
+
+extern "C" int mpk_version(void) { return 100; }
+extern "C" const char *mpk_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, const double *Glist,
+                                const double *Mcom, int flags, mpk_robot **out) {
+    if (!out) return fail(MPK_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n < 1 || n > MPK_MAX_DOF)
+        return fail(MPK_EUNSUPPORTED, "supported joint counts are 1.." + std::to_string(MPK_MAX_DOF));
+    if (!S_list || !M) return fail(MPK_EINVAL, "S_list and M are required");
+    if ((Glist == nullptr) != (Mcom == nullptr))
+        return fail(MPK_EINVAL, "Glist and Mlist_per_link must be given together");
+
+    mpk_robot *rb = new mpk_robot();
+    std::memset(rb, 0, sizeof *rb);
+    rb->n = n;
+    rb->has_dynamics = Glist != nullptr;
+    bool rigid = true;
+
+    SE3 Fprev = identity();
+    for (int i = 0; i < n; ++i) {
+        double w[3], v[3];
+        for (int r = 0; r < 3; ++r) {
+            w[r] = S_list[r * n + i];
+            v[r] = S_list[(r + 3) * n + i];
+        }
+        SE3 F;
+        const double nw = norm3(w), nv = norm3(v);
+        double sr, st;
+        if (nw == 0.0) {
+            sr = 0.0;
+            st = nv;
+            double z[3] = {0, 0, 1};
+            if (nv > 0.0)
+                for (int r = 0; r < 3; ++r) z[r] = v[r] / nv;
+            frame_from_z(z, F.R);
+            F.p[0] = F.p[1] = F.p[2] = 0.0;
+        } else {
+            if (std::fabs(nw - 1.0) > 1e-9) {
+                delete rb;
+                return fail(MPK_EUNSUPPORTED,
+                            "screw axis " + std::to_string(i) +
+                                " has a non-unit angular part; the reference's transform_from_twist "
+                                "(utils/se3.py:33-42) is only a rigid motion for unit omega or omega = 0");
+            }
+            double z[3] = {w[0] / nw, w[1] / nw, w[2] / nw};
+            frame_from_z(z, F.R);
+            cross(z, v, F.p);  // q = w x v
+            double h = z[0] * v[0] + z[1] * v[1] + z[2] * v[2];
+            if (std::fabs(h) <= 1e-12 * (nv > 1.0 ? nv : 1.0)) h = 0.0;
+            sr = 1.0;
+            st = h;
+        }
+        const SE3 X = mul(inverse(Fprev), F);
+        for (int k = 0; k < 9; ++k) rb->pack.Rx[i][k] = X.R[k];
+        for (int k = 0; k < 3; ++k) rb->pack.px[i][k] = X.p[k];
+        rb->pack.sr[i] = sr;
+        rb->pack.st[i] = st;
+
+        if (Glist) {
+            const double *G = Glist + 36 * i;
+            double Gs[36];
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) Gs[6 * r + c] = 0.5 * (G[6 * r + c] + G[6 * c + r]);
+            // rigid body at its centre of mass: block diagonal [I, m 1]
+            bool rg = Gs[21] == Gs[28] && Gs[21] == Gs[35];
+            for (int r = 0; r < 3 && rg; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    if (Gs[6 * r + c + 3] != 0.0) rg = false;
+                    if (r != c && Gs[6 * (r + 3) + c + 3] != 0.0) rg = false;
+                }
+            rigid = rigid && rg;
+            const SE3 Mc = from_mat4(Mcom + 16 * i);
+            const SE3 C = mul(inverse(Mc), F);   // V_com = Ad(C) V_frame
+            const SE3 Ci = mul(inverse(F), Mc);  // CoM frame pose in frame i
+            double Ad[36], GA[36], Gp[36];
+            adjoint(C, Ad);
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) {
+                    double s = 0;
+                    for (int k = 0; k < 6; ++k) s += Gs[6 * r + k] * Ad[6 * k + c];
+                    GA[6 * r + c] = s;
+                }
+            for (int r = 0; r < 6; ++r)
+                for (int c = 0; c < 6; ++c) {
+                    double s = 0;
+                    for (int k = 0; k < 6; ++k) s += Ad[6 * k + r] * GA[6 * k + c];
+                    Gp[6 * r + c] = s;
+                }
+            int t = 0;
+            for (int r = 0; r < 6; ++r)
+                for (int c = r; c < 6; ++c) rb->pack.G[i][t++] = 0.5 * (Gp[6 * r + c] + Gp[6 * c + r]);
+            for (int k = 0; k < 3; ++k) rb->pack.cg[i][k] = Ci.p[k];
+            rb->pack.mg[i] = G[21];
+            if (rg) {
+                // analytic rigid form: I about the frame origin = Rc Icom Rc^T + m((c.c)1 - c c^T)
+                const double m = Gs[21];
+                const double *c = Ci.p;
+                double RI[9], Ir[9];
+                for (int r = 0; r < 3; ++r)
+                    for (int cc = 0; cc < 3; ++cc) {
+                        double s = 0;
+                        for (int k = 0; k < 3; ++k) s += Ci.R[3 * r + k] * Gs[6 * k + cc];
+                        RI[3 * r + cc] = s;
+                    }
+                for (int r = 0; r < 3; ++r)
+                    for (int cc = 0; cc < 3; ++cc) {
+                        double s = 0;
+                        for (int k = 0; k < 3; ++k) s += RI[3 * r + k] * Ci.R[3 * cc + k];
+                        Ir[3 * r + cc] = s;
+                    }
+                const double c2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+                for (int r = 0; r < 3; ++r)
+                    for (int cc = 0; cc < 3; ++cc)
+                        Ir[3 * r + cc] += m * ((r == cc ? c2 : 0.0) - c[r] * c[cc]);
+                rb->pack.I[i][0] = Ir[0];
+                rb->pack.I[i][1] = 0.5 * (Ir[1] + Ir[3]);
+                rb->pack.I[i][2] = 0.5 * (Ir[2] + Ir[6]);
+                rb->pack.I[i][3] = Ir[4];
+                rb->pack.I[i][4] = 0.5 * (Ir[5] + Ir[7]);
+                rb->pack.I[i][5] = Ir[8];
+                for (int k = 0; k < 3; ++k) rb->pack.h[i][k] = m * c[k];
+                rb->pack.m[i] = m;
+            }
+        }
+        Fprev = F;
+    }
+    const SE3 E = mul(inverse(Fprev), from_mat4(M));
+    for (int k = 0; k < 9; ++k) rb->pack.Ree[k] = E.R[k];
+    for (int k = 0; k < 3; ++k) rb->pack.pee[k] = E.p[k];
+    rb->rigid = (rigid && !(flags & MPK_ROBOT_FORCE_GENERAL)) ? 1 : 0;
+    *out = rb;
+    return MPK_OK;
+}
+
+extern "C" void mpk_robot_destroy(mpk_robot *rb) { delete rb; }
+extern "C" int mpk_robot_dof(const mpk_robot *rb) { return rb ? rb->n : MPK_EINVAL; }
+extern "C" int mpk_robot_is_rigid(const mpk_robot *rb) { return rb ? rb->rigid : MPK_EINVAL; }
+
+// ---- FMA peak micro-benchmark ---------------------------------------------------
+template <typename T>
+__global__ void fma_peak_kernel(int64_t iters, double *sink) {
+    T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
+    T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
+    const T m = T(0.999999), b = T(1e-7);
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = a0 * m + b; a1 = a1 * m + b; a2 = a2 * m + b; a3 = a3 * m + b;
+        a4 = a4 * m + b; a5 = a5 * m + b; a6 = a6 * m + b; a7 = a7 * m + b;
+    }
+    const T s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == T(-1.2345)) sink[0] = (double)s;  // never true; keeps the chains alive
+}
+
+extern "C" int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, double *sink_dev,
+                            void *stream) {
+    if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink_dev)
+        return fail(MPK_EINVAL, "bad fma_peak arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dtype == MPK_F64) fma_peak_kernel<double><<<blocks, threads, 0, s>>>(iters, sink_dev);
+    else if (dtype == MPK_F32) fma_peak_kernel<float><<<blocks, threads, 0, s>>>(iters, sink_dev);
+    else return fail(MPK_EINVAL, "bad dtype");
+    return check_launch("fma_peak");
+}

@@ -1,0 +1,116 @@
+"""``ManipulatorDynamics`` -- drop-in mirror of ``ManipulaPy.dynamics.ManipulatorDynamics``
+(dynamics/manipulator_dynamics.py:43-86) for the batched dynamics hot path.
+
+Every method takes one ``(n,)`` sample (reference behaviour: float64 result of the
+reference's shape) or a batch ``(P, n)``:
+
+=============================  ===============================  ==========================
+method                         reference                        result
+=============================  ===============================  ==========================
+``mass_matrix``                dynamics/mass_matrix.py:16-99    ``(n, n)`` / ``(P, n, n)``
+``velocity_quadratic_forces``  dynamics/forces.py:26-59         ``(n,)`` / ``(P, n)``
+``gravity_forces``             dynamics/forces.py:61-133        ``(n,)`` / ``(P, n)``
+``inverse_dynamics``           dynamics/id_fd.py:16-48          ``(n,)`` / ``(P, n)``
+``forward_dynamics``           dynamics/id_fd.py:50-83          ``(n,)`` / ``(P, n)``
+=============================  ===============================  ==========================
+
+The reference evaluates ``tau = M ddth + c + g + Js^T Ftip`` with a finite-difference
+Coriolis term (dynamics/cache.py:23-56, eps = 1e-6); the kernels evaluate the same
+quantity analytically (Newton-Euler recursion over the link-CoM inertias), so results agree
+with the reference to its own finite-difference noise (~1e-9 absolute) and with the
+reference's mass matrix / gravity to rounding (1e-15).  The legacy path of the reference
+(``Mlist_per_link is None``, documented there as incorrect) is not reproduced and raises.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy as np
+
+from . import _host, _native
+from .kinematics import RobotHandle, SerialManipulator
+
+
+class ManipulatorDynamics(SerialManipulator):
+    def __init__(self, M_list, omega_list=None, r_list=None, b_list=None, S_list=None, B_list=None,
+                 Glist=None, Mlist_per_link=None, *, device: Optional[Any] = None,
+                 force_general_inertia: bool = False):
+        super().__init__(M_list, omega_list, r_list, b_list, S_list, B_list, device=device)
+        if Glist is None:
+            raise ValueError("Glist is required")
+        if Mlist_per_link is None:
+            raise NotImplementedError(
+                "the legacy dynamics path (Mlist_per_link=None; dynamics/mass_matrix.py:101-132, "
+                "documented as incorrect by the reference) is not part of the B200 hot path: pass "
+                "Mlist_per_link or use the reference implementation")
+        self.Glist = np.asarray(Glist, dtype=np.float64)
+        self.Mlist_per_link = np.asarray(Mlist_per_link, dtype=np.float64)
+        n = self.num_joints
+        if self.Glist.shape != (n, 6, 6) or self.Mlist_per_link.shape != (n, 4, 4):
+            raise ValueError("Glist must be (n, 6, 6) and Mlist_per_link (n, 4, 4)")
+        self._force_general = bool(force_general_inertia)
+
+    @classmethod
+    def from_reference(cls, dynamics, **kw) -> "ManipulatorDynamics":
+        """Wrap a reference ``ManipulatorDynamics`` (or anything exposing its constant pack)."""
+        return cls(dynamics.M_list, getattr(dynamics, "omega_list", None), getattr(dynamics, "r_list", None),
+                   getattr(dynamics, "b_list", None), dynamics.S_list, getattr(dynamics, "B_list", None),
+                   dynamics.Glist, dynamics.Mlist_per_link, **kw)
+
+    def _make_robot(self) -> RobotHandle:
+        return RobotHandle(self.S_list, self.M_list, self.Glist, self.Mlist_per_link,
+                           flags=1 if self._force_general else 0)
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _ftip(self, Ftip, P: int, device):
+        """-> (single wrench list | None, per-point device rows | None)"""
+        if Ftip is None:
+            return None, None
+        if _host.is_device_tensor(Ftip):
+            if Ftip.dim() == 1:
+                return _host.vec(Ftip, 6, "Ftip"), None
+            return None, _host.to_device(Ftip, device).reshape(P, 6)
+        a = np.asarray(Ftip, dtype=np.float64)
+        if a.ndim == 1:
+            return _host.vec(a, 6, "Ftip"), None
+        if a.shape != (P, 6):
+            raise ValueError(f"per-point Ftip must be ({P}, 6), got {a.shape}")
+        return None, _host.to_device(a, device)
+
+    def _id(self, th, dth, ddth, g, Ftip, out_f32=False, limits=None):
+        P = th.shape[0]
+        ftip, rows = self._ftip(Ftip, P, th.device)
+        return _native.ops().inverse_dynamics(self.robot.handle, th, dth, ddth, g, ftip, rows, limits, out_f32)
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def mass_matrix(self, thetalist):
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        M = _native.ops().mass_matrix(self.robot.handle, th)
+        return self._finish(M, single, on_dev)
+
+    def velocity_quadratic_forces(self, thetalist, dthetalist):
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        dth, _, _ = self._rows(dthetalist, "dthetalist")
+        c = self._id(th, dth.to(th.dtype), None, [0.0, 0.0, 0.0], None)
+        return self._finish(c, single, on_dev)
+
+    def gravity_forces(self, thetalist, g=None):
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        out = self._id(th, None, None, _host.gravity(g), None)
+        return self._finish(out, single, on_dev)
+
+    def inverse_dynamics(self, thetalist, dthetalist, ddthetalist, g=None, Ftip=None):
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        dth, _, _ = self._rows(dthetalist, "dthetalist")
+        ddth, _, _ = self._rows(ddthetalist, "ddthetalist")
+        tau = self._id(th, dth.to(th.dtype), ddth.to(th.dtype), _host.gravity(g), Ftip)
+        return self._finish(tau, single, on_dev)
+
+    def forward_dynamics(self, thetalist, dthetalist, taulist, g=None, Ftip=None):
+        th, single, on_dev = self._rows(thetalist, "thetalist", keep_f32=False)
+        dth, _, _ = self._rows(dthetalist, "dthetalist", keep_f32=False)
+        tau, _, _ = self._rows(taulist, "taulist", keep_f32=False)
+        ftip, rows = self._ftip(Ftip, th.shape[0], th.device)
+        dd = _native.ops().forward_dynamics(self.robot.handle, th, dth, tau, _host.gravity(g), ftip, rows)
+        return self._finish(dd, single, on_dev)

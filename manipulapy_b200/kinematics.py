@@ -1,0 +1,144 @@
+"""``SerialManipulator`` -- drop-in mirror of ``ManipulaPy.kinematics.SerialManipulator``
+(kinematics/serial_manipulator.py:43-162) for the batched space-frame hot path.
+
+``forward_kinematics`` (kinematics/fk.py:39-86) and ``jacobian``
+(kinematics/jacobian.py:39-93) accept a single ``(n,)`` configuration (reference behaviour:
+returns ``(4, 4)`` / ``(6, n)`` float64) or a batch ``(P, n)`` (returns ``(P, 4, 4)`` /
+``(P, 6, n)``).  Both run in hand-written CUDA kernels; there is no CPU path.  Body-frame
+variants and the IK solvers are out of scope and raise
+``NotImplementedError``.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import _host, _native
+
+
+def _screws_from_axes(omega_list, r_list) -> np.ndarray:
+    """S = [w; -w x r] per joint (reference utils/screw.py extract_screw_list semantics)."""
+    w = np.asarray(omega_list, dtype=np.float64)
+    r = np.asarray(r_list, dtype=np.float64)
+    if w.ndim == 1:
+        w = w.reshape(3, -1, order="F")
+    if r.ndim == 1:
+        r = r.reshape(3, -1, order="F")
+    v = -np.cross(w.T, r.T).T
+    return np.vstack([w, v])
+
+
+class RobotHandle:
+    """Owns one ``mpk_robot`` (the constant pack in joint-aligned frames, host resident)."""
+
+    def __init__(self, S_list, M, Glist=None, Mlist_per_link=None, flags: int = 0):
+        S = np.ascontiguousarray(np.asarray(S_list, dtype=np.float64))
+        if S.ndim != 2 or S.shape[0] != 6:
+            raise ValueError(f"S_list must be (6, n), got {S.shape}")
+        Mh = np.asarray(M, dtype=np.float64)
+        if Mh.ndim == 3:  # stack of poses: the reference uses the last one (kinematics/fk.py:69)
+            Mh = Mh[-1]
+        G = None if Glist is None else np.ascontiguousarray(np.asarray(Glist, dtype=np.float64))
+        Mc = None if Mlist_per_link is None else np.ascontiguousarray(
+            np.asarray(Mlist_per_link, dtype=np.float64))
+        ops = _native.ops()
+        self.n = int(S.shape[1])
+        self._ops = ops
+        self.handle = ops.robot_create(
+            torch.from_numpy(S), torch.from_numpy(np.ascontiguousarray(Mh)),
+            None if G is None else torch.from_numpy(G), None if Mc is None else torch.from_numpy(Mc), flags)
+        self.rigid = bool(ops.robot_is_rigid(self.handle))
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", 0), 0
+        if h:
+            try:
+                self._ops.robot_destroy(h)
+            except Exception:
+                pass
+
+
+class SerialManipulator:
+    """Kinematic model of a serial manipulator (space-frame product of exponentials)."""
+
+    def __init__(self, M_list, omega_list=None, r_list=None, b_list=None, S_list=None, B_list=None,
+                 G_list=None, joint_limits=None, *, device: Optional[Any] = None):
+        self.M_list = np.asarray(M_list, dtype=np.float64)
+        self.G_list = G_list
+        self.omega_list = omega_list
+        if S_list is None:
+            if omega_list is None or r_list is None:
+                raise ValueError("either S_list or (omega_list, r_list) is required")
+            S_list = _screws_from_axes(omega_list, r_list)
+        self.S_list = np.asarray(S_list, dtype=np.float64)
+        self.B_list = None if B_list is None else np.asarray(B_list, dtype=np.float64)
+        self.r_list = r_list
+        self.b_list = b_list
+        n = self.S_list.shape[1]
+        self.joint_limits = joint_limits if joint_limits is not None else [(None, None)] * n
+        self._device_arg = device
+        self._robot: Optional[RobotHandle] = None
+
+    # -- native handle ---------------------------------------------------------------------
+    def _make_robot(self) -> RobotHandle:
+        return RobotHandle(self.S_list, self.M_list)
+
+    @property
+    def robot(self) -> RobotHandle:
+        if self._robot is None:
+            self._robot = self._make_robot()
+        return self._robot
+
+    @property
+    def device(self) -> torch.device:
+        return _host.default_device(self._device_arg)
+
+    @property
+    def num_joints(self) -> int:
+        return int(self.S_list.shape[1])
+
+    def _rows(self, x, name: str, keep_f32: bool = True):
+        """-> (device tensor (P, n), single?, on_device?)"""
+        on_dev = _host.is_device_tensor(x)
+        t = _host.to_device(x, x.device if on_dev else self.device, keep_f32=keep_f32)
+        single = t.dim() == 1
+        n = self.num_joints
+        if t.shape[-1] != n:
+            raise ValueError(f"{name} must have {n} joint values per row, got shape {tuple(t.shape)}")
+        return t.reshape(-1, n), single, on_dev
+
+    @staticmethod
+    def _finish(t: torch.Tensor, single: bool, on_dev: bool):
+        if single:
+            t = t[0]
+        return t if on_dev else _host.to_host(t)
+
+    # -- hot path ---------------------------------------------------------------------------
+    def forward_kinematics(self, thetalist, frame: str = "space"):
+        """End-effector pose(s) ``T = prod_i exp([S_i] theta_i) M`` (kinematics/fk.py:61-70)."""
+        if frame == "body":
+            raise NotImplementedError("body-frame FK is outside the B200 hot path (SURVEY.md 8f)")
+        if frame != "space":
+            raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        T, _ = _native.ops().fk_jacobian(self.robot.handle, th, True, False)
+        return self._finish(T, single, on_dev)
+
+    def jacobian(self, thetalist, frame: str = "space"):
+        """Space Jacobian(s) ``J[:, i] = Ad(prod_{j<i} exp([S_j] theta_j)) S_i`` (kinematics/jacobian.py:62-73)."""
+        if frame == "body":
+            raise NotImplementedError("body-frame Jacobian is outside the B200 hot path (SURVEY.md 8f)")
+        if frame != "space":
+            raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        _, J = _native.ops().fk_jacobian(self.robot.handle, th, False, True)
+        return self._finish(J, single, on_dev)
+
+    def forward_kinematics_and_jacobian(self, thetalist):
+        """Both outputs from one fused kernel launch (batched extension)."""
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        T, J = _native.ops().fk_jacobian(self.robot.handle, th, True, True)
+        return self._finish(T, single, on_dev), self._finish(J, single, on_dev)

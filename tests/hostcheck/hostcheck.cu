@@ -1,0 +1,126 @@
+// hostcheck.cu -- TEST INFRASTRUCTURE ONLY.
+//
+// Executes the kernels' own per-thread templates (manipulapy_b200/csrc/mpk_device.cuh) on
+// the host CPU, one point at a time, so that the algebra of the CUDA path (joint-aligned
+// frames, Newton-Euler recursion, CRBA, LDL^T, time scaling) can be checked against the
+// oracle and the reference's golden vectors in the GPU-less build container.  Nothing in
+// manipulapy_b200/ links or loads this library; it is not a CPU fallback.
+#include "../../manipulapy_b200/csrc/mpk_common.cuh"
+
+using namespace mpk;
+
+template <int N>
+static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                   const double *ddth, const double *g, const double *ftip, double *tau) {
+    const RobotPack<double, N> pk = narrow<N>(rb);
+    for (int64_t p = 0; p < P; ++p) {
+        double a[N], b[N], c[N], t[N], g3[3] = {g[0], g[1], g[2]};
+        for (int j = 0; j < N; ++j) {
+            a[j] = th[p * N + j];
+            b[j] = dth ? dth[p * N + j] : 0.0;
+            c[j] = ddth ? ddth[p * N + j] : 0.0;
+        }
+        JointCS<double, N> q;
+        joint_cs(pk, a, q);
+        if (rb->rigid) rnea<double, N, false>(pk, q, b, c, g3, ftip, t);
+        else rnea<double, N, true>(pk, q, b, c, g3, ftip, t);
+        for (int j = 0; j < N; ++j) tau[p * N + j] = t[j];
+    }
+}
+
+template <int N>
+static void mass_n(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
+    const RobotPack<double, N> pk = narrow<N>(rb);
+    for (int64_t p = 0; p < P; ++p) {
+        double a[N], Mm[N][N];
+        for (int j = 0; j < N; ++j) a[j] = th[p * N + j];
+        JointCS<double, N> q;
+        joint_cs(pk, a, q);
+        if (rb->rigid) mass_matrix<double, N, false>(pk, q, Mm);
+        else mass_matrix<double, N, true>(pk, q, Mm);
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) Mo[(p * N + i) * N + j] = Mm[i][j];
+    }
+}
+
+template <int N>
+static void fk_n(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
+    const RobotPack<double, N> pk = narrow<N>(rb);
+    for (int64_t p = 0; p < P; ++p) {
+        double a[N];
+        for (int j = 0; j < N; ++j) a[j] = th[p * N + j];
+        JointCS<double, N> q;
+        joint_cs(pk, a, q);
+        fk_jacobian<double, N>(pk, q, T ? T + p * 16 : nullptr, J ? J + p * 6 * N : nullptr);
+    }
+}
+
+template <int N>
+static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                 const double *tau, const double *g, const double *ftip_rows, double *dd) {
+    const RobotPack<double, N> pk = narrow<N>(rb);
+    for (int64_t p = 0; p < P; ++p) {
+        double a[N], b[N], c[N], o[N], g3[3] = {g[0], g[1], g[2]};
+        for (int j = 0; j < N; ++j) {
+            a[j] = th[p * N + j];
+            b[j] = dth[p * N + j];
+            c[j] = tau[p * N + j];
+        }
+        const double *ft = ftip_rows ? ftip_rows + 6 * p : nullptr;
+        if (rb->rigid) forward_dynamics<double, N, false>(pk, a, b, c, g3, ft, o);
+        else forward_dynamics<double, N, true>(pk, a, b, c, g3, ft, o);
+        for (int j = 0; j < N; ++j) dd[p * N + j] = o[j];
+    }
+}
+
+#define HC_DISPATCH(n, ...)                                      \
+    switch (n) {                                                 \
+        case 1: { constexpr int N_ = 1; __VA_ARGS__; } break;    \
+        case 2: { constexpr int N_ = 2; __VA_ARGS__; } break;    \
+        case 3: { constexpr int N_ = 3; __VA_ARGS__; } break;    \
+        case 4: { constexpr int N_ = 4; __VA_ARGS__; } break;    \
+        case 5: { constexpr int N_ = 5; __VA_ARGS__; } break;    \
+        case 6: { constexpr int N_ = 6; __VA_ARGS__; } break;    \
+        case 7: { constexpr int N_ = 7; __VA_ARGS__; } break;    \
+        case 8: { constexpr int N_ = 8; __VA_ARGS__; } break;    \
+        default: return -2;                                      \
+    }
+
+extern "C" int hc_rnea(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                       const double *ddth, const double *g, const double *ftip, double *tau) {
+    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau));
+    return 0;
+}
+extern "C" int hc_mass(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
+    HC_DISPATCH(rb->n, mass_n<N_>(rb, P, th, Mo));
+    return 0;
+}
+extern "C" int hc_fk(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
+    HC_DISPATCH(rb->n, fk_n<N_>(rb, P, th, T, J));
+    return 0;
+}
+extern "C" int hc_fd(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                     const double *tau, const double *g, const double *ftip_rows, double *dd) {
+    HC_DISPATCH(rb->n, fd_n<N_>(rb, P, th, dth, tau, g, ftip_rows, dd));
+    return 0;
+}
+extern "C" int hc_traj(int n, int64_t N, const double *start, const double *end, int inputs_f32,
+                       double Tf, int method, const float *limits, float *pos, float *vel, float *acc) {
+    for (int64_t t = 0; t < N; ++t) {
+        const TimeScale ts = time_scaling(t, N, Tf, method);
+        for (int j = 0; j < n; ++j) {
+            double st, dth;
+            if (inputs_f32) {
+                const float s32 = (float)start[j], e32 = (float)end[j];
+                st = (double)s32;
+                dth = (double)rn_fsub(e32, s32);
+            } else {
+                st = start[j];
+                dth = rn_sub(end[j], start[j]);
+            }
+            traj_point(ts, st, dth, limits ? limits[2 * j] : 0.f, limits ? limits[2 * j + 1] : 0.f,
+                       limits != nullptr, pos[t * n + j], vel[t * n + j], acc[t * n + j]);
+        }
+    }
+    return 0;
+}
