@@ -208,10 +208,11 @@ class OptimizedTrajectoryPlanning:
         B = th0.shape[0]
         dth0 = _host.to_device(dthetalist, dev).reshape(B, n)
         tm = _host.to_device(taumat, dev, keep_f32=True)
-        tm = tm.reshape(B, -1, n)
-        N = tm.shape[1]
-        if N == 0:
+        N = int(tm.shape[-2]) if tm.dim() >= 2 else 0
+        if N == 0 or tm.numel() == 0:
+            # the reference indexes row 0 of an empty result (trajectory_dynamics.py:612-615)
             raise IndexError("index 0 is out of bounds for axis 0 with size 0")
+        tm = tm.reshape(B, N, n)
         fm = None
         if Ftipmat is not None:
             fm = _host.to_device(Ftipmat, dev).reshape(B, N, 6)

@@ -57,3 +57,136 @@ def planar_2r_pack(L1=1.0, L2=1.0, m1=1.0, m2=1.0) -> dict:
     G = np.stack([np.diag([0, 0, 0, m, m, m]) for m in (m1, m2)]).astype(float)
     lim = np.array([[-np.pi, np.pi]] * 2)
     return dict(S_list=S, M=M, Glist=G, Mlist_per_link=Mc, joint_limits=lim)
+
+
+# ---- native library helpers ----------------------------------------------------------------
+import ctypes as _C
+import subprocess as _sp
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_C.c_void_p)
+
+
+class HostCheck:
+    """The kernels' own per-thread templates executed on the CPU (tests/hostcheck/hostcheck.cu).
+
+    Lets the GPU-less container verify the CUDA path's algebra against the oracle and the
+    reference's golden vectors.  Test infrastructure only."""
+
+    def __init__(self):
+        from manipulapy_b200 import _native
+
+        here = REPO / "tests" / "hostcheck"
+        src, so = here / "hostcheck.cu", here / "libhostcheck.so"
+        deps = [src, REPO / "manipulapy_b200" / "csrc" / "mpk_device.cuh",
+                REPO / "manipulapy_b200" / "csrc" / "mpk_common.cuh"]
+        if not so.exists() or so.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+            _sp.run(["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
+                     "-Wno-deprecated-gpu-targets", "--expt-relaxed-constexpr", "-I", str(REPO / "include"),
+                     str(src), "-o", str(so), f"-L{_native.LIB_PATH.parent}", "-l:libmpk.so",
+                     "-Xlinker", "-rpath", "-Xlinker", str(_native.LIB_PATH.parent)], check=True)
+        self.L = _native.lib()
+        self.H = _C.CDLL(str(so))
+
+    def robot(self, pack, flags=0):
+        h = _C.c_void_p()
+        S = np.ascontiguousarray(pack["S_list"], dtype=np.float64)
+        rc = self.L.mpk_robot_create(S.shape[1], _ptr(S), _ptr(np.ascontiguousarray(pack["M"], dtype=np.float64)),
+                                     _ptr(np.ascontiguousarray(pack["Glist"], dtype=np.float64)),
+                                     _ptr(np.ascontiguousarray(pack["Mlist_per_link"], dtype=np.float64)),
+                                     flags, _C.byref(h))
+        if rc != 0:
+            raise RuntimeError(self.L.mpk_last_error().decode())
+        return h, S.shape[1]
+
+    def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None):
+        h, n = rb
+        th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
+        P = th.shape[0]
+        cv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(P, n)
+        dth, ddth = cv(dth), cv(ddth)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        out = np.empty((P, n))
+        if ftip is not None and np.ndim(ftip) == 2:
+            for i in range(P):
+                f = np.ascontiguousarray(ftip[i], dtype=np.float64)
+                self.H.hc_rnea(h, _C.c_int64(1), _ptr(th[i:i + 1]), _ptr(None if dth is None else dth[i:i + 1]),
+                               _ptr(None if ddth is None else ddth[i:i + 1]), _ptr(g),
+                               _ptr(f) if f.any() else None, _ptr(out[i:i + 1]))
+            return out
+        f = None if ftip is None else np.ascontiguousarray(ftip, dtype=np.float64)
+        self.H.hc_rnea(h, _C.c_int64(P), _ptr(th), _ptr(dth), _ptr(ddth), _ptr(g), _ptr(f), _ptr(out))
+        return out
+
+    def mass(self, rb, th):
+        h, n = rb
+        th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
+        out = np.empty((th.shape[0], n, n))
+        self.H.hc_mass(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(out))
+        return out
+
+    def fk(self, rb, th):
+        h, n = rb
+        th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
+        T, J = np.empty((th.shape[0], 4, 4)), np.empty((th.shape[0], 6, n))
+        self.H.hc_fk(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(T), _ptr(J))
+        return T, J
+
+    def fd(self, rb, th, dth, tau, g=(0, 0, -9.81), ftip_rows=None):
+        h, n = rb
+        c = lambda a: np.ascontiguousarray(a, dtype=np.float64).reshape(-1, n)
+        th, dth, tau = c(th), c(dth), c(tau)
+        f = None if ftip_rows is None else np.ascontiguousarray(ftip_rows, dtype=np.float64).reshape(-1, 6)
+        out = np.empty_like(th)
+        self.H.hc_fd(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(dth), _ptr(tau),
+                     _ptr(np.ascontiguousarray(g, dtype=np.float64)), _ptr(f), _ptr(out))
+        return out
+
+    def traj(self, start, end, Tf, N, method, limits=None, inputs_f32=True):
+        s = np.ascontiguousarray(start, dtype=np.float64)
+        e = np.ascontiguousarray(end, dtype=np.float64)
+        n = s.shape[0]
+        lim = None if limits is None else np.ascontiguousarray(limits, dtype=np.float32)
+        out = [np.empty((N, n), np.float32) for _ in range(3)]
+        self.H.hc_traj(n, _C.c_int64(N), _ptr(s), _ptr(e), int(inputs_f32), _C.c_double(Tf), int(method),
+                       _ptr(lim), *[_ptr(o) for o in out])
+        return out
+
+
+@pytest.fixture(scope="session")
+def hostcheck():
+    return HostCheck()
+
+
+def random_general_pack(n, seed):
+    """A chain with arbitrary unit screws / one prismatic joint, arbitrary CoM frames and full
+    symmetric positive-definite 6x6 inertias (not rigid-body structured)."""
+    rng = np.random.default_rng(seed)
+    S = np.zeros((6, n))
+    for i in range(n):
+        w = rng.normal(size=3)
+        w /= np.linalg.norm(w)
+        q = rng.uniform(-0.5, 0.5, 3)
+        if i == n // 2:
+            S[3:, i] = w * 0.7  # prismatic with a non-unit direction
+        else:
+            S[:3, i] = w
+            S[3:, i] = -np.cross(w, q)
+    def rand_T():
+        A = rng.normal(size=(3, 3))
+        Q, _ = np.linalg.qr(A)
+        if np.linalg.det(Q) < 0:
+            Q[:, 0] *= -1
+        T = np.eye(4)
+        T[:3, :3] = Q
+        T[:3, 3] = rng.uniform(-0.5, 0.5, 3)
+        return T
+    M = rand_T()
+    Mc = np.stack([rand_T() for _ in range(n)])
+    G = []
+    for _ in range(n):
+        A = rng.normal(size=(6, 6))
+        G.append(A @ A.T + 0.5 * np.eye(6))
+    lim = np.array([[-np.pi, np.pi]] * n)
+    return dict(S_list=S, M=M, Glist=np.stack(G), Mlist_per_link=Mc, joint_limits=lim)

@@ -1,0 +1,416 @@
+"""Parity of the CUDA path (through torch.ops.mpk -> C ABI -> sm_100a kernels) with the oracle.
+
+Tolerances (BASELINE.json north_star):
+  * fp64 kernels: per-vector inf-norm relative 1e-9, i.e. max|d| <= 1e-9 * max(1, |ref|_inf)
+    (element-wise relative is unattainable even reference-vs-itself);
+    against the reference's own goldens its own tolerances rtol 1e-7 / atol 1e-9, 1e-8;
+  * float32 trajectory-level outputs: within one float32 ulp-scale of the oracle (rtol 3e-7);
+  * time-scaling / trajectory rows: bit-exact.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, load_pack, planar_2r_pack, random_general_pack
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROBOTS = ["ur5", "panda", "iiwa14", "xarm6"]
+
+
+def _rel_rows(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    sc = np.maximum(1.0, np.abs(ref).reshape(ref.shape[0], -1).max(1))
+    d = np.abs(np.asarray(got, dtype=np.float64) - ref).reshape(ref.shape[0], -1).max(1)
+    return float((d / sc).max())
+
+
+def _bits_equal(a, b):
+    return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.fixture(scope="module")
+def robots():
+    from manipulapy_b200 import load_robot
+
+    assert torch.cuda.is_available()
+    return {name: load_robot(name) for name in ROBOTS}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot", ["ur5", "panda", "iiwa14"])
+def test_dynamics_golden(robots, robot):
+    g = load_golden(f"dynamics_{robot}")
+    dyn = robots[robot].dynamics
+    th, dth, ddth = g["thetas"], g["dthetas"], g["ddthetas"]
+    np.testing.assert_allclose(dyn.forward_kinematics(th), g["forward_kinematics"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(dyn.jacobian(th), g["jacobian"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(dyn.mass_matrix(th), g["mass_matrix"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(dyn.gravity_forces(th, g["g"]), g["gravity_forces"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(dyn.velocity_quadratic_forces(th, dth), g["velocity_quadratic_forces"],
+                               rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(dyn.inverse_dynamics(th, dth, ddth, g["g"], g["ftips"]), g["inverse_dynamics"],
+                               rtol=1e-7, atol=1e-8)
+    i = g["fd_index"]
+    dd = dyn.forward_dynamics(th[i], dth[i], g["fd_tau"], g["g"], g["ftips"][i])
+    assert _rel_rows(dd, g["forward_dynamics"]) < 1e-9
+    # single-sample calls keep the reference's shapes and dtype
+    M1 = dyn.mass_matrix(th[3])
+    n = th.shape[1]
+    assert M1.shape == (n, n) and M1.dtype == np.float64
+    assert np.array_equal(M1, dyn.mass_matrix(th[3:4])[0])
+    assert dyn.forward_kinematics(th[3]).shape == (4, 4) and dyn.jacobian(th[3]).shape == (6, n)
+    tau1 = dyn.inverse_dynamics(th[5], dth[5], ddth[5], g["g"], g["ftips"][5])
+    np.testing.assert_allclose(tau1, g["inverse_dynamics"][5], rtol=1e-7, atol=1e-8)
+
+
+def test_joint_trajectory_golden(robots):
+    g = load_golden("trajectory")
+    rb = robots["ur5"]
+    assert np.array_equal(rb.joint_limits, g["joint_limits"])
+    planner = rb.planner()
+    for name in ("cfg1", "cubic50", "two", "clipped", "odd_tf"):
+        Tf, N, method = g[f"{name}_args"]
+        r = planner.joint_trajectory(g[f"{name}_start"], g[f"{name}_end"], Tf, int(N), int(method))
+        for k in ("positions", "velocities", "accelerations"):
+            got, ref = r[k], g[f"{name}_{k}"]
+            assert got.dtype == np.float32 and got.shape == ref.shape
+            neq = got.view(np.uint32) != ref.view(np.uint32)
+            # the reference's Numba fastmath kernel leaves O(1e-16) residues at exact-cancellation
+            # points (tau = 0.5, 1) where IEEE arithmetic gives 0: see tests/test_oracle_golden.py
+            assert np.all(got[neq] == 0) and np.all(np.abs(ref[neq]) <= 1e-12), (name, k)
+        if name in ("cfg1", "odd_tf"):
+            assert all(_bits_equal(r[k], g[f"{name}_{k}"]) for k in r)
+    Tf, N, method = g["batch_args"]
+    r = planner.batch_joint_trajectory(g["batch_start"], g["batch_end"], Tf, int(N), int(method))
+    for k in ("positions", "velocities", "accelerations"):
+        neq = r[k].view(np.uint32) != g[f"batch_{k}"].view(np.uint32)
+        assert np.all(r[k][neq] == 0) and np.all(np.abs(g[f"batch_{k}"][neq]) <= 1e-12)
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_dynamics_trajectory_golden(robots, robot):
+    g = load_golden("id_trajectory")
+    rb = robots[robot]
+    tl = g[f"{robot}_torque_limits"]
+    planner = rb.planner(torque_limits=tl)
+    th, dth, ddth = g[f"{robot}_theta"], g[f"{robot}_dtheta"], g[f"{robot}_ddtheta"]
+    t0 = planner.inverse_dynamics_trajectory(th, dth, ddth)
+    t1 = planner.inverse_dynamics_trajectory(th, dth, ddth, g[f"{robot}_g1"], g[f"{robot}_ftip1"])
+    lo32, hi32 = tl[:, 0].astype(np.float32), tl[:, 1].astype(np.float32)
+    for got, ref in ((t0, g[f"{robot}_tau_default"]), (t1, g[f"{robot}_tau_g1_ftip1"])):
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-7)
+        assert np.array_equal(got == lo32, ref == lo32) and np.array_equal(got == hi32, ref == hi32)
+
+
+@pytest.mark.parametrize("robot", ["iiwa14", "ur5"])
+def test_forward_dynamics_trajectory_golden(robots, robot):
+    g = load_golden("fd_trajectory")
+    rb = robots[robot]
+    planner = rb.planner()
+    assert np.array_equal(rb.joint_limits, g[f"{robot}_joint_limits"])
+    dt, intres = g[f"{robot}_a_args"]
+    r = planner.forward_dynamics_trajectory(g[f"{robot}_a_theta0"], g[f"{robot}_a_dtheta0"], g[f"{robot}_a_tau"],
+                                            [0, 0, -9.81], None, dt, int(intres))
+    for k in ("positions", "velocities", "accelerations"):
+        assert r[k].dtype == np.float32 and _rel_rows(r[k], g[f"{robot}_a_{k}"]) <= 1e-6, k
+    dt, intres = g[f"{robot}_b_args"]
+    r = planner.forward_dynamics_trajectory(g[f"{robot}_b_theta0"], g[f"{robot}_b_dtheta0"], g[f"{robot}_b_tau"],
+                                            g[f"{robot}_b_g"], g[f"{robot}_b_ftip"], dt, int(intres))
+    for k in ("positions", "velocities", "accelerations"):
+        assert _rel_rows(r[k], g[f"{robot}_b_{k}"]) <= 1e-6, k
+    hi32 = rb.joint_limits[:, 1].astype(np.float32)
+    assert np.array_equal(r["positions"] == hi32, g[f"{robot}_b_positions"] == hi32)
+    with pytest.raises(IndexError):
+        planner.forward_dynamics_trajectory(np.zeros(rb.num_joints), np.zeros(rb.num_joints),
+                                            np.zeros((0, rb.num_joints)), [0, 0, -9.81], None, 1e-3, 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded random inputs against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_kinematics_dynamics_vs_oracle(robots, oracle_factory, robot):
+    rb, o = robots[robot], oracle_factory(robot)
+    n = rb.num_joints
+    rng = np.random.default_rng(21)
+    P = 4099  # ragged: not a multiple of the 128-thread block
+    th = rng.uniform(rb.joint_limits[:, 0], rb.joint_limits[:, 1], (P, n))
+    dth, ddth = rng.uniform(-2, 2, (P, n)), rng.uniform(-5, 5, (P, n))
+    g, ft = np.array([0.3, -0.2, -9.81]), rng.uniform(-10, 10, 6)
+    dyn = rb.dynamics
+    T, J = dyn.forward_kinematics_and_jacobian(th)
+    assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
+    assert np.abs(J - o.jacobian(th)).max() < 1e-12
+    assert np.array_equal(T, dyn.forward_kinematics(th)) and np.array_equal(J, dyn.jacobian(th))
+    assert _rel_rows(dyn.inverse_dynamics(th, dth, ddth, g, ft), o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)) < 1e-9
+    rows = rng.uniform(-10, 10, (P, 6))
+    assert _rel_rows(dyn.inverse_dynamics(th, dth, ddth, g, rows), o.inverse_dynamics(th, dth, ddth, g, rows, analytic=True)) < 1e-9
+    assert _rel_rows(dyn.gravity_forces(th, g), o.gravity_forces(th, g, analytic=True)) < 1e-9
+    assert _rel_rows(dyn.velocity_quadratic_forces(th, dth), o.velocity_quadratic_forces(th, dth, analytic=True)) < 1e-9
+    assert _rel_rows(dyn.mass_matrix(th[:513]), o.mass_matrix(th[:513])) < 1e-9
+    tau = rng.uniform(-20, 20, (513, n))
+    assert _rel_rows(dyn.forward_dynamics(th[:513], dth[:513], tau, g, ft),
+                     o.forward_dynamics(th[:513], dth[:513], tau, g, ft, analytic=True)) < 1e-9
+    # a small sample against the LITERAL reference algorithm (finite-difference Coriolis noise ~1e-9 abs)
+    lit = o.inverse_dynamics(th[:16], dth[:16], ddth[:16], g, ft, analytic=False)
+    np.testing.assert_allclose(dyn.inverse_dynamics(th[:16], dth[:16], ddth[:16], g, ft), lit, rtol=1e-7, atol=1e-7)
+    # float32 theta storage is upcast exactly
+    th32 = th.astype(np.float32)
+    assert np.array_equal(dyn.mass_matrix(th32[:64]), dyn.mass_matrix(th32[:64].astype(np.float64)))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8])
+def test_general_inertia_robot_vs_oracle(n):
+    """Arbitrary unit screws, one non-unit prismatic joint, full symmetric 6x6 inertias."""
+    from manipulapy_b200 import ManipulatorDynamics
+    from oracle import Oracle
+
+    p = random_general_pack(n, seed=100 + n)
+    o = Oracle(p["S_list"], p["M"], p["Glist"], p["Mlist_per_link"])
+    dyn = ManipulatorDynamics(p["M"], None, None, None, p["S_list"], None, p["Glist"], p["Mlist_per_link"])
+    assert not dyn.robot.rigid
+    rng = np.random.default_rng(n)
+    P = 300
+    th, dth, ddth = rng.uniform(-2, 2, (P, n)), rng.uniform(-2, 2, (P, n)), rng.uniform(-3, 3, (P, n))
+    g, ft = np.array([1.0, 2.0, -9.0]), rng.uniform(-5, 5, 6)
+    assert np.abs(dyn.forward_kinematics(th) - o.forward_kinematics(th)).max() < 1e-12
+    assert np.abs(dyn.jacobian(th) - o.jacobian(th)).max() < 1e-12
+    assert _rel_rows(dyn.inverse_dynamics(th, dth, ddth, g, ft), o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)) < 1e-9
+    assert _rel_rows(dyn.mass_matrix(th), o.mass_matrix(th)) < 1e-9
+    assert _rel_rows(dyn.gravity_forces(th, g), o.gravity_forces(th, g)) < 1e-9
+    tau = rng.uniform(-5, 5, (P, n))
+    assert _rel_rows(dyn.forward_dynamics(th, dth, tau, g, ft), o.forward_dynamics(th, dth, tau, g, ft, analytic=True)) < 1e-9
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_rigid_and_general_kernels_agree(robots, robot):
+    from manipulapy_b200 import ManipulatorDynamics
+
+    p = load_pack(robot)
+    gen = ManipulatorDynamics(p["M"], None, None, None, p["S_list"], None, p["Glist"], p["Mlist_per_link"],
+                              force_general_inertia=True)
+    rig = robots[robot].dynamics
+    assert rig.robot.rigid and not gen.robot.rigid
+    rng = np.random.default_rng(5)
+    n = rig.num_joints
+    th, dth, ddth = rng.uniform(-3, 3, (777, n)), rng.uniform(-2, 2, (777, n)), rng.uniform(-5, 5, (777, n))
+    assert _rel_rows(gen.inverse_dynamics(th, dth, ddth, [0, 0, -9.81]), rig.inverse_dynamics(th, dth, ddth, [0, 0, -9.81])) < 1e-11
+    assert _rel_rows(gen.mass_matrix(th), rig.mass_matrix(th)) < 1e-11
+
+
+def test_planar_2r_known_answers():
+    from manipulapy_b200 import ManipulatorDynamics
+
+    p = planar_2r_pack()
+    dyn = ManipulatorDynamics(p["M"], None, None, None, p["S_list"], None, p["Glist"], p["Mlist_per_link"])
+    th = np.array([0.0, np.pi / 2])
+    c2 = np.cos(th[1])
+    np.testing.assert_allclose(dyn.mass_matrix(th), [[1 + (2 + 2 * c2), 1 + c2], [1 + c2, 1.0]], atol=1e-12)
+    np.testing.assert_allclose(dyn.gravity_forces(th, [-9.81, 0, 0]), [-9.81, -9.81], atol=1e-12)
+    np.testing.assert_allclose(dyn.gravity_forces(th, [0, -9.81, 0]), [19.62, 0.0], atol=1e-12)
+    np.testing.assert_allclose(dyn.gravity_forces(th, [0, 0, -9.81]), [0.0, 0.0], atol=1e-12)
+    with pytest.raises(ValueError):
+        dyn.forward_kinematics(th, frame="nope")
+
+
+@pytest.mark.parametrize("robot,B,N,method", [("ur5", 37, 301, 5), ("iiwa14", 5, 129, 3), ("panda", 3, 128, 5),
+                                              ("ur5", 300, 2, 5), ("ur5", 4, 1, 5), ("xarm6", 2, 50, 7)])
+def test_batch_trajectory_bit_exact_vs_oracle(robots, robot, B, N, method):
+    from oracle import Oracle
+
+    rb = robots[robot]
+    n = rb.num_joints
+    rng = np.random.default_rng(B * 1000 + N)
+    s, e = rng.uniform(-4, 4, (B, n)), rng.uniform(-4, 4, (B, n))
+    planner = rb.planner()
+    for dt in (np.float64, np.float32):
+        r = planner.batch_joint_trajectory(s.astype(dt), e.astype(dt), 1.7, N, method)
+        ref = Oracle.joint_trajectory(s.astype(dt), e.astype(dt), 1.7, N, method, rb.joint_limits)
+        for k in ref:
+            a, b = r[k], ref[k]
+            assert a.shape == (B, N, n) and a.dtype == np.float32
+            if N == 1:  # 0 * inf = NaN on the reference's CPU path
+                assert np.array_equal(np.isnan(a), np.isnan(b))
+            else:
+                assert _bits_equal(a, b), (k, dt)
+    r = planner.batch_joint_trajectory(np.zeros((0, n)), np.zeros((0, n)), 1.0, 10, 5)
+    assert r["positions"].shape == (0, 10, n)
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14", "panda"])
+def test_fused_trajectory_inverse_dynamics_equals_two_calls(robots, oracle_factory, robot):
+    rb, o = robots[robot], oracle_factory(robot)
+    n = rb.num_joints
+    rng = np.random.default_rng(8)
+    B, N = 19, 333
+    s, e = rng.uniform(-3, 3, (B, n)), rng.uniform(-3, 3, (B, n))
+    tl = np.array([[-60.0, 55.0]] * n)
+    planner = rb.planner(torque_limits=tl)
+    ft = [1.0, -2.0, 0.5, 3.0, 0.0, -1.0]
+    tr = planner.batch_joint_trajectory(s, e, 2.0, N, 5)
+    two = planner.inverse_dynamics_trajectory(tr["positions"], tr["velocities"], tr["accelerations"], [0, 0, -9.81], ft)
+    tau, tr2 = planner.trajectory_inverse_dynamics(s, e, 2.0, N, 5, [0, 0, -9.81], ft, return_trajectory=True)
+    assert two.shape == (B, N, n) and _bits_equal(tau, two)
+    assert all(_bits_equal(tr[k], tr2[k]) for k in tr)
+    assert _bits_equal(planner.trajectory_inverse_dynamics(s, e, 2.0, N, 5, [0, 0, -9.81], ft), two)
+    ref = o.inverse_dynamics_trajectory(tr["positions"].reshape(-1, n), tr["velocities"].reshape(-1, n),
+                                        tr["accelerations"].reshape(-1, n), [0, 0, -9.81], ft, tl, analytic=True)
+    np.testing.assert_allclose(two.reshape(-1, n), ref, rtol=3e-7, atol=1e-7)
+    assert (two == np.float32(55.0)).any() or (two == np.float32(-60.0)).any()
+
+
+@pytest.mark.parametrize("robot,B,N,intres", [("iiwa14", 70, 60, 1), ("ur5", 33, 40, 3), ("panda", 9, 30, 2)])
+def test_batched_rollouts_vs_oracle(robots, oracle_factory, robot, B, N, intres):
+    rb, o = robots[robot], oracle_factory(robot)
+    n = rb.num_joints
+    rng = np.random.default_rng(B)
+    lo, hi = rb.joint_limits[:, 0], rb.joint_limits[:, 1]
+    th0 = rng.uniform(0.5 * lo, 0.5 * hi, (B, n))
+    th0[0] = hi - 1e-4  # start next to the upper limit so the clip is exercised
+    dth0 = rng.uniform(-0.5, 0.5, (B, n))
+    dth0[0] = 2.0
+    tau = rng.uniform(-20, 20, (B, N, n))
+    ftip = rng.uniform(-3, 3, (B, N, 6))
+    planner = rb.planner()
+    for fm in (None, ftip):
+        r = planner.forward_dynamics_trajectory(th0, dth0, tau, [0, 0, -9.81], fm, 1e-3, intres)
+        ref = o.forward_dynamics_trajectory(th0, dth0, tau, [0, 0, -9.81], fm, 1e-3, intres, rb.joint_limits, analytic=True)
+        for k in ref:
+            assert r[k].shape == (B, N, n) and r[k].dtype == np.float32
+            assert _rel_rows(r[k].reshape(B * N, n), ref[k].reshape(B * N, n)) <= 1e-6, k
+        hi32 = hi.astype(np.float32)
+        assert (ref["positions"][0, 1:] == hi32).any()
+        assert np.array_equal(r["positions"] == hi32, ref["positions"] == hi32)
+    # float32 torque storage is upcast exactly
+    r32 = planner.forward_dynamics_trajectory(th0, dth0, tau.astype(np.float32), [0, 0, -9.81], None, 1e-3, intres)
+    r64 = planner.forward_dynamics_trajectory(th0, dth0, tau.astype(np.float32).astype(np.float64), [0, 0, -9.81], None, 1e-3, intres)
+    assert all(_bits_equal(r32[k], r64[k]) for k in r32)
+
+
+def test_device_resident_path(robots):
+    rb = robots["ur5"]
+    planner = rb.planner()
+    s = torch.rand(6, 6, dtype=torch.float64, device="cuda")
+    e = torch.rand(6, 6, dtype=torch.float64, device="cuda")
+    tr = planner.batch_joint_trajectory(s, e, 2.0, 100, 5)
+    assert all(isinstance(v, torch.Tensor) and v.is_cuda and v.dtype == torch.float32 for v in tr.values())
+    tau = planner.inverse_dynamics_trajectory(tr["positions"], tr["velocities"], tr["accelerations"])
+    assert tau.is_cuda and tau.shape == (6, 100, 6)
+    host = planner.batch_joint_trajectory(s.cpu().numpy(), e.cpu().numpy(), 2.0, 100, 5)
+    assert _bits_equal(tr["positions"].cpu().numpy(), host["positions"])
+    M = rb.dynamics.mass_matrix(tr["positions"].reshape(-1, 6)[:10])
+    assert M.is_cuda and M.shape == (10, 6, 6)
+    st = planner.get_performance_stats()
+    assert st["gpu_calls"] >= 3 and st["cpu_calls"] == 0
+
+
+def test_registry_launcher_runs_on_gpu():
+    from manipulapy_b200 import execute_registered_kernel
+    from oracle import Oracle
+
+    s, e = np.array([0.1, -0.2, 0.3]), np.array([1.0, 0.5, -0.7])
+    pos, vel, acc = execute_registered_kernel("trajectory.vectorized", s, e, 2.0, 64, 5)
+    ref = Oracle.joint_trajectory(s, e, 2.0, 64, 5)
+    assert _bits_equal(pos, ref["positions"]) and _bits_equal(vel, ref["velocities"]) and _bits_equal(acc, ref["accelerations"])
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: sampled oracle comparison + size-independent properties
+# ---------------------------------------------------------------------------------------------
+def test_full_size_cfg3_ur5_trajectory_rnea(robots, oracle_factory):
+    """UR5, 4096 trajectories x 2441 steps (9,998,336 points), quintic, fused."""
+    from oracle import Oracle
+
+    rb, o = robots["ur5"], oracle_factory("ur5")
+    rng = np.random.default_rng(3)
+    B, N = 4096, 2441
+    s = torch.from_numpy(rng.uniform(-np.pi, np.pi, (B, 6))).cuda()
+    e = torch.from_numpy(rng.uniform(-np.pi, np.pi, (B, 6))).cuda()
+    planner = rb.planner()
+    tau, tr = planner.trajectory_inverse_dynamics(s, e, 2.0, N, 5, return_trajectory=True)
+    assert tau.shape == (B, N, 6) and bool(torch.isfinite(tau).all())
+    # (1) sampled trajectories against the oracle: rows bit-exact, torques to float32 rounding
+    for b in (0, 1, 777, 4095):
+        ref = Oracle.joint_trajectory(s[b].cpu().numpy()[None], e[b].cpu().numpy()[None], 2.0, N, 5, rb.joint_limits)
+        for k in ref:
+            assert _bits_equal(tr[k][b].cpu().numpy(), ref[k][0]), (b, k)
+        rt = o.inverse_dynamics_trajectory(ref["positions"][0], ref["velocities"][0], ref["accelerations"][0], analytic=True)
+        np.testing.assert_allclose(tau[b].cpu().numpy(), rt, rtol=3e-7, atol=1e-7)
+    # (2) unfused two-kernel pipeline gives the same bits everywhere (checksum over all 6e7 values)
+    two = planner.inverse_dynamics_trajectory(tr["positions"], tr["velocities"], tr["accelerations"])
+    assert bool(torch.equal(two.view(torch.int32), tau.view(torch.int32)))
+    # (3) endpoints: velocity / acceleration vanish, so torque = gravity torque at the end poses
+    grav = rb.dynamics.gravity_forces(tr["positions"][:, 0].double())
+    assert float((tau[:, 0].double() - grav).abs().max()) < 1e-4
+    # (4) linearity of the torque in ddtheta at fixed (theta, dtheta): tau(a) - tau(0) = M a
+    idx = torch.randint(0, B * N, (5000,), device="cuda")
+    th = tr["positions"].reshape(-1, 6)[idx].double()
+    dth = tr["velocities"].reshape(-1, 6)[idx].double()
+    dd = tr["accelerations"].reshape(-1, 6)[idx].double()
+    dyn = rb.dynamics
+    lhs = dyn.inverse_dynamics(th, dth, dd, [0, 0, -9.81]) - dyn.inverse_dynamics(th, dth, torch.zeros_like(dd), [0, 0, -9.81])
+    rhs = torch.einsum("pij,pj->pi", dyn.mass_matrix(th), dd)
+    assert float((lhs - rhs).abs().max()) < 1e-9 * max(1.0, float(rhs.abs().max()))
+
+
+def test_full_size_cfg2_million_fk_jacobian(robots, oracle_factory):
+    """iiwa14 (true 7-DOF) and the reference's 8-DOF Panda: 1,000,000 random configurations."""
+    for robot in ("iiwa14", "panda"):
+        rb, o = robots[robot], oracle_factory(robot)
+        n = rb.num_joints
+        rng = np.random.default_rng(2)
+        P = 1_000_000
+        th = torch.from_numpy(rng.uniform(rb.joint_limits[:, 0], rb.joint_limits[:, 1], (P, n))).cuda()
+        T, J = rb.dynamics.forward_kinematics_and_jacobian(th)
+        assert T.shape == (P, 4, 4) and J.shape == (P, 6, n)
+        R = T[:, :3, :3]
+        eye = torch.eye(3, dtype=torch.float64, device="cuda")
+        assert float((R @ R.transpose(1, 2) - eye).abs().max()) < 1e-13
+        assert bool((T[:, 3] == torch.tensor([0.0, 0, 0, 1], dtype=torch.float64, device="cuda")).all())
+        idx = rng.integers(0, P, 3000)
+        thh = th[idx].cpu().numpy()
+        assert np.abs(T[idx].cpu().numpy() - o.forward_kinematics(thh)).max() < 1e-12
+        assert np.abs(J[idx].cpu().numpy() - o.jacobian(thh)).max() < 1e-12
+        # finite-difference property: dp/dtheta_i = v_i + w_i x p for the space Jacobian
+        eps = 1e-6
+        k = 3
+        thp, thm = th[:2000].clone(), th[:2000].clone()
+        thp[:, k] += eps
+        thm[:, k] -= eps
+        dp = (rb.dynamics.forward_kinematics(thp)[:, :3, 3] - rb.dynamics.forward_kinematics(thm)[:, :3, 3]) / (2 * eps)
+        Jk = J[:2000, :, k]
+        pred = Jk[:, 3:] + torch.linalg.cross(Jk[:, :3], T[:2000, :3, 3])
+        assert float((dp - pred).abs().max()) < 1e-8
+
+
+def test_full_size_cfg4_iiwa_rollouts(robots, oracle_factory):
+    """iiwa14, 65,536 rollouts x 1000 Euler steps; sampled rollouts against the oracle."""
+    rb, o = robots["iiwa14"], oracle_factory("iiwa14")
+    B, N, n = 65536, 1000, 7
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    lo = torch.from_numpy(rb.joint_limits[:, 0]).cuda()
+    hi = torch.from_numpy(rb.joint_limits[:, 1]).cuda()
+    th0 = 0.5 * (lo + (hi - lo) * torch.rand(B, n, dtype=torch.float64, device="cuda", generator=gen))
+    dth0 = torch.rand(B, n, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    tau = (torch.rand(B, N, n, dtype=torch.float32, device="cuda", generator=gen) - 0.5) * 40.0
+    planner = rb.planner()
+    r = planner.forward_dynamics_trajectory(th0, dth0, tau, [0, 0, -9.81], None, 1e-3, 1)
+    pos, vel, acc = r["positions"], r["velocities"], r["accelerations"]
+    assert pos.shape == (B, N, n) and bool(torch.isfinite(pos).all()) and bool(torch.isfinite(acc).all())
+    assert bool((pos[:, 0] == th0.float()).all()) and bool((acc[:, 0] == 0).all())
+    lo32, hi32 = lo.float(), hi.float()
+    assert bool((pos >= lo32).all()) and bool((pos <= hi32).all())
+    sel = [0, 1, 4097, 65535]
+    ref = o.forward_dynamics_trajectory(th0[sel].cpu().numpy(), dth0[sel].cpu().numpy(), tau[sel].double().cpu().numpy(),
+                                        [0, 0, -9.81], None, 1e-3, 1, rb.joint_limits, analytic=True)
+    # 1000 chaotic steps amplify rounding differences between LDL^T and the oracle's LU: 1e-5 per row
+    for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
+        assert _rel_rows(got[sel].cpu().numpy().reshape(-1, n), ref[k].reshape(-1, n)) < 1e-4, k
+    # the first 50 steps agree to float32 rounding
+    for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
+        assert _rel_rows(got[sel, :50].cpu().numpy().reshape(-1, n), ref[k][:, :50].reshape(-1, n)) < 1e-6, k

@@ -1,0 +1,256 @@
+"""CPU-side checks of the native path (no GPU needed).
+
+* the C-ABI library loads and exports every symbol ``include/mpk.h`` declares;
+* host-only entry points (robot pack construction) behave and report errors;
+* the kernels' own per-thread templates, executed on the CPU through tests/hostcheck,
+  reproduce the reference's golden vectors and the oracle -- the algebra the GPU will run
+  is pinned before any GPU time is spent;
+* host logic: operator registry contract, sharding under gloo (world_size 2), and that the
+  product path refuses to run without CUDA instead of falling back.
+"""
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import REPO, load_golden, load_pack, planar_2r_pack, random_general_pack
+
+ROBOTS = ["ur5", "panda", "iiwa14", "xarm6"]
+
+
+def test_abi_exports_every_declared_symbol():
+    from manipulapy_b200 import _native
+
+    lib = _native.lib()
+    syms = _native.declared_symbols()
+    assert len(syms) >= 14 and "mpk_inverse_dynamics" in syms and "mpk_forward_dynamics_trajectory" in syms
+    for s in syms:
+        assert hasattr(lib, s), f"libmpk.so does not export {s}"
+    assert lib.mpk_version() >= 100
+
+
+def test_torch_ops_register():
+    from manipulapy_b200 import _native
+
+    ops = _native.ops()
+    for name in ("robot_create", "joint_trajectory", "fk_jacobian", "inverse_dynamics",
+                 "trajectory_inverse_dynamics", "mass_matrix", "forward_dynamics",
+                 "forward_dynamics_trajectory", "fma_peak"):
+        assert hasattr(ops, name)
+
+
+def test_robot_create_errors(hostcheck):
+    p = load_pack("ur5")
+    bad = dict(p)
+    bad["S_list"] = p["S_list"].copy()
+    bad["S_list"][:3, 2] *= 1.5  # non-unit omega: the reference formula is not a rigid motion
+    with pytest.raises(RuntimeError, match="non-unit"):
+        hostcheck.robot(bad)
+    big = random_general_pack(8, 0)
+    big9 = {k: np.concatenate([v, v[..., :1]], -1) if k == "S_list" else v for k, v in big.items()}
+    big9["Glist"] = np.concatenate([big["Glist"], big["Glist"][:1]])
+    big9["Mlist_per_link"] = np.concatenate([big["Mlist_per_link"], big["Mlist_per_link"][:1]])
+    with pytest.raises(RuntimeError, match="1..8"):
+        hostcheck.robot(big9)
+    h, n = hostcheck.robot(p)
+    assert hostcheck.L.mpk_robot_dof(h) == 6 and hostcheck.L.mpk_robot_is_rigid(h) == 1
+    h2, _ = hostcheck.robot(p, flags=1)
+    assert hostcheck.L.mpk_robot_is_rigid(h2) == 0
+
+
+@pytest.mark.parametrize("flags", [0, 1], ids=["rigid", "general"])
+@pytest.mark.parametrize("robot", ["ur5", "panda", "iiwa14"])
+def test_kernel_algebra_vs_reference_golden(hostcheck, robot, flags):
+    """Reference tolerances (tests/test_dynamics_golden.py:77-83): rtol 1e-7, atol 1e-9 / 1e-8."""
+    g = load_golden(f"dynamics_{robot}")
+    rb = hostcheck.robot(load_pack(robot), flags)
+    th, dth, ddth = g["thetas"], g["dthetas"], g["ddthetas"]
+    T, J = hostcheck.fk(rb, th)
+    np.testing.assert_allclose(T, g["forward_kinematics"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(J, g["jacobian"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(hostcheck.mass(rb, th), g["mass_matrix"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(hostcheck.rnea(rb, th, g=g["g"]), g["gravity_forces"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(hostcheck.rnea(rb, th, dth, g=(0, 0, 0)), g["velocity_quadratic_forces"],
+                               rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(hostcheck.rnea(rb, th, dth, ddth, g["g"], g["ftips"]), g["inverse_dynamics"],
+                               rtol=1e-7, atol=1e-8)
+    i = g["fd_index"]
+    dd = hostcheck.fd(rb, th[i], dth[i], g["fd_tau"], g["g"], g["ftips"][i])
+    ref = g["forward_dynamics"]
+    assert np.max(np.abs(dd - ref) / np.maximum(1.0, np.abs(ref).max(1, keepdims=True))) < 1e-9
+
+
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_kernel_algebra_vs_oracle_random(hostcheck, oracle_factory, robot):
+    """Against the analytic oracle the only difference is rounding: 1e-9 * max(1, |ref|_inf)."""
+    p = load_pack(robot)
+    o = oracle_factory(robot)
+    n = p["S_list"].shape[1]
+    rng = np.random.default_rng(11)
+    lo, hi = p["joint_limits"][:, 0], p["joint_limits"][:, 1]
+    th = rng.uniform(lo, hi, (200, n))
+    dth, ddth = rng.uniform(-2, 2, (200, n)), rng.uniform(-5, 5, (200, n))
+    ft = rng.uniform(-10, 10, 6)
+    g = np.array([0.3, -0.2, -9.81])
+    for flags in (0, 1):
+        rb = hostcheck.robot(p, flags)
+        T, J = hostcheck.fk(rb, th)
+        assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
+        assert np.abs(J - o.jacobian(th)).max() < 1e-12
+        ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)
+        got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
+        assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
+        Mref = o.mass_matrix(th[:50])
+        assert np.abs(hostcheck.mass(rb, th[:50]) - Mref).max() < 1e-9 * max(1, np.abs(Mref).max())
+        tau = rng.uniform(-20, 20, (50, n))
+        ref = o.forward_dynamics(th[:50], dth[:50], tau, g, ft, analytic=True)
+        got = hostcheck.fd(rb, th[:50], dth[:50], tau, g, np.tile(ft, (50, 1)))
+        assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8])
+def test_general_inertia_and_prismatic_vs_oracle(hostcheck, n):
+    """Arbitrary unit screws, a non-unit prismatic joint, full symmetric 6x6 inertias."""
+    from oracle import Oracle
+
+    p = random_general_pack(n, seed=100 + n)
+    o = Oracle(p["S_list"], p["M"], p["Glist"], p["Mlist_per_link"])
+    rb = hostcheck.robot(p)
+    assert hostcheck.L.mpk_robot_is_rigid(rb[0]) == 0
+    rng = np.random.default_rng(n)
+    th, dth, ddth = rng.uniform(-2, 2, (40, n)), rng.uniform(-2, 2, (40, n)), rng.uniform(-3, 3, (40, n))
+    g, ft = np.array([1.0, 2.0, -9.0]), rng.uniform(-5, 5, 6)
+    T, J = hostcheck.fk(rb, th)
+    assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
+    assert np.abs(J - o.jacobian(th)).max() < 1e-12
+    for analytic, tol in ((True, 1e-11), (False, 1e-7)):  # literal path carries its finite-difference noise
+        ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=analytic)
+        got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
+        assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < tol
+    Mref = o.mass_matrix(th)  # literal sum_k Jk^T Gk Jk
+    assert np.abs(hostcheck.mass(rb, th) - Mref).max() < 1e-10 * max(1, np.abs(Mref).max())
+    gref = o.gravity_forces(th, g)
+    assert np.abs(hostcheck.rnea(rb, th, g=g) - gref).max() < 1e-10 * max(1, np.abs(gref).max())
+
+
+def test_planar_2r_known_answers(hostcheck):
+    """Murray-Li-Sastry Ex. 4.3 (reference tests/test_v132_regressions.py:126-192, 229-286)."""
+    rb = hostcheck.robot(planar_2r_pack())
+    th = np.array([[0.0, np.pi / 2]])
+    c2 = np.cos(th[0, 1])
+    Mexp = np.array([[1 + (1 + 1 + 2 * c2), 1 + c2], [1 + c2, 1.0]])
+    np.testing.assert_allclose(hostcheck.mass(rb, th)[0], Mexp, atol=1e-12)
+    np.testing.assert_allclose(hostcheck.rnea(rb, th, g=[-9.81, 0, 0])[0], [-9.81, -9.81], atol=1e-12)
+    np.testing.assert_allclose(hostcheck.rnea(rb, th, g=[0, -9.81, 0])[0], [19.62, 0.0], atol=1e-12)
+    np.testing.assert_allclose(hostcheck.rnea(rb, th, g=[0, 0, -9.81])[0], [0.0, 0.0], atol=1e-12)
+
+
+def test_time_scaling_bit_exact_vs_golden(hostcheck):
+    """The kernel's time scaling + rounding restated on the host is bit-identical to the oracle
+    (itself pinned bit-exact on the reference in test_oracle_golden.py)."""
+    from oracle import Oracle
+
+    g = load_golden("trajectory")
+    lim = g["joint_limits"]
+    for name in ("cfg1", "cubic50", "two", "clipped", "odd_tf"):
+        Tf, N, method = g[f"{name}_args"]
+        got = hostcheck.traj(g[f"{name}_start"], g[f"{name}_end"], Tf, int(N), int(method), lim)
+        ref = Oracle.joint_trajectory(g[f"{name}_start"], g[f"{name}_end"], Tf, int(N), int(method), lim)
+        for a, k in zip(got, ("positions", "velocities", "accelerations")):
+            assert np.array_equal(a.view(np.uint32), ref[k].view(np.uint32)), (name, k)
+    # other methods -> zero scaling; N = 1 -> NaN (the planner's CPU contract)
+    got = hostcheck.traj(np.zeros(3), np.ones(3), 2.0, 5, 7, None)
+    assert np.all(got[0] == 0) and np.all(got[1] == 0)
+    got = hostcheck.traj(np.zeros(3), np.ones(3), 2.0, 1, 5, None)
+    ref = Oracle.joint_trajectory(np.zeros(3), np.ones(3), 2.0, 1, 5)
+    assert np.array_equal(np.isnan(got[0]), np.isnan(ref["positions"]))
+
+
+def test_registry_contract():
+    from manipulapy_b200 import KERNEL_REGISTRY, KernelRegistration
+
+    names = KERNEL_REGISTRY.names()
+    for v in ("auto", "auto_tune", "standard", "vectorized", "memory_optimized", "warp_optimized", "cache_friendly"):
+        assert f"trajectory.{v}" in names
+    assert "dynamics.inverse" in names and "dynamics.forward_rollout" in names
+    with pytest.raises(KeyError, match="Unknown CUDA kernel 'nope'. Available kernels:"):
+        KERNEL_REGISTRY.get("nope")
+    e = KERNEL_REGISTRY.get("trajectory.auto")
+    with pytest.raises(ValueError, match="already registered"):
+        KERNEL_REGISTRY.register(e)
+    with pytest.raises(TypeError):
+        e.metadata["x"] = 1
+    with pytest.raises(RuntimeError, match="no CPU"):
+        e.cpu_launcher()
+    assert isinstance(e, KernelRegistration)
+
+
+def test_no_cpu_fallback():
+    """Without CUDA the product path refuses to run; it never routes through the oracle."""
+    import torch
+
+    from manipulapy_b200 import load_robot
+
+    rb = load_robot("ur5")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        rb.planner(use_cuda=False)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            rb.planner()
+        with pytest.raises(RuntimeError):
+            rb.dynamics.mass_matrix(np.zeros(6))
+    src = "".join(p.read_text() for p in (REPO / "manipulapy_b200").rglob("*.py"))
+    assert "import oracle" not in src and "from oracle" not in src
+
+
+def test_legacy_path_raises():
+    from manipulapy_b200 import ManipulatorDynamics
+
+    p = load_pack("ur5")
+    with pytest.raises(NotImplementedError, match="legacy"):
+        ManipulatorDynamics(p["M"], None, None, None, p["S_list"], None, p["Glist"], None)
+
+
+def test_shard_range():
+    from manipulapy_b200 import shard_range
+
+    for units in (0, 1, 7, 4096, 9998336):
+        for world in (1, 2, 4, 8):
+            spans = [shard_range(units, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == units
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) == -(-units // world)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from manipulapy_b200.sharding import shard_range, gather_rows
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2],
+                        rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+units = 11
+full = torch.arange(units * 3, dtype=torch.float32).reshape(units, 3)
+lo, hi = shard_range(units, 2, rank)
+out = gather_rows(full[lo:hi].clone(), units)
+assert torch.equal(out, full), out
+out = gather_rows(full[lo:hi].clone(), units, dst=0)
+assert (out is None) if rank else torch.equal(out, full)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_rows_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(REPO), port, str(r)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
