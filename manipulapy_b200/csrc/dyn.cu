@@ -8,11 +8,14 @@
 //   forward dynamics            dynamics/id_fd.py:50-83
 // One thread owns one point; all link state lives in registers (mpk_device.cuh); robot
 // constants are constant-bank operands.  fp64 FMA-pipe bound.
+#include <cstdlib>
+
 #include "mpk_common.cuh"
 
 namespace mpk {
 
 constexpr int kDynThreads = 128;
+constexpr int kRneaMinBlocks = 5;  // 96-register cap: 20 warps / SM hide the fp64 latency
 
 struct TipArgs {
     double g[3];
@@ -47,23 +50,32 @@ __device__ __forceinline__ void store_tau(void *out, int out_dtype, bool vec, in
     }
 }
 
-template <int N, bool GEN>
-__global__ void __launch_bounds__(kDynThreads)
+// Joint values of row p read from global memory when the recursion reaches the link.  Each
+// thread walks its own contiguous row, rows of neighbouring threads are adjacent, so every
+// fetched sector is fully consumed (through L1) although the individual loads are strided.
+template <int N>
+struct RowIn {
+    const void *th, *dth, *ddth;
+    int dtype;
+    int64_t row;  // p * N
+    __device__ __forceinline__ double at(const void *base, int i) const {
+        if (base == nullptr) return 0.0;
+        return dtype == MPK_F64 ? __ldg(static_cast<const double *>(base) + row + i)
+                                : (double)__ldg(static_cast<const float *>(base) + row + i);
+    }
+    __device__ __forceinline__ void joint(int i, double &a, double &b, double &c) const {
+        a = at(th, i);
+        b = at(dth, i);
+        c = at(ddth, i);
+    }
+};
+
+template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks>
+__global__ void __launch_bounds__(THREADS, MINB)
     rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
-    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    extern __shared__ __align__(16) double wsm[];
+    const int64_t p = (int64_t)blockIdx.x * THREADS + threadIdx.x;
     if (p >= a.P) return;
-    double th[N], dth[N], ddth[N];
-    load_row<N>(a.th, a.in_dtype, a.vec_in, p, th);
-    if (a.dth) load_row<N>(a.dth, a.in_dtype, a.vec_in, p, dth);
-    else {
-#pragma unroll
-        for (int j = 0; j < N; ++j) dth[j] = 0.0;
-    }
-    if (a.ddth) load_row<N>(a.ddth, a.in_dtype, a.vec_in, p, ddth);
-    else {
-#pragma unroll
-        for (int j = 0; j < N; ++j) ddth[j] = 0.0;
-    }
     double ft[6];
     const double *ftp = nullptr;
     if (a.tip.ftip_rows) {
@@ -75,10 +87,10 @@ __global__ void __launch_bounds__(kDynThreads)
         for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
         ftp = ft;
     }
-    JointCS<double, N> q;
-    joint_cs(rb, th, q);
+    const RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N};
+    SmemStore<double, N, THREADS> st{wsm + threadIdx.x};
     double tau[N];
-    rnea<double, N, GEN>(rb, q, dth, ddth, a.tip.g, ftp, tau);
+    rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
     store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
 }
 
@@ -94,49 +106,61 @@ struct TrajRneaArgs {
     float *tau, *pos, *vel, *acc;
 };
 
-template <int N, bool GEN>
-__global__ void __launch_bounds__(kDynThreads)
+// Joint values produced from the time scaling when the recursion reaches the link: the
+// float32-rounded, clipped trajectory row entries the two-call sequence would have stored.
+template <int N>
+struct TrajIn {
+    const TrajRneaArgs &a;
+    TimeScale ts;
+    int64_t row;  // b * N
+    __device__ __forceinline__ void joint(int i, double &th, double &qd, double &qdd) const {
+        double st, dth;
+        endpoint(a.start, a.end, a.inputs_f32, row + i, st, dth);
+        float p, v, ac;
+        traj_point(ts, st, dth, a.jlim.lo[i], a.jlim.hi[i], a.jlim.on, p, v, ac);
+        th = (double)p;
+        qd = (double)v;
+        qdd = (double)ac;
+    }
+};
+
+template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks>
+__global__ void __launch_bounds__(THREADS, MINB)
     traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
-    __shared__ __align__(16) float sm[kDynThreads * N];
+    // dynamic shared memory: per-thread link state during the recursion, then (aliased, after a
+    // barrier) the block's output rows staged for coalesced stores
+    extern __shared__ __align__(16) double wsm[];
+    float *sm = reinterpret_cast<float *>(wsm);
     int64_t b, t;
     point_coords(a.N, b, t);
-    const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
+    const int64_t p0 = (int64_t)blockIdx.x * THREADS;
     const bool live = p0 + threadIdx.x < a.P;
     const int64_t rem = a.P - p0;
-    const int cnt = (int)(rem < kDynThreads ? rem : kDynThreads) * N;
+    const int cnt = (int)(rem < THREADS ? rem : THREADS) * N;
     const int64_t off = p0 * N;
-    float pf[N], vf[N], af[N];
-    if (live) {
-        const TimeScale ts = time_scaling(t, a.N, a.Tf, a.method);
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            double st, dth;
-            endpoint(a.start, a.end, a.inputs_f32, b * N + j, st, dth);
-            traj_point(ts, st, dth, a.jlim.lo[j], a.jlim.hi[j], a.jlim.on, pf[j], vf[j], af[j]);
-        }
-    }
+    TrajIn<N> in{a, TimeScale{0.0, 0.0, 0.0}, b * N};
+    if (live) in.ts = time_scaling(t, a.N, a.Tf, a.method);
     // optional materialisation of the trajectory rows (coalesced through shared memory)
-    float *outs[3] = {a.pos, a.vel, a.acc};
+    if (a.pos || a.vel || a.acc) {
+        float *outs[3] = {a.pos, a.vel, a.acc};
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {
+            if (!outs[k]) continue;  // uniform
+            if (live) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        if (!outs[k]) continue;  // uniform
-        if (live) {
-#pragma unroll
-            for (int j = 0; j < N; ++j)
-                sm[threadIdx.x * N + j] = k == 0 ? pf[j] : (k == 1 ? vf[j] : af[j]);
+                for (int j = 0; j < N; ++j) {
+                    double th, qd, qdd;
+                    in.joint(j, th, qd, qdd);
+                    sm[threadIdx.x * N + j] = (float)(k == 0 ? th : (k == 1 ? qd : qdd));
+                }
+            }
+            __syncthreads();
+            tile_store(outs[k] + off, sm, cnt);
+            __syncthreads();
         }
-        __syncthreads();
-        tile_store(outs[k] + off, sm, cnt);
-        __syncthreads();
     }
+    double tau[N];
     if (live) {
-        double th[N], dth[N], ddth[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            th[j] = (double)pf[j];
-            dth[j] = (double)vf[j];
-            ddth[j] = (double)af[j];
-        }
         double ft[6];
         const double *ftp = nullptr;
         if (a.tip.has_ftip) {
@@ -144,10 +168,11 @@ __global__ void __launch_bounds__(kDynThreads)
             for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
             ftp = ft;
         }
-        JointCS<double, N> q;
-        joint_cs(rb, th, q);
-        double tau[N];
-        rnea<double, N, GEN>(rb, q, dth, ddth, a.tip.g, ftp, tau);
+        SmemStore<double, N, THREADS> st{wsm + threadIdx.x};
+        rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
+    }
+    __syncthreads();  // every thread is done with its link state: reuse the memory for the rows
+    if (live) {
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             float x = (float)tau[j];
@@ -177,7 +202,7 @@ __global__ void __launch_bounds__(kDynThreads)
     JointCS<double, N> q;
     joint_cs(rb, th, q);
     double Mm[N][N];
-    mass_matrix<double, N, GEN>(rb, q, Mm);
+    mass_matrix<double, N, GEN>(rb, th, q, Mm);
     double flat[N * N];
 #pragma unroll
     for (int i = 0; i < N; ++i)
@@ -231,6 +256,26 @@ static TipArgs make_tip(const double *g, const double *Ftip, const double *Ftip_
     return t;
 }
 
+// Bytes of shared memory the RNEA kernels need for the per-link wrenches of one block.
+template <int N>
+constexpr size_t wrench_smem(int threads) {
+    const size_t link_state = (size_t)(N > 1 ? N - 1 : 0) * 8 * threads * sizeof(double);
+    const size_t rows = (size_t)threads * N * sizeof(float);  // aliased output staging (fused kernel)
+    return link_state > rows ? link_state : rows;
+}
+
+// Launch with dynamic shared memory, asking for the largest shared-memory carveout so that
+// __launch_bounds__' blocks-per-SM target is not cut short by the L1 / shared split.
+template <typename... KArgs, typename... Args>
+static void launch_smem(void (*kern)(KArgs...), unsigned grid, int threads, size_t smem,
+                        cudaStream_t s, Args &&...args) {
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    kern<<<grid, threads, smem, s>>>(args...);
+}
+
 static int grid_for(int64_t P, unsigned &grid) {
     const int64_t blocks = (P + kDynThreads - 1) / kDynThreads;
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "point count exceeds the grid limit");
@@ -274,9 +319,9 @@ extern "C" int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *
     if (int rc = grid_for(P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (rb->rigid) {
-        MPK_DISPATCH_DOF(rb->n, (rnea_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+        MPK_DISPATCH_DOF(rb->n, launch_smem(rnea_kernel<N_, false>, grid, kDynThreads, wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
     } else {
-        MPK_DISPATCH_DOF(rb->n, (rnea_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+        MPK_DISPATCH_DOF(rb->n, launch_smem(rnea_kernel<N_, true>, grid, kDynThreads, wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
     }
     return check_launch("inverse_dynamics");
 }
@@ -313,10 +358,31 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     unsigned grid;
     if (int rc = grid_for(a.P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const char *var = getenv("MPK_VARIANT");
+    if (var && rb->rigid && rb->n == 6) {
+        const int v = atoi(var);
+        auto pk = narrow<6>(rb);
+#define MPK_VAR(T_, MB_) { const unsigned g_ = (unsigned)((a.P + T_ - 1) / T_); \
+        launch_smem(traj_rnea_kernel<6, false, T_, MB_>, g_, T_, wrench_smem<6>(T_), s, pk, a); }
+        switch (v) {
+            case 1: MPK_VAR(128, 3) break;
+            case 2: MPK_VAR(128, 4) break;
+            case 3: MPK_VAR(128, 6) break;
+            case 4: MPK_VAR(64, 10) break;
+            case 5: MPK_VAR(64, 12) break;
+            case 6: MPK_VAR(256, 2) break;
+            case 7: MPK_VAR(256, 3) break;
+            case 8: MPK_VAR(192, 3) break;
+            case 9: MPK_VAR(32, 16) break;
+            default: MPK_VAR(128, 5) break;
+        }
+#undef MPK_VAR
+        return check_launch("trajectory_inverse_dynamics");
+    }
     if (rb->rigid) {
-        MPK_DISPATCH_DOF(rb->n, (traj_rnea_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+        MPK_DISPATCH_DOF(rb->n, launch_smem(traj_rnea_kernel<N_, false>, grid, kDynThreads, wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
     } else {
-        MPK_DISPATCH_DOF(rb->n, (traj_rnea_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+        MPK_DISPATCH_DOF(rb->n, launch_smem(traj_rnea_kernel<N_, true>, grid, kDynThreads, wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
     }
     return check_launch("trajectory_inverse_dynamics");
 }

@@ -45,7 +45,7 @@ struct RobotPack {
     T Rx[N][9];  // rotation of frame i in frame i-1 at theta_i = 0 (row-major)
     T px[N][3];  // origin of frame i in frame i-1
     T sr[N];     // 1 revolute / helical, 0 prismatic
-    T st[N];     // z translation per unit theta (|v| prismatic, pitch if helical, else 0)
+    T st[N];     // z translation per unit theta (|v| for a prismatic joint, else 0)
     T I[N][6];   // rigid: rotational inertia about the frame-i origin (xx,xy,xz,yy,yz,zz)
     T h[N][3];   // rigid: mass * centre of mass (in frame i)
     T m[N];      // rigid: mass
@@ -102,10 +102,10 @@ MPK_HD void twist_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T d,
                                                T (&w)[3], T (&v)[3]) {
     const T *R = rb.Rx[i];
     const T *p = rb.px[i];
-    // u = v + w x p
-    const T ux = v[0] + (w[1] * p[2] - w[2] * p[1]);
-    const T uy = v[1] + (w[2] * p[0] - w[0] * p[2]);
-    const T uz = v[2] + (w[0] * p[1] - w[1] * p[0]);
+    // u = v + w x p   (written so that every product contracts into an FMA chain)
+    const T ux = v[0] + w[1] * p[2] - w[2] * p[1];
+    const T uy = v[1] + w[2] * p[0] - w[0] * p[2];
+    const T uz = v[2] + w[0] * p[1] - w[1] * p[0];
     // Rx^T *
     const T w1x = R[0] * w[0] + R[3] * w[1] + R[6] * w[2];
     const T w1y = R[1] * w[0] + R[4] * w[1] + R[7] * w[2];
@@ -145,9 +145,9 @@ MPK_HD void wrench_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T d,
     const T *R = rb.Rx[i];
     const T *p = rb.px[i];
     // u = n - p x f
-    const T ux = n[0] - (p[1] * f[2] - p[2] * f[1]);
-    const T uy = n[1] - (p[2] * f[0] - p[0] * f[2]);
-    const T uz = n[2] - (p[0] * f[1] - p[1] * f[0]);
+    const T ux = n[0] - p[1] * f[2] + p[2] * f[1];
+    const T uy = n[1] - p[2] * f[0] + p[0] * f[2];
+    const T uz = n[2] - p[0] * f[1] + p[1] * f[0];
     const T f1x = R[0] * f[0] + R[3] * f[1] + R[6] * f[2];
     const T f1y = R[1] * f[0] + R[4] * f[1] + R[7] * f[2];
     const T f1z = R[2] * f[0] + R[5] * f[1] + R[8] * f[2];
@@ -166,10 +166,11 @@ MPK_HD void wrench_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T d,
     f[2] = f1z;
 }
 
-// Wrench (n, f) of frame i coordinates -> frame i-1 coordinates: Ad(T_{i-1,i}^{-1})^T.
+// Wrench (n, f) of frame i coordinates -> frame i-1 coordinates, Ad(T_{i-1,i}^{-1})^T, ADDED to
+// (an, af):  (an, af) += Ad^T (n, f).  Every term is one link of an FMA chain seeded by an / af.
 template <typename T, int N>
-MPK_HD void wrench_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T d,
-                                                 T (&n)[3], T (&f)[3]) {
+MPK_HD void wrench_to_parent_acc(const RobotPack<T, N> &rb, int i, T c, T s, T d, const T (&n)[3],
+                                 const T (&f)[3], T (&an)[3], T (&af)[3]) {
     const T *R = rb.Rx[i];
     const T *p = rb.px[i];
     // Rz *
@@ -187,12 +188,24 @@ MPK_HD void wrench_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T d,
     const T f2x = R[0] * f1x + R[1] * f1y + R[2] * f1z;
     const T f2y = R[3] * f1x + R[4] * f1y + R[5] * f1z;
     const T f2z = R[6] * f1x + R[7] * f1y + R[8] * f1z;
-    n[0] = R[0] * n1x + R[1] * n1y + R[2] * n1z + (p[1] * f2z - p[2] * f2y);
-    n[1] = R[3] * n1x + R[4] * n1y + R[5] * n1z + (p[2] * f2x - p[0] * f2z);
-    n[2] = R[6] * n1x + R[7] * n1y + R[8] * n1z + (p[0] * f2y - p[1] * f2x);
-    f[0] = f2x;
-    f[1] = f2y;
-    f[2] = f2z;
+    an[0] = an[0] + R[0] * n1x + R[1] * n1y + R[2] * n1z + p[1] * f2z - p[2] * f2y;
+    an[1] = an[1] + R[3] * n1x + R[4] * n1y + R[5] * n1z + p[2] * f2x - p[0] * f2z;
+    an[2] = an[2] + R[6] * n1x + R[7] * n1y + R[8] * n1z + p[0] * f2y - p[1] * f2x;
+    af[0] += f2x;
+    af[1] += f2y;
+    af[2] += f2z;
+}
+
+// Wrench (n, f) of frame i coordinates -> frame i-1 coordinates, in place.
+template <typename T, int N>
+MPK_HD void wrench_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T d, T (&n)[3], T (&f)[3]) {
+    T an[3] = {T(0), T(0), T(0)}, af[3] = {T(0), T(0), T(0)};
+    wrench_to_parent_acc(rb, i, c, s, d, n, f, an, af);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        n[k] = an[k];
+        f[k] = af[k];
+    }
 }
 
 // Spatial momentum (n, f) = G_i [w; v].
@@ -212,12 +225,12 @@ MPK_HD void inertia_mul(const RobotPack<T, N> &rb, int i, const T (&w)[3],
         const T *h = rb.h[i];
         const T m = rb.m[i];
         // n = I w + h x v ;  f = m v + w x h
-        n[0] = I[0] * w[0] + I[1] * w[1] + I[2] * w[2] + (h[1] * v[2] - h[2] * v[1]);
-        n[1] = I[1] * w[0] + I[3] * w[1] + I[4] * w[2] + (h[2] * v[0] - h[0] * v[2]);
-        n[2] = I[2] * w[0] + I[4] * w[1] + I[5] * w[2] + (h[0] * v[1] - h[1] * v[0]);
-        f[0] = m * v[0] + (w[1] * h[2] - w[2] * h[1]);
-        f[1] = m * v[1] + (w[2] * h[0] - w[0] * h[2]);
-        f[2] = m * v[2] + (w[0] * h[1] - w[1] * h[0]);
+        n[0] = I[0] * w[0] + I[1] * w[1] + I[2] * w[2] + h[1] * v[2] - h[2] * v[1];
+        n[1] = I[1] * w[0] + I[3] * w[1] + I[4] * w[2] + h[2] * v[0] - h[0] * v[2];
+        n[2] = I[2] * w[0] + I[4] * w[1] + I[5] * w[2] + h[0] * v[1] - h[1] * v[0];
+        f[0] = m * v[0] + w[1] * h[2] - w[2] * h[1];
+        f[1] = m * v[1] + w[2] * h[0] - w[0] * h[2];
+        f[2] = m * v[2] + w[0] * h[1] - w[1] * h[0];
     }
 }
 
@@ -229,24 +242,76 @@ MPK_HD void inertia_mul(const RobotPack<T, N> &rb, int i, const T (&w)[3],
 //   general (GEN = true): G_i is any symmetric 6x6; gravity is the reference's explicit
 //   wrench [0; G_i[3,3] R_i^T(-g)] at the link-CoM frame origin (dynamics/forces.py:121-131).
 //   ftip: space-frame wrench (moment; force) or nullptr.
-template <typename T, int N, bool GEN>
-MPK_HD void rnea(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
-                                     const T (&dth)[N], const T (&ddth)[N], const T (&g)[3],
-                                     const T *ftip, T (&tau)[N]) {
-    T Fn[N][3], Ff[N][3];  // local link wrenches, then accumulated in place
-    T w[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)};
-    T dw[3] = {T(0), T(0), T(0)}, dv[3];
-    T ag[3];  // general path: -g in the current frame
-    if (GEN) {
-        dv[0] = dv[1] = dv[2] = T(0);
-        ag[0] = -g[0];
-        ag[1] = -g[1];
-        ag[2] = -g[2];
-    } else {
-        dv[0] = -g[0];
-        dv[1] = -g[1];
-        dv[2] = -g[2];
+// Storage of the per-link state the backward pass needs (local wrench of link i, and the
+// joint rotation c, s, d of link i+1 that moves link i+1's wrench into frame i):
+//   RegStore  : registers (small DOF, and the forward-dynamics path which reuses c, s for CRBA);
+//   SmemStore : one shared-memory column per thread (stride = block size, so a warp's
+//               accesses are conflict-free); frees 8 (N-1) fp64 registers per thread, which
+//               is what lets 20 warps per SM hide the fp64 pipe latency.
+// A prismatic joint has c = 1, s = 0 exactly, so SmemStore keeps its z offset d in the s slot.
+template <typename T, int N>
+struct RegStore {
+    T x[N][6];
+    JointCS<T, N> q;
+    MPK_HD void put(int i, int k, T v) { x[i][k] = v; }
+    MPK_HD T get(int i, int k) const { return x[i][k]; }
+    MPK_HD void put_cs(const RobotPack<T, N> &, int i, T c, T s, T d) {
+        q.c[i] = c;
+        q.s[i] = s;
+        q.d[i] = d;
     }
+    MPK_HD void get_cs(const RobotPack<T, N> &, int i, T &c, T &s, T &d) const {
+        c = q.c[i];
+        s = q.s[i];
+        d = q.d[i];
+    }
+};
+template <typename T, int N, int THREADS>
+struct SmemStore {
+    T *base;  // shared memory + threadIdx.x; slot l = wrench of link l, (c, s) of link l + 1
+    static constexpr int kSlots = N > 1 ? N - 1 : 0;
+    static constexpr size_t kBytes = (size_t)kSlots * 8 * THREADS * sizeof(T);
+    MPK_HD void put(int i, int k, T v) { base[(i * 8 + k) * THREADS] = v; }
+    MPK_HD T get(int i, int k) const { return base[(i * 8 + k) * THREADS]; }
+    MPK_HD void put_cs(const RobotPack<T, N> &rb, int i, T c, T s, T d) {
+        if (i == 0) return;
+        base[((i - 1) * 8 + 6) * THREADS] = c;
+        base[((i - 1) * 8 + 7) * THREADS] = rb.sr[i] != T(0) ? s : d;
+    }
+    MPK_HD void get_cs(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
+        c = base[((i - 1) * 8 + 6) * THREADS];
+        const T x = base[((i - 1) * 8 + 7) * THREADS];
+        if (rb.sr[i] != T(0)) {
+            s = x;
+            d = T(0);  // helical joints are rejected by mpk_robot_create
+        } else {
+            s = T(0);
+            d = x;
+        }
+    }
+};
+
+// Joint values straight from register arrays.
+template <typename T, int N>
+struct ArrayIn {
+    const T (&th)[N];
+    const T (&dth)[N];
+    const T (&ddth)[N];
+    MPK_HD void joint(int i, T &a, T &b, T &c) const {
+        a = th[i];
+        b = dth[i];
+        c = ddth[i];
+    }
+};
+
+// `in.joint(i, theta, dtheta, ddtheta)` yields joint i's values when link i is reached, so a
+// kernel can produce them lazily (from global memory or from the time scaling) instead of
+// holding 3 N values in registers for the whole recursion.
+template <typename T, int N, bool GEN, typename In, typename St>
+MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const T *ftip,
+                 T (&tau)[N], St &st_) {
+    T w[3], v[3], dw[3], dv[3];
+    T ag[3];         // general path: -g in the current frame
     T tn[3], tf[3];  // tip wrench carried down to the last frame
     const bool has_tip = ftip != nullptr;
     if (has_tip) {
@@ -255,63 +320,114 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const T c = q.c[i], s = q.s[i], d = q.d[i];
         const T sr = rb.sr[i], st = rb.st[i];
-        twist_to_child(rb, i, c, s, d, w, v);
-        twist_to_child(rb, i, c, s, d, dw, dv);
-        if (GEN) vec_to_child(rb, i, c, s, ag);
+        T th_i, qd, qdd, c, s;
+        in.joint(i, th_i, qd, qdd);
+        if (sr != T(0)) {
+            sincos_t(th_i, &s, &c);
+        } else {
+            s = T(0);
+            c = T(1);
+        }
+        const T d = st * th_i;
+        st_.put_cs(rb, i, c, s, d);
+        if (i == 0) {
+            // base twist is zero and the base acceleration is [0; -g]: V_1 = A_1 qd,
+            // dV_1 = [0; R^T(-g)] + A_1 qdd  (ad(V_1) A_1 = 0)
+            T a0[3] = {-g[0], -g[1], -g[2]};
+            vec_to_child(rb, 0, c, s, a0);
+            w[0] = T(0); w[1] = T(0); w[2] = sr * qd;
+            v[0] = T(0); v[1] = T(0); v[2] = st * qd;
+            dw[0] = T(0); dw[1] = T(0); dw[2] = sr * qdd;
+            if (GEN) {
+                ag[0] = a0[0]; ag[1] = a0[1]; ag[2] = a0[2];
+                dv[0] = T(0); dv[1] = T(0); dv[2] = st * qdd;
+            } else {
+                dv[0] = a0[0]; dv[1] = a0[1]; dv[2] = a0[2] + st * qdd;
+            }
+        } else {
+            twist_to_child(rb, i, c, s, d, w, v);
+            twist_to_child(rb, i, c, s, d, dw, dv);
+            if (GEN) vec_to_child(rb, i, c, s, ag);
+            // V_i += A_i dth_i ;  dV_i += ad(V_i) A_i dth_i + A_i ddth_i
+            w[2] += sr * qd;
+            v[2] += st * qd;
+            const T a = sr * qd, b = st * qd;
+            dw[0] += a * w[1];
+            dw[1] -= a * w[0];
+            dw[2] += sr * qdd;
+            dv[0] = dv[0] + a * v[1] + b * w[1];
+            dv[1] = dv[1] - a * v[0] - b * w[0];
+            dv[2] += st * qdd;
+        }
         if (has_tip) wrench_to_child(rb, i, c, s, d, tn, tf);
-        // V_i += A_i dth_i ;  dV_i += ad(V_i) A_i dth_i + A_i ddth_i
-        const T qd = dth[i], qdd = ddth[i];
-        w[2] += sr * qd;
-        v[2] += st * qd;
-        const T a = sr * qd, b = st * qd;
-        dw[0] += a * w[1];
-        dw[1] -= a * w[0];
-        dw[2] += sr * qdd;
-        dv[0] += a * v[1] + b * w[1];
-        dv[1] -= a * v[0] + b * w[0];
-        dv[2] += st * qdd;
         // F_i = G dV - ad(V)^T (G V) = G dV + [w x n + v x f ; w x f]
         T n[3], f[3], dn[3], df[3];
         inertia_mul<T, N, GEN>(rb, i, w, v, n, f);
         inertia_mul<T, N, GEN>(rb, i, dw, dv, dn, df);
-        Fn[i][0] = dn[0] + (w[1] * n[2] - w[2] * n[1]) + (v[1] * f[2] - v[2] * f[1]);
-        Fn[i][1] = dn[1] + (w[2] * n[0] - w[0] * n[2]) + (v[2] * f[0] - v[0] * f[2]);
-        Fn[i][2] = dn[2] + (w[0] * n[1] - w[1] * n[0]) + (v[0] * f[1] - v[1] * f[0]);
-        Ff[i][0] = df[0] + (w[1] * f[2] - w[2] * f[1]);
-        Ff[i][1] = df[1] + (w[2] * f[0] - w[0] * f[2]);
-        Ff[i][2] = df[2] + (w[0] * f[1] - w[1] * f[0]);
+        T Fn[3], Ff[3];
+        Fn[0] = dn[0] + w[1] * n[2] - w[2] * n[1] + v[1] * f[2] - v[2] * f[1];
+        Fn[1] = dn[1] + w[2] * n[0] - w[0] * n[2] + v[2] * f[0] - v[0] * f[2];
+        Fn[2] = dn[2] + w[0] * n[1] - w[1] * n[0] + v[0] * f[1] - v[1] * f[0];
+        Ff[0] = df[0] + w[1] * f[2] - w[2] * f[1];
+        Ff[1] = df[1] + w[2] * f[0] - w[0] * f[2];
+        Ff[2] = df[2] + w[0] * f[1] - w[1] * f[0];
         if (GEN) {
             const T mg = rb.mg[i];
             const T *cg = rb.cg[i];
             const T fx = mg * ag[0], fy = mg * ag[1], fz = mg * ag[2];
-            Ff[i][0] += fx;
-            Ff[i][1] += fy;
-            Ff[i][2] += fz;
-            Fn[i][0] += cg[1] * fz - cg[2] * fy;
-            Fn[i][1] += cg[2] * fx - cg[0] * fz;
-            Fn[i][2] += cg[0] * fy - cg[1] * fx;
+            Ff[0] += fx;
+            Ff[1] += fy;
+            Ff[2] += fz;
+            Fn[0] = Fn[0] + cg[1] * fz - cg[2] * fy;
+            Fn[1] = Fn[1] + cg[2] * fx - cg[0] * fz;
+            Fn[2] = Fn[2] + cg[0] * fy - cg[1] * fx;
+        }
+        if (i < N - 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                st_.put(i, k, Fn[k]);
+                st_.put(i, 3 + k, Ff[k]);
+            }
+        } else {
+            // last link: the backward pass starts straight from registers
+            T an[3] = {Fn[0], Fn[1], Fn[2]}, af[3] = {Ff[0], Ff[1], Ff[2]};
+            if (has_tip) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    an[k] += tn[k];
+                    af[k] += tf[k];
+                }
+            }
+            T cj = c, sj = s, dj = d;
+#pragma unroll
+            for (int j = N - 1; j >= 0; --j) {
+                tau[j] = rb.sr[j] * an[2] + rb.st[j] * af[2];
+                if (j > 0) {
+                    // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
+                    if (j < N - 1) st_.get_cs(rb, j, cj, sj, dj);
+                    T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};
+                    T bf[3] = {st_.get(j - 1, 3), st_.get(j - 1, 4), st_.get(j - 1, 5)};
+                    wrench_to_parent_acc(rb, j, cj, sj, dj, an, af, bn, bf);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        an[k] = bn[k];
+                        af[k] = bf[k];
+                    }
+                }
+            }
         }
     }
-    if (has_tip) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            Fn[N - 1][k] += tn[k];
-            Ff[N - 1][k] += tf[k];
-        }
-    }
-    T an[3] = {T(0), T(0), T(0)}, af[3] = {T(0), T(0), T(0)};
-#pragma unroll
-    for (int i = N - 1; i >= 0; --i) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            an[k] += Fn[i][k];
-            af[k] += Ff[i][k];
-        }
-        tau[i] = rb.sr[i] * an[2] + rb.st[i] * af[2];
-        if (i > 0) wrench_to_parent(rb, i, q.c[i], q.s[i], q.d[i], an, af);
-    }
+}
+
+// Register-resident convenience form over arrays; `q` receives the joint sines / cosines.
+template <typename T, int N, bool GEN>
+MPK_HD void rnea(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N], const T (&ddth)[N],
+                 const T (&g)[3], const T *ftip, T (&tau)[N], JointCS<T, N> &q) {
+    RegStore<T, N> st_;
+    const ArrayIn<T, N> in{th, dth, ddth};
+    rnea<T, N, GEN>(rb, in, g, ftip, tau, st_);
+    q = st_.q;
 }
 
 // ---- composite rigid body algorithm (rigid inertias) -------------------------
@@ -413,8 +529,7 @@ MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
 // General inertias: column j of M = rnea(theta, 0, e_j, g = 0), symmetrised like
 // dynamics/mass_matrix.py:96.
 template <typename T, int N>
-MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb,
-                                                    const JointCS<T, N> &q, T (&Mm)[N][N]) {
+MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb, const T (&th)[N], T (&Mm)[N][N]) {
     T zero[N], g0[3] = {T(0), T(0), T(0)};
 #pragma unroll
     for (int i = 0; i < N; ++i) zero[i] = T(0);
@@ -423,7 +538,8 @@ MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb,
         T e[N], col[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) e[i] = (i == j) ? T(1) : T(0);
-        rnea<T, N, true>(rb, q, zero, e, g0, nullptr, col);
+        JointCS<T, N> q;
+        rnea<T, N, true>(rb, th, zero, e, g0, nullptr, col, q);
 #pragma unroll
         for (int i = 0; i < N; ++i) Mm[i][j] = col[i];
     }
@@ -438,9 +554,9 @@ MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb,
 }
 
 template <typename T, int N, bool GEN>
-MPK_HD void mass_matrix(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
-                                            T (&Mm)[N][N]) {
-    if (GEN) mass_matrix_general<T, N>(rb, q, Mm);
+MPK_HD void mass_matrix(const RobotPack<T, N> &rb, const T (&th)[N], const JointCS<T, N> &q,
+                        T (&Mm)[N][N]) {
+    if (GEN) mass_matrix_general<T, N>(rb, th, Mm);
     else crba<T, N>(rb, q, Mm);
 }
 
@@ -478,19 +594,17 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
 
 // ddtheta = M(theta)^-1 (tau - rnea(theta, dtheta, 0, g, Ftip))  (dynamics/id_fd.py:50-83).
 template <typename T, int N, bool GEN>
-MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N],
-                                                 const T (&dth)[N], const T (&tau)[N],
-                                                 const T (&g)[3], const T *ftip, T (&dd)[N]) {
+MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N],
+                             const T (&tau)[N], const T (&g)[3], const T *ftip, T (&dd)[N]) {
     JointCS<T, N> q;
-    joint_cs(rb, th, q);
     T zero[N], bias[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) zero[i] = T(0);
-    rnea<T, N, GEN>(rb, q, dth, zero, g, ftip, bias);
+    rnea<T, N, GEN>(rb, th, dth, zero, g, ftip, bias, q);
 #pragma unroll
     for (int i = 0; i < N; ++i) dd[i] = tau[i] - bias[i];
     T Mm[N][N];
-    mass_matrix<T, N, GEN>(rb, q, Mm);
+    mass_matrix<T, N, GEN>(rb, th, q, Mm);
     ldlt_solve<T, N>(Mm, dd);
 }
 

@@ -6,7 +6,7 @@
 // frames (see mpk_device.cuh).  For joint i with space screw S_i = (w, v) at the
 // home configuration:
 //   revolute (|w| = 1): frame origin q = w x v (the point of the axis closest to the
-//       space origin), z = w, pitch h = w.v (0 for URDF joints);
+//       space origin), z = w; the pitch w.v must be 0 (helical joints are rejected);
 //   prismatic (w = 0):  z = v/|v|, origin at the space origin, st = |v|.
 // With F_i that home pose,  e^{[S_i] th} F_i = F_i Jz(th), so
 //   prod_j e^{[S_j] th_j} = prod_j (X_j Jz(th_j)) F_n^{-1},   X_j = F_{j-1}^{-1} F_j,
@@ -165,9 +165,15 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
             frame_from_z(z, F.R);
             cross(z, v, F.p);  // q = w x v
             double h = z[0] * v[0] + z[1] * v[1] + z[2] * v[2];
-            if (std::fabs(h) <= 1e-12 * (nv > 1.0 ? nv : 1.0)) h = 0.0;
+            if (std::fabs(h) > 1e-12 * (nv > 1.0 ? nv : 1.0)) {
+                delete rb;
+                return fail(MPK_EUNSUPPORTED,
+                            "screw axis " + std::to_string(i) +
+                                " is helical (omega . v != 0); only revolute (v = -omega x q) and "
+                                "prismatic (omega = 0) joints are supported");
+            }
             sr = 1.0;
-            st = h;
+            st = 0.0;
         }
         const SE3 X = mul(inverse(Fprev), F);
         for (int k = 0; k < 9; ++k) rb->pack.Rx[i][k] = X.R[k];

@@ -100,8 +100,9 @@ class HostCheck:
             raise RuntimeError(self.L.mpk_last_error().decode())
         return h, S.shape[1]
 
-    def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None):
+    def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None, smem_store=False):
         h, n = rb
+        fn = self.H.hc_rnea_smem if smem_store else self.H.hc_rnea
         th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
         P = th.shape[0]
         cv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(P, n)
@@ -111,12 +112,12 @@ class HostCheck:
         if ftip is not None and np.ndim(ftip) == 2:
             for i in range(P):
                 f = np.ascontiguousarray(ftip[i], dtype=np.float64)
-                self.H.hc_rnea(h, _C.c_int64(1), _ptr(th[i:i + 1]), _ptr(None if dth is None else dth[i:i + 1]),
+                fn(h, _C.c_int64(1), _ptr(th[i:i + 1]), _ptr(None if dth is None else dth[i:i + 1]),
                                _ptr(None if ddth is None else ddth[i:i + 1]), _ptr(g),
                                _ptr(f) if f.any() else None, _ptr(out[i:i + 1]))
             return out
         f = None if ftip is None else np.ascontiguousarray(ftip, dtype=np.float64)
-        self.H.hc_rnea(h, _C.c_int64(P), _ptr(th), _ptr(dth), _ptr(ddth), _ptr(g), _ptr(f), _ptr(out))
+        fn(h, _C.c_int64(P), _ptr(th), _ptr(dth), _ptr(ddth), _ptr(g), _ptr(f), _ptr(out))
         return out
 
     def mass(self, rb, th):

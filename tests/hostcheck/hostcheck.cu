@@ -11,7 +11,8 @@ using namespace mpk;
 
 template <int N>
 static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
-                   const double *ddth, const double *g, const double *ftip, double *tau) {
+                   const double *ddth, const double *g, const double *ftip, double *tau,
+                   bool use_smem_store) {
     const RobotPack<double, N> pk = narrow<N>(rb);
     for (int64_t p = 0; p < P; ++p) {
         double a[N], b[N], c[N], t[N], g3[3] = {g[0], g[1], g[2]};
@@ -20,10 +21,18 @@ static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const doubl
             b[j] = dth ? dth[p * N + j] : 0.0;
             c[j] = ddth ? ddth[p * N + j] : 0.0;
         }
-        JointCS<double, N> q;
-        joint_cs(pk, a, q);
-        if (rb->rigid) rnea<double, N, false>(pk, q, b, c, g3, ftip, t);
-        else rnea<double, N, true>(pk, q, b, c, g3, ftip, t);
+        if (use_smem_store) {
+            // the shared-memory state store of the kernels, exercised with a one-thread "block"
+            double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
+            SmemStore<double, N, 1> st{buf};
+            const ArrayIn<double, N> in{a, b, c};
+            if (rb->rigid) rnea<double, N, false>(pk, in, g3, ftip, t, st);
+            else rnea<double, N, true>(pk, in, g3, ftip, t, st);
+        } else {
+            JointCS<double, N> q;
+            if (rb->rigid) rnea<double, N, false>(pk, a, b, c, g3, ftip, t, q);
+            else rnea<double, N, true>(pk, a, b, c, g3, ftip, t, q);
+        }
         for (int j = 0; j < N; ++j) tau[p * N + j] = t[j];
     }
 }
@@ -36,8 +45,8 @@ static void mass_n(const mpk_robot *rb, int64_t P, const double *th, double *Mo)
         for (int j = 0; j < N; ++j) a[j] = th[p * N + j];
         JointCS<double, N> q;
         joint_cs(pk, a, q);
-        if (rb->rigid) mass_matrix<double, N, false>(pk, q, Mm);
-        else mass_matrix<double, N, true>(pk, q, Mm);
+        if (rb->rigid) mass_matrix<double, N, false>(pk, a, q, Mm);
+        else mass_matrix<double, N, true>(pk, a, q, Mm);
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) Mo[(p * N + i) * N + j] = Mm[i][j];
     }
@@ -88,7 +97,12 @@ static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double 
 
 extern "C" int hc_rnea(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                        const double *ddth, const double *g, const double *ftip, double *tau) {
-    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau));
+    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, false));
+    return 0;
+}
+extern "C" int hc_rnea_smem(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                            const double *ddth, const double *g, const double *ftip, double *tau) {
+    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, true));
     return 0;
 }
 extern "C" int hc_mass(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {

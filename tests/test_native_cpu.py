@@ -50,6 +50,11 @@ def test_robot_create_errors(hostcheck):
     bad["S_list"][:3, 2] *= 1.5  # non-unit omega: the reference formula is not a rigid motion
     with pytest.raises(RuntimeError, match="non-unit"):
         hostcheck.robot(bad)
+    hel = dict(p)
+    hel["S_list"] = p["S_list"].copy()
+    hel["S_list"][3:, 1] += 0.1 * hel["S_list"][:3, 1]  # pitch: omega . v != 0
+    with pytest.raises(RuntimeError, match="helical"):
+        hostcheck.robot(hel)
     big = random_general_pack(8, 0)
     big9 = {k: np.concatenate([v, v[..., :1]], -1) if k == "S_list" else v for k, v in big.items()}
     big9["Glist"] = np.concatenate([big["Glist"], big["Glist"][:1]])
@@ -104,6 +109,8 @@ def test_kernel_algebra_vs_oracle_random(hostcheck, oracle_factory, robot):
         ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)
         got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
         assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
+        # the shared-memory state store used by the kernels gives the same bits as the register store
+        assert np.array_equal(got, hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=True))
         Mref = o.mass_matrix(th[:50])
         assert np.abs(hostcheck.mass(rb, th[:50]) - Mref).max() < 1e-9 * max(1, np.abs(Mref).max())
         tau = rng.uniform(-20, 20, (50, n))
@@ -127,6 +134,7 @@ def test_general_inertia_and_prismatic_vs_oracle(hostcheck, n):
     T, J = hostcheck.fk(rb, th)
     assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
     assert np.abs(J - o.jacobian(th)).max() < 1e-12
+    assert np.array_equal(hostcheck.rnea(rb, th, dth, ddth, g, ft), hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=True))
     for analytic, tol in ((True, 1e-11), (False, 1e-7)):  # literal path carries its finite-difference noise
         ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=analytic)
         got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
