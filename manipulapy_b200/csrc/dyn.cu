@@ -70,7 +70,26 @@ struct RowIn {
     }
 };
 
-template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks>
+// Torque j of row p straight to global memory (float64, or float32 after the clip).  A thread
+// fills its own contiguous row, so sectors are completed in L2 before they reach HBM.
+template <int N>
+struct TauOut {
+    void *out;
+    int dtype;
+    int64_t row;
+    const Limits &lim;
+    __device__ __forceinline__ void put(int j, double tau) const {
+        if (dtype == MPK_F64) {
+            static_cast<double *>(out)[row + j] = tau;
+        } else {
+            float x = (float)tau;
+            if (lim.on) x = clip_f32(x, lim.lo[j], lim.hi[j]);
+            static_cast<float *>(out)[row + j] = x;
+        }
+    }
+};
+
+template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks, bool ROLLED = true>
 __global__ void __launch_bounds__(THREADS, MINB)
     rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
     extern __shared__ __align__(16) double wsm[];
@@ -89,9 +108,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
     }
     const RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N};
     SmemStore<double, N, THREADS> st{wsm + threadIdx.x};
-    double tau[N];
-    rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
-    store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
+    if (ROLLED) {
+        TauOut<N> out{a.out, a.out_dtype, p * N, a.lim};
+        rnea_rolled<double, N, GEN>(rb, in, a.tip.g, ftp, st, out);
+    } else {
+        double tau[N];
+        rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
+        store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
+    }
 }
 
 // ---- fused trajectory + inverse dynamics ----------------------------------------
@@ -124,13 +148,25 @@ struct TrajIn {
     }
 };
 
-template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks>
+// Torque j staged in shared memory as the float32, clipped row entry.
+template <int N>
+struct StageOut {
+    float *row;  // staging + threadIdx.x * N
+    const Limits &lim;
+    __device__ __forceinline__ void put(int j, double tau) const {
+        float x = (float)tau;
+        if (lim.on) x = clip_f32(x, lim.lo[j], lim.hi[j]);
+        row[j] = x;
+    }
+};
+
+template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks, bool ROLLED = true>
 __global__ void __launch_bounds__(THREADS, MINB)
     traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
-    // dynamic shared memory: per-thread link state during the recursion, then (aliased, after a
-    // barrier) the block's output rows staged for coalesced stores
+    // dynamic shared memory: [per-thread link state of the recursion | the block's output rows,
+    // staged for coalesced stores]
     extern __shared__ __align__(16) double wsm[];
-    float *sm = reinterpret_cast<float *>(wsm);
+    float *sm = reinterpret_cast<float *>(wsm + SmemStore<double, N, THREADS>::kSlots * 8 * THREADS);
     int64_t b, t;
     point_coords(a.N, b, t);
     const int64_t p0 = (int64_t)blockIdx.x * THREADS;
@@ -147,7 +183,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         for (int k = 0; k < 3; ++k) {
             if (!outs[k]) continue;  // uniform
             if (live) {
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < N; ++j) {
                     double th, qd, qdd;
                     in.joint(j, th, qd, qdd);
@@ -159,7 +195,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
             __syncthreads();
         }
     }
-    double tau[N];
     if (live) {
         double ft[6];
         const double *ftp = nullptr;
@@ -169,15 +204,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
             ftp = ft;
         }
         SmemStore<double, N, THREADS> st{wsm + threadIdx.x};
-        rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
-    }
-    __syncthreads();  // every thread is done with its link state: reuse the memory for the rows
-    if (live) {
+        StageOut<N> out{sm + threadIdx.x * N, a.tlim};
+        if (ROLLED) {
+            rnea_rolled<double, N, GEN>(rb, in, a.tip.g, ftp, st, out);
+        } else {
+            double tau[N];
+            rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            float x = (float)tau[j];
-            if (a.tlim.on) x = clip_f32(x, a.tlim.lo[j], a.tlim.hi[j]);
-            sm[threadIdx.x * N + j] = x;
+            for (int j = 0; j < N; ++j) out.put(j, tau[j]);
         }
     }
     __syncthreads();
@@ -260,8 +294,8 @@ static TipArgs make_tip(const double *g, const double *Ftip, const double *Ftip_
 template <int N>
 constexpr size_t wrench_smem(int threads) {
     const size_t link_state = (size_t)(N > 1 ? N - 1 : 0) * 8 * threads * sizeof(double);
-    const size_t rows = (size_t)threads * N * sizeof(float);  // aliased output staging (fused kernel)
-    return link_state > rows ? link_state : rows;
+    const size_t rows = (size_t)threads * N * sizeof(float);  // output staging (fused kernel)
+    return link_state + rows;
 }
 
 // Launch with dynamic shared memory, asking for the largest shared-memory carveout so that
@@ -269,7 +303,7 @@ constexpr size_t wrench_smem(int threads) {
 template <typename... KArgs, typename... Args>
 static void launch_smem(void (*kern)(KArgs...), unsigned grid, int threads, size_t smem,
                         cudaStream_t s, Args &&...args) {
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)  // (static shared memory counts against the 48 KB default limit too)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);
@@ -362,19 +396,18 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     if (var && rb->rigid && rb->n == 6) {
         const int v = atoi(var);
         auto pk = narrow<6>(rb);
-#define MPK_VAR(T_, MB_) { const unsigned g_ = (unsigned)((a.P + T_ - 1) / T_); \
-        launch_smem(traj_rnea_kernel<6, false, T_, MB_>, g_, T_, wrench_smem<6>(T_), s, pk, a); }
+#define MPK_VAR(T_, MB_, R_) { const unsigned g_ = (unsigned)((a.P + T_ - 1) / T_); \
+        launch_smem(traj_rnea_kernel<6, false, T_, MB_, R_>, g_, T_, wrench_smem<6>(T_), s, pk, a); }
         switch (v) {
-            case 1: MPK_VAR(128, 3) break;
-            case 2: MPK_VAR(128, 4) break;
-            case 3: MPK_VAR(128, 6) break;
-            case 4: MPK_VAR(64, 10) break;
-            case 5: MPK_VAR(64, 12) break;
-            case 6: MPK_VAR(256, 2) break;
-            case 7: MPK_VAR(256, 3) break;
-            case 8: MPK_VAR(192, 3) break;
-            case 9: MPK_VAR(32, 16) break;
-            default: MPK_VAR(128, 5) break;
+            case 1: MPK_VAR(128, 3, true) break;
+            case 2: MPK_VAR(128, 4, true) break;
+            case 3: MPK_VAR(256, 2, true) break;
+            case 4: MPK_VAR(64, 10, true) break;
+            case 5: MPK_VAR(128, 5, false) break;
+            case 6: MPK_VAR(128, 4, false) break;
+            case 7: MPK_VAR(256, 1, true) break;
+            case 8: MPK_VAR(128, 2, true) break;
+            default: MPK_VAR(128, 5, true) break;
         }
 #undef MPK_VAR
         return check_launch("trajectory_inverse_dynamics");

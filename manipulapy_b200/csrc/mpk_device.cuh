@@ -420,6 +420,109 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const
     }
 }
 
+// The same recursion with ROLLED link loops (one copy of the link body, `#pragma unroll 1`).
+// The fully unrolled form above is ~37 KB of straight-line SASS per pass for N = 6: with a
+// dozen unsynchronised warps per SM streaming through it the instruction fetch path (GCC /
+// L1.5 instruction cache) saturates -- ncu: gcc instruction requests at 98 % of peak, icc hit
+// rate 78 %, `no_instruction` the top stall (profiles/r1_traj_rnea_unrolled.md).  Rolled, the
+// whole kernel is a few KB and stays I-cache resident; robot constants are then read from the
+// constant bank with a warp-uniform dynamic link index, the backward-pass state comes from
+// `st_` and torques leave through `out.put(j, tau_j)` (no dynamically indexed registers).
+template <typename T, int N, bool GEN, typename In, typename St, typename Out>
+MPK_HD void rnea_rolled(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const T *ftip,
+                        St &st_, Out &out) {
+    T w[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, dw[3] = {T(0), T(0), T(0)};
+    T dv[3], ag[3];
+    if (GEN) {
+        dv[0] = dv[1] = dv[2] = T(0);
+        ag[0] = -g[0]; ag[1] = -g[1]; ag[2] = -g[2];
+    } else {
+        dv[0] = -g[0]; dv[1] = -g[1]; dv[2] = -g[2];
+        ag[0] = ag[1] = ag[2] = T(0);
+    }
+    T tn[3] = {T(0), T(0), T(0)}, tf[3] = {T(0), T(0), T(0)};
+    const bool has_tip = ftip != nullptr;
+    if (has_tip) {
+        tn[0] = ftip[0]; tn[1] = ftip[1]; tn[2] = ftip[2];
+        tf[0] = ftip[3]; tf[1] = ftip[4]; tf[2] = ftip[5];
+    }
+    T c = T(1), s = T(0), d = T(0);
+    T Fn[3], Ff[3];
+#pragma unroll 1
+    for (int i = 0; i < N; ++i) {
+        const T sr = rb.sr[i], st = rb.st[i];
+        T th_i, qd, qdd;
+        in.joint(i, th_i, qd, qdd);
+        if (sr != T(0)) {
+            sincos_t(th_i, &s, &c);
+        } else {
+            s = T(0);
+            c = T(1);
+        }
+        d = st * th_i;
+        if (i > 0) st_.put_cs(rb, i, c, s, d);
+        // (for link 0 the incoming twist is zero; the general transform then costs a few wasted
+        // flops but keeps a single copy of the body)
+        twist_to_child(rb, i, c, s, d, w, v);
+        twist_to_child(rb, i, c, s, d, dw, dv);
+        if (GEN) vec_to_child(rb, i, c, s, ag);
+        w[2] += sr * qd;
+        v[2] += st * qd;
+        const T a = sr * qd, b = st * qd;
+        dw[0] += a * w[1];
+        dw[1] -= a * w[0];
+        dw[2] += sr * qdd;
+        dv[0] = dv[0] + a * v[1] + b * w[1];
+        dv[1] = dv[1] - a * v[0] - b * w[0];
+        dv[2] += st * qdd;
+        if (has_tip) wrench_to_child(rb, i, c, s, d, tn, tf);
+        T n[3], f[3], dn[3], df[3];
+        inertia_mul<T, N, GEN>(rb, i, w, v, n, f);
+        inertia_mul<T, N, GEN>(rb, i, dw, dv, dn, df);
+        Fn[0] = dn[0] + w[1] * n[2] - w[2] * n[1] + v[1] * f[2] - v[2] * f[1];
+        Fn[1] = dn[1] + w[2] * n[0] - w[0] * n[2] + v[2] * f[0] - v[0] * f[2];
+        Fn[2] = dn[2] + w[0] * n[1] - w[1] * n[0] + v[0] * f[1] - v[1] * f[0];
+        Ff[0] = df[0] + w[1] * f[2] - w[2] * f[1];
+        Ff[1] = df[1] + w[2] * f[0] - w[0] * f[2];
+        Ff[2] = df[2] + w[0] * f[1] - w[1] * f[0];
+        if (GEN) {
+            const T mg = rb.mg[i];
+            const T *cg = rb.cg[i];
+            const T fx = mg * ag[0], fy = mg * ag[1], fz = mg * ag[2];
+            Ff[0] += fx;
+            Ff[1] += fy;
+            Ff[2] += fz;
+            Fn[0] = Fn[0] + cg[1] * fz - cg[2] * fy;
+            Fn[1] = Fn[1] + cg[2] * fx - cg[0] * fz;
+            Fn[2] = Fn[2] + cg[0] * fy - cg[1] * fx;
+        }
+        if (i < N - 1) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                st_.put(i, k, Fn[k]);
+                st_.put(i, 3 + k, Ff[k]);
+            }
+        }
+    }
+    // backward pass, starting from the last link's wrench and rotation still in registers
+    T an[3] = {Fn[0] + tn[0], Fn[1] + tn[1], Fn[2] + tn[2]};
+    T af[3] = {Ff[0] + tf[0], Ff[1] + tf[1], Ff[2] + tf[2]};
+#pragma unroll 1
+    for (int j = N - 1; j >= 1; --j) {
+        out.put(j, rb.sr[j] * an[2] + rb.st[j] * af[2]);
+        if (j < N - 1) st_.get_cs(rb, j, c, s, d);
+        T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};
+        T bf[3] = {st_.get(j - 1, 3), st_.get(j - 1, 4), st_.get(j - 1, 5)};
+        wrench_to_parent_acc(rb, j, c, s, d, an, af, bn, bf);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            an[k] = bn[k];
+            af[k] = bf[k];
+        }
+    }
+    out.put(0, rb.sr[0] * an[2] + rb.st[0] * af[2]);
+}
+
 // Register-resident convenience form over arrays; `q` receives the joint sines / cosines.
 template <typename T, int N, bool GEN>
 MPK_HD void rnea(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N], const T (&ddth)[N],

@@ -12,7 +12,7 @@ using namespace mpk;
 template <int N>
 static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                    const double *ddth, const double *g, const double *ftip, double *tau,
-                   bool use_smem_store) {
+                   int use_smem_store) {
     const RobotPack<double, N> pk = narrow<N>(rb);
     for (int64_t p = 0; p < P; ++p) {
         double a[N], b[N], c[N], t[N], g3[3] = {g[0], g[1], g[2]};
@@ -21,7 +21,15 @@ static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const doubl
             b[j] = dth ? dth[p * N + j] : 0.0;
             c[j] = ddth ? ddth[p * N + j] : 0.0;
         }
-        if (use_smem_store) {
+        if (use_smem_store == 2) {
+            // the rolled-loop form of the kernels (shared-memory store, torques through `out.put`)
+            double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
+            SmemStore<double, N, 1> st{buf};
+            const ArrayIn<double, N> in{a, b, c};
+            struct { double *t; void put(int j, double x) { t[j] = x; } } out{t};
+            if (rb->rigid) rnea_rolled<double, N, false>(pk, in, g3, ftip, st, out);
+            else rnea_rolled<double, N, true>(pk, in, g3, ftip, st, out);
+        } else if (use_smem_store) {
             // the shared-memory state store of the kernels, exercised with a one-thread "block"
             double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
             SmemStore<double, N, 1> st{buf};
@@ -97,12 +105,17 @@ static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double 
 
 extern "C" int hc_rnea(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                        const double *ddth, const double *g, const double *ftip, double *tau) {
-    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, false));
+    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, 0));
     return 0;
 }
 extern "C" int hc_rnea_smem(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                             const double *ddth, const double *g, const double *ftip, double *tau) {
-    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, true));
+    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, 1));
+    return 0;
+}
+extern "C" int hc_rnea_rolled(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                              const double *ddth, const double *g, const double *ftip, double *tau) {
+    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, 2));
     return 0;
 }
 extern "C" int hc_mass(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {

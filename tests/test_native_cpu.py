@@ -110,7 +110,10 @@ def test_kernel_algebra_vs_oracle_random(hostcheck, oracle_factory, robot):
         got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
         assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
         # the shared-memory state store used by the kernels gives the same bits as the register store
-        assert np.array_equal(got, hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=True))
+        assert np.array_equal(got, hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=1))
+        # the rolled-loop form differs only by rounding in link 0 (general transform of a zero twist)
+        rolled = hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=2)
+        assert np.max(np.abs(rolled - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
         Mref = o.mass_matrix(th[:50])
         assert np.abs(hostcheck.mass(rb, th[:50]) - Mref).max() < 1e-9 * max(1, np.abs(Mref).max())
         tau = rng.uniform(-20, 20, (50, n))
@@ -134,7 +137,10 @@ def test_general_inertia_and_prismatic_vs_oracle(hostcheck, n):
     T, J = hostcheck.fk(rb, th)
     assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
     assert np.abs(J - o.jacobian(th)).max() < 1e-12
-    assert np.array_equal(hostcheck.rnea(rb, th, dth, ddth, g, ft), hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=True))
+    assert np.array_equal(hostcheck.rnea(rb, th, dth, ddth, g, ft), hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=1))
+    rolled = hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=2)
+    refa = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)
+    assert np.max(np.abs(rolled - refa) / np.maximum(1, np.abs(refa).max(1, keepdims=True))) < 1e-11
     for analytic, tol in ((True, 1e-11), (False, 1e-7)):  # literal path carries its finite-difference noise
         ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=analytic)
         got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
