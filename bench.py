@@ -198,12 +198,12 @@ def run_ours(args) -> None:
     if args.mode == "fused":
         def step():
             return ops.trajectory_inverse_dynamics(handle, s, e, False, TF, N_STEPS, METHOD, jl, g, None, None, False)[0]
-        launches_per_step, dom_kernel, dom_bytes = 1, "traj_rnea_kernel<6,false>", BYTES_FUSED
+        launches_per_step, dom_kernel, dom_bytes = 2, "traj_rnea_kernel<6,false>", BYTES_FUSED  # + time-scaling table kernel
     else:
         def step():
             pos, vel, acc = ops.joint_trajectory(s, e, False, TF, N_STEPS, METHOD, jl)
             return ops.inverse_dynamics(handle, pos.view(-1, 6), vel.view(-1, 6), acc.view(-1, 6), g, None, None, None, True)
-        launches_per_step, dom_kernel, dom_bytes = 2, "rnea_kernel<6,false>", BYTES_RNEA
+        launches_per_step, dom_kernel, dom_bytes = 3, "rnea_kernel<6,false>", BYTES_RNEA  # table + trajectory + RNEA
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 

@@ -75,11 +75,14 @@ int mpk_robot_is_rigid(const mpk_robot *rb);
  *   method       3 cubic, 5 quintic, anything else zero scaling (planner CPU contract :67-68)
  *   limits       host (n, 2) float32 joint limits or NULL (no clip)
  *   pos/vel/acc  dev (B, N, n) float32; any may be NULL (not written)
+ *   ts_scratch   dev (3, N) float64 workspace or NULL.  The time scaling (s, ds, dds) depends
+ *                on the step only, so with a workspace it is evaluated once per step by a
+ *                small pre-kernel instead of once per (trajectory, step); results are identical.
  * Time scaling runs in float64 with the reference's operation order and one
  * rounding to float32, so outputs are bit-identical to the reference's. */
 int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const double *end,
                          int inputs_f32, double Tf, int method, const float *limits, float *pos,
-                         float *vel, float *acc, void *stream);
+                         float *vel, float *acc, double *ts_scratch, void *stream);
 
 /* SerialManipulator.forward_kinematics(theta, "space") (kinematics/fk.py:39-86) and
  * SerialManipulator.jacobian(theta, "space") (kinematics/jacobian.py:39-93), batched.
@@ -107,12 +110,13 @@ int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *theta, cons
  * produced in registers, rounded to float32 and clipped exactly as the two-call
  * sequence would, and fed to the inverse dynamics without touching HBM.
  *   start, end dev (B, n) float64;  tau dev (B, N, n) float32
- *   pos/vel/acc dev (B, N, n) float32 or NULL (optional materialisation) */
+ *   pos/vel/acc dev (B, N, n) float32 or NULL (optional materialisation)
+ *   ts_scratch  dev (3, N) float64 workspace or NULL (see mpk_joint_trajectory) */
 int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, int64_t N, const double *start,
                                     const double *end, int inputs_f32, double Tf, int method,
                                     const float *joint_limits, const double *g, const double *Ftip,
                                     const float *tau_limits, float *tau, float *pos, float *vel,
-                                    float *acc, void *stream);
+                                    float *acc, double *ts_scratch, void *stream);
 
 /* ManipulatorDynamics.mass_matrix (dynamics/mass_matrix.py:16-99), batched.
  *   theta dev (P, n) theta_dtype;  Mout dev (P, n, n) float64 (symmetric) */

@@ -71,6 +71,42 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return t.cpu().numpy()
 
 
+_copy_streams: dict = {}
+
+
+def _copy_stream(device: torch.device) -> torch.cuda.Stream:
+    key = (device.type, device.index)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
+def chunked_to_host(launch, rows: int, tail: Sequence[int], dtype: torch.dtype, device: torch.device,
+                    chunks: int = 8, min_rows: int = 64) -> np.ndarray:
+    """Run ``launch(lo, hi) -> CUDA tensor (hi - lo, *tail)`` over contiguous row chunks and
+    stream every finished chunk to pinned host memory on a second stream, so the PCIe copy of
+    chunk k overlaps the kernel of chunk k + 1.  Returns a fresh host array ``(rows, *tail)``."""
+    out = torch.empty((rows, *tail), dtype=dtype, pin_memory=True)
+    if rows == 0:
+        return out.numpy()
+    per = max(min_rows, -(-rows // max(1, chunks)))
+    compute = torch.cuda.current_stream(device)
+    side = _copy_stream(device)
+    keep = []
+    for lo in range(0, rows, per):
+        hi = min(rows, lo + per)
+        t = launch(lo, hi)
+        done = torch.cuda.Event()
+        done.record(compute)
+        side.wait_event(done)
+        with torch.cuda.stream(side):
+            out[lo:hi].copy_(t, non_blocking=True)
+        t.record_stream(side)
+        keep.append(t)
+    side.synchronize()
+    return out.numpy()
+
+
 def limits_tensor(limits: Any) -> Optional[torch.Tensor]:
     """(n, 2) float32 host tensor, or None when every bound is infinite (clip is a no-op)."""
     if limits is None:

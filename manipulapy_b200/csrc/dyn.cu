@@ -8,8 +8,6 @@
 //   forward dynamics            dynamics/id_fd.py:50-83
 // One thread owns one point; all link state lives in registers (mpk_device.cuh); robot
 // constants are constant-bank operands.  fp64 FMA-pipe bound.
-#include <cstdlib>
-
 #include "mpk_common.cuh"
 
 namespace mpk {
@@ -89,7 +87,7 @@ struct TauOut {
     }
 };
 
-template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks, bool ROLLED = true>
+template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks, bool ROLLED = false>
 __global__ void __launch_bounds__(THREADS, MINB)
     rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
     extern __shared__ __align__(16) double wsm[];
@@ -128,6 +126,7 @@ struct TrajRneaArgs {
     Limits jlim, tlim;
     TipArgs tip;
     float *tau, *pos, *vel, *acc;
+    const double *ts_table;
 };
 
 // Joint values produced from the time scaling when the recursion reaches the link: the
@@ -160,7 +159,7 @@ struct StageOut {
     }
 };
 
-template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks, bool ROLLED = true>
+template <int N, bool GEN, int THREADS = kDynThreads, int MINB = kRneaMinBlocks, int MODE = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
     traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
     // dynamic shared memory: [per-thread link state of the recursion | the block's output rows,
@@ -174,28 +173,31 @@ __global__ void __launch_bounds__(THREADS, MINB)
     const int64_t rem = a.P - p0;
     const int cnt = (int)(rem < THREADS ? rem : THREADS) * N;
     const int64_t off = p0 * N;
-    TrajIn<N> in{a, TimeScale{0.0, 0.0, 0.0}, b * N};
-    if (live) in.ts = time_scaling(t, a.N, a.Tf, a.method);
+    // tail threads of the last block recompute point 0 (they take part in every barrier and
+    // their staged rows are never stored)
+    if (!live) {
+        b = 0;
+        t = 0;
+    }
+    const TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
     // optional materialisation of the trajectory rows (coalesced through shared memory)
     if (a.pos || a.vel || a.acc) {
         float *outs[3] = {a.pos, a.vel, a.acc};
 #pragma unroll 1
         for (int k = 0; k < 3; ++k) {
             if (!outs[k]) continue;  // uniform
-            if (live) {
 #pragma unroll 1
-                for (int j = 0; j < N; ++j) {
-                    double th, qd, qdd;
-                    in.joint(j, th, qd, qdd);
-                    sm[threadIdx.x * N + j] = (float)(k == 0 ? th : (k == 1 ? qd : qdd));
-                }
+            for (int j = 0; j < N; ++j) {
+                double th, qd, qdd;
+                in.joint(j, th, qd, qdd);
+                sm[threadIdx.x * N + j] = (float)(k == 0 ? th : (k == 1 ? qd : qdd));
             }
             __syncthreads();
             tile_store(outs[k] + off, sm, cnt);
             __syncthreads();
         }
     }
-    if (live) {
+    {
         double ft[6];
         const double *ftp = nullptr;
         if (a.tip.has_ftip) {
@@ -205,11 +207,11 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         SmemStore<double, N, THREADS> st{wsm + threadIdx.x};
         StageOut<N> out{sm + threadIdx.x * N, a.tlim};
-        if (ROLLED) {
+        if (MODE == 1) {
             rnea_rolled<double, N, GEN>(rb, in, a.tip.g, ftp, st, out);
         } else {
             double tau[N];
-            rnea<double, N, GEN>(rb, in, a.tip.g, ftp, tau, st);
+            rnea<double, N, GEN, TrajIn<N>, SmemStore<double, N, THREADS>, MODE == 2>(rb, in, a.tip.g, ftp, tau, st);
 #pragma unroll
             for (int j = 0; j < N; ++j) out.put(j, tau[j]);
         }
@@ -366,7 +368,7 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
                                                const float *joint_limits, const double *g,
                                                const double *Ftip, const float *tau_limits,
                                                float *tau, float *pos, float *vel, float *acc,
-                                               void *stream) {
+                                               double *ts_scratch, void *stream) {
     MPK_REQUIRE_DYN(rb);
     if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
     if (B == 0 || N == 0) return MPK_OK;
@@ -392,26 +394,7 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     unsigned grid;
     if (int rc = grid_for(a.P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const char *var = getenv("MPK_VARIANT");
-    if (var && rb->rigid && rb->n == 6) {
-        const int v = atoi(var);
-        auto pk = narrow<6>(rb);
-#define MPK_VAR(T_, MB_, R_) { const unsigned g_ = (unsigned)((a.P + T_ - 1) / T_); \
-        launch_smem(traj_rnea_kernel<6, false, T_, MB_, R_>, g_, T_, wrench_smem<6>(T_), s, pk, a); }
-        switch (v) {
-            case 1: MPK_VAR(128, 3, true) break;
-            case 2: MPK_VAR(128, 4, true) break;
-            case 3: MPK_VAR(256, 2, true) break;
-            case 4: MPK_VAR(64, 10, true) break;
-            case 5: MPK_VAR(128, 5, false) break;
-            case 6: MPK_VAR(128, 4, false) break;
-            case 7: MPK_VAR(256, 1, true) break;
-            case 8: MPK_VAR(128, 2, true) break;
-            default: MPK_VAR(128, 5, true) break;
-        }
-#undef MPK_VAR
-        return check_launch("trajectory_inverse_dynamics");
-    }
+    a.ts_table = prepare_time_scaling(ts_scratch, B, N, Tf, method, s);
     if (rb->rigid) {
         MPK_DISPATCH_DOF(rb->n, launch_smem(traj_rnea_kernel<N_, false>, grid, kDynThreads, wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
     } else {

@@ -156,6 +156,18 @@ inline Limits make_limits(const float *lim, int n) {
     return L;
 }
 
+// Time scaling of step t: from the (3, N) table written by time_scaling_table_kernel when the
+// caller supplied a workspace, else evaluated in place.  Same arithmetic either way.
+__device__ __forceinline__ TimeScale time_scaling_at(const double *table, int64_t t, int64_t N,
+                                                     double Tf, int method) {
+    if (table) return TimeScale{__ldg(table + t), __ldg(table + N + t), __ldg(table + 2 * N + t)};
+    return time_scaling(t, N, Tf, method);
+}
+
+// Fills the workspace if it is worth it (more than one trajectory); returns the table to use.
+const double *prepare_time_scaling(double *scratch, int64_t B, int64_t N, double Tf, int method,
+                                   cudaStream_t s);
+
 // (trajectory, step) of the flattened point index blockIdx.x*128 + threadIdx.x: one
 // 64-bit division per block, plus one per warp that straddles a trajectory boundary.
 __device__ __forceinline__ void point_coords(int64_t N, int64_t &b, int64_t &t) {

@@ -307,7 +307,10 @@ struct ArrayIn {
 // `in.joint(i, theta, dtheta, ddtheta)` yields joint i's values when link i is reached, so a
 // kernel can produce them lazily (from global memory or from the time scaling) instead of
 // holding 3 N values in registers for the whole recursion.
-template <typename T, int N, bool GEN, typename In, typename St>
+// SYNC: a block barrier at every link boundary keeps the warps of a block within one link of
+// each other, so they fetch the same (large, straight-line) code region at the same time and
+// share instruction-cache lines instead of each streaming the whole body on its own.
+template <typename T, int N, bool GEN, typename In, typename St, bool SYNC = false>
 MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const T *ftip,
                  T (&tau)[N], St &st_) {
     T w[3], v[3], dw[3], dv[3];
@@ -320,6 +323,9 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+#ifdef __CUDA_ARCH__
+        if (SYNC) __syncthreads();
+#endif
         const T sr = rb.sr[i], st = rb.st[i];
         T th_i, qd, qdd, c, s;
         in.joint(i, th_i, qd, qdd);
@@ -404,6 +410,9 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const
             for (int j = N - 1; j >= 0; --j) {
                 tau[j] = rb.sr[j] * an[2] + rb.st[j] * af[2];
                 if (j > 0) {
+#ifdef __CUDA_ARCH__
+                    if (SYNC) __syncthreads();
+#endif
                     // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
                     if (j < N - 1) st_.get_cs(rb, j, cj, sj, dj);
                     T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};

@@ -93,9 +93,11 @@ std::tuple<Tensor, Tensor, Tensor> joint_trajectory(const Tensor &start, const T
     auto opt = s.options().dtype(at::kFloat);
     Tensor pos = at::empty({B, N, n}, opt), vel = at::empty({B, N, n}, opt), acc = at::empty({B, N, n}, opt);
     auto lim = host_limits(limits, n, "joint_limits");
+    Tensor scratch = at::empty({3, N}, s.options());  // time-scaling table workspace
     check(mpk_joint_trajectory((int)n, B, N, s.data_ptr<double>(), e.data_ptr<double>(), inputs_f32, Tf,
                                (int)method, ptr_or_null(lim), pos.data_ptr<float>(),
-                               vel.data_ptr<float>(), acc.data_ptr<float>(), stream_of(s)),
+                               vel.data_ptr<float>(), acc.data_ptr<float>(), scratch.data_ptr<double>(),
+                               stream_of(s)),
           "joint_trajectory");
     return {pos, vel, acc};
 }
@@ -184,10 +186,12 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
     } else {
         pos = vel = acc = at::empty({0}, opt);
     }
+    Tensor scratch = at::empty({3, N}, s.options());  // time-scaling table workspace
     check(mpk_trajectory_inverse_dynamics(rb, B, N, s.data_ptr<double>(), e.data_ptr<double>(), inputs_f32,
                                           Tf, (int)method, ptr_or_null(jl), gv.data(),
                                           fv.empty() ? nullptr : fv.data(), ptr_or_null(tl),
-                                          tau.data_ptr<float>(), pp, vp, ap, stream_of(s)),
+                                          tau.data_ptr<float>(), pp, vp, ap, scratch.data_ptr<double>(),
+                                          stream_of(s)),
           "trajectory_inverse_dynamics");
     return {tau, pos, vel, acc};
 }

@@ -23,7 +23,24 @@ struct TrajArgs {
     int method;
     Limits lim;
     float *pos, *vel, *acc;
+    const double *ts_table;
 };
+
+__global__ void time_scaling_table_kernel(int64_t N, double Tf, int method, double *table) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N) return;
+    const TimeScale ts = time_scaling(t, N, Tf, method);
+    table[t] = ts.s;
+    table[N + t] = ts.sd;
+    table[2 * N + t] = ts.sdd;
+}
+
+const double *prepare_time_scaling(double *scratch, int64_t B, int64_t N, double Tf, int method,
+                                   cudaStream_t s) {
+    if (!scratch || B < 2 || N < 1) return nullptr;
+    time_scaling_table_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(N, Tf, method, scratch);
+    return scratch;
+}
 
 template <int N>
 __global__ void __launch_bounds__(kTrajThreads) traj_kernel(const TrajArgs a) {
@@ -32,7 +49,7 @@ __global__ void __launch_bounds__(kTrajThreads) traj_kernel(const TrajArgs a) {
     point_coords(a.N, b, t);
     const int64_t p0 = (int64_t)blockIdx.x * kTrajThreads;
     if (p0 + threadIdx.x < a.P) {
-        const TimeScale ts = time_scaling(t, a.N, a.Tf, a.method);
+        const TimeScale ts = time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             double st, dth;
@@ -60,7 +77,7 @@ using namespace mpk;
 extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start,
                                     const double *end, int inputs_f32, double Tf, int method,
                                     const float *limits, float *pos, float *vel, float *acc,
-                                    void *stream) {
+                                    double *ts_scratch, void *stream) {
     if (n < 1 || n > MPK_MAX_DOF) return fail(MPK_EUNSUPPORTED, "dof must be in 1..8");
     if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
     if (B == 0 || N == 0) return MPK_OK;
@@ -82,7 +99,9 @@ extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *s
     a.acc = acc;
     const int64_t blocks = (a.P + kTrajThreads - 1) / kTrajThreads;
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B*N exceeds the grid limit (2^38 points)");
+    if ((N + 255) / 256 > 0x7fffffffLL) return fail(MPK_EINVAL, "N exceeds the grid limit");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    a.ts_table = prepare_time_scaling(ts_scratch, B, N, Tf, method, s);
     MPK_DISPATCH_DOF(n, (traj_kernel<N_><<<(unsigned)blocks, kTrajThreads, 0, s>>>(a)));
     return check_launch("joint_trajectory");
 }

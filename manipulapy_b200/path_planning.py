@@ -181,15 +181,26 @@ class OptimizedTrajectoryPlanning:
         s = _host.to_device(thetastart_batch, dev).reshape(-1, n)
         e = _host.to_device(thetaend_batch, dev).reshape(-1, n)
         ftip = None if Ftip is None else _host.vec(Ftip, 6, "Ftip")
-        tau, pos, vel, acc = _native.ops().trajectory_inverse_dynamics(
-            self.dynamics.robot.handle, s, e, f32, float(Tf), int(N), int(method), self._jl,
-            _host.gravity(gravity_vector), ftip, self._tl, bool(return_trajectory))
+        ops, handle, g = _native.ops(), self.dynamics.robot.handle, _host.gravity(gravity_vector)
+        if not on_dev and not return_trajectory and s.shape[0] >= 64:
+            # host result: pipeline the kernel with the device->host copy, chunk by chunk
+            def launch(lo, hi):
+                return ops.trajectory_inverse_dynamics(handle, s[lo:hi], e[lo:hi], f32, float(Tf), int(N),
+                                                       int(method), self._jl, g, ftip, self._tl, False)[0]
+
+            B = int(s.shape[0])
+            out = _host.chunked_to_host(launch, B, (int(N), n), torch.float32, dev)
+            self._tick(t0, launches=2 * min(8, B), transfers=2 + min(8, B), kernel="trajectory_inverse_dynamics")
+            return out
+        tau, pos, vel, acc = ops.trajectory_inverse_dynamics(
+            handle, s, e, f32, float(Tf), int(N), int(method), self._jl, g, ftip, self._tl,
+            bool(return_trajectory))
         outs = [tau] + ([pos, vel, acc] if return_trajectory else [])
         if single:
             outs = [o[0] for o in outs]
         if not on_dev:
             outs = [_host.to_host(o) for o in outs]
-        self._tick(t0, transfers=0 if on_dev else 2 + len(outs), kernel="trajectory_inverse_dynamics")
+        self._tick(t0, launches=2, transfers=0 if on_dev else 2 + len(outs), kernel="trajectory_inverse_dynamics")
         if return_trajectory:
             return outs[0], {"positions": outs[1], "velocities": outs[2], "accelerations": outs[3]}
         return outs[0]

@@ -2,7 +2,8 @@
 # One gpurun call: GPU parity tests, smoke, bench (both modes), ncu launch list and a full
 # capture of the dominant kernel.  Usage (from the build container):
 #   gpurun --timeout 1500 -- 'bash scripts/gpu_check.sh [tag] [sections]'
-# sections: any of  tests smoke bench launches ncu micro   (default: all but micro)
+# sections: any of  tests smoke bench launches ncu ncu_micro micro
+
 set -u
 TAG=${1:-r1}
 SECTIONS=${2:-"tests smoke bench launches ncu"}
@@ -33,6 +34,12 @@ ncu)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:traj_rnea_kernel -s 2 -c 2 \
       -f -o $OUT/${TAG}_traj_rnea python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu.log 2>&1
   tail -2 $OUT/${TAG}_ncu.log ;;
+ncu_micro)
+  # full captures of the other kernels (one launch each) while running the micro-benchmark
+  timeout 1200 ncu --set full --clock-control none --import-source on \
+      -k regex:'traj_kernel|fk_jacobian_kernel|fd_rollout_kernel|mass_matrix_kernel|rnea_kernel' -c 14 \
+      -f -o $OUT/${TAG}_micro python scripts/microbench.py --quick > $OUT/${TAG}_ncu_micro.log 2>&1
+  tail -2 $OUT/${TAG}_ncu_micro.log ;;
 micro)
   timeout 900 python scripts/microbench.py > $OUT/${TAG}_micro.json 2> $OUT/${TAG}_micro.err
   cat $OUT/${TAG}_micro.json; tail -3 $OUT/${TAG}_micro.err ;;

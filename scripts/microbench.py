@@ -20,8 +20,13 @@ from manipulapy_b200 import _native, load_robot  # noqa: E402
 HBM = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
 
 
+QUICK = "--quick" in sys.argv  # one launch per kernel (for ncu captures)
+
+
 def timeit(fn, iters=10, warmup=3):
     flush = timeit.flush
+    if QUICK:
+        iters, warmup = 1, 0
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -103,7 +108,15 @@ def main():
     lo = torch.from_numpy(iiwa.joint_limits[:, 0]).to(dev)
     hi = torch.from_numpy(iiwa.joint_limits[:, 1]).to(dev)
     jl7 = iiwa.planner()._jl
-    for Bf in (65536, 8192):
+    # write-only and copy ceilings of this GPU for the roofline of the store-bound kernels
+    big = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    sec = timeit(lambda: big.zero_(), 5, 2)
+    res["memset_gbs"] = big.numel() / sec[0] / 1e9
+    src = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    sec = timeit(lambda: big.copy_(src), 5, 2)
+    res["copy_gbs"] = 2 * big.numel() / sec[0] / 1e9
+    del big, src
+    for Bf in ((8192,) if QUICK else (65536, 8192)):
         Nf = 1000 if Bf == 65536 else 1000
         th0 = 0.5 * (lo + (hi - lo) * torch.rand(Bf, 7, dtype=torch.float64, device=dev, generator=gen))
         dth0 = rand(Bf, 7, lo=-0.5, hi=0.5)
