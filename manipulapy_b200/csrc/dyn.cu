@@ -55,16 +55,23 @@ template <int N>
 struct RowIn {
     const void *th, *dth, *ddth;
     int dtype;
-    int64_t row;  // p * N
+    int64_t row;          // p * N
+    double nx[3];         // joint i's values, loaded while link i - 1 was being processed
     __device__ __forceinline__ double at(const void *base, int i) const {
         if (base == nullptr) return 0.0;
         return dtype == MPK_F64 ? __ldg(static_cast<const double *>(base) + row + i)
                                 : (double)__ldg(static_cast<const float *>(base) + row + i);
     }
-    __device__ __forceinline__ void joint(int i, double &a, double &b, double &c) const {
-        a = at(th, i);
-        b = at(dth, i);
-        c = at(ddth, i);
+    __device__ __forceinline__ void prefetch(int i) {
+        nx[0] = at(th, i);
+        nx[1] = at(dth, i);
+        nx[2] = at(ddth, i);
+    }
+    __device__ __forceinline__ void joint(int i, double &a, double &b, double &c) {
+        a = nx[0];
+        b = nx[1];
+        c = nx[2];
+        if (i + 1 < N) prefetch(i + 1);  // overlaps the load latency with link i's arithmetic
     }
 };
 
@@ -104,7 +111,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
         for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
         ftp = ft;
     }
-    const RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N};
+    RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {0.0, 0.0, 0.0}};
+    in.prefetch(0);
     SmemStore<double, N, THREADS> st{wsm + threadIdx.x};
     if (ROLLED) {
         TauOut<N> out{a.out, a.out_dtype, p * N, a.lim};
@@ -127,6 +135,7 @@ struct TrajRneaArgs {
     TipArgs tip;
     float *tau, *pos, *vel, *acc;
     const double *ts_table;
+    FastDiv div;
 };
 
 // Joint values produced from the time scaling when the recursion reaches the link: the
@@ -136,7 +145,7 @@ struct TrajIn {
     const TrajRneaArgs &a;
     TimeScale ts;
     int64_t row;  // b * N
-    __device__ __forceinline__ void joint(int i, double &th, double &qd, double &qdd) const {
+    __device__ __forceinline__ void joint(int i, double &th, double &qd, double &qdd) {
         double st, dth;
         endpoint(a.start, a.end, a.inputs_f32, row + i, st, dth);
         float p, v, ac;
@@ -166,20 +175,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
     // staged for coalesced stores]
     extern __shared__ __align__(16) double wsm[];
     float *sm = reinterpret_cast<float *>(wsm + SmemStore<double, N, THREADS>::kSlots * 8 * THREADS);
-    int64_t b, t;
-    point_coords(a.N, b, t);
     const int64_t p0 = (int64_t)blockIdx.x * THREADS;
     const bool live = p0 + threadIdx.x < a.P;
+    int64_t b, t;
+    point_coords(a.div, a.N, live ? p0 + threadIdx.x : 0, b, t);
     const int64_t rem = a.P - p0;
     const int cnt = (int)(rem < THREADS ? rem : THREADS) * N;
     const int64_t off = p0 * N;
-    // tail threads of the last block recompute point 0 (they take part in every barrier and
+    // (tail threads of the last block recompute point 0: they take part in every barrier and
     // their staged rows are never stored)
-    if (!live) {
-        b = 0;
-        t = 0;
-    }
-    const TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
+    TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
     // optional materialisation of the trajectory rows (coalesced through shared memory)
     if (a.pos || a.vel || a.acc) {
         float *outs[3] = {a.pos, a.vel, a.acc};
@@ -231,20 +236,29 @@ struct MassArgs {
 template <int N, bool GEN>
 __global__ void __launch_bounds__(kDynThreads)
     mass_matrix_kernel(const __grid_constant__ RobotPack<double, N> rb, const MassArgs a) {
-    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
-    if (p >= a.P) return;
-    double th[N];
-    load_row<N>(a.th, a.th_dtype, a.vec_in, p, th);
-    JointCS<double, N> q;
-    joint_cs(rb, th, q);
-    double Mm[N][N];
-    mass_matrix<double, N, GEN>(rb, th, q, Mm);
-    double flat[N * N];
+    // N^2 doubles per configuration: staged per warp and flushed coalesced (one thread writing
+    // its own 8 N^2-byte row with scalar stores throttles the LSU: ncu lg_throttle 6.7)
+    extern __shared__ __align__(16) double msm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *buf = msm + warp * WarpStage<N * N>::kDoubles;
+    const int64_t pw = (int64_t)blockIdx.x * kDynThreads + warp * 32;
+    if (pw >= a.P) return;
+    const int64_t rem = a.P - pw;
+    const int rows = (int)(rem < 32 ? rem : 32);
+    if (lane < rows) {
+        double th[N];
+        load_row<N>(a.th, a.th_dtype, a.vec_in, pw + lane, th);
+        JointCS<double, N> q;
+        joint_cs(rb, th, q);
+        double Mm[N][N];
+        mass_matrix<double, N, GEN>(rb, th, q, Mm);
+        double *row = buf + lane * WarpStage<N * N>::S;
 #pragma unroll
-    for (int i = 0; i < N; ++i)
+        for (int i = 0; i < N; ++i)
 #pragma unroll
-        for (int j = 0; j < N; ++j) flat[i * N + j] = Mm[i][j];
-    store_row_f64<N * N>(a.out, a.vec_out, p, flat);
+            for (int j = 0; j < N; ++j) row[i * N + j] = Mm[i][j];
+    }
+    WarpStage<N * N>::flush(buf, a.out + pw * (N * N), rows);
 }
 
 // ---- per-point forward dynamics --------------------------------------------------------
@@ -379,6 +393,7 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     a.B = B;
     a.N = N;
     a.P = B * N;
+    a.div = make_fastdiv(N, a.P);
     a.start = start;
     a.end = end;
     a.inputs_f32 = inputs_f32;
@@ -421,9 +436,13 @@ extern "C" int mpk_mass_matrix(const mpk_robot *rb, int64_t P, const void *theta
     if (int rc = grid_for(P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (rb->rigid) {
-        MPK_DISPATCH_DOF(rb->n, (mass_matrix_kernel<N_, false><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+        MPK_DISPATCH_DOF(rb->n, launch_smem(mass_matrix_kernel<N_, false>, grid, kDynThreads,
+                                            sizeof(double) * WarpStage<N_ * N_>::kDoubles * (kDynThreads / 32), s,
+                                            narrow<N_>(rb), a));
     } else {
-        MPK_DISPATCH_DOF(rb->n, (mass_matrix_kernel<N_, true><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+        MPK_DISPATCH_DOF(rb->n, launch_smem(mass_matrix_kernel<N_, true>, grid, kDynThreads,
+                                            sizeof(double) * WarpStage<N_ * N_>::kDoubles * (kDynThreads / 32), s,
+                                            narrow<N_>(rb), a));
     }
     return check_launch("mass_matrix");
 }

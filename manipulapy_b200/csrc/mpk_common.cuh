@@ -168,24 +168,70 @@ __device__ __forceinline__ TimeScale time_scaling_at(const double *table, int64_
 const double *prepare_time_scaling(double *scratch, int64_t B, int64_t N, double Tf, int method,
                                    cudaStream_t s);
 
-// (trajectory, step) of the flattened point index blockIdx.x*128 + threadIdx.x: one
-// 64-bit division per block, plus one per warp that straddles a trajectory boundary.
-__device__ __forceinline__ void point_coords(int64_t N, int64_t &b, int64_t &t) {
-    __shared__ int64_t s_b0, s_t0;
-    if (threadIdx.x == 0) {
-        const int64_t p0 = (int64_t)blockIdx.x * blockDim.x;
-        s_b0 = p0 / N;
-        s_t0 = p0 - s_b0 * N;
+// Division of a flattened point index by the trajectory length without a 64-bit divide:
+// for n < 2^31, floor(n / d) = (n * M) >> s with M = ceil(2^s / d), s = 31 + ceil(log2 d)
+// (Granlund-Montgomery); larger batches fall back to the hardware-emulated 64-bit division.
+struct FastDiv {
+    uint32_t d, M;
+    int shift;  // s - 32, or log2(d) when pow2
+    int pow2, wide;
+};
+
+inline FastDiv make_fastdiv(int64_t d, int64_t max_n) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.M = 0;
+    f.shift = 0;
+    f.pow2 = 0;
+    f.wide = (max_n >= (1LL << 31)) || (d >= (1LL << 31));
+    if (f.wide) return f;
+    int l = 0;
+    while ((1LL << l) < d) ++l;
+    if ((1LL << l) == d) {
+        f.pow2 = 1;
+        f.shift = l;
+        return f;
     }
-    __syncthreads();
-    b = s_b0;
-    t = s_t0 + threadIdx.x;
-    if (t >= N) {
-        const int64_t q = t / N;
-        b += q;
-        t -= q * N;
+    const int s = 31 + l;
+    const unsigned __int128 num = (unsigned __int128)1 << s;
+    f.M = (uint32_t)((num + (unsigned __int128)d - 1) / (unsigned __int128)d);
+    f.shift = s - 32;
+    return f;
+}
+
+// (trajectory, step) of flattened point p = b * N + t.
+__device__ __forceinline__ void point_coords(const FastDiv &f, int64_t N, int64_t p, int64_t &b,
+                                             int64_t &t) {
+    if (f.wide) {
+        b = p / N;
+        t = p - b * N;
+    } else {
+        const uint32_t n = (uint32_t)p;
+        const uint32_t q = f.pow2 ? (n >> f.shift) : (__umulhi(n, f.M) >> f.shift);
+        b = q;
+        t = n - q * f.d;
     }
 }
+
+// Per-warp output staging: each lane owns one row of K values; the warp then writes the
+// (up to) 32 rows, which are contiguous in global memory, with fully coalesced stores.  The
+// row stride is odd (in 8-byte words) so neither phase has shared-memory bank conflicts.
+template <int K>
+struct WarpStage {
+    static constexpr int S = (K % 2 == 0) ? K + 1 : K;
+    static constexpr int kDoubles = 32 * S;  // per warp
+    // gout: global address of the warp's first row; rows: live rows of this warp (<= 32)
+    __device__ static __forceinline__ void flush(const double *buf, double *gout, int rows) {
+        __syncwarp();
+        const int lane = threadIdx.x & 31;
+        const int cnt = rows * K;
+        for (int e = lane; e < cnt; e += 32) {
+            const int r = e / K, k = e - r * K;
+            __stcs(gout + e, buf[r * S + k]);
+        }
+        __syncwarp();
+    }
+};
 
 // start and (end - start) of joint j of trajectory b, in the precision the reference uses.
 __device__ __forceinline__ void endpoint(const double *start, const double *end, int inputs_f32,

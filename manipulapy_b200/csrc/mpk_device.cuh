@@ -297,7 +297,7 @@ struct ArrayIn {
     const T (&th)[N];
     const T (&dth)[N];
     const T (&ddth)[N];
-    MPK_HD void joint(int i, T &a, T &b, T &c) const {
+    MPK_HD void joint(int i, T &a, T &b, T &c) {
         a = th[i];
         b = dth[i];
         c = ddth[i];
@@ -311,7 +311,7 @@ struct ArrayIn {
 // each other, so they fetch the same (large, straight-line) code region at the same time and
 // share instruction-cache lines instead of each streaming the whole body on its own.
 template <typename T, int N, bool GEN, typename In, typename St, bool SYNC = false>
-MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const T *ftip,
+MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ftip,
                  T (&tau)[N], St &st_) {
     T w[3], v[3], dw[3], dv[3];
     T ag[3];         // general path: -g in the current frame
@@ -438,7 +438,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const
 // constant bank with a warp-uniform dynamic link index, the backward-pass state comes from
 // `st_` and torques leave through `out.put(j, tau_j)` (no dynamically indexed registers).
 template <typename T, int N, bool GEN, typename In, typename St, typename Out>
-MPK_HD void rnea_rolled(const RobotPack<T, N> &rb, const In &in, const T (&g)[3], const T *ftip,
+MPK_HD void rnea_rolled(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ftip,
                         St &st_, Out &out) {
     T w[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, dw[3] = {T(0), T(0), T(0)};
     T dv[3], ag[3];
@@ -537,7 +537,7 @@ template <typename T, int N, bool GEN>
 MPK_HD void rnea(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N], const T (&ddth)[N],
                  const T (&g)[3], const T *ftip, T (&tau)[N], JointCS<T, N> &q) {
     RegStore<T, N> st_;
-    const ArrayIn<T, N> in{th, dth, ddth};
+    ArrayIn<T, N> in{th, dth, ddth};
     rnea<T, N, GEN>(rb, in, g, ftip, tau, st_);
     q = st_.q;
 }

@@ -13,10 +13,11 @@
 
 namespace mpk {
 
-constexpr int kTrajThreads = 128;
+constexpr int kTrajThreads = 256;
 
 struct TrajArgs {
     int64_t B, N, P;
+    FastDiv div;
     const double *start, *end;
     int inputs_f32;
     double Tf;
@@ -42,32 +43,62 @@ const double *prepare_time_scaling(double *scratch, int64_t B, int64_t N, double
     return scratch;
 }
 
+// One thread = one (trajectory, step) point, all joints.  Each warp stages its 32 rows of the
+// three outputs in its own shared-memory slice and writes them out with 16-byte-per-lane
+// coalesced streaming stores (a warp's rows are contiguous: 32 N floats, a multiple of 128 B).
+// Only __syncwarp: warps never wait for each other.
 template <int N>
 __global__ void __launch_bounds__(kTrajThreads) traj_kernel(const TrajArgs a) {
-    __shared__ __align__(16) float sm[3][kTrajThreads * N];
-    int64_t b, t;
-    point_coords(a.N, b, t);
-    const int64_t p0 = (int64_t)blockIdx.x * kTrajThreads;
-    if (p0 + threadIdx.x < a.P) {
+    __shared__ __align__(16) float sm[kTrajThreads / 32][3][32 * N];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pw = (int64_t)blockIdx.x * kTrajThreads + warp * 32;  // warp's first point
+    if (pw >= a.P) return;                                               // whole warp out of range
+    const int64_t p = pw + lane;
+    if (p < a.P) {
+        int64_t b, t;
+        point_coords(a.div, a.N, p, b, t);
         const TimeScale ts = time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method);
+        float pr[N], vr[N], ar[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             double st, dth;
             endpoint(a.start, a.end, a.inputs_f32, b * N + j, st, dth);
-            float p, v, ac;
-            traj_point(ts, st, dth, a.lim.lo[j], a.lim.hi[j], a.lim.on, p, v, ac);
-            sm[0][threadIdx.x * N + j] = p;
-            sm[1][threadIdx.x * N + j] = v;
-            sm[2][threadIdx.x * N + j] = ac;
+            traj_point(ts, st, dth, a.lim.lo[j], a.lim.hi[j], a.lim.on, pr[j], vr[j], ar[j]);
+        }
+        // row stores: 8-byte vectors when N is even (conflict-free at a 4 N byte lane stride)
+        float *r0 = &sm[warp][0][lane * N], *r1 = &sm[warp][1][lane * N], *r2 = &sm[warp][2][lane * N];
+        if (N % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                *reinterpret_cast<float2 *>(r0 + j) = make_float2(pr[j], pr[j + 1]);
+                *reinterpret_cast<float2 *>(r1 + j) = make_float2(vr[j], vr[j + 1]);
+                *reinterpret_cast<float2 *>(r2 + j) = make_float2(ar[j], ar[j + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                r0[j] = pr[j];
+                r1[j] = vr[j];
+                r2[j] = ar[j];
+            }
         }
     }
-    __syncthreads();
-    const int64_t rem = a.P - p0;
-    const int cnt = (int)(rem < kTrajThreads ? rem : kTrajThreads) * N;
-    const int64_t off = p0 * N;
-    if (a.pos) tile_store(a.pos + off, sm[0], cnt);
-    if (a.vel) tile_store(a.vel + off, sm[1], cnt);
-    if (a.acc) tile_store(a.acc + off, sm[2], cnt);
+    __syncwarp();
+    const int64_t rem = a.P - pw;
+    const int cnt = (int)(rem < 32 ? rem : 32) * N;  // floats of this warp per output
+    const int64_t off = pw * N;
+    float *outs[3] = {a.pos, a.vel, a.acc};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float *o = outs[k];
+        if (!o) continue;
+        o += off;
+        const float4 *s4 = reinterpret_cast<const float4 *>(sm[warp][k]);
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        const int n4 = cnt >> 2;
+        for (int i = lane; i < n4; i += 32) __stcs(o4 + i, s4[i]);
+        for (int i = (n4 << 2) + lane; i < cnt; i += 32) o[i] = sm[warp][k][i];
+    }
 }
 
 }  // namespace mpk
@@ -88,6 +119,7 @@ extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *s
     a.B = B;
     a.N = N;
     a.P = B * N;
+    a.div = make_fastdiv(N, a.P);
     a.start = start;
     a.end = end;
     a.inputs_f32 = inputs_f32;

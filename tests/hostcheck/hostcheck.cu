@@ -25,7 +25,7 @@ static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const doubl
             // the rolled-loop form of the kernels (shared-memory store, torques through `out.put`)
             double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
             SmemStore<double, N, 1> st{buf};
-            const ArrayIn<double, N> in{a, b, c};
+            ArrayIn<double, N> in{a, b, c};
             struct { double *t; void put(int j, double x) { t[j] = x; } } out{t};
             if (rb->rigid) rnea_rolled<double, N, false>(pk, in, g3, ftip, st, out);
             else rnea_rolled<double, N, true>(pk, in, g3, ftip, st, out);
@@ -33,7 +33,7 @@ static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const doubl
             // the shared-memory state store of the kernels, exercised with a one-thread "block"
             double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
             SmemStore<double, N, 1> st{buf};
-            const ArrayIn<double, N> in{a, b, c};
+            ArrayIn<double, N> in{a, b, c};
             if (rb->rigid) rnea<double, N, false>(pk, in, g3, ftip, t, st);
             else rnea<double, N, true>(pk, in, g3, ftip, t, st);
         } else {
