@@ -185,23 +185,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
     // (tail threads of the last block recompute point 0: they take part in every barrier and
     // their staged rows are never stored)
     TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
-    // optional materialisation of the trajectory rows (coalesced through shared memory)
-    if (a.pos || a.vel || a.acc) {
-        float *outs[3] = {a.pos, a.vel, a.acc};
-#pragma unroll 1
-        for (int k = 0; k < 3; ++k) {
-            if (!outs[k]) continue;  // uniform
-#pragma unroll 1
-            for (int j = 0; j < N; ++j) {
-                double th, qd, qdd;
-                in.joint(j, th, qd, qdd);
-                sm[threadIdx.x * N + j] = (float)(k == 0 ? th : (k == 1 ? qd : qdd));
-            }
-            __syncthreads();
-            tile_store(outs[k] + off, sm, cnt);
-            __syncthreads();
-        }
-    }
     {
         double ft[6];
         const double *ftp = nullptr;
@@ -410,6 +393,13 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     if (int rc = grid_for(a.P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     a.ts_table = prepare_time_scaling(ts_scratch, B, N, Tf, method, s);
+    if (pos || vel || acc) {
+        // optional materialisation of the trajectory rows: the store-bound trajectory kernel
+        // does it at the write-bandwidth ceiling; the fused kernel then only writes torques
+        if (int rc = launch_joint_trajectory(rb->n, B, N, start, end, inputs_f32, Tf, method, joint_limits,
+                                             pos, vel, acc, a.ts_table, s))
+            return rc;
+    }
     if (rb->rigid) {
         MPK_DISPATCH_DOF(rb->n, launch_smem(traj_rnea_kernel<N_, false>, grid, kDynThreads, wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
     } else {

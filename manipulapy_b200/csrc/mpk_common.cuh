@@ -164,6 +164,11 @@ __device__ __forceinline__ TimeScale time_scaling_at(const double *table, int64_
     return time_scaling(t, N, Tf, method);
 }
 
+// Launches the trajectory kernel (traj.cu) with an already prepared time-scaling table.
+int launch_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const double *end,
+                            int inputs_f32, double Tf, int method, const float *limits, float *pos,
+                            float *vel, float *acc, const double *ts_table, cudaStream_t s);
+
 // Fills the workspace if it is worth it (more than one trajectory); returns the table to use.
 const double *prepare_time_scaling(double *scratch, int64_t B, int64_t N, double Tf, int method,
                                    cudaStream_t s);

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #define MPK_HD __host__ __device__ __forceinline__
 
@@ -57,12 +58,16 @@ struct RobotPack {
 };
 
 // ---- scalar helpers ---------------------------------------------------------
-MPK_HD void sincos_t(double x, double *s, double *c) {
+// sin and cos together.  The CUDA library's float64 sincos() is already minimal on its fast
+// path (3-FMA reduction + two 7-term polynomials = 22 fp64 instructions, large arguments
+// handled by an out-of-line subroutine); a hand-written Cody-Waite + fdlibm-kernel version
+// was measured at the same fp64 count with more select instructions and was dropped.
+MPK_HD void sincos_t(double x, double *sn, double *cs) {
 #ifdef __CUDA_ARCH__
-    sincos(x, s, c);
+    sincos(x, sn, cs);
 #else
-    *s = sin(x);
-    *c = cos(x);
+    *sn = sin(x);
+    *cs = cos(x);
 #endif
 }
 MPK_HD void sincos_t(float x, float *s, float *c) {

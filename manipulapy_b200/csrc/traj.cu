@@ -101,18 +101,9 @@ __global__ void __launch_bounds__(kTrajThreads) traj_kernel(const TrajArgs a) {
     }
 }
 
-}  // namespace mpk
-
-using namespace mpk;
-
-extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start,
-                                    const double *end, int inputs_f32, double Tf, int method,
-                                    const float *limits, float *pos, float *vel, float *acc,
-                                    double *ts_scratch, void *stream) {
-    if (n < 1 || n > MPK_MAX_DOF) return fail(MPK_EUNSUPPORTED, "dof must be in 1..8");
-    if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
-    if (B == 0 || N == 0) return MPK_OK;
-    if (!start || !end) return fail(MPK_EINVAL, "start/end are NULL");
+int launch_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const double *end,
+                            int inputs_f32, double Tf, int method, const float *limits, float *pos,
+                            float *vel, float *acc, const double *ts_table, cudaStream_t s) {
     for (float *o : {pos, vel, acc})
         if (o && !aligned16(o)) return fail(MPK_EINVAL, "outputs must be 16-byte aligned");
     TrajArgs a;
@@ -129,11 +120,27 @@ extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *s
     a.pos = pos;
     a.vel = vel;
     a.acc = acc;
+    a.ts_table = ts_table;
     const int64_t blocks = (a.P + kTrajThreads - 1) / kTrajThreads;
-    if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B*N exceeds the grid limit (2^38 points)");
-    if ((N + 255) / 256 > 0x7fffffffLL) return fail(MPK_EINVAL, "N exceeds the grid limit");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    a.ts_table = prepare_time_scaling(ts_scratch, B, N, Tf, method, s);
+    if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B*N exceeds the grid limit (2^39 points)");
     MPK_DISPATCH_DOF(n, (traj_kernel<N_><<<(unsigned)blocks, kTrajThreads, 0, s>>>(a)));
     return check_launch("joint_trajectory");
+}
+
+}  // namespace mpk
+
+using namespace mpk;
+
+extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start,
+                                    const double *end, int inputs_f32, double Tf, int method,
+                                    const float *limits, float *pos, float *vel, float *acc,
+                                    double *ts_scratch, void *stream) {
+    if (n < 1 || n > MPK_MAX_DOF) return fail(MPK_EUNSUPPORTED, "dof must be in 1..8");
+    if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
+    if (B == 0 || N == 0) return MPK_OK;
+    if (!start || !end) return fail(MPK_EINVAL, "start/end are NULL");
+    if ((N + 255) / 256 > 0x7fffffffLL) return fail(MPK_EINVAL, "N exceeds the grid limit");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const double *table = prepare_time_scaling(ts_scratch, B, N, Tf, method, s);
+    return launch_joint_trajectory(n, B, N, start, end, inputs_f32, Tf, method, limits, pos, vel, acc, table, s);
 }
