@@ -52,6 +52,9 @@ BYTES_RNEA = 3 * 6 * 4 + 6 * 4        # float32 theta, dtheta, ddtheta in; float
 BYTES_TRAJ = 3 * 6 * 4                # float32 pos, vel, acc out
 
 
+_RESULT: list = []  # the JSON line, printed by main() once stdout is restored
+
+
 def _env_int(name: str, default: int) -> int:
     return int(os.environ.get(name, default))
 
@@ -150,7 +153,7 @@ def run_reference(args) -> None:
     rate, cores, pts, sec = cpu_reference_rate(sample, args.steps, args.warmup)
     desc = (f"{sample} of {B_TRAJ} trajectories x {N_STEPS} steps per step ({pts} points); "
             "oracle/oracle.c literal port of the reference algorithm (the Python reference cannot travel)")
-    print(json.dumps({
+    _RESULT.append(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -314,7 +317,7 @@ def run_ours(args) -> None:
             "value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{args.cpu_sample_traj} of {B_TRAJ} trajectories x {N_STEPS} steps ({cpu_pts} points), "
                       "oracle/oracle.c literal port of the reference algorithm, all host threads"}
-    print(json.dumps(line))
+    _RESULT.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -331,7 +334,19 @@ def main() -> None:
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    (run_reference if args.impl == "reference" else run_ours)(args)
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (e.g. NCCL's
+    # version banner) is diverted to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        (run_reference if args.impl == "reference" else run_ours)(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _RESULT:
+        print(_RESULT[0], flush=True)
 
 
 if __name__ == "__main__":
