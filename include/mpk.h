@@ -57,8 +57,9 @@ const char *mpk_last_error(void);
  *   Glist  (n,6,6)  spatial inertias in the link-CoM frames (NULL: kinematics only)
  *   Mcom   (n,4,4)  Mlist_per_link (NULL with Glist NULL)
  * All host, float64.  1 <= n <= MPK_MAX_DOF.  The pack is re-expressed in
- * joint-aligned link frames on the host and later passed to every kernel as a
- * __grid_constant__ parameter (constant bank), so there is no device allocation. */
+ * joint-aligned (Denavit-Hartenberg / Hayati) link frames on the host and later
+ * passed to every kernel as a __grid_constant__ parameter (constant bank), so
+ * there is no device allocation. */
 int mpk_robot_create(int n, const double *S_list, const double *M, const double *Glist,
                      const double *Mcom, int flags, mpk_robot **out);
 void mpk_robot_destroy(mpk_robot *rb);
@@ -66,6 +67,8 @@ int mpk_robot_dof(const mpk_robot *rb);
 /* 1 if every link inertia is a rigid body expressed at its centre of mass
  * (block-diagonal [I, m*1]); 0 if the general symmetric-6x6 kernels are used. */
 int mpk_robot_is_rigid(const mpk_robot *rb);
+/* 1 if no joint is prismatic (the kernels then drop the prismatic terms at compile time). */
+int mpk_robot_all_revolute(const mpk_robot *rb);
 
 /* joint_trajectory / batch_joint_trajectory
  * (planning/trajectory.py:103-169, 276-333, 335-502; kernel :15-75; clip :311-313).

@@ -27,8 +27,13 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--expt-relaxed-constexpr",
 ]
-CU_SOURCES = ["robot.cu", "traj.cu", "kin.cu", "dyn.cu", "fd.cu"]
-HEADERS = [CSRC / "mpk_device.cuh", CSRC / "mpk_common.cuh", INCLUDE / "mpk.h"]
+# (source, object stem, extra defines).  The dynamics kernels exist in three flavours (rigid +
+# all-revolute, rigid, general inertias; csrc/dyn_kernels.cuh), each its own translation unit
+# so that the build uses every core.
+CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", []), ("kin.cu", "kin", []), ("dyn.cu", "dyn", [])]
+CU_UNITS += [(f"{base}_flavour.cu", f"{base}_flavour{k}", [f"-DMPK_FLAVOUR={k}"])
+             for base in ("dyn", "fd") for k in (0, 1, 2)]
+HEADERS = [CSRC / "mpk_device.cuh", CSRC / "mpk_common.cuh", CSRC / "dyn_kernels.cuh", INCLUDE / "mpk.h"]
 
 
 def _digest(paths, extra="") -> str:
@@ -61,24 +66,27 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     OBJ.mkdir(parents=True, exist_ok=True)
     flags = " ".join(NVCC_FLAGS)
 
-    def compile_one(name: str) -> bool:
+    def compile_one(unit) -> bool:
+        name, stem, defines = unit
         src = CSRC / name
-        obj = OBJ / (src.stem + ".o")
-        stamp = _digest([src, *HEADERS], flags)
+        obj = OBJ / (stem + ".o")
+        stamp = _digest([src, *HEADERS], flags + " ".join(defines))
         if not force and not _stale(obj, stamp):
             return False
         if verbose:
-            print(f"[mpk build] nvcc {name}", flush=True)
-        _run([NVCC, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj], OBJ / (src.stem + ".ptxas.log"))
+            print(f"[mpk build] nvcc {name} {' '.join(defines)}", flush=True)
+        _run([NVCC, *NVCC_FLAGS, *defines, "-I", INCLUDE, "-c", src, "-o", obj], OBJ / (stem + ".ptxas.log"))
         _mark(obj, stamp)
         return True
 
-    with ThreadPoolExecutor(max_workers=min(len(CU_SOURCES), os.cpu_count() or 1)) as ex:
-        rebuilt = list(ex.map(compile_one, CU_SOURCES))
+    # the heavy flavour units first so that they overlap with each other
+    units = sorted(CU_UNITS, key=lambda u: "flavour" not in u[0])
+    with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
+        rebuilt = list(ex.map(compile_one, units))
     if any(rebuilt) or not LIB.exists():
         if verbose:
             print("[mpk build] link libmpk.so", flush=True)
-        _run([NVCC, "-shared", "-o", LIB, *[OBJ / (Path(s).stem + ".o") for s in CU_SOURCES],
+        _run([NVCC, "-shared", "-o", LIB, *[OBJ / (stem + ".o") for _, stem, _ in CU_UNITS],
               "-cudart", "static"])
     return LIB
 

@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
         L.mpk_robot_destroy.argtypes = [C.c_void_p]
         L.mpk_robot_dof.argtypes = [C.c_void_p]
         L.mpk_robot_is_rigid.argtypes = [C.c_void_p]
+        L.mpk_robot_all_revolute.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 

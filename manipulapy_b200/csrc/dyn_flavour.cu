@@ -1,0 +1,51 @@
+// dyn_flavour.cu -- inverse dynamics, fused trajectory + inverse dynamics and mass-matrix
+// kernels of ONE flavour (compiled three times, -DMPK_FLAVOUR=0|1|2; see dyn_kernels.cuh).
+#define MPK_FLAVOUR_KERNELS
+#include "dyn_kernels.cuh"
+
+#ifndef MPK_FLAVOUR
+#error "compile with -DMPK_FLAVOUR=0|1|2"
+#endif
+
+namespace mpk {
+
+#define MPK_DISPATCH_DOF_V(n, ...)                               \
+    switch (n) {                                                 \
+        case 1: { constexpr int N_ = 1; __VA_ARGS__; } break;    \
+        case 2: { constexpr int N_ = 2; __VA_ARGS__; } break;    \
+        case 3: { constexpr int N_ = 3; __VA_ARGS__; } break;    \
+        case 4: { constexpr int N_ = 4; __VA_ARGS__; } break;    \
+        case 5: { constexpr int N_ = 5; __VA_ARGS__; } break;    \
+        case 6: { constexpr int N_ = 6; __VA_ARGS__; } break;    \
+        case 7: { constexpr int N_ = 7; __VA_ARGS__; } break;    \
+        case 8: { constexpr int N_ = 8; __VA_ARGS__; } break;    \
+        default: break;                                          \
+    }
+
+template <int F>
+void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    MPK_DISPATCH_DOF_V(rb->n, launch_smem(rnea_kernel<N_, GEN, REV>, grid, kDynThreads,
+                                          wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
+}
+
+template <int F>
+void launch_traj_rnea(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<N_, GEN, REV>, grid, kDynThreads,
+                                          wrench_smem<N_>(kDynThreads), s, narrow<N_>(rb), a));
+}
+
+template <int F>
+void launch_mass(const mpk_robot *rb, const MassArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    MPK_DISPATCH_DOF_V(rb->n, launch_smem(mass_matrix_kernel<N_, GEN, REV>, grid, kDynThreads,
+                                          sizeof(double) * WarpStage<N_ * N_>::kDoubles * (kDynThreads / 32),
+                                          s, narrow<N_>(rb), a));
+}
+
+template void launch_rnea<MPK_FLAVOUR>(const mpk_robot *, const RneaArgs &, unsigned, cudaStream_t);
+template void launch_traj_rnea<MPK_FLAVOUR>(const mpk_robot *, const TrajRneaArgs &, unsigned, cudaStream_t);
+template void launch_mass<MPK_FLAVOUR>(const mpk_robot *, const MassArgs &, unsigned, cudaStream_t);
+
+}  // namespace mpk

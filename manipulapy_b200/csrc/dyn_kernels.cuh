@@ -1,0 +1,369 @@
+// dyn_kernels.cuh -- kernels and argument blocks of the dynamics launchers.
+//
+// Replace the per-point Python loops of the reference:
+//   inverse dynamics            dynamics/id_fd.py:16-48 and planning/trajectory_dynamics.py:308-380
+//   gravity / Coriolis forces   dynamics/forces.py:26-133 (ddtheta = 0 / g = 0 calls)
+//   mass matrix                 dynamics/mass_matrix.py:16-99
+//   forward dynamics            dynamics/id_fd.py:50-83
+//   forward-dynamics rollouts   planning/trajectory_dynamics.py:580-708
+// One thread owns one point (or one rollout); robot constants are constant-bank operands
+// (mpk_device.cuh).  fp64 FMA-pipe bound.
+//
+// Every kernel exists in three FLAVOURS, each compiled in its own translation unit
+// (dyn_flavour.cu / fd_flavour.cu with -DMPK_FLAVOUR=k) so that the build parallelises:
+//   0  rigid link inertias, all joints revolute, plain D-H links   (UR5, iiwa, ...: most URDF arms)
+//   1  rigid link inertias, a prismatic joint or a Hayati link    (the reference's 8-DOF Panda)
+//   2  general symmetric 6x6 link inertias
+#pragma once
+#include "mpk_common.cuh"
+
+namespace mpk {
+
+constexpr int kDynThreads = 128;
+constexpr int kRneaMinBlocks = 5;  // 96-register cap: 20 warps / SM hide the fp64 latency
+
+constexpr bool flavour_gen(int f) { return f == 2; }
+constexpr bool flavour_rev(int f) { return f == 0; }
+inline int flavour_of(const mpk_robot *rb) { return !rb->rigid ? 2 : (rb->plain ? 0 : 1); }
+
+struct TipArgs {
+    double g0[3];  // -g in frame-0 coordinates (base_gravity)
+    double ftip[6];
+    int has_ftip;
+    const double *ftip_rows;  // (P, 6) or nullptr
+};
+
+struct RneaArgs {
+    int64_t P;
+    const void *th, *dth, *ddth;
+    int in_dtype, vec_in;
+    TipArgs tip;
+    Limits lim;
+    void *out;
+    int out_dtype, vec_out;
+};
+
+struct TrajRneaArgs {
+    int64_t B, N, P;
+    const double *start, *end;
+    int inputs_f32;
+    double Tf;
+    int method;
+    Limits jlim, tlim;
+    TipArgs tip;
+    float *tau;
+    const double *ts_table;
+    FastDiv div;
+};
+
+struct MassArgs {
+    int64_t P;
+    const void *th;
+    int th_dtype, vec_in, vec_out;
+    double *out;
+};
+
+struct FdArgs {
+    int64_t P;
+    const double *th, *dth, *tau;
+    int vec;
+    TipArgs tip;
+    double *out;
+};
+
+struct RolloutArgs {
+    int64_t B, N;
+    const double *th0, *dth0;
+    const void *taumat;
+    int tau_dtype, vec_tau;
+    double g0[3];
+    const double *ftipmat;
+    double dts;
+    int intRes;
+    Limits lim;
+    float *pos, *vel, *acc;
+};
+
+// Flavour launchers: defined and explicitly instantiated in dyn_flavour.cu / fd_flavour.cu.
+template <int FLAVOUR> void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s);
+template <int FLAVOUR> void launch_traj_rnea(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s);
+template <int FLAVOUR> void launch_mass(const mpk_robot *rb, const MassArgs &a, unsigned grid, cudaStream_t s);
+template <int FLAVOUR> void launch_fd_point(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaStream_t s);
+template <int FLAVOUR> void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, unsigned grid, int threads, cudaStream_t s);
+
+#define MPK_DISPATCH_FLAVOUR(rb, CALL)                 \
+    switch (flavour_of(rb)) {                          \
+        case 0: { constexpr int F_ = 0; CALL; } break; \
+        case 1: { constexpr int F_ = 1; CALL; } break; \
+        default: { constexpr int F_ = 2; CALL; } break; \
+    }
+
+// Bytes of shared memory the RNEA kernels need for the per-link wrenches of one block.
+template <int N>
+constexpr size_t wrench_smem(int threads) {
+    const size_t link_state = (size_t)(N > 1 ? N - 1 : 0) * 8 * threads * sizeof(double);
+    const size_t rows = (size_t)threads * N * sizeof(float);  // output staging (fused kernel)
+    return link_state + rows;
+}
+
+// Launch with dynamic shared memory, asking for the largest shared-memory carveout so that
+// __launch_bounds__' blocks-per-SM target is not cut short by the L1 / shared split.
+template <typename... KArgs, typename... Args>
+static void launch_smem(void (*kern)(KArgs...), unsigned grid, int threads, size_t smem,
+                        cudaStream_t s, Args &&...args) {
+    if (smem > 32 * 1024)  // (static shared memory counts against the 48 KB default limit too)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);
+    kern<<<grid, threads, smem, s>>>(args...);
+}
+
+#ifdef MPK_FLAVOUR_KERNELS
+// ======================================================================================
+// kernels (only the flavour translation units see this part)
+// ======================================================================================
+
+template <int N>
+__device__ __forceinline__ void store_tau(void *out, int out_dtype, bool vec, int64_t p,
+                                          const double (&tau)[N], const Limits &lim) {
+    if (out_dtype == MPK_F64) {
+        store_row_f64<N>(static_cast<double *>(out), vec, p, tau);
+    } else {
+        float t32[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            t32[j] = (float)tau[j];
+            if (lim.on) t32[j] = clip_f32(t32[j], lim.lo[j], lim.hi[j]);
+        }
+        store_row_f32<N>(static_cast<float *>(out), vec, p, t32);
+    }
+}
+
+__device__ __forceinline__ const double *load_tip(const TipArgs &tip, int64_t p, double (&ft)[6]) {
+    if (tip.ftip_rows) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[k] = __ldg(tip.ftip_rows + p * 6 + k);
+        return ft;
+    }
+    if (tip.has_ftip) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ft[k] = tip.ftip[k];
+        return ft;
+    }
+    return nullptr;
+}
+
+// Joint values of row p read from global memory when the recursion reaches the link.  Each
+// thread walks its own contiguous row, rows of neighbouring threads are adjacent, so every
+// fetched sector is fully consumed (through L1) although the individual loads are strided.
+template <int N>
+struct RowIn {
+    const void *th, *dth, *ddth;
+    int dtype;
+    int64_t row;          // p * N
+    double nx[3];         // joint i's values, loaded while link i - 1 was being processed
+    __device__ __forceinline__ double at(const void *base, int i) const {
+        if (base == nullptr) return 0.0;
+        return dtype == MPK_F64 ? __ldg(static_cast<const double *>(base) + row + i)
+                                : (double)__ldg(static_cast<const float *>(base) + row + i);
+    }
+    __device__ __forceinline__ void prefetch(int i) {
+        nx[0] = at(th, i);
+        nx[1] = at(dth, i);
+        nx[2] = at(ddth, i);
+    }
+    __device__ __forceinline__ void joint(int i, double &a, double &b, double &c) {
+        a = nx[0];
+        b = nx[1];
+        c = nx[2];
+        if (i + 1 < N) prefetch(i + 1);  // overlaps the load latency with link i's arithmetic
+    }
+};
+
+template <int N, bool GEN, bool REV>
+__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
+    rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
+    extern __shared__ __align__(16) double wsm[];
+    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    if (p >= a.P) return;
+    double ft[6];
+    const double *ftp = load_tip(a.tip, p, ft);
+    RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {0.0, 0.0, 0.0}};
+    in.prefetch(0);
+    SmemStore<double, N, kDynThreads> st{wsm + threadIdx.x};
+    double tau[N];
+    rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
+    store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
+}
+
+// ---- fused trajectory + inverse dynamics ----------------------------------------
+// Joint values produced from the time scaling when the recursion reaches the link: the
+// float32-rounded, clipped trajectory row entries the two-call sequence would have stored.
+template <int N>
+struct TrajIn {
+    const TrajRneaArgs &a;
+    TimeScale ts;
+    int64_t row;  // b * N
+    __device__ __forceinline__ void joint(int i, double &th, double &qd, double &qdd) {
+        double st, dth;
+        endpoint(a.start, a.end, a.inputs_f32, row + i, st, dth);
+        float p, v, ac;
+        traj_point(ts, st, dth, a.jlim.lo[i], a.jlim.hi[i], a.jlim.on, p, v, ac);
+        th = (double)p;
+        qd = (double)v;
+        qdd = (double)ac;
+    }
+};
+
+template <int N, bool GEN, bool REV>
+__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
+    traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
+    // dynamic shared memory: [per-thread link state of the recursion | the block's output rows,
+    // staged for coalesced stores]
+    extern __shared__ __align__(16) double wsm[];
+    float *sm = reinterpret_cast<float *>(wsm + SmemStore<double, N, kDynThreads>::kSlots * 8 * kDynThreads);
+    const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
+    const bool live = p0 + threadIdx.x < a.P;
+    int64_t b, t;
+    point_coords(a.div, a.N, live ? p0 + threadIdx.x : 0, b, t);
+    const int64_t rem = a.P - p0;
+    const int cnt = (int)(rem < kDynThreads ? rem : kDynThreads) * N;
+    const int64_t off = p0 * N;
+    // (tail threads of the last block recompute point 0: they take part in the barrier and
+    // their staged rows are never stored)
+    TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
+    {
+        double ft[6];
+        const double *ftp = nullptr;
+        if (a.tip.has_ftip) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
+            ftp = ft;
+        }
+        SmemStore<double, N, kDynThreads> st{wsm + threadIdx.x};
+        double tau[N];
+        rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
+        float *row = sm + threadIdx.x * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            float x = (float)tau[j];
+            if (a.tlim.on) x = clip_f32(x, a.tlim.lo[j], a.tlim.hi[j]);
+            row[j] = x;
+        }
+    }
+    __syncthreads();
+    tile_store(a.tau + off, sm, cnt);
+}
+
+// ---- mass matrix -------------------------------------------------------------------
+template <int N, bool GEN, bool REV>
+__global__ void __launch_bounds__(kDynThreads)
+    mass_matrix_kernel(const __grid_constant__ RobotPack<double, N> rb, const MassArgs a) {
+    // N^2 doubles per configuration: staged per warp and flushed coalesced (one thread writing
+    // its own 8 N^2-byte row with scalar stores throttles the LSU: ncu lg_throttle 6.7)
+    extern __shared__ __align__(16) double msm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *buf = msm + warp * WarpStage<N * N>::kDoubles;
+    const int64_t pw = (int64_t)blockIdx.x * kDynThreads + warp * 32;
+    if (pw >= a.P) return;
+    const int64_t rem = a.P - pw;
+    const int rows = (int)(rem < 32 ? rem : 32);
+    if (lane < rows) {
+        double th[N];
+        load_row<N>(a.th, a.th_dtype, a.vec_in, pw + lane, th);
+        JointCS<double, N> q;
+        joint_cs<double, N, REV>(rb, th, q);
+        double Mm[N][N];
+        mass_matrix<double, N, GEN, REV>(rb, th, q, Mm);
+        double *row = buf + lane * WarpStage<N * N>::S;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+#pragma unroll
+            for (int j = 0; j < N; ++j) row[i * N + j] = Mm[i][j];
+    }
+    WarpStage<N * N>::flush(buf, a.out + pw * (N * N), rows);
+}
+
+// ---- per-point forward dynamics --------------------------------------------------------
+template <int N, bool GEN, bool REV>
+__global__ void __launch_bounds__(kDynThreads)
+    forward_dynamics_kernel(const __grid_constant__ RobotPack<double, N> rb, const FdArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
+    if (p >= a.P) return;
+    double th[N], dth[N], tau[N], dd[N];
+    load_row<N>(a.th, MPK_F64, a.vec, p, th);
+    load_row<N>(a.dth, MPK_F64, a.vec, p, dth);
+    load_row<N>(a.tau, MPK_F64, a.vec, p, tau);
+    double ft[6];
+    const double *ftp = load_tip(a.tip, p, ft);
+    forward_dynamics<double, N, GEN, REV>(rb, th, dth, tau, a.tip.g0, ftp, dd);
+    store_row_f64<N>(a.out, a.vec, p, dd);
+}
+
+// ---- forward-dynamics rollouts, parallel across trajectories, sequential in time ------
+// Replaces forward_dynamics_trajectory's CPU loop (planning/trajectory_dynamics.py:580-708):
+// per row i >= 1, intRes semi-implicit Euler sub-steps of
+//   ddth = M(th)^-1 (taumat[i] - c - g - Js^T Ftipmat[i]);  dth += ddth*dts;  th += dth*dts;
+//   th = clip(th, float32 limits);
+// rows are stored as float32 and the acceleration row is the last sub-step's.  Row 0 is the
+// initial state with zero acceleration and taumat[0] is never used.  The Euler updates use
+// explicit round-to-nearest multiplies and adds (no FMA contraction) like the reference's
+// NumPy.  One thread owns one trajectory; state, mass matrix and LDL^T factor live in registers.
+template <int N>
+__device__ __forceinline__ void store_state(float *o, int64_t row, const double (&x)[N]) {
+    float *r = o + row * N;
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = (float)x[j];
+}
+
+template <int N, bool GEN, bool REV>
+__global__ void __launch_bounds__(128)
+    fd_rollout_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    double th[N], dth[N], last[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        th[j] = a.th0[b * N + j];
+        dth[j] = a.dth0[b * N + j];
+        last[j] = 0.0;
+    }
+    const int64_t base = b * a.N;
+    store_state<N>(a.pos, base, th);
+    store_state<N>(a.vel, base, dth);
+    store_state<N>(a.acc, base, last);
+    for (int64_t i = 1; i < a.N; ++i) {
+        double tau[N];
+        load_row<N>(a.taumat, a.tau_dtype, a.vec_tau, base + i, tau);
+        double ft[6];
+        const double *ftp = nullptr;
+        if (a.ftipmat) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) ft[k] = __ldg(a.ftipmat + (base + i) * 6 + k);
+            ftp = ft;
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) last[j] = 0.0;
+        for (int r = 0; r < a.intRes; ++r) {
+            double dd[N];
+            forward_dynamics<double, N, GEN, REV>(rb, th, dth, tau, a.g0, ftp, dd);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                dth[j] = rn_add(dth[j], rn_mul(dd[j], a.dts));
+                double x = rn_add(th[j], rn_mul(dth[j], a.dts));
+                if (a.lim.on) {
+                    const double lo = (double)a.lim.lo[j], hi = (double)a.lim.hi[j];
+                    x = x < lo ? lo : (x > hi ? hi : x);
+                }
+                th[j] = x;
+                last[j] = dd[j];
+            }
+        }
+        store_state<N>(a.pos, base + i, th);
+        store_state<N>(a.vel, base + i, dth);
+        store_state<N>(a.acc, base + i, last);
+    }
+}
+#endif  // MPK_FLAVOUR_KERNELS
+
+}  // namespace mpk

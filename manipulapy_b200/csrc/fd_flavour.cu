@@ -1,0 +1,40 @@
+// fd_flavour.cu -- per-point forward dynamics and forward-dynamics rollout kernels of ONE
+// flavour (compiled three times, -DMPK_FLAVOUR=0|1|2; see dyn_kernels.cuh).
+#define MPK_FLAVOUR_KERNELS
+#include "dyn_kernels.cuh"
+
+#ifndef MPK_FLAVOUR
+#error "compile with -DMPK_FLAVOUR=0|1|2"
+#endif
+
+namespace mpk {
+
+#define MPK_DISPATCH_DOF_V(n, ...)                               \
+    switch (n) {                                                 \
+        case 1: { constexpr int N_ = 1; __VA_ARGS__; } break;    \
+        case 2: { constexpr int N_ = 2; __VA_ARGS__; } break;    \
+        case 3: { constexpr int N_ = 3; __VA_ARGS__; } break;    \
+        case 4: { constexpr int N_ = 4; __VA_ARGS__; } break;    \
+        case 5: { constexpr int N_ = 5; __VA_ARGS__; } break;    \
+        case 6: { constexpr int N_ = 6; __VA_ARGS__; } break;    \
+        case 7: { constexpr int N_ = 7; __VA_ARGS__; } break;    \
+        case 8: { constexpr int N_ = 8; __VA_ARGS__; } break;    \
+        default: break;                                          \
+    }
+
+template <int F>
+void launch_fd_point(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    MPK_DISPATCH_DOF_V(rb->n, (forward_dynamics_kernel<N_, GEN, REV><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
+}
+
+template <int F>
+void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, unsigned grid, int threads, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    MPK_DISPATCH_DOF_V(rb->n, (fd_rollout_kernel<N_, GEN, REV><<<grid, threads, 0, s>>>(narrow<N_>(rb), a)));
+}
+
+template void launch_fd_point<MPK_FLAVOUR>(const mpk_robot *, const FdArgs &, unsigned, cudaStream_t);
+template void launch_rollout<MPK_FLAVOUR>(const mpk_robot *, const RolloutArgs &, unsigned, int, cudaStream_t);
+
+}  // namespace mpk

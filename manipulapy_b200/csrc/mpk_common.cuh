@@ -9,7 +9,9 @@
 
 struct mpk_robot {
     int n;
-    int rigid;
+    int rigid;         // every link inertia is a rigid body at its centre of mass
+    int all_revolute;  // no prismatic joint
+    int plain;         // all revolute and every link plain Denavit-Hartenberg (beta = 0): flavour 0
     int has_dynamics;
     mpk::RobotPack<double, MPK_MAX_DOF> pack;  // host copy, frames 0..n-1 valid
 };
@@ -26,9 +28,16 @@ inline RobotPack<double, N> narrow(const mpk_robot *rb) {
     RobotPack<double, N> o;
     const auto &s = rb->pack;
     for (int i = 0; i < N; ++i) {
-        for (int k = 0; k < 9; ++k) o.Rx[i][k] = s.Rx[i][k];
+        o.a[i] = s.a[i];
+        o.ca[i] = s.ca[i];
+        o.sa[i] = s.sa[i];
+        o.cb[i] = s.cb[i];
+        o.sb[i] = s.sb[i];
+        o.phi[i] = s.phi[i];
+        o.d[i] = s.d[i];
+        o.cphi[i] = s.cphi[i];
+        o.sphi[i] = s.sphi[i];
         for (int k = 0; k < 3; ++k) {
-            o.px[i][k] = s.px[i][k];
             o.h[i][k] = s.h[i][k];
             o.cg[i][k] = s.cg[i][k];
         }
@@ -39,8 +48,14 @@ inline RobotPack<double, N> narrow(const mpk_robot *rb) {
         o.m[i] = s.m[i];
         o.mg[i] = s.mg[i];
     }
-    for (int k = 0; k < 9; ++k) o.Ree[k] = s.Ree[k];
-    for (int k = 0; k < 3; ++k) o.pee[k] = s.pee[k];
+    for (int k = 0; k < 9; ++k) {
+        o.Rb[k] = s.Rb[k];
+        o.Ree[k] = s.Ree[k];
+    }
+    for (int k = 0; k < 3; ++k) {
+        o.pb[k] = s.pb[k];
+        o.pee[k] = s.pee[k];
+    }
     return o;
 }
 

@@ -1,20 +1,37 @@
 // mpk_device.cuh -- per-thread, register-resident rigid-body algebra for sm_100a.
 //
-// Every quantity is expressed in JOINT-ALIGNED link frames: frame i is fixed to
-// link i, its z axis is the axis of joint i and (for a revolute joint) its
-// origin lies on that axis.  In these frames the joint motion is a pure z
-// rotation by theta (plus a z translation st*theta for prismatic / helical
-// joints), the joint screw is A_i = [0,0,sr, 0,0,st], and the only per-link
-// constants are the pose X_i of frame i in frame i-1 at theta_i = 0 and the
-// link inertia re-expressed in frame i.  This is mathematically the reference's
-// product of exponentials (kinematics/fk.py:61-70, kinematics/jacobian.py:62-73)
-// and its link-CoM inertia model (dynamics/mass_matrix.py:66-96) after a
-// constant change of frames done once on the host (robot.cu), and costs about
-// half the flops of evaluating e^{[S]theta} per joint.
+// Every quantity is expressed in JOINT-ALIGNED link frames: frame i is fixed to link i, its
+// z axis is the axis of joint i and its origin lies on that axis.  The freedom that is left
+// (the direction of x_i and the position of the origin along the axis) is spent the way the
+// Denavit-Hartenberg convention spends it: x_{i-1} points along the common normal of the
+// axes i-1 and i, so that the constant pose of frame i in frame i-1 factors into planar
+// rotations and axis-aligned translations,
 //
-// The constant pack is passed to kernels by value as a __grid_constant__
-// parameter: with the link loops fully unrolled every constant is a
-// constant-bank operand of the FMA that uses it -- no loads, no registers.
+//     T_{i-1,i}(theta_i) = Tx(a_i) Rx(alpha_i) [Ry(beta_i)] Rz(phi_i + theta_i) Tz(d_i)       (revolute)
+//                        = Tx(a_i) Rx(alpha_i) [Ry(beta_i)] Rz(phi_i) Tz(d_i + |v| theta_i)   (prismatic)
+//
+// and moving a twist or a wrench across a joint costs 20-22 fp64 operations instead of the
+// 32-35 of a general (R, p) pair.  The optional Ry(beta) factor (Hayati's parametrisation) is
+// only non-trivial for consecutive axes that are nearly but not exactly parallel, where the
+// common normal is ill-conditioned; robot.cu decides per link, and the kernels skip the
+// factor under a warp-uniform test (beta = 0 for every robot shipped with the reference).
+// Frame 0 sits in the space frame with a general constant pose (Rb, pb).
+//
+// This is mathematically the reference's product of exponentials (kinematics/fk.py:61-70,
+// kinematics/jacobian.py:62-73) and its link-CoM inertia model (dynamics/mass_matrix.py:66-96)
+// after a constant change of frames done once on the host (robot.cu: e^{[S_i] th} F_i =
+// F_i Rz(th) for the home pose F_i of frame i), at well under half the flops of evaluating
+// e^{[S]theta} per joint.
+//
+// The constant pack is passed to kernels by value as a __grid_constant__ parameter: with the
+// link loops fully unrolled every constant is a constant-bank operand of the FMA that uses
+// it -- no loads, no registers.
+//
+// Template flags used throughout:
+//   GEN  general symmetric 6x6 link inertias (else rigid bodies: I about the origin, m c, m)
+//   REV  a "plain" chain: every joint revolute (sr = 1, st = 0) and every link plain
+//        Denavit-Hartenberg (beta = 0); drops the prismatic and Hayati terms at compile time
+//   HAY  (transform helpers) keep the warp-uniform Ry(beta) step; kernels pass HAY = !REV
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -43,18 +60,21 @@ MPK_HD float rn_fsub(float a, float b) { volatile float r = a - b; return r; }
 
 template <typename T, int N>
 struct RobotPack {
-    T Rx[N][9];  // rotation of frame i in frame i-1 at theta_i = 0 (row-major)
-    T px[N][3];  // origin of frame i in frame i-1
-    T sr[N];     // 1 revolute / helical, 0 prismatic
-    T st[N];     // z translation per unit theta (|v| for a prismatic joint, else 0)
-    T I[N][6];   // rigid: rotational inertia about the frame-i origin (xx,xy,xz,yy,yz,zz)
-    T h[N][3];   // rigid: mass * centre of mass (in frame i)
-    T m[N];      // rigid: mass
-    T G[N][21];  // general: upper triangle (row-major) of the symmetric 6x6 inertia in frame i
-    T cg[N][3];  // general: origin of the reference's link-CoM frame in frame i
-    T mg[N];     // general: G[3,3] in the CoM frame, the mass the reference's gravity term uses
-    T Ree[9];    // end-effector home pose in frame n
-    T pee[3];
+    T Rb[9], pb[3];        // pose of frame 0 in the space frame at theta_0 = 0 (R row-major)
+    T a[N];                // i >= 1: length of the common normal, along x_{i-1}
+    T ca[N], sa[N];        // i >= 1: twist alpha_i about x_{i-1}
+    T cb[N], sb[N];        // i >= 1: Hayati angle beta_i about y (sb = 0: plain Denavit-Hartenberg)
+    T phi[N], d[N];        // i >= 1: joint angle offset about z_i and offset along z_i
+    T cphi[N], sphi[N];    // cos / sin(phi_i): the constant z rotation of a prismatic joint
+    T sr[N];               // 1 revolute, 0 prismatic
+    T st[N];               // z translation per unit theta (|v| for a prismatic joint, else 0)
+    T I[N][6];             // rigid: rotational inertia about the frame-i origin (xx,xy,xz,yy,yz,zz)
+    T h[N][3];             // rigid: mass * centre of mass (in frame i)
+    T m[N];                // rigid: mass
+    T G[N][21];            // general: upper triangle (row-major) of the symmetric 6x6 inertia in frame i
+    T cg[N][3];            // general: origin of the reference's link-CoM frame in frame i
+    T mg[N];               // general: G[3,3] in the CoM frame, the mass the reference's gravity term uses
+    T Ree[9], pee[3];      // end-effector home pose in frame n-1
 };
 
 // ---- scalar helpers ---------------------------------------------------------
@@ -79,144 +99,244 @@ MPK_HD void sincos_t(float x, float *s, float *c) {
 #endif
 }
 
+// Planar rotation of the pair (p, q) by the angle whose cosine / sine are (c, s):
+//   rot  : p' = c p - s q,  q' = s p + c q      (Rz on (x, y); Rx on (y, z); Ry on (z, x))
+//   rot_t: the inverse rotation
+template <typename T>
+MPK_HD void rot(T c, T s, T &p, T &q) {
+    const T p1 = c * p - s * q;
+    q = s * p + c * q;
+    p = p1;
+}
+template <typename T>
+MPK_HD void rot_t(T c, T s, T &p, T &q) {
+    const T p1 = c * p + s * q;
+    q = c * q - s * p;
+    p = p1;
+}
+
 template <typename T, int N>
 struct JointCS {
-    T c[N], s[N], d[N];
+    T c[N], s[N], d[N];  // cos / sin of (phi_i + theta_i) and the total z offset d_i + st_i theta_i
 };
 
-// sin/cos (and z offset) of every joint; prismatic joints get the identity rotation.
-template <typename T, int N>
-MPK_HD void joint_cs(const RobotPack<T, N> &rb, const T (&th)[N],
-                                         JointCS<T, N> &q) {
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
+// Joint rotation and z offset of joint i at joint value th.
+template <typename T, int N, bool REV>
+MPK_HD void joint_rot(const RobotPack<T, N> &rb, int i, T th, T &c, T &s, T &dz) {
+    if (REV) {
+        sincos_t(rb.phi[i] + th, &s, &c);
+        dz = rb.d[i];
+    } else {
         if (rb.sr[i] != T(0)) {
-            sincos_t(th[i], &q.s[i], &q.c[i]);
+            sincos_t(rb.phi[i] + th, &s, &c);
         } else {
-            q.s[i] = T(0);
-            q.c[i] = T(1);
+            c = rb.cphi[i];
+            s = rb.sphi[i];
         }
-        q.d[i] = rb.st[i] * th[i];
+        dz = rb.d[i] + rb.st[i] * th;
     }
 }
 
-// Twist (w, v) of frame i-1 coordinates -> frame i coordinates: Ad(T_{i-1,i}^{-1}),
-// T_{i-1,i} = X_i * Jz(theta_i).
+template <typename T, int N, bool REV = false>
+MPK_HD void joint_cs(const RobotPack<T, N> &rb, const T (&th)[N], JointCS<T, N> &q) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) joint_rot<T, N, REV>(rb, i, th[i], q.c[i], q.s[i], q.d[i]);
+}
+
+// -g expressed in frame 0 at theta_0 = 0 (uniform over a batch: launchers compute it once on
+// the host and pass it as a kernel argument).
 template <typename T, int N>
-MPK_HD void twist_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T d,
-                                               T (&w)[3], T (&v)[3]) {
-    const T *R = rb.Rx[i];
-    const T *p = rb.px[i];
-    // u = v + w x p   (written so that every product contracts into an FMA chain)
-    const T ux = v[0] + w[1] * p[2] - w[2] * p[1];
-    const T uy = v[1] + w[2] * p[0] - w[0] * p[2];
-    const T uz = v[2] + w[0] * p[1] - w[1] * p[0];
-    // Rx^T *
-    const T w1x = R[0] * w[0] + R[3] * w[1] + R[6] * w[2];
-    const T w1y = R[1] * w[0] + R[4] * w[1] + R[7] * w[2];
-    const T w1z = R[2] * w[0] + R[5] * w[1] + R[8] * w[2];
-    T v1x = R[0] * ux + R[3] * uy + R[6] * uz;
-    T v1y = R[1] * ux + R[4] * uy + R[7] * uz;
-    const T v1z = R[2] * ux + R[5] * uy + R[8] * uz;
-    if (rb.st[i] != T(0)) {  // + w1 x (0,0,d)
-        v1x += w1y * d;
-        v1y -= w1x * d;
+MPK_HD void base_gravity(const RobotPack<T, N> &rb, const T *g, T (&g0)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g0[k] = -(rb.Rb[k] * g[0] + rb.Rb[3 + k] * g[1] + rb.Rb[6 + k] * g[2]);
+}
+
+// ---- moving twists and wrenches across joint i >= 1 -----------------------------
+// Twist (w, v) of frame i-1 coordinates -> frame i coordinates, Ad(T_{i-1,i}^{-1}); (c, s, dz)
+// from joint_rot.  20 fp64 operations.
+template <typename T, int N, bool HAY = true>
+MPK_HD void twist_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&w)[3], T (&v)[3]) {
+    const T a = rb.a[i], ca = rb.ca[i], sa = rb.sa[i];
+    // Tx(a): the origin moves to a x  =>  v += w x (a, 0, 0)
+    T vy = v[1] + a * w[2];
+    T vz = v[2] - a * w[1];
+    T vx = v[0], wx = w[0], wy = w[1], wz = w[2];
+    rot_t(ca, sa, wy, wz);
+    rot_t(ca, sa, vy, vz);
+    if (HAY && rb.sb[i] != T(0)) {
+        rot_t(rb.cb[i], rb.sb[i], wz, wx);
+        rot_t(rb.cb[i], rb.sb[i], vz, vx);
     }
-    // Rz^T *
-    w[0] = c * w1x + s * w1y;
-    w[1] = c * w1y - s * w1x;
-    w[2] = w1z;
-    v[0] = c * v1x + s * v1y;
-    v[1] = c * v1y - s * v1x;
-    v[2] = v1z;
+    rot_t(c, s, wx, wy);
+    rot_t(c, s, vx, vy);
+    // Tz(dz): v += w x (0, 0, dz)
+    v[0] = vx + wy * dz;
+    v[1] = vy - wx * dz;
+    v[2] = vz;
+    w[0] = wx;
+    w[1] = wy;
+    w[2] = wz;
+}
+
+// The same for the twist of a revolute link 0 at rest in translation: w = (0, 0, wz), v = 0
+// (10 operations; products with the known zeros are not something the compiler may drop).
+template <typename T, int N, bool HAY = true>
+MPK_HD void twist_to_child_z(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T wz0, T (&w)[3],
+                             T (&v)[3]) {
+    if (HAY && rb.sb[i] != T(0)) {
+        w[0] = T(0); w[1] = T(0); w[2] = wz0;
+        v[0] = T(0); v[1] = T(0); v[2] = T(0);
+        twist_to_child(rb, i, c, s, dz, w, v);
+        return;
+    }
+    const T a = rb.a[i];
+    const T wy1 = rb.sa[i] * wz0, wz1 = rb.ca[i] * wz0;
+    const T vy1 = a * wz1, vz1 = -(a * wy1);
+    w[0] = s * wy1;
+    w[1] = c * wy1;
+    w[2] = wz1;
+    v[0] = s * vy1 + w[1] * dz;
+    v[1] = c * vy1 - w[0] * dz;
+    v[2] = vz1;
+}
+
+// ... and for its acceleration: dw = (0, 0, dwz), dv full (15 operations).
+template <typename T, int N, bool HAY = true>
+MPK_HD void accel_to_child_z(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T dwz0,
+                             const T (&dv0)[3], T (&dw)[3], T (&dv)[3]) {
+    if (HAY && rb.sb[i] != T(0)) {
+        dw[0] = T(0); dw[1] = T(0); dw[2] = dwz0;
+        dv[0] = dv0[0]; dv[1] = dv0[1]; dv[2] = dv0[2];
+        twist_to_child(rb, i, c, s, dz, dw, dv);
+        return;
+    }
+    const T ca = rb.ca[i], sa = rb.sa[i];
+    const T wy1 = sa * dwz0, wz1 = ca * dwz0;
+    T vy = dv0[1] + rb.a[i] * dwz0, vz = dv0[2];
+    rot_t(ca, sa, vy, vz);
+    dw[0] = s * wy1;
+    dw[1] = c * wy1;
+    dw[2] = wz1;
+    dv[0] = c * dv0[0] + s * vy + dw[1] * dz;
+    dv[1] = c * vy - s * dv0[0] - dw[0] * dz;
+    dv[2] = vz;
 }
 
 // Rotate a free vector from frame i-1 coordinates to frame i coordinates.
-template <typename T, int N>
-MPK_HD void vec_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T (&a)[3]) {
-    const T *R = rb.Rx[i];
-    const T x = R[0] * a[0] + R[3] * a[1] + R[6] * a[2];
-    const T y = R[1] * a[0] + R[4] * a[1] + R[7] * a[2];
-    const T z = R[2] * a[0] + R[5] * a[1] + R[8] * a[2];
-    a[0] = c * x + s * y;
-    a[1] = c * y - s * x;
-    a[2] = z;
+template <typename T, int N, bool HAY = true>
+MPK_HD void vec_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T (&u)[3]) {
+    rot_t(rb.ca[i], rb.sa[i], u[1], u[2]);
+    if (HAY && rb.sb[i] != T(0)) rot_t(rb.cb[i], rb.sb[i], u[2], u[0]);
+    rot_t(c, s, u[0], u[1]);
 }
 
-// Wrench (n, f) of frame i-1 coordinates -> frame i coordinates (dual of twist_to_child's inverse).
+// Wrench (n, f) of frame i-1 coordinates -> frame i coordinates.
+template <typename T, int N, bool HAY = true>
+MPK_HD void wrench_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&n)[3], T (&f)[3]) {
+    const T a = rb.a[i];
+    // Tx(a): n -= (a, 0, 0) x f
+    n[1] += a * f[2];
+    n[2] -= a * f[1];
+    rot_t(rb.ca[i], rb.sa[i], n[1], n[2]);
+    rot_t(rb.ca[i], rb.sa[i], f[1], f[2]);
+    if (HAY && rb.sb[i] != T(0)) {
+        rot_t(rb.cb[i], rb.sb[i], n[2], n[0]);
+        rot_t(rb.cb[i], rb.sb[i], f[2], f[0]);
+    }
+    rot_t(c, s, n[0], n[1]);
+    rot_t(c, s, f[0], f[1]);
+    // Tz(dz): n -= (0, 0, dz) x f
+    n[0] += dz * f[1];
+    n[1] -= dz * f[0];
+}
+
+// Space-frame wrench -> frame 0 coordinates (general base pose, then the joint rotation).
 template <typename T, int N>
-MPK_HD void wrench_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T d,
-                                                T (&n)[3], T (&f)[3]) {
-    const T *R = rb.Rx[i];
-    const T *p = rb.px[i];
-    // u = n - p x f
+MPK_HD void wrench_to_base(const RobotPack<T, N> &rb, T c, T s, T dz, T (&n)[3], T (&f)[3]) {
+    const T *R = rb.Rb;
+    const T *p = rb.pb;
     const T ux = n[0] - p[1] * f[2] + p[2] * f[1];
     const T uy = n[1] - p[2] * f[0] + p[0] * f[2];
     const T uz = n[2] - p[0] * f[1] + p[1] * f[0];
-    const T f1x = R[0] * f[0] + R[3] * f[1] + R[6] * f[2];
-    const T f1y = R[1] * f[0] + R[4] * f[1] + R[7] * f[2];
-    const T f1z = R[2] * f[0] + R[5] * f[1] + R[8] * f[2];
-    T n1x = R[0] * ux + R[3] * uy + R[6] * uz;
-    T n1y = R[1] * ux + R[4] * uy + R[7] * uz;
-    const T n1z = R[2] * ux + R[5] * uy + R[8] * uz;
-    if (rb.st[i] != T(0)) {  // - (0,0,d) x f1
-        n1x += d * f1y;
-        n1y -= d * f1x;
-    }
-    n[0] = c * n1x + s * n1y;
-    n[1] = c * n1y - s * n1x;
-    n[2] = n1z;
-    f[0] = c * f1x + s * f1y;
-    f[1] = c * f1y - s * f1x;
-    f[2] = f1z;
+    const T fx = R[0] * f[0] + R[3] * f[1] + R[6] * f[2];
+    const T fy = R[1] * f[0] + R[4] * f[1] + R[7] * f[2];
+    const T fz = R[2] * f[0] + R[5] * f[1] + R[8] * f[2];
+    n[0] = R[0] * ux + R[3] * uy + R[6] * uz;
+    n[1] = R[1] * ux + R[4] * uy + R[7] * uz;
+    n[2] = R[2] * ux + R[5] * uy + R[8] * uz;
+    f[0] = fx; f[1] = fy; f[2] = fz;
+    rot_t(c, s, n[0], n[1]);
+    rot_t(c, s, f[0], f[1]);
+    n[0] += dz * f[1];
+    n[1] -= dz * f[0];
 }
 
 // Wrench (n, f) of frame i coordinates -> frame i-1 coordinates, Ad(T_{i-1,i}^{-1})^T, ADDED to
-// (an, af):  (an, af) += Ad^T (n, f).  Every term is one link of an FMA chain seeded by an / af.
-template <typename T, int N>
-MPK_HD void wrench_to_parent_acc(const RobotPack<T, N> &rb, int i, T c, T s, T d, const T (&n)[3],
+// (an, af).  22 operations; the rotated terms are links of FMA chains seeded by an / af.
+template <typename T, int N, bool HAY = true>
+MPK_HD void wrench_to_parent_acc(const RobotPack<T, N> &rb, int i, T c, T s, T dz, const T (&n)[3],
                                  const T (&f)[3], T (&an)[3], T (&af)[3]) {
-    const T *R = rb.Rx[i];
-    const T *p = rb.px[i];
-    // Rz *
-    const T f1x = c * f[0] - s * f[1];
-    const T f1y = s * f[0] + c * f[1];
-    const T f1z = f[2];
-    T n1x = c * n[0] - s * n[1];
-    T n1y = s * n[0] + c * n[1];
-    const T n1z = n[2];
-    if (rb.st[i] != T(0)) {  // + (0,0,d) x f1
-        n1x -= d * f1y;
-        n1y += d * f1x;
+    const T a = rb.a[i], ca = rb.ca[i], sa = rb.sa[i];
+    // Tz(dz): n += (0, 0, dz) x f
+    T nx = n[0] - dz * f[1];
+    T ny = n[1] + dz * f[0];
+    T nz = n[2], fx = f[0], fy = f[1], fz = f[2];
+    rot(c, s, nx, ny);
+    rot(c, s, fx, fy);
+    if (HAY && rb.sb[i] != T(0)) {
+        rot(rb.cb[i], rb.sb[i], nz, nx);
+        rot(rb.cb[i], rb.sb[i], fz, fx);
     }
-    // Rx *
-    const T f2x = R[0] * f1x + R[1] * f1y + R[2] * f1z;
-    const T f2y = R[3] * f1x + R[4] * f1y + R[5] * f1z;
-    const T f2z = R[6] * f1x + R[7] * f1y + R[8] * f1z;
-    an[0] = an[0] + R[0] * n1x + R[1] * n1y + R[2] * n1z + p[1] * f2z - p[2] * f2y;
-    an[1] = an[1] + R[3] * n1x + R[4] * n1y + R[5] * n1z + p[2] * f2x - p[0] * f2z;
-    an[2] = an[2] + R[6] * n1x + R[7] * n1y + R[8] * n1z + p[0] * f2y - p[1] * f2x;
-    af[0] += f2x;
-    af[1] += f2y;
-    af[2] += f2z;
+    // Rx(alpha), then Tx(a): n += (a, 0, 0) x f -- with Tx applied first (they commute)
+    ny -= a * fz;
+    nz += a * fy;
+    an[0] += nx;
+    an[1] = an[1] + ca * ny - sa * nz;
+    an[2] = an[2] + sa * ny + ca * nz;
+    af[0] += fx;
+    af[1] = af[1] + ca * fy - sa * fz;
+    af[2] = af[2] + sa * fy + ca * fz;
+}
+
+// Only the z moment of the moved wrench (all a revolute joint i-1 needs): 10 operations.
+template <typename T, int N, bool HAY = true>
+MPK_HD T wrench_to_parent_nz(const RobotPack<T, N> &rb, int i, T c, T s, T dz, const T (&n)[3],
+                             const T (&f)[3], T acc) {
+    if (HAY && rb.sb[i] != T(0)) {
+        T an[3] = {T(0), T(0), acc}, af[3] = {T(0), T(0), T(0)};
+        wrench_to_parent_acc(rb, i, c, s, dz, n, f, an, af);
+        return an[2];
+    }
+    const T nx = n[0] - dz * f[1];
+    const T ny = n[1] + dz * f[0];
+    const T ny1 = s * nx + c * ny - rb.a[i] * f[2];
+    const T fy1 = s * f[0] + c * f[1];
+    const T nz1 = n[2] + rb.a[i] * fy1;
+    return acc + rb.sa[i] * ny1 + rb.ca[i] * nz1;
 }
 
 // Wrench (n, f) of frame i coordinates -> frame i-1 coordinates, in place.
-template <typename T, int N>
-MPK_HD void wrench_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T d, T (&n)[3], T (&f)[3]) {
-    T an[3] = {T(0), T(0), T(0)}, af[3] = {T(0), T(0), T(0)};
-    wrench_to_parent_acc(rb, i, c, s, d, n, f, an, af);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        n[k] = an[k];
-        f[k] = af[k];
+template <typename T, int N, bool HAY = true>
+MPK_HD void wrench_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&n)[3], T (&f)[3]) {
+    const T a = rb.a[i];
+    n[0] -= dz * f[1];
+    n[1] += dz * f[0];
+    rot(c, s, n[0], n[1]);
+    rot(c, s, f[0], f[1]);
+    if (HAY && rb.sb[i] != T(0)) {
+        rot(rb.cb[i], rb.sb[i], n[2], n[0]);
+        rot(rb.cb[i], rb.sb[i], f[2], f[0]);
     }
+    n[1] -= a * f[2];
+    n[2] += a * f[1];
+    rot(rb.ca[i], rb.sa[i], n[1], n[2]);
+    rot(rb.ca[i], rb.sa[i], f[1], f[2]);
 }
 
 // Spatial momentum (n, f) = G_i [w; v].
 template <typename T, int N, bool GEN>
-MPK_HD void inertia_mul(const RobotPack<T, N> &rb, int i, const T (&w)[3],
-                                            const T (&v)[3], T (&n)[3], T (&f)[3]) {
+MPK_HD void inertia_mul(const RobotPack<T, N> &rb, int i, const T (&w)[3], const T (&v)[3],
+                        T (&n)[3], T (&f)[3]) {
     if (GEN) {
         const T *G = rb.G[i];  // rows: 0:[0..5] 1:[6..10] 2:[11..14] 3:[15..17] 4:[18..19] 5:[20]
         n[0] = G[0] * w[0] + G[1] * w[1] + G[2] * w[2] + G[3] * v[0] + G[4] * v[1] + G[5] * v[2];
@@ -240,31 +360,35 @@ MPK_HD void inertia_mul(const RobotPack<T, N> &rb, int i, const T (&w)[3],
 }
 
 // ---- inverse dynamics -------------------------------------------------------
-// Newton-Euler recursion in the joint-aligned frames (SURVEY.md App. C restated
-// in those frames).  Equals the reference's  M ddth + c + g + Js^T Ftip
-// (dynamics/id_fd.py:38-47) without its finite-difference noise.
+// Newton-Euler recursion in the joint-aligned frames (SURVEY.md App. C restated in those
+// frames).  Equals the reference's  M ddth + c + g + Js^T Ftip  (dynamics/id_fd.py:38-47)
+// without its finite-difference noise.
 //   rigid (GEN = false): gravity enters as a base acceleration [0; -g].
 //   general (GEN = true): G_i is any symmetric 6x6; gravity is the reference's explicit
 //   wrench [0; G_i[3,3] R_i^T(-g)] at the link-CoM frame origin (dynamics/forces.py:121-131).
-//   ftip: space-frame wrench (moment; force) or nullptr.
+//   g0  : -g in frame-0 coordinates (base_gravity);  ftip: space-frame wrench (moment; force)
+//         or nullptr.
 // Storage of the per-link state the backward pass needs (local wrench of link i, and the
-// joint rotation c, s, d of link i+1 that moves link i+1's wrench into frame i):
-//   RegStore  : registers (small DOF, and the forward-dynamics path which reuses c, s for CRBA);
+// joint rotation of link i+1 that moves link i+1's wrench into frame i):
+//   RegStore  : registers (the forward-dynamics path, which reuses c, s for CRBA);
 //   SmemStore : one shared-memory column per thread (stride = block size, so a warp's
 //               accesses are conflict-free); frees 8 (N-1) fp64 registers per thread, which
 //               is what lets 20 warps per SM hide the fp64 pipe latency.
-// A prismatic joint has c = 1, s = 0 exactly, so SmemStore keeps its z offset d in the s slot.
+// A prismatic joint's rotation is the constant (cphi, sphi), so SmemStore keeps its variable
+// z offset in the s slot instead.
 template <typename T, int N>
 struct RegStore {
     T x[N][6];
     JointCS<T, N> q;
     MPK_HD void put(int i, int k, T v) { x[i][k] = v; }
     MPK_HD T get(int i, int k) const { return x[i][k]; }
+    template <bool REV>
     MPK_HD void put_cs(const RobotPack<T, N> &, int i, T c, T s, T d) {
         q.c[i] = c;
         q.s[i] = s;
         q.d[i] = d;
     }
+    template <bool REV>
     MPK_HD void get_cs(const RobotPack<T, N> &, int i, T &c, T &s, T &d) const {
         c = q.c[i];
         s = q.s[i];
@@ -278,19 +402,22 @@ struct SmemStore {
     static constexpr size_t kBytes = (size_t)kSlots * 8 * THREADS * sizeof(T);
     MPK_HD void put(int i, int k, T v) { base[(i * 8 + k) * THREADS] = v; }
     MPK_HD T get(int i, int k) const { return base[(i * 8 + k) * THREADS]; }
+    template <bool REV>
     MPK_HD void put_cs(const RobotPack<T, N> &rb, int i, T c, T s, T d) {
         if (i == 0) return;
         base[((i - 1) * 8 + 6) * THREADS] = c;
-        base[((i - 1) * 8 + 7) * THREADS] = rb.sr[i] != T(0) ? s : d;
+        base[((i - 1) * 8 + 7) * THREADS] = (REV || rb.sr[i] != T(0)) ? s : d;
     }
+    template <bool REV>
     MPK_HD void get_cs(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
-        c = base[((i - 1) * 8 + 6) * THREADS];
         const T x = base[((i - 1) * 8 + 7) * THREADS];
-        if (rb.sr[i] != T(0)) {
+        if (REV || rb.sr[i] != T(0)) {
+            c = base[((i - 1) * 8 + 6) * THREADS];
             s = x;
-            d = T(0);  // helical joints are rejected by mpk_robot_create
+            d = rb.d[i];
         } else {
-            s = T(0);
+            c = rb.cphi[i];
+            s = rb.sphi[i];
             d = x;
         }
     }
@@ -312,15 +439,16 @@ struct ArrayIn {
 // `in.joint(i, theta, dtheta, ddtheta)` yields joint i's values when link i is reached, so a
 // kernel can produce them lazily (from global memory or from the time scaling) instead of
 // holding 3 N values in registers for the whole recursion.
-// SYNC: a block barrier at every link boundary keeps the warps of a block within one link of
-// each other, so they fetch the same (large, straight-line) code region at the same time and
-// share instruction-cache lines instead of each streaming the whole body on its own.
-template <typename T, int N, bool GEN, typename In, typename St, bool SYNC = false>
-MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ftip,
-                 T (&tau)[N], St &st_) {
+template <typename T, int N, bool GEN, bool REV, typename In, typename St>
+MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *ftip, T (&tau)[N],
+                 St &st_) {
+    // a rigid all-revolute chain: link 0 only contributes the z moment about its own axis, and
+    // link 1 receives a twist with known zeros
+    constexpr bool FAST0 = REV && !GEN && N >= 2;
     T w[3], v[3], dw[3], dv[3];
     T ag[3];         // general path: -g in the current frame
     T tn[3], tf[3];  // tip wrench carried down to the last frame
+    T wz0 = T(0), dwz0 = T(0);
     const bool has_tip = ftip != nullptr;
     if (has_tip) {
         tn[0] = ftip[0]; tn[1] = ftip[1]; tn[2] = ftip[2];
@@ -328,25 +456,26 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ft
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-#ifdef __CUDA_ARCH__
-        if (SYNC) __syncthreads();
-#endif
-        const T sr = rb.sr[i], st = rb.st[i];
-        T th_i, qd, qdd, c, s;
+        T th_i, qd, qdd, c, s, dz;
         in.joint(i, th_i, qd, qdd);
-        if (sr != T(0)) {
-            sincos_t(th_i, &s, &c);
-        } else {
-            s = T(0);
-            c = T(1);
-        }
-        const T d = st * th_i;
-        st_.put_cs(rb, i, c, s, d);
+        joint_rot<T, N, REV>(rb, i, th_i, c, s, dz);
+        st_.template put_cs<REV>(rb, i, c, s, dz);
         if (i == 0) {
-            // base twist is zero and the base acceleration is [0; -g]: V_1 = A_1 qd,
-            // dV_1 = [0; R^T(-g)] + A_1 qdd  (ad(V_1) A_1 = 0)
-            T a0[3] = {-g[0], -g[1], -g[2]};
-            vec_to_child(rb, 0, c, s, a0);
+            // base twist is zero and the base acceleration is [0; -g]: V_0 = A_0 qd,
+            // dV_0 = [0; Rz^T g0] + A_0 qdd  (ad(V_0) A_0 = 0)
+            T a0[3] = {g0[0], g0[1], g0[2]};
+            rot_t(c, s, a0[0], a0[1]);
+            if (has_tip) wrench_to_base(rb, c, s, dz, tn, tf);
+            if (FAST0) {
+                wz0 = qd;
+                dwz0 = qdd;
+                dv[0] = a0[0]; dv[1] = a0[1]; dv[2] = a0[2];
+                // z moment of link 0's own wrench: (I dw + h x dv)_z (w x I w has no z part
+                // for w along z)
+                st_.put(0, 2, rb.I[0][5] * qdd + rb.h[0][0] * a0[1] - rb.h[0][1] * a0[0]);
+                continue;
+            }
+            const T sr = REV ? T(1) : rb.sr[0], st = REV ? T(0) : rb.st[0];
             w[0] = T(0); w[1] = T(0); w[2] = sr * qd;
             v[0] = T(0); v[1] = T(0); v[2] = st * qd;
             dw[0] = T(0); dw[1] = T(0); dw[2] = sr * qdd;
@@ -357,21 +486,37 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ft
                 dv[0] = a0[0]; dv[1] = a0[1]; dv[2] = a0[2] + st * qdd;
             }
         } else {
-            twist_to_child(rb, i, c, s, d, w, v);
-            twist_to_child(rb, i, c, s, d, dw, dv);
-            if (GEN) vec_to_child(rb, i, c, s, ag);
+            if (FAST0 && i == 1) {
+                T dv0[3] = {dv[0], dv[1], dv[2]};
+                twist_to_child_z<T, N, !REV>(rb, 1, c, s, dz, wz0, w, v);
+                accel_to_child_z<T, N, !REV>(rb, 1, c, s, dz, dwz0, dv0, dw, dv);
+            } else {
+                twist_to_child<T, N, !REV>(rb, i, c, s, dz, w, v);
+                twist_to_child<T, N, !REV>(rb, i, c, s, dz, dw, dv);
+            }
+            if (GEN) vec_to_child<T, N, !REV>(rb, i, c, s, ag);
+            if (has_tip) wrench_to_child<T, N, !REV>(rb, i, c, s, dz, tn, tf);
             // V_i += A_i dth_i ;  dV_i += ad(V_i) A_i dth_i + A_i ddth_i
-            w[2] += sr * qd;
-            v[2] += st * qd;
-            const T a = sr * qd, b = st * qd;
-            dw[0] += a * w[1];
-            dw[1] -= a * w[0];
-            dw[2] += sr * qdd;
-            dv[0] = dv[0] + a * v[1] + b * w[1];
-            dv[1] = dv[1] - a * v[0] - b * w[0];
-            dv[2] += st * qdd;
+            if (REV) {
+                w[2] += qd;
+                dw[0] += qd * w[1];
+                dw[1] -= qd * w[0];
+                dw[2] += qdd;
+                dv[0] += qd * v[1];
+                dv[1] -= qd * v[0];
+            } else {
+                const T sr = rb.sr[i], st = rb.st[i];
+                w[2] += sr * qd;
+                v[2] += st * qd;
+                const T a = sr * qd, b = st * qd;
+                dw[0] += a * w[1];
+                dw[1] -= a * w[0];
+                dw[2] += sr * qdd;
+                dv[0] = dv[0] + a * v[1] + b * w[1];
+                dv[1] = dv[1] - a * v[0] - b * w[0];
+                dv[2] += st * qdd;
+            }
         }
-        if (has_tip) wrench_to_child(rb, i, c, s, d, tn, tf);
         // F_i = G dV - ad(V)^T (G V) = G dV + [w x n + v x f ; w x f]
         T n[3], f[3], dn[3], df[3];
         inertia_mul<T, N, GEN>(rb, i, w, v, n, f);
@@ -410,19 +555,18 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ft
                     af[k] += tf[k];
                 }
             }
-            T cj = c, sj = s, dj = d;
+            T cj = c, sj = s, dj = dz;
 #pragma unroll
-            for (int j = N - 1; j >= 0; --j) {
-                tau[j] = rb.sr[j] * an[2] + rb.st[j] * af[2];
-                if (j > 0) {
-#ifdef __CUDA_ARCH__
-                    if (SYNC) __syncthreads();
-#endif
-                    // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
-                    if (j < N - 1) st_.get_cs(rb, j, cj, sj, dj);
+            for (int j = N - 1; j >= 1; --j) {
+                tau[j] = REV ? an[2] : rb.sr[j] * an[2] + rb.st[j] * af[2];
+                // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
+                if (j < N - 1) st_.template get_cs<REV>(rb, j, cj, sj, dj);
+                if (FAST0 && j == 1) {
+                    an[2] = wrench_to_parent_nz<T, N, !REV>(rb, 1, cj, sj, dj, an, af, st_.get(0, 2));
+                } else {
                     T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};
                     T bf[3] = {st_.get(j - 1, 3), st_.get(j - 1, 4), st_.get(j - 1, 5)};
-                    wrench_to_parent_acc(rb, j, cj, sj, dj, an, af, bn, bf);
+                    wrench_to_parent_acc<T, N, !REV>(rb, j, cj, sj, dj, an, af, bn, bf);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         an[k] = bn[k];
@@ -430,130 +574,76 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ft
                     }
                 }
             }
+            tau[0] = REV ? an[2] : rb.sr[0] * an[2] + rb.st[0] * af[2];
         }
     }
 }
 
-// The same recursion with ROLLED link loops (one copy of the link body, `#pragma unroll 1`).
-// The fully unrolled form above is ~37 KB of straight-line SASS per pass for N = 6: with a
-// dozen unsynchronised warps per SM streaming through it the instruction fetch path (GCC /
-// L1.5 instruction cache) saturates -- ncu: gcc instruction requests at 98 % of peak, icc hit
-// rate 78 %, `no_instruction` the top stall (profiles/r1_traj_rnea_unrolled.md).  Rolled, the
-// whole kernel is a few KB and stays I-cache resident; robot constants are then read from the
-// constant bank with a warp-uniform dynamic link index, the backward-pass state comes from
-// `st_` and torques leave through `out.put(j, tau_j)` (no dynamically indexed registers).
-template <typename T, int N, bool GEN, typename In, typename St, typename Out>
-MPK_HD void rnea_rolled(const RobotPack<T, N> &rb, In &in, const T (&g)[3], const T *ftip,
-                        St &st_, Out &out) {
-    T w[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, dw[3] = {T(0), T(0), T(0)};
-    T dv[3], ag[3];
-    if (GEN) {
-        dv[0] = dv[1] = dv[2] = T(0);
-        ag[0] = -g[0]; ag[1] = -g[1]; ag[2] = -g[2];
-    } else {
-        dv[0] = -g[0]; dv[1] = -g[1]; dv[2] = -g[2];
-        ag[0] = ag[1] = ag[2] = T(0);
-    }
-    T tn[3] = {T(0), T(0), T(0)}, tf[3] = {T(0), T(0), T(0)};
-    const bool has_tip = ftip != nullptr;
-    if (has_tip) {
-        tn[0] = ftip[0]; tn[1] = ftip[1]; tn[2] = ftip[2];
-        tf[0] = ftip[3]; tf[1] = ftip[4]; tf[2] = ftip[5];
-    }
-    T c = T(1), s = T(0), d = T(0);
-    T Fn[3], Ff[3];
-#pragma unroll 1
-    for (int i = 0; i < N; ++i) {
-        const T sr = rb.sr[i], st = rb.st[i];
-        T th_i, qd, qdd;
-        in.joint(i, th_i, qd, qdd);
-        if (sr != T(0)) {
-            sincos_t(th_i, &s, &c);
-        } else {
-            s = T(0);
-            c = T(1);
-        }
-        d = st * th_i;
-        if (i > 0) st_.put_cs(rb, i, c, s, d);
-        // (for link 0 the incoming twist is zero; the general transform then costs a few wasted
-        // flops but keeps a single copy of the body)
-        twist_to_child(rb, i, c, s, d, w, v);
-        twist_to_child(rb, i, c, s, d, dw, dv);
-        if (GEN) vec_to_child(rb, i, c, s, ag);
-        w[2] += sr * qd;
-        v[2] += st * qd;
-        const T a = sr * qd, b = st * qd;
-        dw[0] += a * w[1];
-        dw[1] -= a * w[0];
-        dw[2] += sr * qdd;
-        dv[0] = dv[0] + a * v[1] + b * w[1];
-        dv[1] = dv[1] - a * v[0] - b * w[0];
-        dv[2] += st * qdd;
-        if (has_tip) wrench_to_child(rb, i, c, s, d, tn, tf);
-        T n[3], f[3], dn[3], df[3];
-        inertia_mul<T, N, GEN>(rb, i, w, v, n, f);
-        inertia_mul<T, N, GEN>(rb, i, dw, dv, dn, df);
-        Fn[0] = dn[0] + w[1] * n[2] - w[2] * n[1] + v[1] * f[2] - v[2] * f[1];
-        Fn[1] = dn[1] + w[2] * n[0] - w[0] * n[2] + v[2] * f[0] - v[0] * f[2];
-        Fn[2] = dn[2] + w[0] * n[1] - w[1] * n[0] + v[0] * f[1] - v[1] * f[0];
-        Ff[0] = df[0] + w[1] * f[2] - w[2] * f[1];
-        Ff[1] = df[1] + w[2] * f[0] - w[0] * f[2];
-        Ff[2] = df[2] + w[0] * f[1] - w[1] * f[0];
-        if (GEN) {
-            const T mg = rb.mg[i];
-            const T *cg = rb.cg[i];
-            const T fx = mg * ag[0], fy = mg * ag[1], fz = mg * ag[2];
-            Ff[0] += fx;
-            Ff[1] += fy;
-            Ff[2] += fz;
-            Fn[0] = Fn[0] + cg[1] * fz - cg[2] * fy;
-            Fn[1] = Fn[1] + cg[2] * fx - cg[0] * fz;
-            Fn[2] = Fn[2] + cg[0] * fy - cg[1] * fx;
-        }
-        if (i < N - 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                st_.put(i, k, Fn[k]);
-                st_.put(i, 3 + k, Ff[k]);
-            }
-        }
-    }
-    // backward pass, starting from the last link's wrench and rotation still in registers
-    T an[3] = {Fn[0] + tn[0], Fn[1] + tn[1], Fn[2] + tn[2]};
-    T af[3] = {Ff[0] + tf[0], Ff[1] + tf[1], Ff[2] + tf[2]};
-#pragma unroll 1
-    for (int j = N - 1; j >= 1; --j) {
-        out.put(j, rb.sr[j] * an[2] + rb.st[j] * af[2]);
-        if (j < N - 1) st_.get_cs(rb, j, c, s, d);
-        T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};
-        T bf[3] = {st_.get(j - 1, 3), st_.get(j - 1, 4), st_.get(j - 1, 5)};
-        wrench_to_parent_acc(rb, j, c, s, d, an, af, bn, bf);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            an[k] = bn[k];
-            af[k] = bf[k];
-        }
-    }
-    out.put(0, rb.sr[0] * an[2] + rb.st[0] * af[2]);
-}
-
-// Register-resident convenience form over arrays; `q` receives the joint sines / cosines.
-template <typename T, int N, bool GEN>
+// Register-resident convenience form over arrays; `q` receives the joint rotations.
+template <typename T, int N, bool GEN, bool REV>
 MPK_HD void rnea(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N], const T (&ddth)[N],
-                 const T (&g)[3], const T *ftip, T (&tau)[N], JointCS<T, N> &q) {
+                 const T (&g0)[3], const T *ftip, T (&tau)[N], JointCS<T, N> &q) {
     RegStore<T, N> st_;
     ArrayIn<T, N> in{th, dth, ddth};
-    rnea<T, N, GEN>(rb, in, g, ftip, tau, st_);
+    rnea<T, N, GEN, REV>(rb, in, g0, ftip, tau, st_);
     q = st_.q;
 }
 
 // ---- composite rigid body algorithm (rigid inertias) -------------------------
+// Rotation of a symmetric 3x3 in the (p, q) plane (r the third axis):  p' = c p - s q,
+// q' = s p + c q.
+template <typename T>
+MPK_HD void rot_inertia(T c, T s, T &pp, T &qq, T &pq, T &pr, T &qr) {
+    const T cc = c * c, ss = s * s, cs2 = T(2) * (c * s);
+    const T dpq = pp - qq;
+    const T pp1 = cc * pp - cs2 * pq + ss * qq;
+    const T qq1 = ss * pp + cs2 * pq + cc * qq;
+    pq = T(0.5) * cs2 * dpq + (cc - ss) * pq;
+    pp = pp1;
+    qq = qq1;
+    rot(c, s, pr, qr);
+}
+
+// Composite inertia (I about the origin, h = m c, m) of frame i coordinates -> frame i-1
+// coordinates:  Tz(dz), Rz, [Ry], Rx, Tx(a).  A shift of the coordinates by p maps
+// I -> I + 2 (q.p) 1 - (q p^T + p q^T), q = h + m p / 2, and h -> h + m p.
+template <typename T, int N, bool HAY = true>
+MPK_HD void inertia_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&I)[6], T (&h)[3],
+                              T m) {
+    {
+        const T t = m * dz;
+        const T e = (T(2) * h[2] + t) * dz;
+        I[0] += e;
+        I[3] += e;
+        I[2] -= h[0] * dz;
+        I[4] -= h[1] * dz;
+        h[2] += t;
+    }
+    rot_inertia(c, s, I[0], I[3], I[1], I[2], I[4]);
+    rot(c, s, h[0], h[1]);
+    if (HAY && rb.sb[i] != T(0)) {
+        rot_inertia(rb.cb[i], rb.sb[i], I[5], I[0], I[2], I[4], I[1]);
+        rot(rb.cb[i], rb.sb[i], h[2], h[0]);
+    }
+    rot_inertia(rb.ca[i], rb.sa[i], I[3], I[5], I[4], I[1], I[2]);
+    rot(rb.ca[i], rb.sa[i], h[1], h[2]);
+    {
+        const T a = rb.a[i];
+        const T t = m * a;
+        const T e = (T(2) * h[0] + t) * a;
+        I[3] += e;
+        I[5] += e;
+        I[1] -= h[1] * a;
+        I[2] -= h[2] * a;
+        h[0] += t;
+    }
+}
+
 // M[i][j] for j <= i is written to Mm[i][j] AND Mm[j][i].  Matches the reference's
 // sym(sum_k J_k^T G_k J_k) (dynamics/mass_matrix.py:62-96).
-template <typename T, int N>
-MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
-                                     T (&Mm)[N][N]) {
-    // composite inertia of links i..N-1 in frame i: (I about origin, h = m*com, m)
+template <typename T, int N, bool REV>
+MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T (&Mm)[N][N]) {
+    // composite inertia of links i..N-1 in frame i
     T I[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, h[3] = {T(0), T(0), T(0)}, m = T(0);
 #pragma unroll
     for (int i = N - 1; i >= 0; --i) {
@@ -563,83 +653,34 @@ MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
         for (int k = 0; k < 3; ++k) h[k] += rb.h[i][k];
         m += rb.m[i];
         // column i: F = Ic A_i
-        const T sr = rb.sr[i], st = rb.st[i];
         T n[3], f[3];
-        n[0] = sr * I[2] + st * h[1];
-        n[1] = sr * I[4] - st * h[0];
-        n[2] = sr * I[5];
-        f[0] = -sr * h[1];
-        f[1] = sr * h[0];
-        f[2] = st * m;
-        Mm[i][i] = sr * n[2] + st * f[2];
+        if (REV) {
+            n[0] = I[2]; n[1] = I[4]; n[2] = I[5];
+            f[0] = -h[1]; f[1] = h[0]; f[2] = T(0);
+            Mm[i][i] = n[2];
+        } else {
+            const T sr = rb.sr[i], st = rb.st[i];
+            n[0] = sr * I[2] + st * h[1];
+            n[1] = sr * I[4] - st * h[0];
+            n[2] = sr * I[5];
+            f[0] = -sr * h[1];
+            f[1] = sr * h[0];
+            f[2] = st * m;
+            Mm[i][i] = sr * n[2] + st * f[2];
+        }
 #pragma unroll
         for (int j = i; j > 0; --j) {
-            wrench_to_parent(rb, j, q.c[j], q.s[j], q.d[j], n, f);
-            const T mij = rb.sr[j - 1] * n[2] + rb.st[j - 1] * f[2];
+            T mij;
+            if (REV && j == 1) {
+                mij = wrench_to_parent_nz<T, N, !REV>(rb, 1, q.c[1], q.s[1], q.d[1], n, f, T(0));
+            } else {
+                wrench_to_parent<T, N, !REV>(rb, j, q.c[j], q.s[j], q.d[j], n, f);
+                mij = REV ? n[2] : rb.sr[j - 1] * n[2] + rb.st[j - 1] * f[2];
+            }
             Mm[i][j - 1] = mij;
             Mm[j - 1][i] = mij;
         }
-        if (i > 0) {
-            // re-express the composite in frame i-1: pose (R, p) = X_i * Jz(theta_i)
-            const T c = q.c[i], s = q.s[i];
-            // rotate by Rz:  I <- Rz I Rz^T, h <- Rz h
-            {
-                const T cc = c * c, ss = s * s, cs = c * s;
-                const T xx = I[0], xy = I[1], xz = I[2], yy = I[3], yz = I[4];
-                I[0] = cc * xx - T(2) * cs * xy + ss * yy;
-                I[3] = ss * xx + T(2) * cs * xy + cc * yy;
-                I[1] = cs * (xx - yy) + (cc - ss) * xy;
-                I[2] = c * xz - s * yz;
-                I[4] = s * xz + c * yz;
-                const T hx = h[0], hy = h[1];
-                h[0] = c * hx - s * hy;
-                h[1] = s * hx + c * hy;
-            }
-            if (rb.st[i] != T(0)) {
-                // shift origin by p = (0,0,d): I += 2(q.p) 1 - (p q^T + q p^T), q = h + m p / 2
-                const T d = q.d[i];
-                const T qz = h[2] + T(0.5) * m * d;
-                const T qp2 = T(2) * qz * d;
-                I[0] += qp2;
-                I[3] += qp2;
-                I[2] -= d * h[0];
-                I[4] -= d * h[1];
-                // zz: 2 qz d - 2 d qz = 0
-                h[2] += m * d;
-            }
-            // rotate by Rx: B = R I ; I <- B R^T ; h <- R h
-            const T *R = rb.Rx[i];
-            const T *p = rb.px[i];
-            T Bm[3][3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                Bm[r][0] = R[3 * r] * I[0] + R[3 * r + 1] * I[1] + R[3 * r + 2] * I[2];
-                Bm[r][1] = R[3 * r] * I[1] + R[3 * r + 1] * I[3] + R[3 * r + 2] * I[4];
-                Bm[r][2] = R[3 * r] * I[2] + R[3 * r + 1] * I[4] + R[3 * r + 2] * I[5];
-            }
-            T J0 = Bm[0][0] * R[0] + Bm[0][1] * R[1] + Bm[0][2] * R[2];
-            T J1 = Bm[0][0] * R[3] + Bm[0][1] * R[4] + Bm[0][2] * R[5];
-            T J2 = Bm[0][0] * R[6] + Bm[0][1] * R[7] + Bm[0][2] * R[8];
-            T J3 = Bm[1][0] * R[3] + Bm[1][1] * R[4] + Bm[1][2] * R[5];
-            T J4 = Bm[1][0] * R[6] + Bm[1][1] * R[7] + Bm[1][2] * R[8];
-            T J5 = Bm[2][0] * R[6] + Bm[2][1] * R[7] + Bm[2][2] * R[8];
-            const T hx = R[0] * h[0] + R[1] * h[1] + R[2] * h[2];
-            const T hy = R[3] * h[0] + R[4] * h[1] + R[5] * h[2];
-            const T hz = R[6] * h[0] + R[7] * h[1] + R[8] * h[2];
-            // shift origin by p: q = h + m p / 2
-            const T hm = T(0.5) * m;
-            const T qx = hx + hm * p[0], qy = hy + hm * p[1], qz = hz + hm * p[2];
-            const T qp2 = T(2) * (qx * p[0] + qy * p[1] + qz * p[2]);
-            I[0] = J0 + qp2 - T(2) * p[0] * qx;
-            I[1] = J1 - (p[0] * qy + qx * p[1]);
-            I[2] = J2 - (p[0] * qz + qx * p[2]);
-            I[3] = J3 + qp2 - T(2) * p[1] * qy;
-            I[4] = J4 - (p[1] * qz + qy * p[2]);
-            I[5] = J5 + qp2 - T(2) * p[2] * qz;
-            h[0] = hx + m * p[0];
-            h[1] = hy + m * p[1];
-            h[2] = hz + m * p[2];
-        }
+        if (i > 0) inertia_to_parent<T, N, !REV>(rb, i, q.c[i], q.s[i], q.d[i], I, h, m);
     }
 }
 
@@ -656,7 +697,7 @@ MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb, const T (&th)[N], T (
 #pragma unroll
         for (int i = 0; i < N; ++i) e[i] = (i == j) ? T(1) : T(0);
         JointCS<T, N> q;
-        rnea<T, N, true>(rb, th, zero, e, g0, nullptr, col, q);
+        rnea<T, N, true, false>(rb, th, zero, e, g0, nullptr, col, q);
 #pragma unroll
         for (int i = 0; i < N; ++i) Mm[i][j] = col[i];
     }
@@ -670,11 +711,11 @@ MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb, const T (&th)[N], T (
         }
 }
 
-template <typename T, int N, bool GEN>
+template <typename T, int N, bool GEN, bool REV>
 MPK_HD void mass_matrix(const RobotPack<T, N> &rb, const T (&th)[N], const JointCS<T, N> &q,
                         T (&Mm)[N][N]) {
     if (GEN) mass_matrix_general<T, N>(rb, th, Mm);
-    else crba<T, N>(rb, q, Mm);
+    else crba<T, N, REV>(rb, q, Mm);
 }
 
 // Solve M x = b in place (b <- x) with an unrolled LDL^T; M symmetric positive definite
@@ -710,18 +751,18 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
 }
 
 // ddtheta = M(theta)^-1 (tau - rnea(theta, dtheta, 0, g, Ftip))  (dynamics/id_fd.py:50-83).
-template <typename T, int N, bool GEN>
+template <typename T, int N, bool GEN, bool REV>
 MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N],
-                             const T (&tau)[N], const T (&g)[3], const T *ftip, T (&dd)[N]) {
+                             const T (&tau)[N], const T (&g0)[3], const T *ftip, T (&dd)[N]) {
     JointCS<T, N> q;
     T zero[N], bias[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) zero[i] = T(0);
-    rnea<T, N, GEN>(rb, th, dth, zero, g, ftip, bias, q);
+    rnea<T, N, GEN, REV>(rb, th, dth, zero, g0, ftip, bias, q);
 #pragma unroll
     for (int i = 0; i < N; ++i) dd[i] = tau[i] - bias[i];
     T Mm[N][N];
-    mass_matrix<T, N, GEN>(rb, th, q, Mm);
+    mass_matrix<T, N, GEN, REV>(rb, th, q, Mm);
     ldlt_solve<T, N>(Mm, dd);
 }
 
@@ -729,45 +770,39 @@ MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const 
 // World pose of frame i accumulated along the chain; Jacobian column i = Ad(T_{0,i}) A_i.
 // Tout: row-major 4x4 (16), Jout: row-major (6, N); either may be nullptr.
 template <typename T, int N>
-MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
-                                            T *Tout, T *Jout) {
-    T R[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
-    T p[3] = {T(0), T(0), T(0)};
+MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T *Tout, T *Jout) {
+    // columns of the world rotation of the current frame, and its origin
+    T X[3] = {rb.Rb[0], rb.Rb[3], rb.Rb[6]}, Y[3] = {rb.Rb[1], rb.Rb[4], rb.Rb[7]},
+      Z[3] = {rb.Rb[2], rb.Rb[5], rb.Rb[8]};
+    T p[3] = {rb.pb[0], rb.pb[1], rb.pb[2]};
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-        const T *X = rb.Rx[i];
-        const T *px = rb.px[i];
-        T Rn[9];
+        if (i > 0) {
+            const T a = rb.a[i], ca = rb.ca[i], sa = rb.sa[i];
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            p[r] += R[3 * r] * px[0] + R[3 * r + 1] * px[1] + R[3 * r + 2] * px[2];
+            for (int r = 0; r < 3; ++r) {
+                p[r] += a * X[r];
+                rot_t(ca, sa, Y[r], Z[r]);  // R Rx(alpha): Y' = ca Y + sa Z, Z' = ca Z - sa Y
+            }
+            if (rb.sb[i] != T(0)) {
 #pragma unroll
-            for (int cidx = 0; cidx < 3; ++cidx)
-                Rn[3 * r + cidx] =
-                    R[3 * r] * X[cidx] + R[3 * r + 1] * X[3 + cidx] + R[3 * r + 2] * X[6 + cidx];
+                for (int r = 0; r < 3; ++r) rot_t(rb.cb[i], rb.sb[i], Z[r], X[r]);  // R Ry(beta)
+            }
         }
         if (Jout) {
             const T sr = rb.sr[i], st = rb.st[i];
-            const T zx = Rn[2], zy = Rn[5], zz = Rn[8];
-            Jout[0 * N + i] = sr * zx;
-            Jout[1 * N + i] = sr * zy;
-            Jout[2 * N + i] = sr * zz;
-            Jout[3 * N + i] = sr * (p[1] * zz - p[2] * zy) + st * zx;
-            Jout[4 * N + i] = sr * (p[2] * zx - p[0] * zz) + st * zy;
-            Jout[5 * N + i] = sr * (p[0] * zy - p[1] * zx) + st * zz;
+            Jout[0 * N + i] = sr * Z[0];
+            Jout[1 * N + i] = sr * Z[1];
+            Jout[2 * N + i] = sr * Z[2];
+            Jout[3 * N + i] = sr * (p[1] * Z[2] - p[2] * Z[1]) + st * Z[0];
+            Jout[4 * N + i] = sr * (p[2] * Z[0] - p[0] * Z[2]) + st * Z[1];
+            Jout[5 * N + i] = sr * (p[0] * Z[1] - p[1] * Z[0]) + st * Z[2];
         }
-        const T c = q.c[i], s = q.s[i];
+        const T c = q.c[i], s = q.s[i], dz = q.d[i];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            R[3 * r] = c * Rn[3 * r] + s * Rn[3 * r + 1];
-            R[3 * r + 1] = c * Rn[3 * r + 1] - s * Rn[3 * r];
-            R[3 * r + 2] = Rn[3 * r + 2];
-        }
-        if (rb.st[i] != T(0)) {
-            const T d = q.d[i];
-            p[0] += d * R[2];
-            p[1] += d * R[5];
-            p[2] += d * R[8];
+            rot_t(c, s, X[r], Y[r]);  // R Rz(psi): X' = c X + s Y, Y' = c Y - s X
+            p[r] += dz * Z[r];
         }
     }
     if (Tout) {
@@ -775,10 +810,8 @@ MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q,
         for (int r = 0; r < 3; ++r) {
 #pragma unroll
             for (int cidx = 0; cidx < 3; ++cidx)
-                Tout[4 * r + cidx] = R[3 * r] * rb.Ree[cidx] + R[3 * r + 1] * rb.Ree[3 + cidx] +
-                                     R[3 * r + 2] * rb.Ree[6 + cidx];
-            Tout[4 * r + 3] =
-                p[r] + R[3 * r] * rb.pee[0] + R[3 * r + 1] * rb.pee[1] + R[3 * r + 2] * rb.pee[2];
+                Tout[4 * r + cidx] = X[r] * rb.Ree[cidx] + Y[r] * rb.Ree[3 + cidx] + Z[r] * rb.Ree[6 + cidx];
+            Tout[4 * r + 3] = p[r] + X[r] * rb.pee[0] + Y[r] * rb.pee[1] + Z[r] * rb.pee[2];
         }
         Tout[12] = T(0);
         Tout[13] = T(0);

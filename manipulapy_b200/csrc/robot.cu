@@ -3,14 +3,23 @@
 //
 // mpk_robot_create re-expresses the reference's constant pack (S_list, M, Glist,
 // Mlist_per_link; dynamics/manipulator_dynamics.py:46-75) in joint-aligned link
-// frames (see mpk_device.cuh).  For joint i with space screw S_i = (w, v) at the
-// home configuration:
-//   revolute (|w| = 1): frame origin q = w x v (the point of the axis closest to the
-//       space origin), z = w; the pitch w.v must be 0 (helical joints are rejected);
-//   prismatic (w = 0):  z = v/|v|, origin at the space origin, st = |v|.
-// With F_i that home pose,  e^{[S_i] th} F_i = F_i Jz(th), so
-//   prod_j e^{[S_j] th_j} = prod_j (X_j Jz(th_j)) F_n^{-1},   X_j = F_{j-1}^{-1} F_j,
-// which is the identity the kernels rely on.
+// frames (see mpk_device.cuh).  Joint i with space screw S_i = (w, v) at the home
+// configuration defines a line:
+//   revolute (|w| = 1): direction z = w through q = w x v (the point of the axis closest to
+//       the space origin); the pitch w.v must be 0 (helical joints are rejected);
+//   prismatic (w = 0):  direction z = v/|v|, st = |v|; the line's position is free and is
+//       put through the previous axis.
+// Frame i has its z axis on line i.  Its x axis and origin are chosen from the NEXT line the
+// way Denavit and Hartenberg do (x_i along the common normal of lines i and i+1, origin at
+// its foot), or, when the two lines are nearly parallel (|z_i x z_{i+1}| < 0.1, where the
+// common normal is ill-conditioned or undefined), the way Hayati does (origin kept where the
+// previous normal met line i, x_i towards the point where line i+1 pierces the plane through
+// that origin normal to z_i).  Either way the home pose of frame i in frame i-1 is exactly
+//   X_i = Tx(a_i) Rx(alpha_i) Ry(beta_i) Rz(phi_i) Tz(d_i),   beta_i = 0 in the D-H case,
+// and with F_i the home pose of frame i in space,  e^{[S_i] th} F_i = F_i Jz(th), so
+//   prod_j e^{[S_j] th_j} = F_0 Jz(th_0) prod_{j>=1} (X_j Jz(th_j)) F_{n-1}^{-1},
+// which is the identity the kernels rely on.  The factorisation is verified against
+// F_{i-1}^{-1} F_i before the pack is accepted.
 #include <cmath>
 #include <cstring>
 
@@ -111,6 +120,183 @@ void frame_from_z(const double *z, double *R) {
     }
 }
 
+double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+SE3 frame_from_axes(const double *x, const double *z, const double *o) {
+    SE3 F;
+    double y[3];
+    cross(z, x, y);
+    for (int r = 0; r < 3; ++r) {
+        F.R[3 * r] = x[r];
+        F.R[3 * r + 1] = y[r];
+        F.R[3 * r + 2] = z[r];
+        F.p[r] = o[r];
+    }
+    return F;
+}
+
+SE3 rot_x(double c, double s) {
+    SE3 o = identity();
+    o.R[4] = c; o.R[5] = -s; o.R[7] = s; o.R[8] = c;
+    return o;
+}
+SE3 rot_y(double c, double s) {
+    SE3 o = identity();
+    o.R[0] = c; o.R[2] = s; o.R[6] = -s; o.R[8] = c;
+    return o;
+}
+SE3 rot_z(double c, double s) {
+    SE3 o = identity();
+    o.R[0] = c; o.R[1] = -s; o.R[3] = s; o.R[4] = c;
+    return o;
+}
+SE3 trans(double x, double y, double z) {
+    SE3 o = identity();
+    o.p[0] = x; o.p[1] = y; o.p[2] = z;
+    return o;
+}
+
+// One joint axis at the home configuration.
+struct Line {
+    double z[3], q[3];
+    bool prismatic;
+};
+
+// Link-frame construction (see the header comment).  F[i]: home pose of frame i in space.
+// Fills a, ca, sa, cb, sb, phi, d (and cphi, sphi) of the pack; returns the largest deviation
+// between the factored X_i and F_{i-1}^{-1} F_i.
+double build_frames(int n, Line *L, RobotPack<double, MPK_MAX_DOF> &pk, SE3 *F) {
+    double xin[3], r[3];  // x axis and point of line i handed over by the previous pair
+    {
+        double R0[9];
+        frame_from_z(L[0].z, R0);
+        for (int k = 0; k < 3; ++k) {
+            xin[k] = R0[3 * k];
+            if (L[0].prismatic) L[0].q[k] = 0.0;
+            r[k] = L[0].q[k];
+        }
+    }
+    double worst = 0.0;
+    SE3 Fprev = identity();
+    for (int i = 0; i < n; ++i) {
+        double x[3], o[3], xin_next[3] = {0, 0, 0}, r_next[3] = {0, 0, 0};
+        double a = 0, ca = 1, sa = 0, cb = 1, sb = 0;
+        if (i + 1 < n) {
+            Line &A = L[i], &Bn = L[i + 1];
+            if (Bn.prismatic)
+                for (int k = 0; k < 3; ++k) Bn.q[k] = r[k];
+            double cr[3];
+            cross(A.z, Bn.z, cr);
+            const double sn = norm3(cr), cd = dot3(A.z, Bn.z);
+            if (sn >= 0.1) {
+                // Denavit-Hartenberg: x along the common normal, origin at its foot on line i
+                for (int k = 0; k < 3; ++k) x[k] = cr[k] / sn;
+                double dq[3] = {Bn.q[0] - A.q[0], Bn.q[1] - A.q[1], Bn.q[2] - A.q[2]};
+                a = dot3(dq, x);
+                const double d1 = dot3(dq, A.z), d2 = dot3(dq, Bn.z), den = 1.0 - cd * cd;
+                const double t1 = (d1 - cd * d2) / den, t2 = (cd * d1 - d2) / den;
+                for (int k = 0; k < 3; ++k) {
+                    o[k] = A.q[k] + t1 * A.z[k];
+                    r_next[k] = Bn.q[k] + t2 * Bn.z[k];
+                    xin_next[k] = x[k];
+                }
+                const double nrm = std::sqrt(sn * sn + cd * cd);
+                sa = sn / nrm;
+                ca = cd / nrm;
+            } else {
+                // Hayati: origin stays at the handed-over point; x towards the point where line
+                // i+1 pierces the plane through it normal to z_i
+                for (int k = 0; k < 3; ++k) o[k] = r[k];
+                double oq[3] = {o[0] - Bn.q[0], o[1] - Bn.q[1], o[2] - Bn.q[2]};
+                const double t = dot3(oq, A.z) / cd;
+                double perp[3];
+                for (int k = 0; k < 3; ++k) {
+                    r_next[k] = Bn.q[k] + t * Bn.z[k];
+                    perp[k] = r_next[k] - o[k];
+                }
+                const double pz = dot3(perp, A.z);
+                for (int k = 0; k < 3; ++k) perp[k] -= pz * A.z[k];
+                a = norm3(perp);
+                if (a > 1e-12) {
+                    for (int k = 0; k < 3; ++k) x[k] = perp[k] / a;
+                } else {
+                    a = 0.0;
+                    for (int k = 0; k < 3; ++k) x[k] = xin[k];
+                }
+                double y[3];
+                cross(A.z, x, y);
+                double zx = dot3(Bn.z, x);
+                const double zy = dot3(Bn.z, y), zz = dot3(Bn.z, A.z);
+                if (std::fabs(zx) < 1e-14) zx = 0.0;
+                sb = zx;
+                cb = std::sqrt(1.0 - sb * sb);
+                const double nrm = std::sqrt(zy * zy + zz * zz);
+                sa = -zy / nrm;
+                ca = zz / nrm;
+                if (std::fabs(sa) < 1e-14) {  // exactly parallel (or anti-parallel) lines
+                    sa = 0.0;
+                    ca = ca > 0 ? 1.0 : -1.0;
+                }
+                // x axis handed to frame i+1: Rx(alpha) Ry(beta) e_x in frame-i coordinates
+                const double hx = cb, hy = sa * sb, hz = -ca * sb;
+                for (int k = 0; k < 3; ++k) xin_next[k] = hx * x[k] + hy * y[k] + hz * A.z[k];
+            }
+        } else {
+            for (int k = 0; k < 3; ++k) {
+                x[k] = xin[k];
+                o[k] = r[k];
+            }
+        }
+        // re-orthogonalise x against z (rounding) and build the frame
+        {
+            const double xz = dot3(x, L[i].z);
+            for (int k = 0; k < 3; ++k) x[k] -= xz * L[i].z[k];
+            const double nx = norm3(x);
+            for (int k = 0; k < 3; ++k) x[k] /= nx;
+        }
+        F[i] = frame_from_axes(x, L[i].z, o);
+        // offsets of this frame against what the previous pair handed over
+        double phi = 0.0, d = 0.0;
+        if (i > 0) {
+            double cx[3];
+            cross(xin, x, cx);
+            phi = std::atan2(dot3(cx, L[i].z), dot3(xin, x));
+            double ro[3] = {o[0] - r[0], o[1] - r[1], o[2] - r[2]};
+            d = dot3(ro, L[i].z);
+        }
+        pk.phi[i] = phi;
+        pk.d[i] = d;
+        pk.cphi[i] = std::cos(phi);
+        pk.sphi[i] = std::sin(phi);
+        if (i == 0) {
+            pk.a[0] = 0; pk.ca[0] = 1; pk.sa[0] = 0; pk.cb[0] = 1; pk.sb[0] = 0;
+            for (int k = 0; k < 9; ++k) pk.Rb[k] = F[0].R[k];
+            for (int k = 0; k < 3; ++k) pk.pb[k] = F[0].p[k];
+        } else {
+            // check the factorisation against the geometric relative pose
+            const SE3 X = mul(inverse(Fprev), F[i]);
+            const SE3 Y = mul(mul(mul(trans(pk.a[i], 0, 0), rot_x(pk.ca[i], pk.sa[i])),
+                                  mul(rot_y(pk.cb[i], pk.sb[i]), rot_z(pk.cphi[i], pk.sphi[i]))),
+                              trans(0, 0, d));
+            for (int k = 0; k < 9; ++k) worst = std::fmax(worst, std::fabs(X.R[k] - Y.R[k]));
+            for (int k = 0; k < 3; ++k) worst = std::fmax(worst, std::fabs(X.p[k] - Y.p[k]));
+        }
+        if (i + 1 < n) {
+            pk.a[i + 1] = a;
+            pk.ca[i + 1] = ca;
+            pk.sa[i + 1] = sa;
+            pk.cb[i + 1] = cb;
+            pk.sb[i + 1] = sb;
+        }
+        for (int k = 0; k < 3; ++k) {
+            xin[k] = xin_next[k];
+            r[k] = r_next[k];
+        }
+        Fprev = F[i];
+    }
+    return worst;
+}
+
 }  // namespace
 }  // namespace mpk
 
@@ -135,24 +321,25 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
     rb->has_dynamics = Glist != nullptr;
     bool rigid = true;
 
-    SE3 Fprev = identity();
+    Line lines[MPK_MAX_DOF];
+    bool all_rev = true;
     for (int i = 0; i < n; ++i) {
         double w[3], v[3];
         for (int r = 0; r < 3; ++r) {
             w[r] = S_list[r * n + i];
             v[r] = S_list[(r + 3) * n + i];
         }
-        SE3 F;
+        Line &ln = lines[i];
         const double nw = norm3(w), nv = norm3(v);
-        double sr, st;
         if (nw == 0.0) {
-            sr = 0.0;
-            st = nv;
-            double z[3] = {0, 0, 1};
+            all_rev = false;
+            ln.prismatic = true;
+            rb->pack.sr[i] = 0.0;
+            rb->pack.st[i] = nv;
+            ln.z[0] = 0; ln.z[1] = 0; ln.z[2] = 1;
             if (nv > 0.0)
-                for (int r = 0; r < 3; ++r) z[r] = v[r] / nv;
-            frame_from_z(z, F.R);
-            F.p[0] = F.p[1] = F.p[2] = 0.0;
+                for (int r = 0; r < 3; ++r) ln.z[r] = v[r] / nv;
+            ln.q[0] = ln.q[1] = ln.q[2] = 0.0;  // placed by build_frames
         } else {
             if (std::fabs(nw - 1.0) > 1e-9) {
                 delete rb;
@@ -161,10 +348,10 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
                                 " has a non-unit angular part; the reference's transform_from_twist "
                                 "(utils/se3.py:33-42) is only a rigid motion for unit omega or omega = 0");
             }
-            double z[3] = {w[0] / nw, w[1] / nw, w[2] / nw};
-            frame_from_z(z, F.R);
-            cross(z, v, F.p);  // q = w x v
-            double h = z[0] * v[0] + z[1] * v[1] + z[2] * v[2];
+            ln.prismatic = false;
+            for (int r = 0; r < 3; ++r) ln.z[r] = w[r] / nw;
+            cross(ln.z, v, ln.q);  // q = w x v
+            const double h = dot3(ln.z, v);
             if (std::fabs(h) > 1e-12 * (nv > 1.0 ? nv : 1.0)) {
                 delete rb;
                 return fail(MPK_EUNSUPPORTED,
@@ -172,15 +359,23 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
                                 " is helical (omega . v != 0); only revolute (v = -omega x q) and "
                                 "prismatic (omega = 0) joints are supported");
             }
-            sr = 1.0;
-            st = 0.0;
+            rb->pack.sr[i] = 1.0;
+            rb->pack.st[i] = 0.0;
         }
-        const SE3 X = mul(inverse(Fprev), F);
-        for (int k = 0; k < 9; ++k) rb->pack.Rx[i][k] = X.R[k];
-        for (int k = 0; k < 3; ++k) rb->pack.px[i][k] = X.p[k];
-        rb->pack.sr[i] = sr;
-        rb->pack.st[i] = st;
+    }
+    SE3 frames[MPK_MAX_DOF];
+    const double dev = build_frames(n, lines, rb->pack, frames);
+    if (!(dev < 1e-10)) {
+        delete rb;
+        return fail(MPK_EUNSUPPORTED, "link-frame factorisation failed (deviation " + std::to_string(dev) + ")");
+    }
+    rb->all_revolute = all_rev ? 1 : 0;
+    rb->plain = rb->all_revolute;
+    for (int i = 0; i < n; ++i)
+        if (rb->pack.sb[i] != 0.0) rb->plain = 0;
 
+    for (int i = 0; i < n; ++i) {
+        const SE3 &F = frames[i];
         if (Glist) {
             const double *G = Glist + 36 * i;
             double Gs[36];
@@ -247,9 +442,8 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
                 rb->pack.m[i] = m;
             }
         }
-        Fprev = F;
     }
-    const SE3 E = mul(inverse(Fprev), from_mat4(M));
+    const SE3 E = mul(inverse(frames[n - 1]), from_mat4(M));
     for (int k = 0; k < 9; ++k) rb->pack.Ree[k] = E.R[k];
     for (int k = 0; k < 3; ++k) rb->pack.pee[k] = E.p[k];
     rb->rigid = (rigid && !(flags & MPK_ROBOT_FORCE_GENERAL)) ? 1 : 0;
@@ -260,6 +454,7 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
 extern "C" void mpk_robot_destroy(mpk_robot *rb) { delete rb; }
 extern "C" int mpk_robot_dof(const mpk_robot *rb) { return rb ? rb->n : MPK_EINVAL; }
 extern "C" int mpk_robot_is_rigid(const mpk_robot *rb) { return rb ? rb->rigid : MPK_EINVAL; }
+extern "C" int mpk_robot_all_revolute(const mpk_robot *rb) { return rb ? rb->all_revolute : MPK_EINVAL; }
 
 // ---- FMA peak micro-benchmark ---------------------------------------------------
 template <typename T>

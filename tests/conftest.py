@@ -102,7 +102,7 @@ class HostCheck:
 
     def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None, smem_store=False):
         h, n = rb
-        fn = {0: self.H.hc_rnea, 1: self.H.hc_rnea_smem, 2: self.H.hc_rnea_rolled}[int(smem_store)]
+        fn = {0: self.H.hc_rnea, 1: self.H.hc_rnea_smem}[int(smem_store)]
         th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
         P = th.shape[0]
         cv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(P, n)

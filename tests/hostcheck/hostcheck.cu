@@ -9,54 +9,69 @@
 
 using namespace mpk;
 
-template <int N>
-static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
-                   const double *ddth, const double *g, const double *ftip, double *tau,
-                   int use_smem_store) {
+// flavour of the kernels this robot is routed to (csrc/dyn_kernels.cuh): 0 rigid + all
+// revolute, 1 rigid, 2 general inertias
+static int flavour(const mpk_robot *rb) { return !rb->rigid ? 2 : (rb->plain ? 0 : 1); }
+
+template <int N, bool GEN, bool REV>
+static void rnea_nf(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                    const double *ddth, const double *g, const double *ftip, double *tau,
+                    int use_smem_store) {
     const RobotPack<double, N> pk = narrow<N>(rb);
+    double g0[3];
+    base_gravity(pk, g, g0);
     for (int64_t p = 0; p < P; ++p) {
-        double a[N], b[N], c[N], t[N], g3[3] = {g[0], g[1], g[2]};
+        double a[N], b[N], c[N], t[N];
         for (int j = 0; j < N; ++j) {
             a[j] = th[p * N + j];
             b[j] = dth ? dth[p * N + j] : 0.0;
             c[j] = ddth ? ddth[p * N + j] : 0.0;
         }
-        if (use_smem_store == 2) {
-            // the rolled-loop form of the kernels (shared-memory store, torques through `out.put`)
-            double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
-            SmemStore<double, N, 1> st{buf};
-            ArrayIn<double, N> in{a, b, c};
-            struct { double *t; void put(int j, double x) { t[j] = x; } } out{t};
-            if (rb->rigid) rnea_rolled<double, N, false>(pk, in, g3, ftip, st, out);
-            else rnea_rolled<double, N, true>(pk, in, g3, ftip, st, out);
-        } else if (use_smem_store) {
+        if (use_smem_store) {
             // the shared-memory state store of the kernels, exercised with a one-thread "block"
             double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
             SmemStore<double, N, 1> st{buf};
             ArrayIn<double, N> in{a, b, c};
-            if (rb->rigid) rnea<double, N, false>(pk, in, g3, ftip, t, st);
-            else rnea<double, N, true>(pk, in, g3, ftip, t, st);
+            rnea<double, N, GEN, REV>(pk, in, g0, ftip, t, st);
         } else {
             JointCS<double, N> q;
-            if (rb->rigid) rnea<double, N, false>(pk, a, b, c, g3, ftip, t, q);
-            else rnea<double, N, true>(pk, a, b, c, g3, ftip, t, q);
+            rnea<double, N, GEN, REV>(pk, a, b, c, g0, ftip, t, q);
         }
         for (int j = 0; j < N; ++j) tau[p * N + j] = t[j];
     }
 }
 
 template <int N>
-static void mass_n(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
+static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                   const double *ddth, const double *g, const double *ftip, double *tau,
+                   int use_smem_store) {
+    switch (flavour(rb)) {
+        case 0: rnea_nf<N, false, true>(rb, P, th, dth, ddth, g, ftip, tau, use_smem_store); break;
+        case 1: rnea_nf<N, false, false>(rb, P, th, dth, ddth, g, ftip, tau, use_smem_store); break;
+        default: rnea_nf<N, true, false>(rb, P, th, dth, ddth, g, ftip, tau, use_smem_store); break;
+    }
+}
+
+template <int N, bool GEN, bool REV>
+static void mass_nf(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
     const RobotPack<double, N> pk = narrow<N>(rb);
     for (int64_t p = 0; p < P; ++p) {
         double a[N], Mm[N][N];
         for (int j = 0; j < N; ++j) a[j] = th[p * N + j];
         JointCS<double, N> q;
-        joint_cs(pk, a, q);
-        if (rb->rigid) mass_matrix<double, N, false>(pk, a, q, Mm);
-        else mass_matrix<double, N, true>(pk, a, q, Mm);
+        joint_cs<double, N, REV>(pk, a, q);
+        mass_matrix<double, N, GEN, REV>(pk, a, q, Mm);
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) Mo[(p * N + i) * N + j] = Mm[i][j];
+    }
+}
+
+template <int N>
+static void mass_n(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
+    switch (flavour(rb)) {
+        case 0: mass_nf<N, false, true>(rb, P, th, Mo); break;
+        case 1: mass_nf<N, false, false>(rb, P, th, Mo); break;
+        default: mass_nf<N, true, false>(rb, P, th, Mo); break;
     }
 }
 
@@ -72,21 +87,32 @@ static void fk_n(const mpk_robot *rb, int64_t P, const double *th, double *T, do
     }
 }
 
-template <int N>
-static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
-                 const double *tau, const double *g, const double *ftip_rows, double *dd) {
+template <int N, bool GEN, bool REV>
+static void fd_nf(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                  const double *tau, const double *g, const double *ftip_rows, double *dd) {
     const RobotPack<double, N> pk = narrow<N>(rb);
+    double g0[3];
+    base_gravity(pk, g, g0);
     for (int64_t p = 0; p < P; ++p) {
-        double a[N], b[N], c[N], o[N], g3[3] = {g[0], g[1], g[2]};
+        double a[N], b[N], c[N], o[N];
         for (int j = 0; j < N; ++j) {
             a[j] = th[p * N + j];
             b[j] = dth[p * N + j];
             c[j] = tau[p * N + j];
         }
         const double *ft = ftip_rows ? ftip_rows + 6 * p : nullptr;
-        if (rb->rigid) forward_dynamics<double, N, false>(pk, a, b, c, g3, ft, o);
-        else forward_dynamics<double, N, true>(pk, a, b, c, g3, ft, o);
+        forward_dynamics<double, N, GEN, REV>(pk, a, b, c, g0, ft, o);
         for (int j = 0; j < N; ++j) dd[p * N + j] = o[j];
+    }
+}
+
+template <int N>
+static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                 const double *tau, const double *g, const double *ftip_rows, double *dd) {
+    switch (flavour(rb)) {
+        case 0: fd_nf<N, false, true>(rb, P, th, dth, tau, g, ftip_rows, dd); break;
+        case 1: fd_nf<N, false, false>(rb, P, th, dth, tau, g, ftip_rows, dd); break;
+        default: fd_nf<N, true, false>(rb, P, th, dth, tau, g, ftip_rows, dd); break;
     }
 }
 
@@ -111,11 +137,6 @@ extern "C" int hc_rnea(const mpk_robot *rb, int64_t P, const double *th, const d
 extern "C" int hc_rnea_smem(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                             const double *ddth, const double *g, const double *ftip, double *tau) {
     HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, 1));
-    return 0;
-}
-extern "C" int hc_rnea_rolled(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
-                              const double *ddth, const double *g, const double *ftip, double *tau) {
-    HC_DISPATCH(rb->n, rnea_n<N_>(rb, P, th, dth, ddth, g, ftip, tau, 2));
     return 0;
 }
 extern "C" int hc_mass(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {

@@ -111,9 +111,6 @@ def test_kernel_algebra_vs_oracle_random(hostcheck, oracle_factory, robot):
         assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
         # the shared-memory state store used by the kernels gives the same bits as the register store
         assert np.array_equal(got, hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=1))
-        # the rolled-loop form differs only by rounding in link 0 (general transform of a zero twist)
-        rolled = hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=2)
-        assert np.max(np.abs(rolled - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
         Mref = o.mass_matrix(th[:50])
         assert np.abs(hostcheck.mass(rb, th[:50]) - Mref).max() < 1e-9 * max(1, np.abs(Mref).max())
         tau = rng.uniform(-20, 20, (50, n))
@@ -138,9 +135,6 @@ def test_general_inertia_and_prismatic_vs_oracle(hostcheck, n):
     assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
     assert np.abs(J - o.jacobian(th)).max() < 1e-12
     assert np.array_equal(hostcheck.rnea(rb, th, dth, ddth, g, ft), hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=1))
-    rolled = hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=2)
-    refa = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)
-    assert np.max(np.abs(rolled - refa) / np.maximum(1, np.abs(refa).max(1, keepdims=True))) < 1e-11
     for analytic, tol in ((True, 1e-11), (False, 1e-7)):  # literal path carries its finite-difference noise
         ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=analytic)
         got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
@@ -149,6 +143,95 @@ def test_general_inertia_and_prismatic_vs_oracle(hostcheck, n):
     assert np.abs(hostcheck.mass(rb, th) - Mref).max() < 1e-10 * max(1, np.abs(Mref).max())
     gref = o.gravity_forces(th, g)
     assert np.abs(hostcheck.rnea(rb, th, g=g) - gref).max() < 1e-10 * max(1, np.abs(gref).max())
+
+
+def _awkward_pack(kind, seed):
+    """Chains that stress the link-frame construction of csrc/robot.cu: consecutive axes that
+    are exactly parallel, coincident, nearly parallel (the Hayati branch, beta != 0), or
+    prismatic at either end."""
+    from conftest import random_general_pack
+
+    rng = np.random.default_rng(seed)
+    n = 5
+    p = random_general_pack(n, seed)
+    S = np.zeros((6, n))
+
+    def rev(w, q):
+        w = np.asarray(w, float) / np.linalg.norm(w)
+        return np.r_[w, -np.cross(w, q)]
+
+    def tilt(w, eps):
+        t = np.cross(w, rng.normal(size=3))
+        return w + eps * t / np.linalg.norm(t)
+
+    w0 = rng.normal(size=3)
+    w0 /= np.linalg.norm(w0)
+    q = lambda: rng.uniform(-0.5, 0.5, 3)
+    if kind == "parallel":
+        for i in range(n):
+            S[:, i] = rev(w0 if i % 2 == 0 else -w0, q())
+    elif kind == "coincident":
+        q0 = q()
+        S[:, 0] = rev(w0, q0)
+        S[:, 1] = rev(w0, q0 + 0.3 * w0)          # same line
+        S[:, 2] = rev(-w0, q0)                     # same line, opposite sense
+        S[:, 3] = rev(rng.normal(size=3), q0)      # intersecting it
+        S[:, 4] = rev(rng.normal(size=3), q())
+    elif kind.startswith("tilt"):
+        eps = float(kind[4:])
+        w = w0
+        for i in range(n):
+            S[:, i] = rev(w, q())
+            w = tilt(w / np.linalg.norm(w), eps)
+    elif kind == "prismatic_ends":
+        S[3:, 0] = w0 * 1.3
+        for i in range(1, n - 1):
+            S[:, i] = rev(rng.normal(size=3), q())
+        S[3:, n - 1] = S[:3, n - 2] * 0.8          # sliding along the previous axis
+    elif kind == "all_prismatic":
+        for i in range(n):
+            v = rng.normal(size=3)
+            S[3:, i] = v / np.linalg.norm(v) * (0.5 + i)
+    p["S_list"] = S
+    return p
+
+
+@pytest.mark.parametrize("rigid", [False, True], ids=["general", "rigid"])
+@pytest.mark.parametrize("kind", ["parallel", "coincident", "tilt1e-2", "tilt1e-5", "tilt1e-9", "tilt0.099",
+                                  "prismatic_ends", "all_prismatic"])
+def test_awkward_axis_arrangements_vs_oracle(hostcheck, kind, rigid):
+    from oracle import Oracle
+
+    p = _awkward_pack(kind, seed=7)
+    n = p["S_list"].shape[1]
+    if rigid:  # rigid bodies at their centres of mass: block-diagonal inertias
+        rng = np.random.default_rng(1)
+        G = np.zeros((n, 6, 6))
+        for i in range(n):
+            A = rng.normal(size=(3, 3))
+            G[i, :3, :3] = A @ A.T + 0.1 * np.eye(3)
+            G[i, 3:, 3:] = np.eye(3) * rng.uniform(0.5, 3.0)
+        p["Glist"] = G
+    o = Oracle(p["S_list"], p["M"], p["Glist"], p["Mlist_per_link"])
+    rb = hostcheck.robot(p)
+    assert hostcheck.L.mpk_robot_is_rigid(rb[0]) == int(rigid)
+    assert hostcheck.L.mpk_robot_all_revolute(rb[0]) == int("prismatic" not in kind)
+    rng = np.random.default_rng(3)
+    th, dth, ddth = rng.uniform(-2, 2, (30, n)), rng.uniform(-2, 2, (30, n)), rng.uniform(-3, 3, (30, n))
+    g, ft = np.array([1.0, 2.0, -9.0]), rng.uniform(-5, 5, 6)
+    T, J = hostcheck.fk(rb, th)
+    assert np.abs(T - o.forward_kinematics(th)).max() < 1e-12
+    assert np.abs(J - o.jacobian(th)).max() < 1e-12
+    ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)
+    got = hostcheck.rnea(rb, th, dth, ddth, g, ft)
+    assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-11
+    assert np.array_equal(got, hostcheck.rnea(rb, th, dth, ddth, g, ft, smem_store=1))
+    Mref = o.mass_matrix(th)
+    assert np.abs(hostcheck.mass(rb, th) - Mref).max() < 1e-10 * max(1, np.abs(Mref).max())
+    tau = rng.uniform(-20, 20, (30, n))
+    ref = o.forward_dynamics(th, dth, tau, g, ft, analytic=True)
+    got = hostcheck.fd(rb, th, dth, tau, g, np.tile(ft, (30, 1)))
+    assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-8
 
 
 def test_planar_2r_known_answers(hostcheck):
