@@ -18,9 +18,10 @@ range of the global batch), no data-path collective.
 `e2e`    : the same through the public host API (planner.trajectory_inverse_dynamics with
            NumPy endpoints in, NumPy float32 torques out): H2D + kernel + D2H per step.
 `roofline`: dominant kernel's algorithmic HBM bytes / its CUDA-event duration against the
-           measured copy bandwidth (MEASURED_PEAKS.json); the kernel is fp64-FMA bound, so
-           `roofline.fp64` carries the binding fraction against an FMA peak measured in
-           this same run.
+           measured copy bandwidth (MEASURED_PEAKS.json); the kernel is bound by the fp64
+           pipe, so `roofline.fp64` carries the binding fractions: executed flops against an
+           FMA peak measured in this same run, and executed fp64 instructions against the
+           pipe's issue rate (peak, and with three distinct register operands per FMA).
 `cpu_baseline` / `--impl reference`: the reference's algorithm (finite-difference Coriolis,
            sum_k Jk^T Gk Jk mass matrix; oracle/oracle.c literal port -- the reference itself
            is Python and cannot travel to the GPU box) on all host cores, on a bounded sample.
@@ -46,7 +47,12 @@ if str(REPO) not in sys.path:
 ROBOT, B_TRAJ, N_STEPS, TF, METHOD = "ur5", 4096, 2441, 2.0, 5
 METRIC, UNIT = "rnea_trajectory_points_per_s", "points/s"
 # algorithmic work per point (DESIGN.md "Kernels")
-FLOP_PER_POINT = 2070 + 60            # fp64 Newton-Euler recursion (n = 6) + time scaling
+FLOP_PER_POINT = 2070 + 60            # textbook fp64 Newton-Euler recursion (n = 6) + time scaling
+# what the fused kernel actually executes per point (ncu, profiles/r1_ncu_traj_rnea_dh.md):
+# 514 DFMA + 181 DMUL + 41 DADD = 736 fp64 instructions = 1250 flop (Denavit-Hartenberg frames,
+# centre-of-mass wrench form)
+FP64_INSTR_PER_POINT = {"fused": 736, "two_kernel": 712}
+FLOP_EXECUTED_PER_POINT = {"fused": 1250, "two_kernel": 1226}
 BYTES_FUSED = 6 * 4                   # float32 torque row out; endpoints amortised over 2441 points
 BYTES_RNEA = 3 * 6 * 4 + 6 * 4        # float32 theta, dtheta, ddtheta in; float32 torque out
 BYTES_TRAJ = 3 * 6 * 4                # float32 pos, vel, acc out
@@ -258,20 +264,41 @@ def run_ours(args) -> None:
     assert out.shape == (B, N_STEPS, 6) and out.dtype == np.float32
     clocks = sampler.stop() if sampler else None
 
-    # fp64 FMA peak measured in this run (register-resident dependent chains, 8 per thread)
+    # fp64 FMA peak measured in this run (register-resident dependent chains, 8 per thread), and
+    # the issue rate of FMAs with three DISTINCT register operands (what rigid-body algebra is
+    # made of): the register file feeds those at about 72 % of the pipe's peak rate
     sink = torch.zeros(1, dtype=torch.float64, device=dev)
     blocks, threads, iters = 148 * 8, 256, 1 << 15
-    ops.fma_peak(sink, 0, blocks, threads, 1024)
-    torch.cuda.synchronize()
-    best = 0.0
-    for _ in range(5):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ops.fma_peak(sink, 0, blocks, threads, iters)
-        b.record()
+
+    def fma_rate(mode):
+        ops.fma_peak(sink, mode << 8, blocks, threads, 1024)
         torch.cuda.synchronize()
-        best = max(best, blocks * threads * iters * 16 / (a.elapsed_time(b) / 1e3))
-    fp64_peak_tf = best / 1e12
+        best = 0.0
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ops.fma_peak(sink, mode << 8, blocks, threads, iters)
+            b.record()
+            torch.cuda.synchronize()
+            best = max(best, blocks * threads * iters * 8 / (a.elapsed_time(b) / 1e3))
+        return best  # fp64 thread-instructions / s
+
+    fp64_instr_peak = fma_rate(0)
+    fp64_instr_3reg = fma_rate(1)
+    fp64_peak_tf = 2 * fp64_instr_peak / 1e12
+
+    # PCIe device -> host rate of this box (pinned memory), the ceiling of the e2e number
+    pin = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    src = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    pin.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    pin.copy_(src, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    d2h_gbs = pin.numel() / (a.elapsed_time(b) / 1e3) / 1e9
+    del pin, src
 
     red = torch.tensor([t_dev, t_dom, t_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -287,7 +314,8 @@ def run_ours(args) -> None:
     hbm_peak, peak_src = _measured_peaks()
     dom_s = t_dom / args.steps
     achieved_gbs = dom_bytes * P / dom_s / 1e9
-    achieved_tf = FLOP_PER_POINT * P / dom_s / 1e12
+    achieved_tf = FLOP_EXECUTED_PER_POINT[args.mode] * P / dom_s / 1e12
+    instr_rate = FP64_INSTR_PER_POINT[args.mode] * P / dom_s
     cpu_rate, cores, cpu_pts, _ = cpu_reference_rate(args.cpu_sample_traj, 1, 0) if args.gpus == 1 and not args.no_cpu else (None, None, None, None)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -302,15 +330,25 @@ def run_ours(args) -> None:
                    "sharding": f"contiguous trajectory ranges, {world} rank(s), no data-path collective"},
         "clocks": clocks,
         "e2e": {"value": world * P * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * 6 * 8),
-                "d2h_bytes_per_step": int(P * 6 * 4), "api": "OptimizedTrajectoryPlanning.trajectory_inverse_dynamics"},
+                "d2h_bytes_per_step": int(P * 6 * 4), "api": "OptimizedTrajectoryPlanning.trajectory_inverse_dynamics",
+                "pcie_d2h_gbs_measured": d2h_gbs,
+                "pcie_bound_points_per_s": world * d2h_gbs * 1e9 / (6 * 4)},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": _traffic(dom_kernel), "peak_source": peak_src,
                      "algorithmic_bytes_per_point": dom_bytes, "kernel_ms": dom_s * 1e3,
-                     "binding": "fp64_fma",
+                     "binding": "fp64_pipe",
                      "fp64": {"achieved": achieved_tf, "peak": fp64_peak_tf, "unit": "TFLOP/s",
-                              "frac": achieved_tf / fp64_peak_tf, "flop_per_point": FLOP_PER_POINT,
-                              "peak_source": "mpk_fma_peak measured in this run"}},
+                              "frac": achieved_tf / fp64_peak_tf,
+                              "flop_per_point": FLOP_EXECUTED_PER_POINT[args.mode],
+                              "flop_per_point_textbook": FLOP_PER_POINT,
+                              "textbook_equivalent_tflops": FLOP_PER_POINT * P / dom_s / 1e12,
+                              "pipe_issue_frac": instr_rate / fp64_instr_peak,
+                              "pipe_issue_frac_vs_3_register_operand_rate": instr_rate / fp64_instr_3reg,
+                              "fp64_instr_per_point": FP64_INSTR_PER_POINT[args.mode],
+                              "instr_peak_per_s": fp64_instr_peak, "instr_3reg_rate_per_s": fp64_instr_3reg,
+                              "peak_source": "mpk_fma_peak measured in this run (mode 0: shared operands = "
+                                             "pipe peak; mode 1: three distinct register operands)"}},
     }
     if cpu_rate is not None:
         line["cpu_baseline"] = {

@@ -20,7 +20,10 @@
 namespace mpk {
 
 constexpr int kDynThreads = 128;
-constexpr int kRneaMinBlocks = 5;  // 96-register cap: 20 warps / SM hide the fp64 latency
+// 4 blocks (16 warps) per SM, 127-register cap.  Measured on B200 (profiles/r1_variants.md): 4, 5
+// and 6 resident blocks run the fused 6-DOF kernel within 2 % of each other -- the fp64 pipe, not
+// latency hiding, is the limit -- and the looser register cap gives the shortest code.
+constexpr int kRneaMinBlocks = 4;
 
 constexpr bool flavour_gen(int f) { return f == 2; }
 constexpr bool flavour_rev(int f) { return f == 0; }
@@ -98,12 +101,13 @@ template <int FLAVOUR> void launch_rollout(const mpk_robot *rb, const RolloutArg
         default: { constexpr int F_ = 2; CALL; } break; \
     }
 
-// Bytes of shared memory the RNEA kernels need for the per-link wrenches of one block.
-template <int N>
-constexpr size_t wrench_smem(int threads) {
-    const size_t link_state = (size_t)(N > 1 ? N - 1 : 0) * 8 * threads * sizeof(double);
-    const size_t rows = (size_t)threads * N * sizeof(float);  // output staging (fused kernel)
-    return link_state + rows;
+// Bytes of shared memory the RNEA kernels need per block: the per-link wrenches of the
+// recursion; the fused kernel re-uses the same bytes to stage its output rows.
+template <int N, bool GEN, bool REV>
+constexpr size_t wrench_smem() {
+    const size_t link_state = SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)>::kBytes;
+    const size_t rows = (size_t)kDynThreads * N * sizeof(float);
+    return link_state > rows ? link_state : rows;
 }
 
 // Launch with dynamic shared memory, asking for the largest shared-memory carveout so that
@@ -180,8 +184,8 @@ struct RowIn {
     }
 };
 
-template <int N, bool GEN, bool REV>
-__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
+template <int N, bool GEN, bool REV, int MINB = kRneaMinBlocks>
+__global__ void __launch_bounds__(kDynThreads, MINB)
     rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
     extern __shared__ __align__(16) double wsm[];
     const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
@@ -190,7 +194,7 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const double *ftp = load_tip(a.tip, p, ft);
     RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {0.0, 0.0, 0.0}};
     in.prefetch(0);
-    SmemStore<double, N, kDynThreads> st{wsm + threadIdx.x};
+    SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
     double tau[N];
     rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
     store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
@@ -215,13 +219,13 @@ struct TrajIn {
     }
 };
 
-template <int N, bool GEN, bool REV>
-__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
+template <int N, bool GEN, bool REV, int MINB = kRneaMinBlocks>
+__global__ void __launch_bounds__(kDynThreads, MINB)
     traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
-    // dynamic shared memory: [per-thread link state of the recursion | the block's output rows,
-    // staged for coalesced stores]
+    // dynamic shared memory: the per-thread link state of the recursion, then (same bytes) the
+    // block's output rows staged for coalesced stores
     extern __shared__ __align__(16) double wsm[];
-    float *sm = reinterpret_cast<float *>(wsm + SmemStore<double, N, kDynThreads>::kSlots * 8 * kDynThreads);
+    float *sm = reinterpret_cast<float *>(wsm);
     const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
     const bool live = p0 + threadIdx.x < a.P;
     int64_t b, t;
@@ -229,9 +233,10 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const int64_t rem = a.P - p0;
     const int cnt = (int)(rem < kDynThreads ? rem : kDynThreads) * N;
     const int64_t off = p0 * N;
-    // (tail threads of the last block recompute point 0: they take part in the barrier and
+    // (tail threads of the last block recompute point 0: they take part in the barriers and
     // their staged rows are never stored)
     TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
+    float out[N];
     {
         double ft[6];
         const double *ftp = nullptr;
@@ -240,17 +245,18 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
             for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
             ftp = ft;
         }
-        SmemStore<double, N, kDynThreads> st{wsm + threadIdx.x};
+        SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
         double tau[N];
         rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
-        float *row = sm + threadIdx.x * N;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            float x = (float)tau[j];
-            if (a.tlim.on) x = clip_f32(x, a.tlim.lo[j], a.tlim.hi[j]);
-            row[j] = x;
+            out[j] = (float)tau[j];
+            if (a.tlim.on) out[j] = clip_f32(out[j], a.tlim.lo[j], a.tlim.hi[j]);
         }
     }
+    __syncthreads();  // every thread is done with its link state: the bytes become the staging tile
+#pragma unroll
+    for (int j = 0; j < N; ++j) sm[threadIdx.x * N + j] = out[j];
     __syncthreads();
     tile_store(a.tau + off, sm, cnt);
 }

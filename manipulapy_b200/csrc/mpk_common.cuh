@@ -39,9 +39,13 @@ inline RobotPack<double, N> narrow(const mpk_robot *rb) {
         o.sphi[i] = s.sphi[i];
         for (int k = 0; k < 3; ++k) {
             o.h[i][k] = s.h[i][k];
+            o.com[i][k] = s.com[i][k];
             o.cg[i][k] = s.cg[i][k];
         }
-        for (int k = 0; k < 6; ++k) o.I[i][k] = s.I[i][k];
+        for (int k = 0; k < 6; ++k) {
+            o.I[i][k] = s.I[i][k];
+            o.Ic[i][k] = s.Ic[i][k];
+        }
         for (int k = 0; k < 21; ++k) o.G[i][k] = s.G[i][k];
         o.sr[i] = s.sr[i];
         o.st[i] = s.st[i];
@@ -56,6 +60,7 @@ inline RobotPack<double, N> narrow(const mpk_robot *rb) {
         o.pb[k] = s.pb[k];
         o.pee[k] = s.pee[k];
     }
+    for (int k = 0; k < 17; ++k) o.trig[k] = s.trig[k];
     return o;
 }
 

@@ -71,17 +71,60 @@ struct RobotPack {
     T I[N][6];             // rigid: rotational inertia about the frame-i origin (xx,xy,xz,yy,yz,zz)
     T h[N][3];             // rigid: mass * centre of mass (in frame i)
     T m[N];                // rigid: mass
+    T Ic[N][6];            // rigid: rotational inertia about the centre of mass, frame-i axes
+    T com[N][3];           // rigid: centre of mass in frame i
     T G[N][21];            // general: upper triangle (row-major) of the symmetric 6x6 inertia in frame i
     T cg[N][3];            // general: origin of the reference's link-CoM frame in frame i
     T mg[N];               // general: G[3,3] in the CoM frame, the mass the reference's gravity term uses
     T Ree[9], pee[3];      // end-effector home pose in frame n-1
+    T trig[17];            // coefficients of sincos_pack (fill_trig_table)
 };
 
 // ---- scalar helpers ---------------------------------------------------------
-// sin and cos together.  The CUDA library's float64 sincos() is already minimal on its fast
-// path (3-FMA reduction + two 7-term polynomials = 22 fp64 instructions, large arguments
-// handled by an out-of-line subroutine); a hand-written Cody-Waite + fdlibm-kernel version
-// was measured at the same fp64 count with more select instructions and was dropped.
+MPK_HD int64_t f64_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(x);
+#else
+    int64_t b;
+    memcpy(&b, &x, sizeof b);
+    return b;
+#endif
+}
+MPK_HD double bits_f64(int64_t b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double x;
+    memcpy(&x, &b, sizeof x);
+    return x;
+#endif
+}
+
+// Coefficient table of sincos_pack: [0] 2/pi, [1] 1.5 * 2^52, [2..4] -(pi/2) split in three
+// (fdlibm's pio2_1, pio2_2, pio2_2t), [5..10] fdlibm __kernel_sin S1..S6, [11..16]
+// __kernel_cos C1..C6.
+template <typename T>
+inline void fill_trig_table(T *t) {
+    t[0] = T(6.36619772367581382433e-01);
+    t[1] = T(6755399441055744.0);
+    t[2] = T(-1.57079632673412561417e+00);
+    t[3] = T(-6.07710050630396597660e-11);
+    t[4] = T(-2.02226624879595063154e-21);
+    t[5] = T(-1.66666666666666324348e-01);
+    t[6] = T(8.33333333332248946124e-03);
+    t[7] = T(-1.98412698298579493134e-04);
+    t[8] = T(2.75573137070700676789e-06);
+    t[9] = T(-2.50507602534068634195e-08);
+    t[10] = T(1.58969099521155010221e-10);
+    t[11] = T(4.16666666666666019037e-02);
+    t[12] = T(-1.38888888888741095749e-03);
+    t[13] = T(2.48015872894767294178e-05);
+    t[14] = T(-2.75573143513906633035e-07);
+    t[15] = T(2.08757232129817482790e-09);
+    t[16] = T(-1.13596475577881948265e-11);
+}
+
+// Library sin and cos together (used for arguments outside sincos_pack's range).
 MPK_HD void sincos_t(double x, double *sn, double *cs) {
 #ifdef __CUDA_ARCH__
     sincos(x, sn, cs);
@@ -98,6 +141,60 @@ MPK_HD void sincos_t(float x, float *s, float *c) {
     *c = cosf(x);
 #endif
 }
+
+// sin and cos of a joint angle, < 1 ulp-ish (fdlibm kernels on [-pi/4, pi/4] after a three-term
+// Cody-Waite reduction, exact for |x| < 1e5).  Same 21 fp64 operations as the CUDA library's
+// sincos(), but every coefficient is a constant-bank operand of its FMA (the library version
+// materialises its 14 coefficients with 28 UMOVs per call) and the quadrant logic is 4 selects
+// and 2 sign XORs: ~35 instructions per call instead of ~80, which matters because a 6-joint
+// inverse dynamics is only ~1600 instructions.
+// (one out-of-line copy per kernel: the library routine is ~400 instructions that the joint
+// range never executes)
+struct SinCos {
+    double s, c;
+};
+__host__ __device__ __noinline__ inline SinCos sincos_far(double x) {
+    SinCos r;
+    sincos_t(x, &r.s, &r.c);
+    return r;
+}
+
+template <typename T>
+MPK_HD void sincos_pack(const T *tc, double x, double *sn, double *cs) {
+    if (!(fabs(x) < 1e5)) {  // also NaN / inf
+        const SinCos far = sincos_far(x);  // (by value: the outputs never have their address taken)
+        *sn = far.s;
+        *cs = far.c;
+        return;
+    }
+    const double t = fma(x, (double)tc[0], (double)tc[1]);
+    const int k = (int)(uint32_t)f64_bits(t);  // round(x * 2/pi) sits in the low mantissa bits
+    const double kd = t - (double)tc[1];
+    double r = fma(kd, (double)tc[2], x);
+    r = fma(kd, (double)tc[3], r);
+    r = fma(kd, (double)tc[4], r);
+    const double z = r * r;
+    double ps = fma((double)tc[10], z, (double)tc[9]);
+    double pc = fma((double)tc[16], z, (double)tc[15]);
+    ps = fma(ps, z, (double)tc[8]);
+    pc = fma(pc, z, (double)tc[14]);
+    ps = fma(ps, z, (double)tc[7]);
+    pc = fma(pc, z, (double)tc[13]);
+    ps = fma(ps, z, (double)tc[6]);
+    pc = fma(pc, z, (double)tc[12]);
+    ps = fma(ps, z, (double)tc[5]);
+    pc = fma(pc, z, (double)tc[11]);
+    const double S = fma(z * r, ps, r);
+    const double C = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const bool swap = (k & 1) != 0;
+    const double s0 = swap ? C : S, c0 = swap ? S : C;
+    // quadrant signs: sin flips for k mod 4 in {2, 3}, cos for {1, 2}
+    const int64_t ss = (int64_t)(uint64_t)((uint32_t)k & 2u) << 62;
+    const int64_t sc = (int64_t)(uint64_t)(((uint32_t)k + 1u) & 2u) << 62;
+    *sn = bits_f64(f64_bits(s0) ^ ss);
+    *cs = bits_f64(f64_bits(c0) ^ sc);
+}
+MPK_HD void sincos_pack(const float *, float x, float *s, float *c) { sincos_t(x, s, c); }
 
 // Planar rotation of the pair (p, q) by the angle whose cosine / sine are (c, s):
 //   rot  : p' = c p - s q,  q' = s p + c q      (Rz on (x, y); Rx on (y, z); Ry on (z, x))
@@ -124,11 +221,11 @@ struct JointCS {
 template <typename T, int N, bool REV>
 MPK_HD void joint_rot(const RobotPack<T, N> &rb, int i, T th, T &c, T &s, T &dz) {
     if (REV) {
-        sincos_t(rb.phi[i] + th, &s, &c);
+        sincos_pack(rb.trig, rb.phi[i] + th, &s, &c);
         dz = rb.d[i];
     } else {
         if (rb.sr[i] != T(0)) {
-            sincos_t(rb.phi[i] + th, &s, &c);
+            sincos_pack(rb.trig, rb.phi[i] + th, &s, &c);
         } else {
             c = rb.cphi[i];
             s = rb.sphi[i];
@@ -359,6 +456,43 @@ MPK_HD void inertia_mul(const RobotPack<T, N> &rb, int i, const T (&w)[3], const
     }
 }
 
+// Net wrench (about the frame origin) that moves rigid link i with twist (w, v) and spatial
+// acceleration (dw, dv), through the centre of mass c:
+//   vc = v + w x c,  ac = dv + dw x c + w x vc,  f = m ac,  n = Ic dw + w x (Ic w) + c x f.
+// 51 operations (the spatial-inertia form G dV - ad(V)^T G V needs 66), and only 12 of them
+// are FMAs with three register operands -- the ones that run at 2/3 rate on the fp64 pipe.
+template <typename T, int N>
+MPK_HD void rigid_wrench(const RobotPack<T, N> &rb, int i, const T (&w)[3], const T (&v)[3],
+                         const T (&dw)[3], const T (&dv)[3], T (&n)[3], T (&f)[3]) {
+    const T *c = rb.com[i];
+    const T *J = rb.Ic[i];
+    const T m = rb.m[i];
+    const T vcx = v[0] + w[1] * c[2] - w[2] * c[1];
+    const T vcy = v[1] + w[2] * c[0] - w[0] * c[2];
+    const T vcz = v[2] + w[0] * c[1] - w[1] * c[0];
+    T ax = dv[0] + dw[1] * c[2] - dw[2] * c[1];
+    T ay = dv[1] + dw[2] * c[0] - dw[0] * c[2];
+    T az = dv[2] + dw[0] * c[1] - dw[1] * c[0];
+    ax = ax + w[1] * vcz - w[2] * vcy;
+    ay = ay + w[2] * vcx - w[0] * vcz;
+    az = az + w[0] * vcy - w[1] * vcx;
+    f[0] = m * ax;
+    f[1] = m * ay;
+    f[2] = m * az;
+    const T lx = J[0] * w[0] + J[1] * w[1] + J[2] * w[2];
+    const T ly = J[1] * w[0] + J[3] * w[1] + J[4] * w[2];
+    const T lz = J[2] * w[0] + J[4] * w[1] + J[5] * w[2];
+    T nx = J[0] * dw[0] + J[1] * dw[1] + J[2] * dw[2];
+    T ny = J[1] * dw[0] + J[3] * dw[1] + J[4] * dw[2];
+    T nz = J[2] * dw[0] + J[4] * dw[1] + J[5] * dw[2];
+    nx = nx + c[1] * f[2] - c[2] * f[1];
+    ny = ny + c[2] * f[0] - c[0] * f[2];
+    nz = nz + c[0] * f[1] - c[1] * f[0];
+    n[0] = nx + w[1] * lz - w[2] * ly;
+    n[1] = ny + w[2] * lx - w[0] * lz;
+    n[2] = nz + w[0] * ly - w[1] * lx;
+}
+
 // ---- inverse dynamics -------------------------------------------------------
 // Newton-Euler recursion in the joint-aligned frames (SURVEY.md App. C restated in those
 // frames).  Equals the reference's  M ddth + c + g + Js^T Ftip  (dynamics/id_fd.py:38-47)
@@ -395,24 +529,32 @@ struct RegStore {
         d = q.d[i];
     }
 };
-template <typename T, int N, int THREADS>
+// Whether rnea() takes the shortcut for link 0 (only the z moment about its own axis is
+// stored for it): a rigid, plain all-revolute chain of at least two links.
+constexpr bool rnea_fast0(bool GEN, bool REV, int N) { return REV && !GEN && N >= 2; }
+
+template <typename T, int N, int THREADS, bool FAST0 = false>
 struct SmemStore {
     T *base;  // shared memory + threadIdx.x; slot l = wrench of link l, (c, s) of link l + 1
-    static constexpr int kSlots = N > 1 ? N - 1 : 0;
-    static constexpr size_t kBytes = (size_t)kSlots * 8 * THREADS * sizeof(T);
-    MPK_HD void put(int i, int k, T v) { base[(i * 8 + k) * THREADS] = v; }
-    MPK_HD T get(int i, int k) const { return base[(i * 8 + k) * THREADS]; }
+    // values per thread: 8 per link 0..N-2; with FAST0 link 0 keeps 3 (its z moment and (c, s) of link 1)
+    static constexpr int kValues = N > 1 ? (FAST0 ? 3 + (N - 2) * 8 : (N - 1) * 8) : 0;
+    static constexpr size_t kBytes = (size_t)kValues * THREADS * sizeof(T);
+    static constexpr MPK_HD int at(int l, int k) {
+        return (FAST0 ? (l == 0 ? (k == 2 ? 0 : k - 5) : 3 + (l - 1) * 8 + k) : l * 8 + k) * THREADS;
+    }
+    MPK_HD void put(int i, int k, T v) { base[at(i, k)] = v; }
+    MPK_HD T get(int i, int k) const { return base[at(i, k)]; }
     template <bool REV>
     MPK_HD void put_cs(const RobotPack<T, N> &rb, int i, T c, T s, T d) {
         if (i == 0) return;
-        base[((i - 1) * 8 + 6) * THREADS] = c;
-        base[((i - 1) * 8 + 7) * THREADS] = (REV || rb.sr[i] != T(0)) ? s : d;
+        base[at(i - 1, 6)] = c;
+        base[at(i - 1, 7)] = (REV || rb.sr[i] != T(0)) ? s : d;
     }
     template <bool REV>
     MPK_HD void get_cs(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
-        const T x = base[((i - 1) * 8 + 7) * THREADS];
+        const T x = base[at(i - 1, 7)];
         if (REV || rb.sr[i] != T(0)) {
-            c = base[((i - 1) * 8 + 6) * THREADS];
+            c = base[at(i - 1, 6)];
             s = x;
             d = rb.d[i];
         } else {
@@ -444,7 +586,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                  St &st_) {
     // a rigid all-revolute chain: link 0 only contributes the z moment about its own axis, and
     // link 1 receives a twist with known zeros
-    constexpr bool FAST0 = REV && !GEN && N >= 2;
+    constexpr bool FAST0 = rnea_fast0(GEN, REV, N);
     T w[3], v[3], dw[3], dv[3];
     T ag[3];         // general path: -g in the current frame
     T tn[3], tf[3];  // tip wrench carried down to the last frame
@@ -517,17 +659,21 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                 dv[2] += st * qdd;
             }
         }
-        // F_i = G dV - ad(V)^T (G V) = G dV + [w x n + v x f ; w x f]
-        T n[3], f[3], dn[3], df[3];
-        inertia_mul<T, N, GEN>(rb, i, w, v, n, f);
-        inertia_mul<T, N, GEN>(rb, i, dw, dv, dn, df);
         T Fn[3], Ff[3];
-        Fn[0] = dn[0] + w[1] * n[2] - w[2] * n[1] + v[1] * f[2] - v[2] * f[1];
-        Fn[1] = dn[1] + w[2] * n[0] - w[0] * n[2] + v[2] * f[0] - v[0] * f[2];
-        Fn[2] = dn[2] + w[0] * n[1] - w[1] * n[0] + v[0] * f[1] - v[1] * f[0];
-        Ff[0] = df[0] + w[1] * f[2] - w[2] * f[1];
-        Ff[1] = df[1] + w[2] * f[0] - w[0] * f[2];
-        Ff[2] = df[2] + w[0] * f[1] - w[1] * f[0];
+        if (GEN) {
+            // F_i = G dV - ad(V)^T (G V) = G dV + [w x n + v x f ; w x f]
+            T n[3], f[3], dn[3], df[3];
+            inertia_mul<T, N, true>(rb, i, w, v, n, f);
+            inertia_mul<T, N, true>(rb, i, dw, dv, dn, df);
+            Fn[0] = dn[0] + w[1] * n[2] - w[2] * n[1] + v[1] * f[2] - v[2] * f[1];
+            Fn[1] = dn[1] + w[2] * n[0] - w[0] * n[2] + v[2] * f[0] - v[0] * f[2];
+            Fn[2] = dn[2] + w[0] * n[1] - w[1] * n[0] + v[0] * f[1] - v[1] * f[0];
+            Ff[0] = df[0] + w[1] * f[2] - w[2] * f[1];
+            Ff[1] = df[1] + w[2] * f[0] - w[0] * f[2];
+            Ff[2] = df[2] + w[0] * f[1] - w[1] * f[0];
+        } else {
+            rigid_wrench(rb, i, w, v, dw, dv, Fn, Ff);
+        }
         if (GEN) {
             const T mg = rb.mg[i];
             const T *cg = rb.cg[i];

@@ -319,6 +319,7 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
     std::memset(rb, 0, sizeof *rb);
     rb->n = n;
     rb->has_dynamics = Glist != nullptr;
+    fill_trig_table(rb->pack.trig);
     bool rigid = true;
 
     Line lines[MPK_MAX_DOF];
@@ -428,6 +429,13 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
                         for (int k = 0; k < 3; ++k) s += RI[3 * r + k] * Ci.R[3 * cc + k];
                         Ir[3 * r + cc] = s;
                     }
+                rb->pack.Ic[i][0] = Ir[0];
+                rb->pack.Ic[i][1] = 0.5 * (Ir[1] + Ir[3]);
+                rb->pack.Ic[i][2] = 0.5 * (Ir[2] + Ir[6]);
+                rb->pack.Ic[i][3] = Ir[4];
+                rb->pack.Ic[i][4] = 0.5 * (Ir[5] + Ir[7]);
+                rb->pack.Ic[i][5] = Ir[8];
+                for (int k = 0; k < 3; ++k) rb->pack.com[i][k] = c[k];
                 const double c2 = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
                 for (int r = 0; r < 3; ++r)
                     for (int cc = 0; cc < 3; ++cc)
@@ -457,17 +465,58 @@ extern "C" int mpk_robot_is_rigid(const mpk_robot *rb) { return rb ? rb->rigid :
 extern "C" int mpk_robot_all_revolute(const mpk_robot *rb) { return rb ? rb->all_revolute : MPK_EINVAL; }
 
 // ---- FMA peak micro-benchmark ---------------------------------------------------
-template <typename T>
-__global__ void fma_peak_kernel(int64_t iters, double *sink) {
-    T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
-    T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
-    const T m = T(0.999999), b = T(1e-7);
-    for (int64_t i = 0; i < iters; ++i) {
-        a0 = a0 * m + b; a1 = a1 * m + b; a2 = a2 * m + b; a3 = a3 * m + b;
-        a4 = a4 * m + b; a5 = a5 * m + b; a6 = a6 * m + b; a7 = a7 * m + b;
+// mode 0: 8 dependent chains a = a*m + b per thread, m and b shared (operand reuse: the
+//         datasheet-style peak);
+// mode 1: 12 registers rotating, x_k = fma(x_{k+1}, x_{k+2}, x_{k+3}): three DISTINCT register
+//         operands per instruction, like the rigid-body algebra of the kernels;
+// mode 2: mode 1 with one operand taken from the constant bank (a kernel parameter);
+// mode 3: the planar-rotation pattern of the kernels: DMUL + DFMA pairs on distinct registers.
+// All modes execute 16 flops per loop iteration per chain slot so the callers' flop count
+// (blocks * threads * iters * 16) holds: modes 1-3 run 8 instructions per iteration too.
+struct PeakConsts {
+    double k[8];
+};
+
+template <typename T, int MODE>
+__global__ void fma_peak_kernel(int64_t iters, double *sink, const __grid_constant__ PeakConsts pc) {
+    if (MODE == 0) {
+        T a0 = T(threadIdx.x) * T(1e-3), a1 = a0 + T(1), a2 = a0 + T(2), a3 = a0 + T(3);
+        T a4 = a0 + T(4), a5 = a0 + T(5), a6 = a0 + T(6), a7 = a0 + T(7);
+        const T m = T(0.999999), b = T(1e-7);
+        for (int64_t i = 0; i < iters; ++i) {
+            a0 = a0 * m + b; a1 = a1 * m + b; a2 = a2 * m + b; a3 = a3 * m + b;
+            a4 = a4 * m + b; a5 = a5 * m + b; a6 = a6 * m + b; a7 = a7 * m + b;
+        }
+        const T s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+        if (s == T(-1.2345)) sink[0] = (double)s;  // never true; keeps the chains alive
+    } else {
+        T x[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) x[k] = T(0.5) + T(threadIdx.x + k) * T(1e-4);
+        for (int64_t i = 0; i < iters; ++i) {
+            if (MODE == 1) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = x[k + 1] * x[k + 2] - x[k + 3];
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = x[k + 1] * T(pc.k[k]) - x[k + 3];
+            } else {
+                // 4 x (t = c*p (DMUL); p' = t - s*q (DFMA)): 8 instructions, 12 flops (counted as 16)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const T t = x[2 * k + 1] * x[2 * k + 2];
+                    x[2 * k] = t - x[2 * k + 3] * x[(2 * k + 5) % 12];
+                }
+            }
+            // rotate so that the next iteration's operands are other registers
+            const T t0 = x[8];
+            x[8] = x[9]; x[9] = x[10]; x[10] = x[11]; x[11] = x[0]; x[0] = t0;
+        }
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) s += x[k];
+        if (s == T(-1.2345)) sink[0] = (double)s;
     }
-    const T s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-    if (s == T(-1.2345)) sink[0] = (double)s;  // never true; keeps the chains alive
 }
 
 extern "C" int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, double *sink_dev,
@@ -475,8 +524,16 @@ extern "C" int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, d
     if (blocks <= 0 || threads <= 0 || threads > 1024 || iters < 0 || !sink_dev)
         return fail(MPK_EINVAL, "bad fma_peak arguments");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (dtype == MPK_F64) fma_peak_kernel<double><<<blocks, threads, 0, s>>>(iters, sink_dev);
-    else if (dtype == MPK_F32) fma_peak_kernel<float><<<blocks, threads, 0, s>>>(iters, sink_dev);
-    else return fail(MPK_EINVAL, "bad dtype");
+    const int mode = dtype >> 8;
+    dtype &= 0xff;
+    PeakConsts pc;
+    for (int k = 0; k < 8; ++k) pc.k[k] = 0.75 + 0.03 * k;
+    if (dtype == MPK_F64 && mode == 0) fma_peak_kernel<double, 0><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 1) fma_peak_kernel<double, 1><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 2) fma_peak_kernel<double, 2><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 3) fma_peak_kernel<double, 3><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F32 && mode == 0) fma_peak_kernel<float, 0><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F32 && mode == 1) fma_peak_kernel<float, 1><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else return fail(MPK_EINVAL, "bad dtype / mode");
     return check_launch("fma_peak");
 }

@@ -69,6 +69,17 @@ def main():
         blocks, threads, iters = 148 * 8, 256, 1 << 15
         sec = timeit(lambda: ops.fma_peak(sink, dt, blocks, threads, iters), 5, 2)
         res[f"fma_peak_{name}_tflops"] = blocks * threads * iters * 16 / sec[1] / 1e12
+    # fp64 issue rate under the operand patterns of the real kernels (csrc/robot.cu fma_peak modes):
+    # instructions per clock per SM, against the 32 (= 64 lanes / 2) of the FMA pipe
+    for mode, label in ((0, "shared_operands"), (1, "three_distinct_registers"), (2, "constant_bank_operand"),
+                        (3, "dmul_dfma_pairs")):
+        blocks, threads, iters = 148 * 8, 256, 1 << 14
+        sec = timeit(lambda: ops.fma_peak(sink, mode << 8, blocks, threads, iters), 5, 2)
+        res[f"fp64_pattern_{label}_ginstr_per_s"] = blocks * threads * iters * 8 / sec[1] / 1e9
+
+    if "--peaks-only" in sys.argv:
+        print(json.dumps(res, indent=1))
+        return
 
     ur5 = load_robot("ur5", device=dev)
     h6 = ur5.dynamics.robot.handle

@@ -144,6 +144,12 @@ class HostCheck:
                      _ptr(np.ascontiguousarray(g, dtype=np.float64)), _ptr(f), _ptr(out))
         return out
 
+    def sincos(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        s, c = np.empty_like(x), np.empty_like(x)
+        self.H.hc_sincos(_C.c_int64(x.size), _ptr(x), _ptr(s), _ptr(c))
+        return s, c
+
     def traj(self, start, end, Tf, N, method, limits=None, inputs_f32=True):
         s = np.ascontiguousarray(start, dtype=np.float64)
         e = np.ascontiguousarray(end, dtype=np.float64)

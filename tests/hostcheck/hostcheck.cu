@@ -29,8 +29,9 @@ static void rnea_nf(const mpk_robot *rb, int64_t P, const double *th, const doub
         }
         if (use_smem_store) {
             // the shared-memory state store of the kernels, exercised with a one-thread "block"
-            double buf[SmemStore<double, N, 1>::kSlots * 8 + 1];
-            SmemStore<double, N, 1> st{buf};
+            using Store = SmemStore<double, N, 1, rnea_fast0(GEN, REV, N)>;
+            double buf[Store::kValues + 1];
+            Store st{buf};
             ArrayIn<double, N> in{a, b, c};
             rnea<double, N, GEN, REV>(pk, in, g0, ftip, t, st);
         } else {
@@ -150,6 +151,12 @@ extern "C" int hc_fk(const mpk_robot *rb, int64_t P, const double *th, double *T
 extern "C" int hc_fd(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                      const double *tau, const double *g, const double *ftip_rows, double *dd) {
     HC_DISPATCH(rb->n, fd_n<N_>(rb, P, th, dth, tau, g, ftip_rows, dd));
+    return 0;
+}
+extern "C" int hc_sincos(int64_t P, const double *x, double *sn, double *cs) {
+    double tab[17];
+    fill_trig_table(tab);
+    for (int64_t p = 0; p < P; ++p) sincos_pack(tab, x[p], sn + p, cs + p);
     return 0;
 }
 extern "C" int hc_traj(int n, int64_t N, const double *start, const double *end, int inputs_f32,

@@ -234,6 +234,30 @@ def test_awkward_axis_arrangements_vs_oracle(hostcheck, kind, rigid):
     assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-8
 
 
+def test_joint_sincos_accuracy(hostcheck):
+    """The kernels' own sin/cos (Cody-Waite + fdlibm kernels with constant-bank coefficients,
+    csrc/mpk_device.cuh sincos_pack) against libm: <= 2 ulp, exact
+    symmetries at the quadrant boundaries, library fallback for huge / non-finite arguments."""
+    rng = np.random.default_rng(0)
+    k = np.arange(-4000, 4001)
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 100000), rng.normal(0, 1e-3, 1000),
+                        k * (np.pi / 4), np.nextafter(k * (np.pi / 4), np.inf), np.nextafter(k * (np.pi / 2), -np.inf),
+                        [0.0, -0.0, 1e-300, 5e-324, 99999.99999, -99999.99999]])
+    s, c = hostcheck.sincos(x)
+    rs, rc = np.sin(x), np.cos(x)
+    assert np.max(np.abs(s - rs)) < 2.3e-16 and np.max(np.abs(c - rc)) < 2.3e-16
+    ulp = lambda got, ref: np.max(np.abs(got - ref) / np.maximum(np.spacing(np.abs(ref)), 1e-300) * (np.abs(ref) > 1e-3))
+    assert ulp(s, rs) <= 2.0 and ulp(c, rc) <= 2.0  # the CUDA library's own bound for sin / cos
+    assert np.abs(s * s + c * c - 1).max() < 5e-16
+    s0, c0 = hostcheck.sincos([0.0])
+    assert s0[0] == 0.0 and c0[0] == 1.0
+    big = np.array([1e5, 1.234e7, -3.3e12, 1e300])
+    s, c = hostcheck.sincos(big)
+    assert np.array_equal(s, np.sin(big)) and np.array_equal(c, np.cos(big))
+    s, c = hostcheck.sincos([np.nan, np.inf, -np.inf])
+    assert np.isnan(s).all() and np.isnan(c).all()
+
+
 def test_planar_2r_known_answers(hostcheck):
     """Murray-Li-Sastry Ex. 4.3 (reference tests/test_v132_regressions.py:126-192, 229-286)."""
     rb = hostcheck.robot(planar_2r_pack())
