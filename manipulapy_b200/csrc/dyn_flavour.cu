@@ -32,8 +32,13 @@ void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStre
 template <int F>
 void launch_traj_rnea(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
-    MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<N_, GEN, REV>, grid, kDynThreads,
-                                          wrench_smem<N_, GEN, REV>(), s, narrow<N_>(rb), a));
+    if (a.tip.has_ftip) {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<N_, GEN, REV, true>, grid, kDynThreads,
+                                              wrench_smem<N_, GEN, REV>(), s, narrow<N_>(rb), a));
+    } else {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<N_, GEN, REV, false>, grid, kDynThreads,
+                                              wrench_smem<N_, GEN, REV>(), s, narrow<N_>(rb), a));
+    }
 }
 
 template <int F>

@@ -219,8 +219,8 @@ struct TrajIn {
     }
 };
 
-template <int N, bool GEN, bool REV, int MINB = kRneaMinBlocks>
-__global__ void __launch_bounds__(kDynThreads, MINB)
+template <int N, bool GEN, bool REV, bool TIP>
+__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
     // dynamic shared memory: the per-thread link state of the recursion, then (same bytes) the
     // block's output rows staged for coalesced stores
@@ -239,12 +239,11 @@ __global__ void __launch_bounds__(kDynThreads, MINB)
     float out[N];
     {
         double ft[6];
-        const double *ftp = nullptr;
-        if (a.tip.has_ftip) {
+        if (TIP) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
-            ftp = ft;
         }
+        const double *ftp = TIP ? ft : nullptr;
         SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
         double tau[N];
         rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
@@ -314,7 +313,12 @@ __global__ void __launch_bounds__(kDynThreads)
 // rows are stored as float32 and the acceleration row is the last sub-step's.  Row 0 is the
 // initial state with zero acceleration and taumat[0] is never used.  The Euler updates use
 // explicit round-to-nearest multiplies and adds (no FMA contraction) like the reference's
-// NumPy.  One thread owns one trajectory; state, mass matrix and LDL^T factor live in registers.
+// NumPy.  One thread owns one trajectory; state, mass matrix and LDL^T factor live in registers
+// (a shared-memory hand-over between the recursion, the mass matrix and the solve that halves
+// the register count and doubles the resident warps was measured 15-40 % SLOWER: the step is a
+// serial dependency chain and the extra shared-memory round trips lengthen it;
+// profiles/r1_variants.md).  The torque row of the next step is fetched with cp.async into a
+// shared-memory staging column a whole step ahead, so its DRAM latency is off the chain.
 template <int N>
 __device__ __forceinline__ void store_state(float *o, int64_t row, const double (&x)[N]) {
     float *r = o + row * N;
@@ -322,9 +326,48 @@ __device__ __forceinline__ void store_state(float *o, int64_t row, const double 
     for (int j = 0; j < N; ++j) r[j] = (float)x[j];
 }
 
-template <int N, bool GEN, bool REV>
+// Asynchronous copy of one torque row (N values of 4 or 8 bytes) from global to the lane's
+// shared-memory staging column: no registers are held while the row is in flight, and the
+// copy is issued a whole step ahead of its use.
+template <int N>
+__device__ __forceinline__ void tau_row_async(double *stage, const void *taumat, int dtype, int64_t row) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(stage);
+    if (dtype == MPK_F64) {
+        const double *src = static_cast<const double *>(taumat) + row * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + j * 32 * 8), "l"(src + j) : "memory");
+    } else {
+        const float *src = static_cast<const float *>(taumat) + row * N;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + j * 32 * 8), "l"(src + j) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void tau_row_take(const double *stage, int dtype, double (&tau)[N]) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const volatile double *p = stage + j * 32;
+        tau[j] = dtype == MPK_F64 ? *p : (double)*reinterpret_cast<const volatile float *>(p);
+    }
+}
+
+// shared memory per warp: two torque-row stages + one word per lane for the rollout's row base
+template <int N>
+constexpr size_t rollout_smem_per_warp() {
+    return sizeof(double) * 32 * (N * 2 + 1);
+}
+
+// TIP: rows of Ftipmat are applied (else every tip-wrench term is compiled out).
+template <int N, bool GEN, bool REV, bool TIP>
 __global__ void __launch_bounds__(128)
     fd_rollout_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
+    extern __shared__ __align__(16) double fsm[];
+    double *stage = fsm + (threadIdx.x >> 5) * (32 * (N * 2 + 1)) + (threadIdx.x & 31);  // + (step & 1) * 32 * N
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     double th[N], dth[N], last[N];
@@ -334,20 +377,31 @@ __global__ void __launch_bounds__(128)
         dth[j] = a.dth0[b * N + j];
         last[j] = 0.0;
     }
-    const int64_t base = b * a.N;
-    store_state<N>(a.pos, base, th);
-    store_state<N>(a.vel, base, dth);
-    store_state<N>(a.acc, base, last);
+    // The step body needs every register; what the loop keeps per thread besides the state is
+    // this one row index, parked in shared memory and re-read each step.  (Left to the compiler,
+    // the four row pointers derived from it are spilled to LOCAL memory, whose reloads miss L1
+    // behind the torque stream and stall the top of every step: ncu long_scoreboard 21 %.)
+    volatile int64_t *base_slot = reinterpret_cast<volatile int64_t *>(stage + 32 * N * 2);
+    {
+        const int64_t base = b * a.N;
+        *base_slot = base;
+        store_state<N>(a.pos, base, th);
+        store_state<N>(a.vel, base, dth);
+        store_state<N>(a.acc, base, last);
+        if (a.N > 1) tau_row_async<N>(stage + 32 * N, a.taumat, a.tau_dtype, base + 1);
+    }
     for (int64_t i = 1; i < a.N; ++i) {
+        const int64_t base = *base_slot;
         double tau[N];
-        load_row<N>(a.taumat, a.tau_dtype, a.vec_tau, base + i, tau);
+        tau_row_take<N>(stage + (i & 1) * 32 * N, a.tau_dtype, tau);
+        // the torque row of step i + 1 travels while step i is being computed
+        if (i + 1 < a.N) tau_row_async<N>(stage + ((i + 1) & 1) * 32 * N, a.taumat, a.tau_dtype, base + i + 1);
         double ft[6];
-        const double *ftp = nullptr;
-        if (a.ftipmat) {
+        if (TIP) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) ft[k] = __ldg(a.ftipmat + (base + i) * 6 + k);
-            ftp = ft;
         }
+        const double *ftp = TIP ? ft : nullptr;
 #pragma unroll
         for (int j = 0; j < N; ++j) last[j] = 0.0;
         for (int r = 0; r < a.intRes; ++r) {

@@ -31,7 +31,13 @@ void launch_fd_point(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaSt
 template <int F>
 void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, unsigned grid, int threads, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
-    MPK_DISPATCH_DOF_V(rb->n, (fd_rollout_kernel<N_, GEN, REV><<<grid, threads, 0, s>>>(narrow<N_>(rb), a)));
+    if (a.ftipmat) {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(fd_rollout_kernel<N_, GEN, REV, true>, grid, threads,
+                                              rollout_smem_per_warp<N_>() * (threads / 32), s, narrow<N_>(rb), a));
+    } else {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(fd_rollout_kernel<N_, GEN, REV, false>, grid, threads,
+                                              rollout_smem_per_warp<N_>() * (threads / 32), s, narrow<N_>(rb), a));
+    }
 }
 
 template void launch_fd_point<MPK_FLAVOUR>(const mpk_robot *, const FdArgs &, unsigned, cudaStream_t);

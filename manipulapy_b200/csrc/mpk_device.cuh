@@ -568,6 +568,7 @@ struct SmemStore {
 // Joint values straight from register arrays.
 template <typename T, int N>
 struct ArrayIn {
+    static constexpr bool kZeroAcc = false;
     const T (&th)[N];
     const T (&dth)[N];
     const T (&ddth)[N];
@@ -576,6 +577,27 @@ struct ArrayIn {
         b = dth[i];
         c = ddth[i];
     }
+};
+// ... with ddtheta = 0 known at compile time (the bias forces of forward dynamics): rnea() then
+// drops the joint-acceleration terms instead of adding zeros.
+template <typename T, int N>
+struct ArrayInNoAcc {
+    static constexpr bool kZeroAcc = true;
+    const T (&th)[N];
+    const T (&dth)[N];
+    MPK_HD void joint(int i, T &a, T &b, T &c) {
+        a = th[i];
+        b = dth[i];
+        c = T(0);
+    }
+};
+template <typename In, typename = void>
+struct zero_acc_of {
+    static constexpr bool value = false;
+};
+template <typename In>
+struct zero_acc_of<In, decltype((void)In::kZeroAcc)> {
+    static constexpr bool value = In::kZeroAcc;
 };
 
 // `in.joint(i, theta, dtheta, ddtheta)` yields joint i's values when link i is reached, so a
@@ -587,6 +609,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
     // a rigid all-revolute chain: link 0 only contributes the z moment about its own axis, and
     // link 1 receives a twist with known zeros
     constexpr bool FAST0 = rnea_fast0(GEN, REV, N);
+    constexpr bool NOACC = zero_acc_of<In>::value;  // ddtheta == 0
     T w[3], v[3], dw[3], dv[3];
     T ag[3];         // general path: -g in the current frame
     T tn[3], tf[3];  // tip wrench carried down to the last frame
@@ -614,7 +637,8 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                 dv[0] = a0[0]; dv[1] = a0[1]; dv[2] = a0[2];
                 // z moment of link 0's own wrench: (I dw + h x dv)_z (w x I w has no z part
                 // for w along z)
-                st_.put(0, 2, rb.I[0][5] * qdd + rb.h[0][0] * a0[1] - rb.h[0][1] * a0[0]);
+                st_.put(0, 2, NOACC ? rb.h[0][0] * a0[1] - rb.h[0][1] * a0[0]
+                                    : rb.I[0][5] * qdd + rb.h[0][0] * a0[1] - rb.h[0][1] * a0[0]);
                 continue;
             }
             const T sr = REV ? T(1) : rb.sr[0], st = REV ? T(0) : rb.st[0];
@@ -643,7 +667,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                 w[2] += qd;
                 dw[0] += qd * w[1];
                 dw[1] -= qd * w[0];
-                dw[2] += qdd;
+                if (!NOACC) dw[2] += qdd;
                 dv[0] += qd * v[1];
                 dv[1] -= qd * v[0];
             } else {
@@ -900,15 +924,14 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
 template <typename T, int N, bool GEN, bool REV>
 MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N],
                              const T (&tau)[N], const T (&g0)[3], const T *ftip, T (&dd)[N]) {
-    JointCS<T, N> q;
-    T zero[N], bias[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) zero[i] = T(0);
-    rnea<T, N, GEN, REV>(rb, th, dth, zero, g0, ftip, bias, q);
+    T bias[N];
+    RegStore<T, N> st_;
+    ArrayInNoAcc<T, N> in{th, dth};
+    rnea<T, N, GEN, REV>(rb, in, g0, ftip, bias, st_);
 #pragma unroll
     for (int i = 0; i < N; ++i) dd[i] = tau[i] - bias[i];
     T Mm[N][N];
-    mass_matrix<T, N, GEN, REV>(rb, th, q, Mm);
+    mass_matrix<T, N, GEN, REV>(rb, th, st_.q, Mm);
     ldlt_solve<T, N>(Mm, dd);
 }
 
