@@ -45,6 +45,7 @@ if str(REPO) not in sys.path:
     sys.path.insert(0, str(REPO))
 
 ROBOT, B_TRAJ, N_STEPS, TF, METHOD = "ur5", 4096, 2441, 2.0, 5
+FD_ROLLOUTS, FD_STEPS = 65536, 1000
 METRIC, UNIT = "rnea_trajectory_points_per_s", "points/s"
 # algorithmic work per point (DESIGN.md "Kernels")
 FLOP_PER_POINT = 2070 + 60            # textbook fp64 Newton-Euler recursion (n = 6) + time scaling
@@ -304,10 +305,29 @@ def run_ours(args) -> None:
     d2h_gbs = pin.numel() / (a.elapsed_time(b) / 1e3) / 1e9
     del pin, src
 
-    red = torch.tensor([t_dev, t_dom, t_e2e], dtype=torch.float64, device=dev)
+    # second metric of BASELINE.json: forward-dynamics rollout steps/s (configs[3]: iiwa14, 65,536
+    # shooting trajectories x 1000 Euler steps per GPU, float32 torque rows resident in HBM)
+    t_fd, fd_steps = 0.0, 0
+    if not args.no_fd:
+        iiwa = load_robot("iiwa14", device=dev)
+        h7, jl7 = iiwa.dynamics.robot.handle, iiwa.planner()._jl
+        Bf, Nf = FD_ROLLOUTS, FD_STEPS
+        gen = torch.Generator(device=dev).manual_seed(4 + rank)
+        lo7 = torch.from_numpy(iiwa.joint_limits[:, 0]).to(dev)
+        hi7 = torch.from_numpy(iiwa.joint_limits[:, 1]).to(dev)
+        th0 = 0.5 * (lo7 + (hi7 - lo7) * torch.rand(Bf, 7, dtype=torch.float64, device=dev, generator=gen))
+        dth0 = torch.rand(Bf, 7, dtype=torch.float64, device=dev, generator=gen) - 0.5
+        amp = torch.tensor([4.0, 4.0, 2.0, 2.0, 0.4, 0.2, 0.08], dtype=torch.float64, device=dev)
+        taum = (iiwa.dynamics.gravity_forces(th0)[:, None, :]
+                + (torch.rand(Bf, Nf, 7, dtype=torch.float64, device=dev, generator=gen) - 0.5) * amp).float()
+        t_fd = timed(lambda: ops.forward_dynamics_trajectory(h7, th0, dth0, taum, g, None, 1e-3, 1, jl7), 3, 1)
+        fd_steps = Bf * (Nf - 1) * 3
+        del taum
+
+    red = torch.tensor([t_dev, t_dom, t_e2e, t_fd], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-    t_dev, t_dom, t_e2e = (float(x) for x in red.cpu())
+    t_dev, t_dom, t_e2e, t_fd = (float(x) for x in red.cpu())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,7 +357,7 @@ def run_ours(args) -> None:
                 "d2h_bytes_per_step": int(P * 6 * 4), "api": "OptimizedTrajectoryPlanning.trajectory_inverse_dynamics",
                 "pcie_d2h_gbs_measured": d2h_gbs,
                 "pcie_bound_points_per_s": world * d2h_gbs * 1e9 / (6 * 4)},
-        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches": launches_per_step * args.steps,  # in the timed region of `value`
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": _traffic(dom_kernel), "peak_source": peak_src,
                      "algorithmic_bytes_per_point": dom_bytes, "kernel_ms": dom_s * 1e3,
@@ -354,6 +374,13 @@ def run_ours(args) -> None:
                               "peak_source": "mpk_fma_peak measured in this run (mode 0: shared operands = "
                                              "pipe peak; mode 1: three distinct register operands)"}},
     }
+    if t_fd > 0:
+        line["fd_rollout"] = {
+            "metric": "fd_rollout_steps_per_s", "value": world * fd_steps / t_fd, "unit": "steps/s",
+            "ms_per_launch": t_fd / 3 * 1e3, "gpu_launches": 3,
+            "config": {"workload": f"iiwa14 {FD_ROLLOUTS} rollouts x {FD_STEPS} Euler steps per GPU, CRBA mass matrix + "
+                                   "LDL^T solve per step (BASELINE.json configs[3])", "dt": 1e-3, "intRes": 1,
+                       "taumat": "float32 (B, N, 7) resident in HBM", "outputs": "3 x float32 (B, N, 7)"}}
     if cpu_rate is not None:
         line["cpu_baseline"] = {
             "value": cpu_rate, "unit": UNIT, "cores": cores, "kind": "port",
@@ -374,6 +401,7 @@ def main() -> None:
     ap.add_argument("--ref-traj", type=int, default=16, help="trajectories per step of the reference arm")
     ap.add_argument("--cpu-sample-traj", type=int, default=256, help="trajectories of the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fd", action="store_true", help="skip the forward-dynamics rollout metric")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (e.g. NCCL's

@@ -1,7 +1,5 @@
 // dyn.cu -- C ABI of the dynamics launchers: argument checking, argument blocks, dispatch to
 // the flavour translation units (dyn_kernels.cuh).
-#include <cstdlib>
-
 #include "dyn_kernels.cuh"
 
 using namespace mpk;
@@ -181,8 +179,8 @@ extern "C" int mpk_forward_dynamics_trajectory(const mpk_robot *rb, int64_t B, i
     a.vel = vel;
     a.acc = acc;
     // few trajectories per GPU: spread them over as many SMs as possible
-    int threads = getenv("MPK_FD_THREADS") ? atoi(getenv("MPK_FD_THREADS")) : 128;  // TEMPORARY tuning switch
-    while (threads > 32 && !getenv("MPK_FD_THREADS") && (B + threads - 1) / threads < 2 * 148) threads >>= 1;
+    int threads = 128;
+    while (threads > 32 && (B + threads - 1) / threads < 2 * 148) threads >>= 1;
     const int64_t blocks = (B + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B exceeds the grid limit");
     cudaStream_t s = static_cast<cudaStream_t>(stream);

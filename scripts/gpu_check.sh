@@ -28,11 +28,11 @@ bench)
   cat $OUT/${TAG}_bench_reference.json ;;
 launches)
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-      --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_launches.log 2>&1
+      --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-fd > $OUT/${TAG}_launches.log 2>&1
   tail -2 $OUT/${TAG}_launches.log ;;
 ncu)
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:traj_rnea_kernel -s 2 -c 2 \
-      -f -o $OUT/${TAG}_traj_rnea python bench.py --steps 2 --warmup 3 --no-cpu > $OUT/${TAG}_ncu.log 2>&1
+      -f -o $OUT/${TAG}_traj_rnea python bench.py --steps 2 --warmup 3 --no-cpu --no-fd > $OUT/${TAG}_ncu.log 2>&1
   tail -2 $OUT/${TAG}_ncu.log ;;
 ncu_micro)
   # full captures of the other kernels (one launch each) while running the micro-benchmark
