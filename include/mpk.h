@@ -92,6 +92,10 @@ int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const
  *   theta dev (P, n) theta_dtype;  T dev (P, 4, 4) float64 or NULL;  J dev (P, 6, n) float64 or NULL */
 int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
                           double *T, double *J, void *stream);
+/* The same in float32 arithmetic with float32 outputs (north-star tolerance 1e-5 on poses):
+ * half the HBM bytes of this store-bound kernel. */
+int mpk_fk_jacobian_space_f32(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
+                              float *T, float *J, void *stream);
 
 /* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
  * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).
@@ -108,6 +112,12 @@ int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *theta, cons
                          const void *ddtheta, int in_dtype, const double *g, const double *Ftip,
                          const double *Ftip_rows, const float *tau_limits, void *tau, int out_dtype,
                          void *stream);
+/* Same arguments, float32 ARITHMETIC (north-star tolerance 1e-4 relative on torques); the
+ * storage types of the arrays are still chosen by in_dtype / out_dtype. */
+int mpk_inverse_dynamics_f32(const mpk_robot *rb, int64_t P, const void *theta, const void *dtheta,
+                             const void *ddtheta, int in_dtype, const double *g, const double *Ftip,
+                             const double *Ftip_rows, const float *tau_limits, void *tau, int out_dtype,
+                             void *stream);
 
 /* joint_trajectory + inverse_dynamics_trajectory fused: the trajectory rows are
  * produced in registers, rounded to float32 and clipped exactly as the two-call
@@ -120,6 +130,13 @@ int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, int64_t N, c
                                     const float *joint_limits, const double *g, const double *Ftip,
                                     const float *tau_limits, float *tau, float *pos, float *vel,
                                     float *acc, double *ts_scratch, void *stream);
+/* Same arguments; the trajectory rows are produced exactly as above (float64 time scaling, one
+ * rounding to float32 -- bit-identical), the inverse dynamics then runs in float32 arithmetic. */
+int mpk_trajectory_inverse_dynamics_f32(const mpk_robot *rb, int64_t B, int64_t N, const double *start,
+                                        const double *end, int inputs_f32, double Tf, int method,
+                                        const float *joint_limits, const double *g, const double *Ftip,
+                                        const float *tau_limits, float *tau, float *pos, float *vel,
+                                        float *acc, double *ts_scratch, void *stream);
 
 /* ManipulatorDynamics.mass_matrix (dynamics/mass_matrix.py:16-99), batched.
  *   theta dev (P, n) theta_dtype;  Mout dev (P, n, n) float64 (symmetric) */

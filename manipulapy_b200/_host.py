@@ -126,3 +126,18 @@ def vec(x: Any, n: int, name: str) -> list:
 
 def gravity(g: Any) -> list:
     return [0.0, 0.0, -9.81] if g is None else vec(g, 3, "gravity vector")
+
+
+def is_f32(precision: Any) -> bool:
+    """``precision`` keyword of the API mirrors: float64 (default: the reference's NumPy path,
+    1e-9) or float32 arithmetic (the north-star's fp32 kernels: 1e-4 on torques, 1e-5 on poses)."""
+    if precision is None:
+        return False
+    p = np.dtype(precision) if not isinstance(precision, str) else np.dtype(
+        {"float64": np.float64, "fp64": np.float64, "f64": np.float64, "double": np.float64,
+         "float32": np.float32, "fp32": np.float32, "f32": np.float32, "single": np.float32}.get(precision.lower(), precision))
+    if p == np.float64:
+        return False
+    if p == np.float32:
+        return True
+    raise ValueError(f"precision must be float64 or float32, got {precision!r}")

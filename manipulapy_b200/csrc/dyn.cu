@@ -33,11 +33,11 @@ int grid_for(int64_t P, unsigned &grid) {
     if (!(rb)->has_dynamics)                                                     \
         return fail(MPK_EINVAL, "robot was created without Glist / Mlist_per_link")
 
-extern "C" int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *theta,
-                                    const void *dtheta, const void *ddtheta, int in_dtype,
-                                    const double *g, const double *Ftip, const double *Ftip_rows,
-                                    const float *tau_limits, void *tau, int out_dtype,
-                                    void *stream) {
+static int inverse_dynamics_impl(const mpk_robot *rb, int64_t P, const void *theta,
+                                 const void *dtheta, const void *ddtheta, int in_dtype,
+                                 const double *g, const double *Ftip, const double *Ftip_rows,
+                                 const float *tau_limits, void *tau, int out_dtype, int compute_f32,
+                                 void *stream) {
     MPK_REQUIRE_DYN(rb);
     if (P < 0) return fail(MPK_EINVAL, "negative size");
     if (P == 0) return MPK_OK;
@@ -56,6 +56,7 @@ extern "C" int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *
     a.out = tau;
     a.out_dtype = out_dtype;
     a.vec_out = aligned16(tau);
+    a.compute_f32 = compute_f32;
     unsigned grid;
     if (int rc = grid_for(P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -63,13 +64,31 @@ extern "C" int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *
     return check_launch("inverse_dynamics");
 }
 
-extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, int64_t N,
-                                               const double *start, const double *end,
-                                               int inputs_f32, double Tf, int method,
-                                               const float *joint_limits, const double *g,
-                                               const double *Ftip, const float *tau_limits,
-                                               float *tau, float *pos, float *vel, float *acc,
-                                               double *ts_scratch, void *stream) {
+extern "C" int mpk_inverse_dynamics(const mpk_robot *rb, int64_t P, const void *theta,
+                                    const void *dtheta, const void *ddtheta, int in_dtype,
+                                    const double *g, const double *Ftip, const double *Ftip_rows,
+                                    const float *tau_limits, void *tau, int out_dtype,
+                                    void *stream) {
+    return inverse_dynamics_impl(rb, P, theta, dtheta, ddtheta, in_dtype, g, Ftip, Ftip_rows, tau_limits, tau,
+                                 out_dtype, 0, stream);
+}
+
+extern "C" int mpk_inverse_dynamics_f32(const mpk_robot *rb, int64_t P, const void *theta,
+                                        const void *dtheta, const void *ddtheta, int in_dtype,
+                                        const double *g, const double *Ftip, const double *Ftip_rows,
+                                        const float *tau_limits, void *tau, int out_dtype,
+                                        void *stream) {
+    return inverse_dynamics_impl(rb, P, theta, dtheta, ddtheta, in_dtype, g, Ftip, Ftip_rows, tau_limits, tau,
+                                 out_dtype, 1, stream);
+}
+
+static int trajectory_inverse_dynamics_impl(const mpk_robot *rb, int64_t B, int64_t N,
+                                            const double *start, const double *end,
+                                            int inputs_f32, double Tf, int method,
+                                            const float *joint_limits, const double *g,
+                                            const double *Ftip, const float *tau_limits,
+                                            float *tau, float *pos, float *vel, float *acc,
+                                            double *ts_scratch, int compute_f32, void *stream) {
     MPK_REQUIRE_DYN(rb);
     if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
     if (B == 0 || N == 0) return MPK_OK;
@@ -90,6 +109,7 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     a.tlim = make_limits(tau_limits, rb->n);
     a.tip = make_tip(rb, g, Ftip, nullptr);
     a.tau = tau;
+    a.compute_f32 = compute_f32;
     unsigned grid;
     if (int rc = grid_for(a.P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -103,6 +123,28 @@ extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, i
     }
     MPK_DISPATCH_FLAVOUR(rb, launch_traj_rnea<F_>(rb, a, grid, s));
     return check_launch("trajectory_inverse_dynamics");
+}
+
+extern "C" int mpk_trajectory_inverse_dynamics(const mpk_robot *rb, int64_t B, int64_t N,
+                                               const double *start, const double *end,
+                                               int inputs_f32, double Tf, int method,
+                                               const float *joint_limits, const double *g,
+                                               const double *Ftip, const float *tau_limits,
+                                               float *tau, float *pos, float *vel, float *acc,
+                                               double *ts_scratch, void *stream) {
+    return trajectory_inverse_dynamics_impl(rb, B, N, start, end, inputs_f32, Tf, method, joint_limits, g, Ftip,
+                                            tau_limits, tau, pos, vel, acc, ts_scratch, 0, stream);
+}
+
+extern "C" int mpk_trajectory_inverse_dynamics_f32(const mpk_robot *rb, int64_t B, int64_t N,
+                                                   const double *start, const double *end,
+                                                   int inputs_f32, double Tf, int method,
+                                                   const float *joint_limits, const double *g,
+                                                   const double *Ftip, const float *tau_limits,
+                                                   float *tau, float *pos, float *vel, float *acc,
+                                                   double *ts_scratch, void *stream) {
+    return trajectory_inverse_dynamics_impl(rb, B, N, start, end, inputs_f32, Tf, method, joint_limits, g, Ftip,
+                                            tau_limits, tau, pos, vel, acc, ts_scratch, 1, stream);
 }
 
 extern "C" int mpk_mass_matrix(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,

@@ -25,19 +25,30 @@ namespace mpk {
 template <int F>
 void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
-    MPK_DISPATCH_DOF_V(rb->n, launch_smem(rnea_kernel<N_, GEN, REV>, grid, kDynThreads,
-                                          wrench_smem<N_, GEN, REV>(), s, narrow<N_>(rb), a));
+    if (a.compute_f32) {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(rnea_kernel<float, N_, GEN, REV>, grid, kDynThreads,
+                                              wrench_smem<float, N_, GEN, REV>(), s, narrow<N_, float>(rb), a));
+    } else {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(rnea_kernel<double, N_, GEN, REV>, grid, kDynThreads,
+                                              wrench_smem<double, N_, GEN, REV>(), s, narrow<N_>(rb), a));
+    }
 }
 
 template <int F>
 void launch_traj_rnea(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
-    if (a.tip.has_ftip) {
-        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<N_, GEN, REV, true>, grid, kDynThreads,
-                                              wrench_smem<N_, GEN, REV>(), s, narrow<N_>(rb), a));
+    if (a.compute_f32 && a.tip.has_ftip) {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<float, N_, GEN, REV, true>, grid, kDynThreads,
+                                              wrench_smem<float, N_, GEN, REV>(), s, narrow<N_, float>(rb), a));
+    } else if (a.compute_f32) {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<float, N_, GEN, REV, false>, grid, kDynThreads,
+                                              wrench_smem<float, N_, GEN, REV>(), s, narrow<N_, float>(rb), a));
+    } else if (a.tip.has_ftip) {
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<double, N_, GEN, REV, true>, grid, kDynThreads,
+                                              wrench_smem<double, N_, GEN, REV>(), s, narrow<N_>(rb), a));
     } else {
-        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<N_, GEN, REV, false>, grid, kDynThreads,
-                                              wrench_smem<N_, GEN, REV>(), s, narrow<N_>(rb), a));
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<double, N_, GEN, REV, false>, grid, kDynThreads,
+                                              wrench_smem<double, N_, GEN, REV>(), s, narrow<N_>(rb), a));
     }
 }
 

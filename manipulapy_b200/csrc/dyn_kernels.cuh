@@ -44,6 +44,7 @@ struct RneaArgs {
     Limits lim;
     void *out;
     int out_dtype, vec_out;
+    int compute_f32;  // run the recursion in float32 (north-star tolerance 1e-4 on torques)
 };
 
 struct TrajRneaArgs {
@@ -57,6 +58,7 @@ struct TrajRneaArgs {
     float *tau;
     const double *ts_table;
     FastDiv div;
+    int compute_f32;
 };
 
 struct MassArgs {
@@ -103,9 +105,9 @@ template <int FLAVOUR> void launch_rollout(const mpk_robot *rb, const RolloutArg
 
 // Bytes of shared memory the RNEA kernels need per block: the per-link wrenches of the
 // recursion; the fused kernel re-uses the same bytes to stage its output rows.
-template <int N, bool GEN, bool REV>
+template <typename T, int N, bool GEN, bool REV>
 constexpr size_t wrench_smem() {
-    const size_t link_state = SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)>::kBytes;
+    const size_t link_state = SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)>::kBytes;
     const size_t rows = (size_t)kDynThreads * N * sizeof(float);
     return link_state > rows ? link_state : rows;
 }
@@ -127,12 +129,16 @@ static void launch_smem(void (*kern)(KArgs...), unsigned grid, int threads, size
 // kernels (only the flavour translation units see this part)
 // ======================================================================================
 
-template <int N>
+template <int N, typename T>
 __device__ __forceinline__ void store_tau(void *out, int out_dtype, bool vec, int64_t p,
-                                          const double (&tau)[N], const Limits &lim) {
+                                          const T (&tau_t)[N], const Limits &lim) {
     if (out_dtype == MPK_F64) {
+        double tau[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) tau[j] = (double)tau_t[j];
         store_row_f64<N>(static_cast<double *>(out), vec, p, tau);
     } else {
+        const T (&tau)[N] = tau_t;
         float t32[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -160,23 +166,23 @@ __device__ __forceinline__ const double *load_tip(const TipArgs &tip, int64_t p,
 // Joint values of row p read from global memory when the recursion reaches the link.  Each
 // thread walks its own contiguous row, rows of neighbouring threads are adjacent, so every
 // fetched sector is fully consumed (through L1) although the individual loads are strided.
-template <int N>
+template <int N, typename T>
 struct RowIn {
     const void *th, *dth, *ddth;
     int dtype;
     int64_t row;          // p * N
-    double nx[3];         // joint i's values, loaded while link i - 1 was being processed
-    __device__ __forceinline__ double at(const void *base, int i) const {
-        if (base == nullptr) return 0.0;
-        return dtype == MPK_F64 ? __ldg(static_cast<const double *>(base) + row + i)
-                                : (double)__ldg(static_cast<const float *>(base) + row + i);
+    T nx[3];              // joint i's values, loaded while link i - 1 was being processed
+    __device__ __forceinline__ T at(const void *base, int i) const {
+        if (base == nullptr) return T(0);
+        return dtype == MPK_F64 ? (T)__ldg(static_cast<const double *>(base) + row + i)
+                                : (T)__ldg(static_cast<const float *>(base) + row + i);
     }
     __device__ __forceinline__ void prefetch(int i) {
         nx[0] = at(th, i);
         nx[1] = at(dth, i);
         nx[2] = at(ddth, i);
     }
-    __device__ __forceinline__ void joint(int i, double &a, double &b, double &c) {
+    __device__ __forceinline__ void joint(int i, T &a, T &b, T &c) {
         a = nx[0];
         b = nx[1];
         c = nx[2];
@@ -184,48 +190,68 @@ struct RowIn {
     }
 };
 
-template <int N, bool GEN, bool REV, int MINB = kRneaMinBlocks>
-__global__ void __launch_bounds__(kDynThreads, MINB)
-    rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const RneaArgs a) {
-    extern __shared__ __align__(16) double wsm[];
+// gravity / tip wrench of the argument block in the kernel's arithmetic type
+template <typename T>
+struct TipT {
+    T g0[3];
+    T ft[6];
+};
+template <typename T>
+__device__ __forceinline__ const T *tip_to(const TipArgs &tip, const double *ftp, TipT<T> &o) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o.g0[k] = (T)tip.g0[k];
+    if (!ftp) return nullptr;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) o.ft[k] = (T)ftp[k];
+    return o.ft;
+}
+
+template <typename T, int N, bool GEN, bool REV>
+__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
+    rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const RneaArgs a) {
+    extern __shared__ __align__(16) double wsm_raw[];
+    T *wsm = reinterpret_cast<T *>(wsm_raw);
     const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
     if (p >= a.P) return;
     double ft[6];
     const double *ftp = load_tip(a.tip, p, ft);
-    RowIn<N> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {0.0, 0.0, 0.0}};
+    TipT<T> tt;
+    const T *ftt = tip_to<T>(a.tip, ftp, tt);
+    RowIn<N, T> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {T(0), T(0), T(0)}};
     in.prefetch(0);
-    SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
-    double tau[N];
-    rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
-    store_tau<N>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
+    SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
+    T tau[N];
+    rnea<T, N, GEN, REV>(rb, in, tt.g0, ftt, tau, st);
+    store_tau<N, T>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
 }
 
 // ---- fused trajectory + inverse dynamics ----------------------------------------
 // Joint values produced from the time scaling when the recursion reaches the link: the
 // float32-rounded, clipped trajectory row entries the two-call sequence would have stored.
-template <int N>
+template <int N, typename T>
 struct TrajIn {
     const TrajRneaArgs &a;
     TimeScale ts;
     int64_t row;  // b * N
-    __device__ __forceinline__ void joint(int i, double &th, double &qd, double &qdd) {
+    __device__ __forceinline__ void joint(int i, T &th, T &qd, T &qdd) {
         double st, dth;
         endpoint(a.start, a.end, a.inputs_f32, row + i, st, dth);
         float p, v, ac;
         traj_point(ts, st, dth, a.jlim.lo[i], a.jlim.hi[i], a.jlim.on, p, v, ac);
-        th = (double)p;
-        qd = (double)v;
-        qdd = (double)ac;
+        th = (T)p;
+        qd = (T)v;
+        qdd = (T)ac;
     }
 };
 
-template <int N, bool GEN, bool REV, bool TIP>
+template <typename T, int N, bool GEN, bool REV, bool TIP>
 __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
-    traj_rnea_kernel(const __grid_constant__ RobotPack<double, N> rb, const TrajRneaArgs a) {
+    traj_rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const TrajRneaArgs a) {
     // dynamic shared memory: the per-thread link state of the recursion, then (same bytes) the
     // block's output rows staged for coalesced stores
-    extern __shared__ __align__(16) double wsm[];
-    float *sm = reinterpret_cast<float *>(wsm);
+    extern __shared__ __align__(16) double wsm_raw[];
+    T *wsm = reinterpret_cast<T *>(wsm_raw);
+    float *sm = reinterpret_cast<float *>(wsm_raw);
     const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
     const bool live = p0 + threadIdx.x < a.P;
     int64_t b, t;
@@ -235,18 +261,20 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const int64_t off = p0 * N;
     // (tail threads of the last block recompute point 0: they take part in the barriers and
     // their staged rows are never stored)
-    TrajIn<N> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
+    TrajIn<N, T> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
     float out[N];
     {
-        double ft[6];
+        T g0[3], ft[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g0[k] = (T)a.tip.g0[k];
         if (TIP) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) ft[k] = a.tip.ftip[k];
+            for (int k = 0; k < 6; ++k) ft[k] = (T)a.tip.ftip[k];
         }
-        const double *ftp = TIP ? ft : nullptr;
-        SmemStore<double, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
-        double tau[N];
-        rnea<double, N, GEN, REV>(rb, in, a.tip.g0, ftp, tau, st);
+        const T *ftp = TIP ? ft : nullptr;
+        SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
+        T tau[N];
+        rnea<T, N, GEN, REV>(rb, in, g0, ftp, tau, st);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             out[j] = (float)tau[j];

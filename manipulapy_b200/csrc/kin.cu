@@ -18,47 +18,50 @@ struct KinArgs {
     const void *theta;
     int theta_dtype;
     int vec;
-    double *T, *J;
+    void *T, *J;  // arrays of the kernel's arithmetic type
 };
 
-template <int N>
+template <typename E, int N>
 __global__ void __launch_bounds__(kKinThreads)
-    fk_jacobian_kernel(const __grid_constant__ RobotPack<double, N> rb, const KinArgs a) {
+    fk_jacobian_kernel(const __grid_constant__ RobotPack<E, N> rb, const KinArgs a) {
     constexpr int KJ = 6 * N;
-    constexpr int kBuf = WarpStage<KJ>::kDoubles > WarpStage<16>::kDoubles ? WarpStage<KJ>::kDoubles
-                                                                            : WarpStage<16>::kDoubles;
-    extern __shared__ __align__(16) double smem[];
+    using StageJ = WarpStage<KJ, E>;
+    using StageT = WarpStage<16, E>;
+    constexpr int kBuf = StageJ::kDoubles > StageT::kDoubles ? StageJ::kDoubles : StageT::kDoubles;
+    extern __shared__ __align__(16) double smem_raw[];
+    E *smem = reinterpret_cast<E *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *buf = smem + warp * kBuf;  // this warp's staging slice, reused for J then T
+    E *buf = smem + warp * kBuf;  // this warp's staging slice, reused for J then T
+    E *Tg = static_cast<E *>(a.T), *Jg = static_cast<E *>(a.J);
     const int64_t pw = (int64_t)blockIdx.x * kKinThreads + warp * 32;
     if (pw >= a.P) return;
     const int64_t rem = a.P - pw;
     const int rows = (int)(rem < 32 ? rem : 32);
-    double Tm[16];
+    E Tm[16];
     if (lane < rows) {
-        double th[N];
-        load_row<N>(a.theta, a.theta_dtype, a.vec, pw + lane, th);
-        JointCS<double, N> q;
+        double th64[N];
+        load_row<N>(a.theta, a.theta_dtype, a.vec, pw + lane, th64);
+        E th[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) th[j] = (E)th64[j];
+        JointCS<E, N> q;
         joint_cs(rb, th, q);
         // Jacobian columns go straight into the lane's staging row as the chain produces them
-        fk_jacobian<double, N>(rb, q, a.T ? Tm : nullptr, a.J ? buf + lane * WarpStage<KJ>::S : nullptr);
+        fk_jacobian<E, N>(rb, q, Tg ? Tm : nullptr, Jg ? buf + lane * StageJ::S : nullptr);
     }
-    if (a.J) WarpStage<KJ>::flush(buf, a.J + pw * KJ, rows);
-    if (a.T) {
+    if (Jg) StageJ::flush(buf, Jg + pw * KJ, rows);
+    if (Tg) {
         if (lane < rows) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) buf[lane * WarpStage<16>::S + k] = Tm[k];
+            for (int k = 0; k < 16; ++k) buf[lane * StageT::S + k] = Tm[k];
         }
-        WarpStage<16>::flush(buf, a.T + pw * 16, rows);
+        StageT::flush(buf, Tg + pw * 16, rows);
     }
 }
 
-}  // namespace mpk
-
-using namespace mpk;
-
-extern "C" int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void *theta,
-                                     int theta_dtype, double *T, double *J, void *stream) {
+template <typename E>
+static int fk_launch(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype, E *T, E *J,
+                     void *stream) {
     if (!rb) return fail(MPK_EINVAL, "robot is NULL");
     if (P < 0) return fail(MPK_EINVAL, "negative size");
     if (P == 0 || (!T && !J)) return MPK_OK;
@@ -77,14 +80,29 @@ extern "C" int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void 
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "P exceeds the grid limit");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     MPK_DISPATCH_DOF(rb->n, {
-        const int per_warp = WarpStage<6 * N_>::kDoubles > WarpStage<16>::kDoubles ? WarpStage<6 * N_>::kDoubles
-                                                                                   : WarpStage<16>::kDoubles;
-        const size_t smem = sizeof(double) * per_warp * (kKinThreads / 32);
-        auto kern = fk_jacobian_kernel<N_>;
+        const int per_warp = WarpStage<6 * N_, E>::kDoubles > WarpStage<16, E>::kDoubles
+                                 ? WarpStage<6 * N_, E>::kDoubles
+                                 : WarpStage<16, E>::kDoubles;
+        const size_t smem = sizeof(E) * per_warp * (kKinThreads / 32);
+        auto kern = fk_jacobian_kernel<E, N_>;
         if (smem > 32 * 1024)
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        kern<<<(unsigned)blocks, kKinThreads, smem, s>>>(narrow<N_>(rb), a);
+        kern<<<(unsigned)blocks, kKinThreads, smem, s>>>(narrow<N_, E>(rb), a);
     });
     return check_launch("fk_jacobian_space");
+}
+
+}  // namespace mpk
+
+using namespace mpk;
+
+extern "C" int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void *theta,
+                                     int theta_dtype, double *T, double *J, void *stream) {
+    return fk_launch<double>(rb, P, theta, theta_dtype, T, J, stream);
+}
+
+extern "C" int mpk_fk_jacobian_space_f32(const mpk_robot *rb, int64_t P, const void *theta,
+                                         int theta_dtype, float *T, float *J, void *stream) {
+    return fk_launch<float>(rb, P, theta, theta_dtype, T, J, stream);
 }

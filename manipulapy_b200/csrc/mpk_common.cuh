@@ -22,10 +22,10 @@ void set_error(const std::string &msg);
 int fail(int code, const std::string &msg);
 int check_launch(const char *what);
 
-// Narrow the max-DOF host pack to the N the kernel is instantiated for.
-template <int N>
-inline RobotPack<double, N> narrow(const mpk_robot *rb) {
-    RobotPack<double, N> o;
+// Narrow the max-DOF host pack to the N (and arithmetic type) the kernel is instantiated for.
+template <int N, typename T = double>
+inline RobotPack<T, N> narrow(const mpk_robot *rb) {
+    RobotPack<T, N> o;
     const auto &s = rb->pack;
     for (int i = 0; i < N; ++i) {
         o.a[i] = s.a[i];
@@ -240,13 +240,14 @@ __device__ __forceinline__ void point_coords(const FastDiv &f, int64_t N, int64_
 
 // Per-warp output staging: each lane owns one row of K values; the warp then writes the
 // (up to) 32 rows, which are contiguous in global memory, with fully coalesced stores.  The
-// row stride is odd (in 8-byte words) so neither phase has shared-memory bank conflicts.
-template <int K>
+// row stride is odd (in words of the element type) so neither phase has shared-memory bank
+// conflicts.
+template <int K, typename E = double>
 struct WarpStage {
     static constexpr int S = (K % 2 == 0) ? K + 1 : K;
-    static constexpr int kDoubles = 32 * S;  // per warp
+    static constexpr int kDoubles = 32 * S;  // elements per warp (the name predates the float variant)
     // gout: global address of the warp's first row; rows: live rows of this warp (<= 32)
-    __device__ static __forceinline__ void flush(const double *buf, double *gout, int rows) {
+    __device__ static __forceinline__ void flush(const E *buf, E *gout, int rows) {
         __syncwarp();
         const int lane = threadIdx.x & 31;
         const int cnt = rows * K;

@@ -102,24 +102,30 @@ std::tuple<Tensor, Tensor, Tensor> joint_trajectory(const Tensor &start, const T
     return {pos, vel, acc};
 }
 
-std::tuple<Tensor, Tensor> fk_jacobian(int64_t h, const Tensor &theta, bool want_T, bool want_J) {
+std::tuple<Tensor, Tensor> fk_jacobian(int64_t h, const Tensor &theta, bool want_T, bool want_J,
+                                       bool compute_f32) {
     mpk_robot *rb = robot(h);
     const int64_t n = mpk_robot_dof(rb);
     Tensor th = dev_rows(theta, n, "theta", true);
     const int64_t P = th.numel() / n;
     c10::cuda::CUDAGuard guard(th.device());
-    auto opt = th.options().dtype(at::kDouble);
+    auto opt = th.options().dtype(compute_f32 ? at::kFloat : at::kDouble);
     Tensor T = want_T ? at::empty({P, 4, 4}, opt) : at::empty({0}, opt);
     Tensor J = want_J ? at::empty({P, 6, n}, opt) : at::empty({0}, opt);
-    check(mpk_fk_jacobian_space(rb, P, th.data_ptr(), dtype_of(th), want_T ? T.data_ptr<double>() : nullptr,
-                                want_J ? J.data_ptr<double>() : nullptr, stream_of(th)),
-          "fk_jacobian_space");
+    if (compute_f32)
+        check(mpk_fk_jacobian_space_f32(rb, P, th.data_ptr(), dtype_of(th), want_T ? T.data_ptr<float>() : nullptr,
+                                        want_J ? J.data_ptr<float>() : nullptr, stream_of(th)),
+              "fk_jacobian_space_f32");
+    else
+        check(mpk_fk_jacobian_space(rb, P, th.data_ptr(), dtype_of(th), want_T ? T.data_ptr<double>() : nullptr,
+                                    want_J ? J.data_ptr<double>() : nullptr, stream_of(th)),
+              "fk_jacobian_space");
     return {T, J};
 }
 
 Tensor inverse_dynamics(int64_t h, const Tensor &theta, const OptT &dtheta, const OptT &ddtheta,
                         c10::ArrayRef<double> g, std::optional<c10::ArrayRef<double>> ftip,
-                        const OptT &ftip_rows, const OptT &tau_limits, bool out_f32) {
+                        const OptT &ftip_rows, const OptT &tau_limits, bool out_f32, bool compute_f32) {
     mpk_robot *rb = robot(h);
     const int64_t n = mpk_robot_dof(rb);
     Tensor th = dev_rows(theta, n, "theta", true);
@@ -148,9 +154,9 @@ Tensor inverse_dynamics(int64_t h, const Tensor &theta, const OptT &dtheta, cons
     auto lim = host_limits(tau_limits, n, "torque_limits");
     c10::cuda::CUDAGuard guard(th.device());
     Tensor tau = at::empty({P, n}, th.options().dtype(out_f32 ? at::kFloat : at::kDouble));
-    check(mpk_inverse_dynamics(rb, P, th.data_ptr(), dp, ddp, dtype_of(th), gv.data(),
-                               fv.empty() ? nullptr : fv.data(), frp, ptr_or_null(lim), tau.data_ptr(),
-                               out_f32 ? MPK_F32 : MPK_F64, stream_of(th)),
+    check((compute_f32 ? mpk_inverse_dynamics_f32 : mpk_inverse_dynamics)(
+              rb, P, th.data_ptr(), dp, ddp, dtype_of(th), gv.data(), fv.empty() ? nullptr : fv.data(), frp,
+              ptr_or_null(lim), tau.data_ptr(), out_f32 ? MPK_F32 : MPK_F64, stream_of(th)),
           "inverse_dynamics");
     return tau;
 }
@@ -158,7 +164,7 @@ Tensor inverse_dynamics(int64_t h, const Tensor &theta, const OptT &dtheta, cons
 std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
     int64_t h, const Tensor &start, const Tensor &end, bool inputs_f32, double Tf, int64_t N,
     int64_t method, const OptT &joint_limits, c10::ArrayRef<double> g,
-    std::optional<c10::ArrayRef<double>> ftip, const OptT &tau_limits, bool want_traj) {
+    std::optional<c10::ArrayRef<double>> ftip, const OptT &tau_limits, bool want_traj, bool compute_f32) {
     mpk_robot *rb = robot(h);
     const int64_t n = mpk_robot_dof(rb);
     TORCH_CHECK(start.dim() == 2, "mpk: start must be (B, n)");
@@ -187,11 +193,10 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
         pos = vel = acc = at::empty({0}, opt);
     }
     Tensor scratch = at::empty({3, N}, s.options());  // time-scaling table workspace
-    check(mpk_trajectory_inverse_dynamics(rb, B, N, s.data_ptr<double>(), e.data_ptr<double>(), inputs_f32,
-                                          Tf, (int)method, ptr_or_null(jl), gv.data(),
-                                          fv.empty() ? nullptr : fv.data(), ptr_or_null(tl),
-                                          tau.data_ptr<float>(), pp, vp, ap, scratch.data_ptr<double>(),
-                                          stream_of(s)),
+    check((compute_f32 ? mpk_trajectory_inverse_dynamics_f32 : mpk_trajectory_inverse_dynamics)(
+              rb, B, N, s.data_ptr<double>(), e.data_ptr<double>(), inputs_f32, Tf, (int)method, ptr_or_null(jl),
+              gv.data(), fv.empty() ? nullptr : fv.data(), ptr_or_null(tl), tau.data_ptr<float>(), pp, vp, ap,
+              scratch.data_ptr<double>(), stream_of(s)),
           "trajectory_inverse_dynamics");
     return {tau, pos, vel, acc};
 }
@@ -286,13 +291,15 @@ TORCH_LIBRARY(mpk, m) {
     m.def("joint_trajectory(Tensor start, Tensor end, bool inputs_f32, float Tf, int N, int method, "
           "Tensor? joint_limits) -> (Tensor, Tensor, Tensor)",
           &joint_trajectory);
-    m.def("fk_jacobian(int robot, Tensor theta, bool want_T, bool want_J) -> (Tensor, Tensor)", &fk_jacobian);
+    m.def("fk_jacobian(int robot, Tensor theta, bool want_T, bool want_J, bool compute_f32=False) -> "
+          "(Tensor, Tensor)",
+          &fk_jacobian);
     m.def("inverse_dynamics(int robot, Tensor theta, Tensor? dtheta, Tensor? ddtheta, float[] g, "
-          "float[]? Ftip, Tensor? Ftip_rows, Tensor? torque_limits, bool out_f32) -> Tensor",
+          "float[]? Ftip, Tensor? Ftip_rows, Tensor? torque_limits, bool out_f32, bool compute_f32=False) -> Tensor",
           &inverse_dynamics);
     m.def("trajectory_inverse_dynamics(int robot, Tensor start, Tensor end, bool inputs_f32, float Tf, "
           "int N, int method, Tensor? joint_limits, float[] g, float[]? Ftip, Tensor? torque_limits, "
-          "bool want_traj) -> (Tensor, Tensor, Tensor, Tensor)",
+          "bool want_traj, bool compute_f32=False) -> (Tensor, Tensor, Tensor, Tensor)",
           &trajectory_inverse_dynamics);
     m.def("mass_matrix(int robot, Tensor theta) -> Tensor", &mass_matrix);
     m.def("forward_dynamics(int robot, Tensor theta, Tensor dtheta, Tensor tau, float[] g, float[]? Ftip, "

@@ -78,10 +78,11 @@ class ManipulatorDynamics(SerialManipulator):
             raise ValueError(f"per-point Ftip must be ({P}, 6), got {a.shape}")
         return None, _host.to_device(a, device)
 
-    def _id(self, th, dth, ddth, g, Ftip, out_f32=False, limits=None):
+    def _id(self, th, dth, ddth, g, Ftip, out_f32=False, limits=None, precision=None):
         P = th.shape[0]
         ftip, rows = self._ftip(Ftip, P, th.device)
-        return _native.ops().inverse_dynamics(self.robot.handle, th, dth, ddth, g, ftip, rows, limits, out_f32)
+        return _native.ops().inverse_dynamics(self.robot.handle, th, dth, ddth, g, ftip, rows, limits, out_f32,
+                                              _host.is_f32(precision))
 
     # -- hot path ---------------------------------------------------------------------------------
     def mass_matrix(self, thetalist):
@@ -89,22 +90,23 @@ class ManipulatorDynamics(SerialManipulator):
         M = _native.ops().mass_matrix(self.robot.handle, th)
         return self._finish(M, single, on_dev)
 
-    def velocity_quadratic_forces(self, thetalist, dthetalist):
+    def velocity_quadratic_forces(self, thetalist, dthetalist, precision=None):
         th, single, on_dev = self._rows(thetalist, "thetalist")
         dth, _, _ = self._rows(dthetalist, "dthetalist")
-        c = self._id(th, dth.to(th.dtype), None, [0.0, 0.0, 0.0], None)
+        c = self._id(th, dth.to(th.dtype), None, [0.0, 0.0, 0.0], None, precision=precision)
         return self._finish(c, single, on_dev)
 
-    def gravity_forces(self, thetalist, g=None):
+    def gravity_forces(self, thetalist, g=None, precision=None):
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        out = self._id(th, None, None, _host.gravity(g), None)
+        out = self._id(th, None, None, _host.gravity(g), None, precision=precision)
         return self._finish(out, single, on_dev)
 
-    def inverse_dynamics(self, thetalist, dthetalist, ddthetalist, g=None, Ftip=None):
+    def inverse_dynamics(self, thetalist, dthetalist, ddthetalist, g=None, Ftip=None, precision=None):
+        """``precision="float32"`` (extension): float32 arithmetic, 1e-4 relative on torques."""
         th, single, on_dev = self._rows(thetalist, "thetalist")
         dth, _, _ = self._rows(dthetalist, "dthetalist")
         ddth, _, _ = self._rows(ddthetalist, "ddthetalist")
-        tau = self._id(th, dth.to(th.dtype), ddth.to(th.dtype), _host.gravity(g), Ftip)
+        tau = self._id(th, dth.to(th.dtype), ddth.to(th.dtype), _host.gravity(g), Ftip, precision=precision)
         return self._finish(tau, single, on_dev)
 
     def forward_dynamics(self, thetalist, dthetalist, taulist, g=None, Ftip=None):

@@ -117,28 +117,30 @@ class SerialManipulator:
         return t if on_dev else _host.to_host(t)
 
     # -- hot path ---------------------------------------------------------------------------
-    def forward_kinematics(self, thetalist, frame: str = "space"):
-        """End-effector pose(s) ``T = prod_i exp([S_i] theta_i) M`` (kinematics/fk.py:61-70)."""
+    def forward_kinematics(self, thetalist, frame: str = "space", precision=None):
+        """End-effector pose(s) ``T = prod_i exp([S_i] theta_i) M`` (kinematics/fk.py:61-70).
+
+        ``precision="float32"`` (extension) runs the float32 kernel and returns float32 arrays."""
         if frame == "body":
             raise NotImplementedError("body-frame FK is outside the B200 hot path (SURVEY.md 8f)")
         if frame != "space":
             raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        T, _ = _native.ops().fk_jacobian(self.robot.handle, th, True, False)
+        T, _ = _native.ops().fk_jacobian(self.robot.handle, th, True, False, _host.is_f32(precision))
         return self._finish(T, single, on_dev)
 
-    def jacobian(self, thetalist, frame: str = "space"):
+    def jacobian(self, thetalist, frame: str = "space", precision=None):
         """Space Jacobian(s) ``J[:, i] = Ad(prod_{j<i} exp([S_j] theta_j)) S_i`` (kinematics/jacobian.py:62-73)."""
         if frame == "body":
             raise NotImplementedError("body-frame Jacobian is outside the B200 hot path (SURVEY.md 8f)")
         if frame != "space":
             raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        _, J = _native.ops().fk_jacobian(self.robot.handle, th, False, True)
+        _, J = _native.ops().fk_jacobian(self.robot.handle, th, False, True, _host.is_f32(precision))
         return self._finish(J, single, on_dev)
 
-    def forward_kinematics_and_jacobian(self, thetalist):
+    def forward_kinematics_and_jacobian(self, thetalist, precision=None):
         """Both outputs from one fused kernel launch (batched extension)."""
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        T, J = _native.ops().fk_jacobian(self.robot.handle, th, True, True)
+        T, J = _native.ops().fk_jacobian(self.robot.handle, th, True, True, _host.is_f32(precision))
         return self._finish(T, single, on_dev), self._finish(J, single, on_dev)

@@ -144,7 +144,8 @@ class OptimizedTrajectoryPlanning:
 
     # -- dynamics over trajectories ------------------------------------------------------------------------
     def inverse_dynamics_trajectory(self, thetalist_trajectory, dthetalist_trajectory,
-                                    ddthetalist_trajectory, gravity_vector=None, Ftip=None):
+                                    ddthetalist_trajectory, gravity_vector=None, Ftip=None, precision=None):
+        """``precision="float32"`` (extension): float32 arithmetic, 1e-4 relative on torques."""
         t0 = time.perf_counter()
         on_dev = _host.any_device(thetalist_trajectory, dthetalist_trajectory, ddthetalist_trajectory)
         dyn = self.dynamics
@@ -157,20 +158,23 @@ class OptimizedTrajectoryPlanning:
         ddth = _host.to_device(ddthetalist_trajectory, dev, keep_f32=True).reshape(-1, n).to(th.dtype)
         ftip = None if Ftip is None else _host.vec(Ftip, 6, "Ftip")
         tau = _native.ops().inverse_dynamics(dyn.robot.handle, th, dth, ddth, _host.gravity(gravity_vector),
-                                             ftip, None, self._tl, True).reshape(shape)
+                                             ftip, None, self._tl, True, _host.is_f32(precision)).reshape(shape)
         out = tau if on_dev else _host.to_host(tau)
         self._tick(t0, transfers=0 if on_dev else 4, kernel="inverse_dynamics")
         return out
 
     def trajectory_inverse_dynamics(self, thetastart_batch, thetaend_batch, Tf, N, method,
-                                    gravity_vector=None, Ftip=None, return_trajectory: bool = False):
+                                    gravity_vector=None, Ftip=None, return_trajectory: bool = False,
+                                    precision=None):
         """``batch_joint_trajectory`` followed by ``inverse_dynamics_trajectory`` in ONE kernel.
 
         Identical results to the two calls (the trajectory rows are rounded to float32 and
         clipped in registers before the dynamics), without the ``3 x 12 n`` bytes per point
         of HBM round trip.  Returns ``(B, N, n)`` float32 torques (and the trajectory dict
-        when ``return_trajectory``).
+        when ``return_trajectory``).  ``precision="float32"``: the trajectory rows are unchanged
+        (bit-exact), the inverse dynamics runs in float32 arithmetic (1e-4 relative on torques).
         """
+        f32c = _host.is_f32(precision)
         t0 = time.perf_counter()
         on_dev = _host.any_device(thetastart_batch, thetaend_batch)
         a = np.asarray(thetastart_batch) if not on_dev else thetastart_batch
@@ -186,7 +190,7 @@ class OptimizedTrajectoryPlanning:
             # host result: pipeline the kernel with the device->host copy, chunk by chunk
             def launch(lo, hi):
                 return ops.trajectory_inverse_dynamics(handle, s[lo:hi], e[lo:hi], f32, float(Tf), int(N),
-                                                       int(method), self._jl, g, ftip, self._tl, False)[0]
+                                                       int(method), self._jl, g, ftip, self._tl, False, f32c)[0]
 
             B = int(s.shape[0])
             out = _host.chunked_to_host(launch, B, (int(N), n), torch.float32, dev)
@@ -194,7 +198,7 @@ class OptimizedTrajectoryPlanning:
             return out
         tau, pos, vel, acc = ops.trajectory_inverse_dynamics(
             handle, s, e, f32, float(Tf), int(N), int(method), self._jl, g, ftip, self._tl,
-            bool(return_trajectory))
+            bool(return_trajectory), f32c)
         outs = [tau] + ([pos, vel, acc] if return_trajectory else [])
         if single:
             outs = [o[0] for o in outs]

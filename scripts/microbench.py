@@ -90,9 +90,11 @@ def main():
     rec("joint_trajectory_ur5", P, timeit(lambda: ops.joint_trajectory(s, e, False, 2.0, N, 5, jl)), 72, 60, "points")
     rec("traj_rnea_fused_ur5", P, timeit(lambda: ops.trajectory_inverse_dynamics(h6, s, e, False, 2.0, N, 5, jl, g, None, None, False)), 24, 2130, "points")
     rec("traj_rnea_fused_with_traj_ur5", P, timeit(lambda: ops.trajectory_inverse_dynamics(h6, s, e, False, 2.0, N, 5, jl, g, None, None, True)), 96, 2130, "points")
+    rec("traj_rnea_fused_f32compute_ur5", P, timeit(lambda: ops.trajectory_inverse_dynamics(h6, s, e, False, 2.0, N, 5, jl, g, None, None, False, True)), 24, 2130, "points")
     pos, vel, acc = ops.joint_trajectory(s, e, False, 2.0, N, 5, jl)
     p2, v2, a2 = pos.view(-1, 6), vel.view(-1, 6), acc.view(-1, 6)
     rec("rnea_f32io_ur5", P, timeit(lambda: ops.inverse_dynamics(h6, p2, v2, a2, g, None, None, None, True)), 96, 2070, "points")
+    rec("rnea_f32io_f32compute_ur5", P, timeit(lambda: ops.inverse_dynamics(h6, p2, v2, a2, g, None, None, None, True, True)), 96, 2070, "points")
     p64, v64, a64 = p2.double(), v2.double(), a2.double()
     rec("rnea_f64io_ur5", P, timeit(lambda: ops.inverse_dynamics(h6, p64, v64, a64, g, None, None, None, False)), 192, 2070, "points")
     ft = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
@@ -109,6 +111,7 @@ def main():
         hi = torch.from_numpy(rb.joint_limits[:, 1]).to(dev)
         th = lo + (hi - lo) * torch.rand(Pk, n, dtype=torch.float64, device=dev, generator=gen)
         rec(f"fk_jacobian_{name}", Pk, timeit(lambda: ops.fk_jacobian(h, th, True, True)), 8 * n + 128 + 48 * n, 170 * n, "configs")
+        rec(f"fk_jacobian_f32_{name}", Pk, timeit(lambda: ops.fk_jacobian(h, th, True, True, True)), 8 * n + 64 + 24 * n, 170 * n, "configs")
         rec(f"fk_only_{name}", Pk, timeit(lambda: ops.fk_jacobian(h, th, True, False)), 8 * n + 128, 110 * n, "configs")
         rec(f"mass_matrix_{name}", Pk, timeit(lambda: ops.mass_matrix(h, th)), 8 * n + 8 * n * n, 64 * n + 100 * n + 53 * n * (n + 1) // 2, "configs")
         dth, tau = rand(Pk, n), rand(Pk, n, lo=-20, hi=20)

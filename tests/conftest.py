@@ -100,9 +100,9 @@ class HostCheck:
             raise RuntimeError(self.L.mpk_last_error().decode())
         return h, S.shape[1]
 
-    def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None, smem_store=False):
+    def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None, smem_store=False, f32=False):
         h, n = rb
-        fn = {0: self.H.hc_rnea, 1: self.H.hc_rnea_smem}[int(smem_store)]
+        fn = self.H.hc_rnea_f32 if f32 else {0: self.H.hc_rnea, 1: self.H.hc_rnea_smem}[int(smem_store)]
         th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
         P = th.shape[0]
         cv = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).reshape(P, n)
@@ -127,11 +127,11 @@ class HostCheck:
         self.H.hc_mass(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(out))
         return out
 
-    def fk(self, rb, th):
+    def fk(self, rb, th, f32=False):
         h, n = rb
         th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
         T, J = np.empty((th.shape[0], 4, 4)), np.empty((th.shape[0], 6, n))
-        self.H.hc_fk(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(T), _ptr(J))
+        (self.H.hc_fk_f32 if f32 else self.H.hc_fk)(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(T), _ptr(J))
         return T, J
 
     def fd(self, rb, th, dth, tau, g=(0, 0, -9.81), ftip_rows=None):

@@ -153,6 +153,61 @@ extern "C" int hc_fd(const mpk_robot *rb, int64_t P, const double *th, const dou
     HC_DISPATCH(rb->n, fd_n<N_>(rb, P, th, dth, tau, g, ftip_rows, dd));
     return 0;
 }
+// float32 arithmetic (the f32 kernel variants): same templates with T = float
+template <int N, bool GEN, bool REV>
+static void rnea32_nf(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                      const double *ddth, const double *g, const double *ftip, double *tau) {
+    const RobotPack<float, N> pk = narrow<N, float>(rb);
+    const RobotPack<double, N> pk64 = narrow<N>(rb);
+    double g064[3];
+    base_gravity(pk64, g, g064);  // (the launchers compute it in float64 on the host)
+    float g0[3] = {(float)g064[0], (float)g064[1], (float)g064[2]};
+    float ft[6];
+    if (ftip)
+        for (int k = 0; k < 6; ++k) ft[k] = (float)ftip[k];
+    for (int64_t p = 0; p < P; ++p) {
+        float a[N], b[N], c[N], t[N];
+        for (int j = 0; j < N; ++j) {
+            a[j] = (float)th[p * N + j];
+            b[j] = dth ? (float)dth[p * N + j] : 0.f;
+            c[j] = ddth ? (float)ddth[p * N + j] : 0.f;
+        }
+        using Store = SmemStore<float, N, 1, rnea_fast0(GEN, REV, N)>;
+        float buf[Store::kValues + 1];
+        Store st{buf};
+        ArrayIn<float, N> in{a, b, c};
+        rnea<float, N, GEN, REV>(pk, in, g0, ftip ? ft : nullptr, t, st);
+        for (int j = 0; j < N; ++j) tau[p * N + j] = (double)t[j];
+    }
+}
+template <int N>
+static void fk32_n(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
+    const RobotPack<float, N> pk = narrow<N, float>(rb);
+    for (int64_t p = 0; p < P; ++p) {
+        float a[N], To[16], Jo[6 * N];
+        for (int j = 0; j < N; ++j) a[j] = (float)th[p * N + j];
+        JointCS<float, N> q;
+        joint_cs(pk, a, q);
+        fk_jacobian<float, N>(pk, q, To, Jo);
+        for (int k = 0; k < 16; ++k) T[p * 16 + k] = To[k];
+        for (int k = 0; k < 6 * N; ++k) J[p * 6 * N + k] = Jo[k];
+    }
+}
+extern "C" int hc_rnea_f32(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
+                           const double *ddth, const double *g, const double *ftip, double *tau) {
+    HC_DISPATCH(rb->n, {
+        switch (flavour(rb)) {
+            case 0: rnea32_nf<N_, false, true>(rb, P, th, dth, ddth, g, ftip, tau); break;
+            case 1: rnea32_nf<N_, false, false>(rb, P, th, dth, ddth, g, ftip, tau); break;
+            default: rnea32_nf<N_, true, false>(rb, P, th, dth, ddth, g, ftip, tau); break;
+        }
+    });
+    return 0;
+}
+extern "C" int hc_fk_f32(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
+    HC_DISPATCH(rb->n, fk32_n<N_>(rb, P, th, T, J));
+    return 0;
+}
 extern "C" int hc_sincos(int64_t P, const double *x, double *sn, double *cs) {
     double tab[17];
     fill_trig_table(tab);

@@ -322,6 +322,66 @@ def test_registry_launcher_runs_on_gpu():
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: sampled oracle comparison + size-independent properties
 # ---------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# float32-arithmetic kernel variants (north_star: 1e-4 relative on torques, 1e-5 on poses)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_float32_kernels_within_north_star_tolerance(robots, oracle_factory, robot):
+    rb, o = robots[robot], oracle_factory(robot)
+    n = rb.num_joints
+    rng = np.random.default_rng(21)
+    lo, hi = rb.joint_limits[:, 0], rb.joint_limits[:, 1]
+    P = 4097  # ragged: not a multiple of the block size
+    th = rng.uniform(lo, hi, (P, n))
+    dth, ddth = rng.uniform(-2, 2, (P, n)), rng.uniform(-5, 5, (P, n))
+    dyn = rb.dynamics
+    ft = rng.uniform(-10, 10, 6)
+    for Ftip in (None, ft):
+        ref = o.inverse_dynamics(th[:600], dth[:600], ddth[:600], [0, 0, -9.81], Ftip, analytic=True)
+        got = dyn.inverse_dynamics(th, dth, ddth, [0, 0, -9.81], Ftip, precision="float32")
+        assert got.shape == (P, n) and got.dtype == np.float64
+        assert _rel_rows(got[:600], ref) < 1e-4
+        # and it really is the float32 kernel: it differs from the float64 one beyond float64 noise
+        assert np.abs(got - dyn.inverse_dynamics(th, dth, ddth, [0, 0, -9.81], Ftip)).max() > 1e-9
+    T, J = dyn.forward_kinematics_and_jacobian(th, precision="float32")
+    assert T.dtype == np.float32 and J.dtype == np.float32 and T.shape == (P, 4, 4) and J.shape == (P, 6, n)
+    Tref, Jref = o.forward_kinematics(th[:600]), o.jacobian(th[:600])
+    assert np.abs(T[:600] - Tref).max() < 1e-5 * max(1.0, np.abs(Tref).max())
+    assert np.abs(J[:600] - Jref).max() < 1e-5 * max(1.0, np.abs(Jref).max())
+    np.testing.assert_array_equal(T[:, 3], np.tile(np.array([0, 0, 0, 1], np.float32), (P, 1)))
+    # single-configuration calls keep their shapes
+    assert dyn.forward_kinematics(th[0], precision="float32").shape == (4, 4)
+    assert dyn.jacobian(th[0], precision=np.float32).shape == (6, n)
+    with pytest.raises(ValueError):
+        dyn.jacobian(th[0], precision="float16")
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14", "panda"])
+def test_float32_fused_trajectory_inverse_dynamics(robots, oracle_factory, robot):
+    """Trajectory rows stay bit-exact; float32 torques within 1e-4 of the float64 oracle; fused
+    float32 kernel = float32 two-call sequence bit for bit; clipping still exact."""
+    rb, o = robots[robot], oracle_factory(robot)
+    n = rb.num_joints
+    rng = np.random.default_rng(9)
+    B, N = 23, 257
+    s, e = rng.uniform(-3, 3, (B, n)), rng.uniform(-3, 3, (B, n))
+    tl = np.array([[-60.0, 55.0]] * n)
+    planner = rb.planner(torque_limits=tl)
+    for ft in (None, [1.0, -2.0, 0.5, 3.0, 0.0, -1.0]):
+        tau32, tr32 = planner.trajectory_inverse_dynamics(s, e, 2.0, N, 5, [0, 0, -9.81], ft, return_trajectory=True,
+                                                          precision="float32")
+        tau64, tr64 = planner.trajectory_inverse_dynamics(s, e, 2.0, N, 5, [0, 0, -9.81], ft, return_trajectory=True)
+        assert all(_bits_equal(tr32[k], tr64[k]) for k in tr64)
+        two32 = planner.inverse_dynamics_trajectory(tr64["positions"], tr64["velocities"], tr64["accelerations"],
+                                                    [0, 0, -9.81], ft, precision="float32")
+        assert _bits_equal(tau32, two32)
+        ref = o.inverse_dynamics_trajectory(tr64["positions"].reshape(-1, n), tr64["velocities"].reshape(-1, n),
+                                            tr64["accelerations"].reshape(-1, n), [0, 0, -9.81], ft, tl, analytic=True)
+        assert _rel_rows(tau32.reshape(-1, n), ref) < 1e-4
+        assert tau32.max() <= np.float32(55.0) and tau32.min() >= np.float32(-60.0)
+        assert not _bits_equal(tau32, tau64)
+
+
 def test_full_size_cfg3_ur5_trajectory_rnea(robots, oracle_factory):
     """UR5, 4096 trajectories x 2441 steps (9,998,336 points), quintic, fused."""
     from oracle import Oracle

@@ -258,6 +258,33 @@ def test_joint_sincos_accuracy(hostcheck):
     assert np.isnan(s).all() and np.isnan(c).all()
 
 
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_float32_kernel_algebra_within_north_star_tolerance(hostcheck, oracle_factory, robot):
+    """The float32 instantiation of the kernel templates: torques within 1e-4 relative and poses
+    within 1e-5 of the float64 oracle (BASELINE.json north_star: "fp32 kernels")."""
+    p = load_pack(robot)
+    o = oracle_factory(robot)
+    n = p["S_list"].shape[1]
+    rng = np.random.default_rng(5)
+    lo, hi = p["joint_limits"][:, 0], p["joint_limits"][:, 1]
+    th = rng.uniform(lo, hi, (300, n))
+    dth, ddth = rng.uniform(-2, 2, (300, n)), rng.uniform(-5, 5, (300, n))
+    g = np.array([0.0, 0.0, -9.81])
+    for flags in (0, 1):
+        rb = hostcheck.robot(p, flags)
+        ref = o.inverse_dynamics(th, dth, ddth, g, None, analytic=True)
+        got = hostcheck.rnea(rb, th, dth, ddth, g, None, f32=True)
+        assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-4
+        ft = rng.uniform(-10, 10, 6)
+        ref = o.inverse_dynamics(th, dth, ddth, g, ft, analytic=True)
+        got = hostcheck.rnea(rb, th, dth, ddth, g, ft, f32=True)
+        assert np.max(np.abs(got - ref) / np.maximum(1, np.abs(ref).max(1, keepdims=True))) < 1e-4
+        T, J = hostcheck.fk(rb, th, f32=True)
+        Tref, Jref = o.forward_kinematics(th), o.jacobian(th)
+        assert np.abs(T - Tref).max() < 1e-5 * max(1, np.abs(Tref).max())
+        assert np.abs(J - Jref).max() < 1e-5 * max(1, np.abs(Jref).max())
+
+
 def test_planar_2r_known_answers(hostcheck):
     """Murray-Li-Sastry Ex. 4.3 (reference tests/test_v132_regressions.py:126-192, 229-286)."""
     rb = hostcheck.robot(planar_2r_pack())
