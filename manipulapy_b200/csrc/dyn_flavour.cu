@@ -26,11 +26,11 @@ template <int F>
 void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
     if (a.compute_f32) {
-        MPK_DISPATCH_DOF_V(rb->n, launch_smem(rnea_kernel<float, N_, GEN, REV>, grid, kDynThreads,
-                                              wrench_smem<float, N_, GEN, REV>(), s, narrow<N_, float>(rb), a));
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem_l1(rnea_kernel<float, N_, GEN, REV>, grid, kDynThreads,
+                                                 wrench_smem<float, N_, GEN, REV>(), 7, s, narrow<N_, float>(rb), a));
     } else {
-        MPK_DISPATCH_DOF_V(rb->n, launch_smem(rnea_kernel<double, N_, GEN, REV>, grid, kDynThreads,
-                                              wrench_smem<double, N_, GEN, REV>(), s, narrow<N_>(rb), a));
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem_l1(rnea_kernel<double, N_, GEN, REV>, grid, kDynThreads,
+                                                 wrench_smem<double, N_, GEN, REV>(), 5, s, narrow<N_>(rb), a));
     }
 }
 

@@ -124,6 +124,21 @@ static void launch_smem(void (*kern)(KArgs...), unsigned grid, int threads, size
     kern<<<grid, threads, smem, s>>>(args...);
 }
 
+// The same, but carving out only the shared memory `blocks` resident blocks need, so that the
+// rest of the 256 KB stays L1: kernels that read their input rows with strided per-joint loads
+// rely on L1 to hold a warp's rows between the loads of consecutive joints.
+template <typename... KArgs, typename... Args>
+static void launch_smem_l1(void (*kern)(KArgs...), unsigned grid, int threads, size_t smem, int blocks,
+                           cudaStream_t s, Args &&...args) {
+    if (smem > 32 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t need = (smem + 1024) * (size_t)blocks;
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    kern<<<grid, threads, smem, s>>>(args...);
+}
+
 #ifdef MPK_FLAVOUR_KERNELS
 // ======================================================================================
 // kernels (only the flavour translation units see this part)
