@@ -42,6 +42,12 @@ extern "C" {
 
 #define MPK_MAX_DOF 8
 
+/* or-ed into `method` of the trajectory launchers: the contract of the reference's registry
+ * launchers and CUDA kernels (cuda_kernels/trajectory_kernels.py:40-76, 179, 195-198) instead
+ * of the planner's: linear time scaling for method not in {3, 5}, and zero scaling ("sit at
+ * start") for N <= 1 or Tf <= 0. */
+#define MPK_TRAJ_REGISTRY_CONTRACT 0x100
+
 /* mpk_robot_create flags */
 #define MPK_ROBOT_FORCE_GENERAL 1 /* route a rigid-body robot through the general-inertia kernels (tests) */
 
@@ -75,7 +81,8 @@ int mpk_robot_all_revolute(const mpk_robot *rb);
  *   start, end   dev (B, n) float64
  *   inputs_f32   1: round start/end to float32 first and subtract in float32
  *                (joint_trajectory, :147-153); 0: keep float64 (batch path, :474-476)
- *   method       3 cubic, 5 quintic, anything else zero scaling (planner CPU contract :67-68)
+ *   method       3 cubic, 5 quintic, anything else zero scaling (planner CPU contract :67-68);
+ *                | MPK_TRAJ_REGISTRY_CONTRACT for the registry launchers' contract
  *   limits       host (n, 2) float32 joint limits or NULL (no clip)
  *   pos/vel/acc  dev (B, N, n) float32; any may be NULL (not written)
  *   ts_scratch   dev (3, N) float64 workspace or NULL.  The time scaling (s, ds, dds) depends
@@ -96,6 +103,17 @@ int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void *theta, int
  * half the HBM bytes of this store-bound kernel. */
 int mpk_fk_jacobian_space_f32(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
                               float *T, float *J, void *stream);
+
+/* General form: frame = MPK_FRAME_SPACE | MPK_FRAME_BODY, out_dtype = MPK_F64 | MPK_F32 selects
+ * arithmetic and output type (T, J are arrays of that type).
+ * MPK_FRAME_BODY mirrors forward_kinematics(theta, "body") = M prod e^{[B_i] theta_i}
+ * (kinematics/fk.py:72-81) and jacobian(theta, "body") (kinematics/jacobian.py:74-90) for a
+ * robot created from the screws S'_i = Ad(M) B_i: then T is that pose and J = Ad(T^-1) J_s'
+ * is the reference's body Jacobian. */
+#define MPK_FRAME_SPACE 0
+#define MPK_FRAME_BODY 1
+int mpk_fk_jacobian(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype, int frame,
+                    int out_dtype, void *T, void *J, void *stream);
 
 /* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
  * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).

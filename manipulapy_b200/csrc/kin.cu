@@ -18,6 +18,7 @@ struct KinArgs {
     const void *theta;
     int theta_dtype;
     int vec;
+    int body;     // body Jacobian Ad(T^-1) J_s instead of the space Jacobian
     void *T, *J;  // arrays of the kernel's arithmetic type
 };
 
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(kKinThreads)
         JointCS<E, N> q;
         joint_cs(rb, th, q);
         // Jacobian columns go straight into the lane's staging row as the chain produces them
-        fk_jacobian<E, N>(rb, q, Tg ? Tm : nullptr, Jg ? buf + lane * StageJ::S : nullptr);
+        fk_jacobian<E, N>(rb, q, Tg ? Tm : nullptr, Jg ? buf + lane * StageJ::S : nullptr, a.body != 0);
     }
     if (Jg) StageJ::flush(buf, Jg + pw * KJ, rows);
     if (Tg) {
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(kKinThreads)
 
 template <typename E>
 static int fk_launch(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype, E *T, E *J,
-                     void *stream) {
+                     void *stream, int body = 0) {
     if (!rb) return fail(MPK_EINVAL, "robot is NULL");
     if (P < 0) return fail(MPK_EINVAL, "negative size");
     if (P == 0 || (!T && !J)) return MPK_OK;
@@ -76,6 +77,7 @@ static int fk_launch(const mpk_robot *rb, int64_t P, const void *theta, int thet
     a.vec = aligned16(theta);
     a.T = T;
     a.J = J;
+    a.body = body;
     const int64_t blocks = (P + kKinThreads - 1) / kKinThreads;
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "P exceeds the grid limit");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -105,4 +107,16 @@ extern "C" int mpk_fk_jacobian_space(const mpk_robot *rb, int64_t P, const void 
 extern "C" int mpk_fk_jacobian_space_f32(const mpk_robot *rb, int64_t P, const void *theta,
                                          int theta_dtype, float *T, float *J, void *stream) {
     return fk_launch<float>(rb, P, theta, theta_dtype, T, J, stream);
+}
+
+extern "C" int mpk_fk_jacobian(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype,
+                               int frame, int out_dtype, void *T, void *J, void *stream) {
+    if (frame != MPK_FRAME_SPACE && frame != MPK_FRAME_BODY) return fail(MPK_EINVAL, "bad frame");
+    if (out_dtype == MPK_F64)
+        return fk_launch<double>(rb, P, theta, theta_dtype, static_cast<double *>(T), static_cast<double *>(J),
+                                 stream, frame == MPK_FRAME_BODY);
+    if (out_dtype == MPK_F32)
+        return fk_launch<float>(rb, P, theta, theta_dtype, static_cast<float *>(T), static_cast<float *>(J),
+                                stream, frame == MPK_FRAME_BODY);
+    return fail(MPK_EINVAL, "bad dtype");
 }

@@ -938,8 +938,12 @@ MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const 
 // ---- kinematics ---------------------------------------------------------------
 // World pose of frame i accumulated along the chain; Jacobian column i = Ad(T_{0,i}) A_i.
 // Tout: row-major 4x4 (16), Jout: row-major (6, N); either may be nullptr.
+// body: return the BODY Jacobian Ad(T^-1) J_s instead (kinematics/jacobian.py:74-90), T the
+// end-effector pose; for a robot built from S' = Ad(M) B this is the reference's
+// J_b[:, i] = Ad(e^{-[B_n] th_n} ... e^{-[B_{i+1}] th_{i+1}}) B_i, and T = M prod e^{[B_i] th_i}.
 template <typename T, int N>
-MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T *Tout, T *Jout) {
+MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T *Tout, T *Jout,
+                        bool body = false) {
     // columns of the world rotation of the current frame, and its origin
     T X[3] = {rb.Rb[0], rb.Rb[3], rb.Rb[6]}, Y[3] = {rb.Rb[1], rb.Rb[4], rb.Rb[7]},
       Z[3] = {rb.Rb[2], rb.Rb[5], rb.Rb[8]};
@@ -974,18 +978,42 @@ MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T *To
             p[r] += dz * Z[r];
         }
     }
-    if (Tout) {
+    if (Tout || (body && Jout)) {
+        T Rf[9], pf[3];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
 #pragma unroll
             for (int cidx = 0; cidx < 3; ++cidx)
-                Tout[4 * r + cidx] = X[r] * rb.Ree[cidx] + Y[r] * rb.Ree[3 + cidx] + Z[r] * rb.Ree[6 + cidx];
-            Tout[4 * r + 3] = p[r] + X[r] * rb.pee[0] + Y[r] * rb.pee[1] + Z[r] * rb.pee[2];
+                Rf[3 * r + cidx] = X[r] * rb.Ree[cidx] + Y[r] * rb.Ree[3 + cidx] + Z[r] * rb.Ree[6 + cidx];
+            pf[r] = p[r] + X[r] * rb.pee[0] + Y[r] * rb.pee[1] + Z[r] * rb.pee[2];
         }
-        Tout[12] = T(0);
-        Tout[13] = T(0);
-        Tout[14] = T(0);
-        Tout[15] = T(1);
+        if (Tout) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int cidx = 0; cidx < 3; ++cidx) Tout[4 * r + cidx] = Rf[3 * r + cidx];
+                Tout[4 * r + 3] = pf[r];
+            }
+            Tout[12] = T(0);
+            Tout[13] = T(0);
+            Tout[14] = T(0);
+            Tout[15] = T(1);
+        }
+        if (body && Jout) {
+            // column by column: w_b = R^T w_s, v_b = R^T (v_s - p x w_s)
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const T wx = Jout[0 * N + i], wy = Jout[1 * N + i], wz = Jout[2 * N + i];
+                const T ux = Jout[3 * N + i] - (pf[1] * wz - pf[2] * wy);
+                const T uy = Jout[4 * N + i] - (pf[2] * wx - pf[0] * wz);
+                const T uz = Jout[5 * N + i] - (pf[0] * wy - pf[1] * wx);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    Jout[k * N + i] = Rf[k] * wx + Rf[3 + k] * wy + Rf[6 + k] * wz;
+                    Jout[(3 + k) * N + i] = Rf[k] * ux + Rf[3 + k] * uy + Rf[6 + k] * uz;
+                }
+            }
+        }
     }
 }
 
@@ -996,7 +1024,15 @@ struct TimeScale {
     double s, sd, sdd;
 };
 
+// `method`: 3 cubic, 5 quintic.  Anything else gives zero scaling (the planner's CPU kernel,
+// planning/trajectory.py:67-68) -- unless MPK_TRAJ_REGISTRY_CONTRACT (0x100) is or-ed in, which
+// selects the contract of the registry launchers and their kernels
+// (cuda_kernels/trajectory_kernels.py:40-76, 179, 195-198): linear scaling for any other method,
+// and s = ds = dds = 0 ("sit at start") when N <= 1 or Tf <= 0.
 MPK_HD TimeScale time_scaling(int64_t idx, int64_t N, double Tf, int method) {
+    const bool registry = (method & 0x100) != 0;
+    method &= 0xff;
+    if (registry && (N <= 1 || !(Tf > 0.0))) return TimeScale{0.0, 0.0, 0.0};
     const double step = rn_div(Tf, (double)(N - 1));
     const double t = rn_mul((double)idx, step);
     const double tau = rn_div(t, Tf);
@@ -1020,6 +1056,10 @@ MPK_HD TimeScale time_scaling(int64_t idx, int64_t N, double Tf, int method) {
         r.sdd = rn_div(
             rn_add(rn_sub(rn_mul(60.0, tau), rn_mul(180.0, t2)), rn_mul(120.0, t3)),
             rn_mul(Tf, Tf));
+    } else if (registry) {
+        r.s = tau;
+        r.sd = rn_div(1.0, Tf);
+        r.sdd = 0.0;
     } else {
         r.s = r.sd = r.sdd = 0.0;
     }

@@ -103,7 +103,7 @@ std::tuple<Tensor, Tensor, Tensor> joint_trajectory(const Tensor &start, const T
 }
 
 std::tuple<Tensor, Tensor> fk_jacobian(int64_t h, const Tensor &theta, bool want_T, bool want_J,
-                                       bool compute_f32) {
+                                       bool compute_f32, bool body) {
     mpk_robot *rb = robot(h);
     const int64_t n = mpk_robot_dof(rb);
     Tensor th = dev_rows(theta, n, "theta", true);
@@ -112,14 +112,10 @@ std::tuple<Tensor, Tensor> fk_jacobian(int64_t h, const Tensor &theta, bool want
     auto opt = th.options().dtype(compute_f32 ? at::kFloat : at::kDouble);
     Tensor T = want_T ? at::empty({P, 4, 4}, opt) : at::empty({0}, opt);
     Tensor J = want_J ? at::empty({P, 6, n}, opt) : at::empty({0}, opt);
-    if (compute_f32)
-        check(mpk_fk_jacobian_space_f32(rb, P, th.data_ptr(), dtype_of(th), want_T ? T.data_ptr<float>() : nullptr,
-                                        want_J ? J.data_ptr<float>() : nullptr, stream_of(th)),
-              "fk_jacobian_space_f32");
-    else
-        check(mpk_fk_jacobian_space(rb, P, th.data_ptr(), dtype_of(th), want_T ? T.data_ptr<double>() : nullptr,
-                                    want_J ? J.data_ptr<double>() : nullptr, stream_of(th)),
-              "fk_jacobian_space");
+    check(mpk_fk_jacobian(rb, P, th.data_ptr(), dtype_of(th), body ? MPK_FRAME_BODY : MPK_FRAME_SPACE,
+                          compute_f32 ? MPK_F32 : MPK_F64, want_T ? T.data_ptr() : nullptr,
+                          want_J ? J.data_ptr() : nullptr, stream_of(th)),
+          "fk_jacobian");
     return {T, J};
 }
 
@@ -291,8 +287,8 @@ TORCH_LIBRARY(mpk, m) {
     m.def("joint_trajectory(Tensor start, Tensor end, bool inputs_f32, float Tf, int N, int method, "
           "Tensor? joint_limits) -> (Tensor, Tensor, Tensor)",
           &joint_trajectory);
-    m.def("fk_jacobian(int robot, Tensor theta, bool want_T, bool want_J, bool compute_f32=False) -> "
-          "(Tensor, Tensor)",
+    m.def("fk_jacobian(int robot, Tensor theta, bool want_T, bool want_J, bool compute_f32=False, "
+          "bool body=False) -> (Tensor, Tensor)",
           &fk_jacobian);
     m.def("inverse_dynamics(int robot, Tensor theta, Tensor? dtheta, Tensor? ddtheta, float[] g, "
           "float[]? Ftip, Tensor? Ftip_rows, Tensor? torque_limits, bool out_f32, bool compute_f32=False) -> Tensor",

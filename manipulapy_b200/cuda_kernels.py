@@ -69,13 +69,23 @@ def _launch_cfg_points(points: int, threads: int = 128):
 
 def _launch_trajectory_gpu(thetastart, thetaend, Tf, N, method, use_pinned=True, *, enable_monitoring=True):
     """Reference launcher signature (registry.py:828-867): host ``(n,)`` endpoints ->
-    ``(pos, vel, acc)`` host float32 ``(N, n)``; endpoints are rounded to float32 first."""
+    ``(pos, vel, acc)`` host float32 ``(N, n)``; endpoints are rounded to float32 first.
+
+    Registry contract (cuda_kernels/trajectory_kernels.py:40-76, 179, 195-198): any method other
+    than 3 / 5 is LINEAR, and ``N <= 1`` or ``Tf <= 0`` sits at the start configuration -- unlike
+    the planner's CPU kernel (zero scaling / NaN), which ``joint_trajectory`` mirrors."""
     dev = _host.default_device()
+    if int(N) <= 0:
+        n = np.asarray(thetastart).shape[-1]
+        return tuple(np.zeros((0, n), np.float32) for _ in range(3))
     s = _host.to_device(np.asarray(thetastart, dtype=np.float32), dev).reshape(1, -1)
     e = _host.to_device(np.asarray(thetaend, dtype=np.float32), dev).reshape(1, -1)
-    pos, vel, acc = _native.ops().joint_trajectory(s, e, True, float(Tf), int(N), int(method), None)
+    pos, vel, acc = _native.ops().joint_trajectory(s, e, True, float(Tf), int(N),
+                                                   (int(method) & 0xFF) | REGISTRY_CONTRACT, None)
     return tuple(_host.to_host(x[0]) for x in (pos, vel, acc))
 
+
+REGISTRY_CONTRACT = 0x100  # MPK_TRAJ_REGISTRY_CONTRACT (include/mpk.h)
 
 KERNEL_REGISTRY = KernelRegistry()
 

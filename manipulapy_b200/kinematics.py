@@ -4,9 +4,8 @@
 ``forward_kinematics`` (kinematics/fk.py:39-86) and ``jacobian``
 (kinematics/jacobian.py:39-93) accept a single ``(n,)`` configuration (reference behaviour:
 returns ``(4, 4)`` / ``(6, n)`` float64) or a batch ``(P, n)`` (returns ``(P, 4, 4)`` /
-``(P, 6, n)``).  Both run in hand-written CUDA kernels; there is no CPU path.  Body-frame
-variants and the IK solvers are out of scope and raise
-``NotImplementedError``.
+``(P, 6, n)``), in the space or the body frame.  Both run in hand-written CUDA kernels; there
+is no CPU path.  The IK solvers are out of scope.
 """
 
 from __future__ import annotations
@@ -17,6 +16,17 @@ import numpy as np
 import torch
 
 from . import _host, _native
+
+
+def _adjoint(T: np.ndarray) -> np.ndarray:
+    """6x6 adjoint [[R, 0], [[p] R, R]] for twists [w; v] (utils/se3.py:45-52)."""
+    R, p = T[:3, :3], T[:3, 3]
+    px = np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+    A = np.zeros((6, 6))
+    A[:3, :3] = R
+    A[3:, 3:] = R
+    A[3:, :3] = px @ R
+    return A
 
 
 def _screws_from_axes(omega_list, r_list) -> np.ndarray:
@@ -81,6 +91,7 @@ class SerialManipulator:
         self.joint_limits = joint_limits if joint_limits is not None else [(None, None)] * n
         self._device_arg = device
         self._robot: Optional[RobotHandle] = None
+        self._robot_body: Optional[RobotHandle] = None
 
     # -- native handle ---------------------------------------------------------------------
     def _make_robot(self) -> RobotHandle:
@@ -91,6 +102,29 @@ class SerialManipulator:
         if self._robot is None:
             self._robot = self._make_robot()
         return self._robot
+
+    def _home_pose(self) -> np.ndarray:
+        M = np.asarray(self.M_list, dtype=np.float64)
+        return M[-1] if M.ndim == 3 else M
+
+    def _body_screws(self) -> np.ndarray:
+        """``B_list`` as the reference derives it (kinematics/serial_manipulator.py:75-95): given,
+        or from (omega_list, b_list), or -- with neither -- the screws consistent with S_list,
+        ``B_i = Ad(M^-1) S_i``."""
+        if self.B_list is not None:
+            return self.B_list
+        if self.b_list is not None and self.omega_list is not None:
+            return _screws_from_axes(self.omega_list, self.b_list)
+        return _adjoint(np.linalg.inv(self._home_pose())) @ self.S_list
+
+    @property
+    def robot_body(self) -> RobotHandle:
+        """Kinematics-only handle of the chain with space screws ``S'_i = Ad(M) B_i``:
+        ``M prod e^{[B_i] th_i} = prod e^{[S'_i] th_i} M`` and ``J_b = Ad(T^-1) J_s'``."""
+        if self._robot_body is None:
+            M = self._home_pose()
+            self._robot_body = RobotHandle(_adjoint(M) @ self._body_screws(), M)
+        return self._robot_body
 
     @property
     def device(self) -> torch.device:
@@ -121,26 +155,29 @@ class SerialManipulator:
         """End-effector pose(s) ``T = prod_i exp([S_i] theta_i) M`` (kinematics/fk.py:61-70).
 
         ``precision="float32"`` (extension) runs the float32 kernel and returns float32 arrays."""
-        if frame == "body":
-            raise NotImplementedError("body-frame FK is outside the B200 hot path (SURVEY.md 8f)")
-        if frame != "space":
+        if frame not in ("space", "body"):
             raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        T, _ = _native.ops().fk_jacobian(self.robot.handle, th, True, False, _host.is_f32(precision))
+        rb = self.robot if frame == "space" else self.robot_body  # same pose law, screws Ad(M) B
+        T, _ = _native.ops().fk_jacobian(rb.handle, th, True, False, _host.is_f32(precision), False)
         return self._finish(T, single, on_dev)
 
     def jacobian(self, thetalist, frame: str = "space", precision=None):
         """Space Jacobian(s) ``J[:, i] = Ad(prod_{j<i} exp([S_j] theta_j)) S_i`` (kinematics/jacobian.py:62-73)."""
-        if frame == "body":
-            raise NotImplementedError("body-frame Jacobian is outside the B200 hot path (SURVEY.md 8f)")
-        if frame != "space":
+        if frame not in ("space", "body"):
             raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        _, J = _native.ops().fk_jacobian(self.robot.handle, th, False, True, _host.is_f32(precision))
+        body = frame == "body"
+        rb = self.robot_body if body else self.robot
+        _, J = _native.ops().fk_jacobian(rb.handle, th, False, True, _host.is_f32(precision), body)
         return self._finish(J, single, on_dev)
 
-    def forward_kinematics_and_jacobian(self, thetalist, precision=None):
+    def forward_kinematics_and_jacobian(self, thetalist, precision=None, frame: str = "space"):
         """Both outputs from one fused kernel launch (batched extension)."""
+        if frame not in ("space", "body"):
+            raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
         th, single, on_dev = self._rows(thetalist, "thetalist")
-        T, J = _native.ops().fk_jacobian(self.robot.handle, th, True, True, _host.is_f32(precision))
+        body = frame == "body"
+        rb = self.robot_body if body else self.robot
+        T, J = _native.ops().fk_jacobian(rb.handle, th, True, True, _host.is_f32(precision), body)
         return self._finish(T, single, on_dev), self._finish(J, single, on_dev)

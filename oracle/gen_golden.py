@@ -16,6 +16,8 @@ Writes
                                        tests/data/dynamics_golden_*.npz) plus FK / Jacobian /
                                        forward_dynamics outputs computed here by the reference.
   tests/golden/trajectory.npz          joint_trajectory / batch_joint_trajectory (float32).
+  tests/golden/body_kinematics.npz     forward_kinematics / jacobian with frame="body".
+  tests/golden/registry_trajectory.npz the registry launcher seam (linear method, N <= 1 / Tf <= 0 guards).
   tests/golden/id_trajectory.npz       inverse_dynamics_trajectory (float32, clipped).
   tests/golden/fd_trajectory.npz       forward_dynamics_trajectory rollouts (float32).
 
@@ -186,6 +188,67 @@ def trajectory_golden() -> None:
     print("trajectory golden written")
 
 
+def body_kinematics_golden() -> None:
+    """forward_kinematics / jacobian with frame="body" of the unmodified reference: the UR5 as
+    loaded from its URDF, and a chain whose B_list is NOT Ad(M^-1) S_list (the reference takes
+    any B_list; kinematics/serial_manipulator.py:75-95)."""
+    from ManipulaPy.kinematics import SerialManipulator
+
+    out = {}
+    rng = np.random.default_rng(6)
+    proc, sm, dyn = load("ur5")
+    th = rng.uniform(-np.pi, np.pi, (9, 6))
+    out.update(ur5_M=np.asarray(sm.M_list), ur5_S=np.asarray(sm.S_list), ur5_B=np.asarray(sm.B_list), ur5_theta=th,
+               ur5_T=np.stack([np.asarray(sm.forward_kinematics(t, frame="body")) for t in th]),
+               ur5_J=np.stack([np.asarray(sm.jacobian(t, frame="body")) for t in th]))
+    # free-standing chain with one prismatic joint and independent body screws
+    n = 5
+    S, B = np.zeros((6, n)), np.zeros((6, n))
+    for A in (S, B):
+        for i in range(n):
+            w = rng.normal(size=3)
+            w /= np.linalg.norm(w)
+            q = rng.uniform(-0.4, 0.4, 3)
+            if i == 2:
+                A[3:, i] = w
+            else:
+                A[:3, i] = w
+                A[3:, i] = -np.cross(w, q)
+    Q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    if np.linalg.det(Q) < 0:
+        Q[:, 0] *= -1
+    M = np.eye(4)
+    M[:3, :3] = Q
+    M[:3, 3] = rng.uniform(-0.5, 0.5, 3)
+    sm2 = SerialManipulator(M_list=M, omega_list=S[:3], S_list=S, B_list=B)
+    th2 = rng.uniform(-2, 2, (7, n))
+    out.update(free_M=M, free_S=S, free_B=B, free_theta=th2,
+               free_T=np.stack([np.asarray(sm2.forward_kinematics(t, frame="body")) for t in th2]),
+               free_J=np.stack([np.asarray(sm2.jacobian(t, frame="body")) for t in th2]))
+    np.savez(GOLD_DIR / "body_kinematics.npz", **out)
+    print("body kinematics golden written")
+
+
+def registry_trajectory_golden() -> None:
+    """The registry seam (cuda_kernels/registry.py:828-867): outputs of the reference's own
+    launcher with CUDA routing off, i.e. trajectory_cpu_fallback."""
+    from ManipulaPy.cuda_kernels import registry
+
+    rng = np.random.default_rng(2)
+    out = {}
+    cases = {"linear": (2.0, 64, 1), "method7": (1.5, 17, 7), "cubic": (0.9, 33, 3), "quintic": (2.0, 100, 5),
+             "n1": (2.0, 1, 5), "tf0": (0.0, 9, 3), "tfneg": (-1.0, 4, 5)}
+    for name, (Tf, N, method) in cases.items():
+        s = rng.uniform(-2, 2, 6).astype(np.float32)
+        e = rng.uniform(-2, 2, 6).astype(np.float32)
+        pos, vel, acc = registry.execute_registered_kernel("trajectory.standard", s, e, Tf, N, method)
+        out.update({f"{name}_start": s, f"{name}_end": e, f"{name}_args": np.array([Tf, N, method], np.float64),
+                    f"{name}_positions": np.asarray(pos), f"{name}_velocities": np.asarray(vel),
+                    f"{name}_accelerations": np.asarray(acc)})
+    np.savez(GOLD_DIR / "registry_trajectory.npz", **out)
+    print("registry trajectory golden written")
+
+
 def id_trajectory_golden() -> None:
     out = {}
     for robot, npts in (("ur5", 24), ("iiwa14", 10)):
@@ -257,6 +320,8 @@ def main() -> None:
     for robot in ("ur5", "panda", "iiwa14"):
         dynamics_golden(robot)
     trajectory_golden()
+    body_kinematics_golden()
+    registry_trajectory_golden()
     id_trajectory_golden()
     fd_trajectory_golden()
 

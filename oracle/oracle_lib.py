@@ -210,6 +210,91 @@ class Oracle:
             pos, vel, acc = pos[0], vel[0], acc[0]
         return {"positions": pos, "velocities": vel, "accelerations": acc}
 
+    # -- body frame (numpy restatement; small cases only) --------------------------------------
+    @staticmethod
+    def _exp_twist(S, th):
+        """utils/se3.py:33-42 transform_from_twist (unit omega or omega = 0)."""
+        w, v = S[:3], S[3:]
+        T = np.eye(4)
+        if np.linalg.norm(w) == 0.0:
+            T[:3, 3] = v * th
+            return T
+        W = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        R = np.eye(3) + np.sin(th) * W + (1 - np.cos(th)) * W @ W
+        T[:3, :3] = R
+        T[:3, 3] = (np.eye(3) * th + (1 - np.cos(th)) * W + (th - np.sin(th)) * W @ W) @ v
+        return T
+
+    @staticmethod
+    def _adjoint(T):
+        R, p = T[:3, :3], T[:3, 3]
+        P = np.array([[0, -p[2], p[1]], [p[2], 0, -p[0]], [-p[1], p[0], 0]])
+        A = np.zeros((6, 6))
+        A[:3, :3] = R
+        A[3:, 3:] = R
+        A[3:, :3] = P @ R
+        return A
+
+    @staticmethod
+    def body_forward_kinematics(M, B_list, theta):
+        """T = M e^{[B_1] th_1} ... e^{[B_n] th_n}  (kinematics/fk.py:72-81)."""
+        th = _d(theta).reshape(-1, B_list.shape[1])
+        out = np.empty((th.shape[0], 4, 4))
+        for p in range(th.shape[0]):
+            T = np.eye(4)
+            for i in range(B_list.shape[1]):
+                T = T @ Oracle._exp_twist(B_list[:, i], th[p, i])
+            out[p] = np.asarray(M, np.float64) @ T
+        return out
+
+    @staticmethod
+    def body_jacobian(B_list, theta):
+        """J_b[:, i] = Ad(e^{-[B_n] th_n} ... e^{-[B_{i+1}] th_{i+1}}) B_i  (kinematics/jacobian.py:74-90)."""
+        n = B_list.shape[1]
+        th = _d(theta).reshape(-1, n)
+        out = np.empty((th.shape[0], 6, n))
+        for p in range(th.shape[0]):
+            T = np.eye(4)
+            out[p, :, n - 1] = B_list[:, n - 1]
+            for i in range(n - 2, -1, -1):
+                T = T @ Oracle._exp_twist(B_list[:, i + 1], -th[p, i + 1])
+                out[p, :, i] = Oracle._adjoint(T) @ B_list[:, i]
+        return out
+
+    @staticmethod
+    def registry_trajectory(thetastart, thetaend, Tf, N, method):
+        """The registry launchers' trajectory contract, restated from the reference's NumPy
+        float32 fallback (cuda_kernels/trajectory_kernels.py:40-85): linear time scaling for a
+        method other than 3 / 5, and s = ds = dds = 0 for N <= 1 or Tf <= 0.  float32 arithmetic
+        throughout, like the reference (its CUDA kernels are float32 fast-math: parity with this
+        path is "allclose", not bit-exact -- tests/test_cuda_kernels_cpu.py:227-262)."""
+        s0 = np.asarray(thetastart, dtype=np.float32)
+        e0 = np.asarray(thetaend, dtype=np.float32)
+        N = int(N)
+        if N <= 1 or Tf <= 0.0:
+            s = np.zeros(N, np.float32)
+            sd = np.zeros(N, np.float32)
+            sdd = np.zeros(N, np.float32)
+        else:
+            t = np.linspace(0, Tf, N, dtype=np.float32)
+            tau = t / Tf
+            if method == 3:
+                s = 3.0 * tau**2 - 2.0 * tau**3
+                sd = 6.0 * tau * (1.0 - tau) / Tf
+                sdd = 6.0 * (1.0 - 2.0 * tau) / (Tf * Tf)
+            elif method == 5:
+                s = 10.0 * tau**3 - 15.0 * tau**4 + 6.0 * tau**5
+                sd = (30.0 * tau**2 - 60.0 * tau**3 + 30.0 * tau**4) / Tf
+                sdd = (60.0 * tau - 180.0 * tau**2 + 120.0 * tau**3) / (Tf * Tf)
+            else:
+                s = tau
+                sd = np.ones_like(tau) / Tf
+                sdd = np.zeros_like(tau)
+        d = e0 - s0
+        pos = s0[None, :] + s[:, None] * d[None, :]
+        return (pos.astype(np.float32), (sd[:, None] * d[None, :]).astype(np.float32),
+                (sdd[:, None] * d[None, :]).astype(np.float32))
+
     def inverse_dynamics_trajectory(self, theta, dtheta, ddtheta, g=(0.0, 0.0, -9.81), Ftip=None,
                                     torque_limits=None, analytic=False):
         th = _d(theta).reshape(-1, self.n)

@@ -127,12 +127,23 @@ class HostCheck:
         self.H.hc_mass(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(out))
         return out
 
-    def fk(self, rb, th, f32=False):
+    def fk(self, rb, th, f32=False, body=False):
         h, n = rb
         th = np.ascontiguousarray(th, dtype=np.float64).reshape(-1, n)
         T, J = np.empty((th.shape[0], 4, 4)), np.empty((th.shape[0], 6, n))
-        (self.H.hc_fk_f32 if f32 else self.H.hc_fk)(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(T), _ptr(J))
+        fn = self.H.hc_fk_body if body else (self.H.hc_fk_f32 if f32 else self.H.hc_fk)
+        fn(h, _C.c_int64(th.shape[0]), _ptr(th), _ptr(T), _ptr(J))
         return T, J
+
+    def kin_robot(self, S, M):
+        """Kinematics-only handle."""
+        h = _C.c_void_p()
+        S = np.ascontiguousarray(S, dtype=np.float64)
+        rc = self.L.mpk_robot_create(S.shape[1], _ptr(S), _ptr(np.ascontiguousarray(M, dtype=np.float64)), None, None,
+                                     0, _C.byref(h))
+        if rc != 0:
+            raise RuntimeError(self.L.mpk_last_error().decode())
+        return h, S.shape[1]
 
     def fd(self, rb, th, dth, tau, g=(0, 0, -9.81), ftip_rows=None):
         h, n = rb

@@ -77,14 +77,14 @@ static void mass_n(const mpk_robot *rb, int64_t P, const double *th, double *Mo)
 }
 
 template <int N>
-static void fk_n(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
+static void fk_n(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J, bool body = false) {
     const RobotPack<double, N> pk = narrow<N>(rb);
     for (int64_t p = 0; p < P; ++p) {
         double a[N];
         for (int j = 0; j < N; ++j) a[j] = th[p * N + j];
         JointCS<double, N> q;
         joint_cs(pk, a, q);
-        fk_jacobian<double, N>(pk, q, T ? T + p * 16 : nullptr, J ? J + p * 6 * N : nullptr);
+        fk_jacobian<double, N>(pk, q, T ? T + p * 16 : nullptr, J ? J + p * 6 * N : nullptr, body);
     }
 }
 
@@ -146,6 +146,10 @@ extern "C" int hc_mass(const mpk_robot *rb, int64_t P, const double *th, double 
 }
 extern "C" int hc_fk(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
     HC_DISPATCH(rb->n, fk_n<N_>(rb, P, th, T, J));
+    return 0;
+}
+extern "C" int hc_fk_body(const mpk_robot *rb, int64_t P, const double *th, double *T, double *J) {
+    HC_DISPATCH(rb->n, fk_n<N_>(rb, P, th, T, J, true));
     return 0;
 }
 extern "C" int hc_fd(const mpk_robot *rb, int64_t P, const double *th, const double *dth,

@@ -309,6 +309,54 @@ def test_device_resident_path(robots):
     assert st["gpu_calls"] >= 3 and st["cpu_calls"] == 0
 
 
+def test_body_frame_kinematics(robots):
+    """frame="body" FK / Jacobian against the reference goldens, against the numpy restatement
+    on a batch, and J_b = Ad(T^-1) J_s for the URDF robots (whose B_list is consistent)."""
+    from manipulapy_b200 import SerialManipulator
+    from manipulapy_b200.kinematics import _adjoint
+    from oracle import Oracle
+
+    g = load_golden("body_kinematics")
+    for k in ("ur5", "free"):
+        sm = SerialManipulator(M_list=g[f"{k}_M"], S_list=g[f"{k}_S"], B_list=g[f"{k}_B"])
+        th = g[f"{k}_theta"]
+        np.testing.assert_allclose(sm.forward_kinematics(th, frame="body"), g[f"{k}_T"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(sm.jacobian(th, frame="body"), g[f"{k}_J"], rtol=0, atol=1e-12)
+        assert sm.forward_kinematics(th[0], "body").shape == (4, 4) and sm.jacobian(th[0], "body").shape == (6, th.shape[1])
+        rng = np.random.default_rng(0)
+        big = rng.uniform(-3, 3, (1025, th.shape[1]))
+        T, J = sm.forward_kinematics_and_jacobian(big, frame="body")
+        np.testing.assert_allclose(T[:200], Oracle.body_forward_kinematics(g[f"{k}_M"], g[f"{k}_B"], big[:200]), rtol=0, atol=1e-12)
+        np.testing.assert_allclose(J[:200], Oracle.body_jacobian(g[f"{k}_B"], big[:200]), rtol=0, atol=1e-12)
+    rb = robots["iiwa14"]
+    th = np.random.default_rng(1).uniform(-2, 2, (300, 7))
+    Ts, Js = rb.dynamics.forward_kinematics_and_jacobian(th)
+    Tb, Jb = rb.dynamics.forward_kinematics_and_jacobian(th, frame="body")
+    np.testing.assert_allclose(Tb, Ts, rtol=0, atol=1e-12)
+    ref = np.stack([_adjoint(np.linalg.inv(T)) @ J for T, J in zip(Ts, Js)])
+    np.testing.assert_allclose(Jb, ref, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        rb.dynamics.jacobian(th[0], frame="tool")
+
+
+def test_registry_launcher_contract_vs_reference_golden():
+    """`trajectory.*` registry launchers: the reference's registry contract (linear for other
+    methods, N <= 1 / Tf <= 0 guards) against outputs of the reference's own launcher."""
+    from manipulapy_b200 import KERNEL_REGISTRY
+
+    g = load_golden("registry_trajectory")
+    for name in ("linear", "method7", "cubic", "quintic", "n1", "tf0", "tfneg"):
+        Tf, N, method = g[f"{name}_args"]
+        got = KERNEL_REGISTRY.execute("trajectory.vectorized", g[f"{name}_start"], g[f"{name}_end"], float(Tf),
+                                      int(N), int(method))
+        for a, k in zip(got, ("positions", "velocities", "accelerations")):
+            ref = g[f"{name}_{k}"]
+            assert a.dtype == np.float32 and a.shape == ref.shape
+            # (the reference's float32 polynomial carries a few float32 ulps of its largest term)
+            np.testing.assert_allclose(a, ref, rtol=2e-6, atol=4e-6 * max(1.0, float(np.abs(ref).max(initial=0.0))),
+                                       err_msg=f"{name} {k}")
+
+
 def test_registry_launcher_runs_on_gpu():
     from manipulapy_b200 import execute_registered_kernel
     from oracle import Oracle

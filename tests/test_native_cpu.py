@@ -318,6 +318,39 @@ def test_time_scaling_bit_exact_vs_golden(hostcheck):
     assert np.array_equal(np.isnan(got[0]), np.isnan(ref["positions"]))
 
 
+def test_body_frame_kinematics_vs_reference_golden(hostcheck):
+    """frame="body": the kernel template with screws S' = Ad(M) B and the Ad(T^-1) column
+    transform against the unmodified reference (tests/golden/body_kinematics.npz)."""
+    from manipulapy_b200.kinematics import _adjoint
+
+    g = load_golden("body_kinematics")
+    for k in ("ur5", "free"):
+        M, B, th = g[f"{k}_M"], g[f"{k}_B"], g[f"{k}_theta"]
+        rb = hostcheck.kin_robot(_adjoint(M) @ B, M)
+        T, J = hostcheck.fk(rb, th, body=True)
+        np.testing.assert_allclose(T, g[f"{k}_T"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(J, g[f"{k}_J"], rtol=0, atol=1e-12)
+
+
+def test_registry_trajectory_contract_vs_golden(hostcheck):
+    """The kernel's time scaling under MPK_TRAJ_REGISTRY_CONTRACT against the reference's registry
+    launcher outputs: linear for other methods, sit-at-start for N <= 1 / Tf <= 0.  The reference
+    computes this path in float32 (and its CUDA kernels with fast-math), the kernel in float64
+    with one rounding: equal to float32 rounding noise."""
+    g = load_golden("registry_trajectory")
+    for name in ("linear", "method7", "cubic", "quintic", "n1", "tf0", "tfneg"):
+        Tf, N, method = g[f"{name}_args"]
+        got = hostcheck.traj(g[f"{name}_start"], g[f"{name}_end"], float(Tf), int(N), int(method) | 0x100, None)
+        for a, k in zip(got, ("positions", "velocities", "accelerations")):
+            ref = g[f"{name}_{k}"]
+            # (the reference's float32 polynomial carries a few float32 ulps of its largest term)
+            np.testing.assert_allclose(a, ref, rtol=2e-6, atol=4e-6 * max(1.0, float(np.abs(ref).max(initial=0.0))),
+                                       err_msg=f"{name} {k}")
+    # the planner contract is untouched: other methods -> zero scaling
+    got = hostcheck.traj(np.zeros(3), np.ones(3), 2.0, 5, 1, None)
+    assert np.all(got[0] == 0) and np.all(got[1] == 0)
+
+
 def test_registry_contract():
     from manipulapy_b200 import KERNEL_REGISTRY, KernelRegistration
 

@@ -166,3 +166,33 @@ def test_quintic_endpoints_and_linear_contract():
     assert np.all(r["accelerations"][0] == 0) and np.allclose(r["accelerations"][-1], 0, atol=1e-6)
     assert np.all(r["positions"][0] == 0) and np.allclose(r["positions"][-1], 1.0)
     assert np.all(r["velocities"][0] == 0)
+
+
+def test_registry_trajectory_restatement_bit_exact_vs_reference():
+    """Oracle.registry_trajectory against the reference's own registry launcher with CUDA
+    routing off (tests/golden/registry_trajectory.npz, oracle/gen_golden.py): linear scaling for
+    other methods, N <= 1 / Tf <= 0 guards.  Same float32 NumPy arithmetic: bit-exact."""
+    from oracle import Oracle
+
+    g = load_golden("registry_trajectory")
+    for name in ("linear", "method7", "cubic", "quintic", "n1", "tf0", "tfneg"):
+        Tf, N, method = g[f"{name}_args"]
+        got = Oracle.registry_trajectory(g[f"{name}_start"], g[f"{name}_end"], float(Tf), int(N), int(method))
+        for a, k in zip(got, ("positions", "velocities", "accelerations")):
+            ref = g[f"{name}_{k}"]
+            assert a.dtype == np.float32 and a.shape == ref.shape
+            assert np.array_equal(a.view(np.uint32), ref.view(np.uint32)), (name, k)
+
+
+def test_body_frame_restatement_vs_reference():
+    """Oracle.body_forward_kinematics / body_jacobian against the unmodified reference
+    (frame="body"; tests/golden/body_kinematics.npz), including a chain whose B_list is
+    independent of its S_list."""
+    from oracle import Oracle
+
+    g = load_golden("body_kinematics")
+    for k in ("ur5", "free"):
+        T = Oracle.body_forward_kinematics(g[f"{k}_M"], g[f"{k}_B"], g[f"{k}_theta"])
+        J = Oracle.body_jacobian(g[f"{k}_B"], g[f"{k}_theta"])
+        np.testing.assert_allclose(T, g[f"{k}_T"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(J, g[f"{k}_J"], rtol=0, atol=1e-13)
