@@ -115,6 +115,22 @@ int mpk_fk_jacobian_space_f32(const mpk_robot *rb, int64_t P, const void *theta,
 int mpk_fk_jacobian(const mpk_robot *rb, int64_t P, const void *theta, int theta_dtype, int frame,
                     int out_dtype, void *T, void *J, void *stream);
 
+/* SerialManipulator.iterative_inverse_kinematics (kinematics/ik.py:39-311), default mode
+ * (adaptive_tuning = backtracking = False), for P independent targets: damped least squares on
+ * the space Jacobian with step cap, joint-limit projection, best-iterate tracking and
+ * stagnation restart.
+ *   T_desired dev (P, 4, 4) float64;  theta0 dev (P, n) float64 (initial guesses, not clipped)
+ *   joint_limits host (n, 2) float64, +-inf for an open side, or NULL
+ *   seed      key of the counter-based generator used by the stagnation restart (the reference
+ *             draws from NumPy's global generator there)
+ *   theta dev (P, n) float64;  iterations dev (P) int32 (the reference's k + 1; max_iterations + 1
+ *   when exhausted);  success dev (P) uint8 */
+int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const double *T_desired,
+                               const double *theta0, double eomg, double ev, int max_iterations,
+                               double damping, double step_cap, double weight_orientation,
+                               double weight_position, const double *joint_limits, uint64_t seed,
+                               double *theta, int32_t *iterations, uint8_t *success, void *stream);
+
 /* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
  * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).
  *   theta/dtheta/ddtheta  dev (P, n) in_dtype; dtheta / ddtheta may be NULL (= 0), which gives

@@ -30,7 +30,8 @@ NVCC_FLAGS = [
 # (source, object stem, extra defines).  The dynamics kernels exist in three flavours (rigid +
 # all-revolute, rigid, general inertias; csrc/dyn_kernels.cuh), each its own translation unit
 # so that the build uses every core.
-CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", []), ("kin.cu", "kin", []), ("dyn.cu", "dyn", [])]
+CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", []), ("kin.cu", "kin", []), ("ik.cu", "ik", []),
+            ("dyn.cu", "dyn", [])]
 CU_UNITS += [(f"{base}_flavour.cu", f"{base}_flavour{k}", [f"-DMPK_FLAVOUR={k}"])
              for base in ("dyn", "fd") for k in (0, 1, 2)]
 HEADERS = [CSRC / "mpk_device.cuh", CSRC / "mpk_common.cuh", CSRC / "dyn_kernels.cuh", INCLUDE / "mpk.h"]

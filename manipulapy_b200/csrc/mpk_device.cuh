@@ -39,6 +39,7 @@
 #include <string.h>
 
 #define MPK_HD __host__ __device__ __forceinline__
+#define MPK_MAX_DOF_ 8  // == MPK_MAX_DOF of include/mpk.h
 
 namespace mpk {
 
@@ -1015,6 +1016,179 @@ MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T *To
             }
         }
     }
+}
+
+// ---- damped-least-squares inverse kinematics (kinematics/ik.py:39-311) -------------------
+template <typename T, int NMAX>
+struct IkParams {
+    T eomg, ev, mu, step_cap, w_rot, w_pos;
+    int max_iter;
+    T lo[NMAX], hi[NMAX];
+};
+
+template <int NMAX = 8>
+inline IkParams<double, NMAX> make_ik_params(int n, double eomg, double ev, int max_iterations, double damping,
+                                             double step_cap, double w_rot, double w_pos,
+                                             const double *joint_limits) {
+    IkParams<double, NMAX> p;
+    p.eomg = eomg;
+    p.ev = ev;
+    p.mu = damping * damping + 1e-12;  // sigma / (sigma^2 + lambda^2 + 1e-12), ik.py:151
+    p.step_cap = step_cap;
+    p.w_rot = w_rot;
+    p.w_pos = w_pos;
+    p.max_iter = max_iterations;
+    for (int j = 0; j < NMAX; ++j) {
+        p.lo[j] = (joint_limits && j < n) ? joint_limits[2 * j] : -INFINITY;
+        p.hi[j] = (joint_limits && j < n) ? joint_limits[2 * j + 1] : INFINITY;
+    }
+    return p;
+}
+
+// Standard normal from a counter: splitmix64 of (seed, target, draw) -> Box-Muller.
+MPK_HD double ik_normal(unsigned long long seed, unsigned long long a, unsigned long long b) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (a + 1) + 0xBF58476D1CE4E5B9ULL * (b + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    const double u1 = ((double)(z >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+    unsigned long long y = z * 0xD6E8FEB86659FD93ULL + 0x2545F4914F6CDD1DULL;
+    y = (y ^ (y >> 32)) * 0xD6E8FEB86659FD93ULL;
+    y ^= y >> 32;
+    const double u2 = (double)(y >> 11) * (1.0 / 9007199254740992.0);
+    return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
+
+MPK_HD double ld_ro(const double *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// Geometric pose error of ik.py:88-140: V = [R_c w; p_d - p_c], rot = |angle|, trans = |p_d - p_c|;
+// Tc: current pose (row-major 4x4), Td: target pose.
+MPK_HD void ik_error(const double (&Tc)[16], const double *Td, double (&V)[6], double &rot, double &trans) {
+    double Rd[9], E[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rd[3 * r + c] = ld_ro(Td + 4 * r + c);
+        V[3 + r] = ld_ro(Td + 4 * r + 3) - Tc[4 * r + 3];
+    }
+    trans = sqrt(V[3] * V[3] + V[4] * V[4] + V[5] * V[5]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            E[3 * i + j] = Tc[i] * Rd[j] + Tc[4 + i] * Rd[3 + j] + Tc[8 + i] * Rd[6 + j];  // R_c^T R_d
+    double tr = ((E[0] + E[4] + E[8]) - 1.0) / 2.0;
+    tr = tr < -1.0 ? -1.0 : (tr > 1.0 ? 1.0 : tr);
+    const double angle = acos(tr);
+    rot = fabs(angle);
+    double w[3];
+    const double vee[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
+    if (angle < 1e-6) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = vee[k] / 2.0;
+    } else if (fabs(angle - 3.141592653589793) < 1e-6) {
+        int idx = 0;  // argmax of the diagonal (first maximum)
+        if (E[4] > E[0]) idx = 1;
+        if (E[8] > E[4 * idx]) idx = 2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = k == idx ? angle : 0.0;
+    } else {
+        const double den = 2.0 * sin(angle) + 1e-10;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w[k] = angle * (vee[k] / den);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) V[r] = Tc[4 * r] * w[0] + Tc[4 * r + 1] * w[1] + Tc[4 * r + 2] * w[2];
+}
+
+// One target.  th: initial guess in, solution out; J: scratch for the 6 x N Jacobian of the
+// current iterate (the kernel passes the thread's shared-memory row); returns success and the
+// reference's iteration count (k + 1; max_iter + 1 when exhausted).
+template <typename T, int N>
+MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], const IkParams<T, MPK_MAX_DOF_> &prm,
+                   unsigned long long seed, unsigned long long target, T *J, int &iterations) {
+    T best[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) best[j] = th[j];
+    double best_err = INFINITY, cur = INFINITY, rot = 0.0, trans = 0.0;
+    int stall = 0, k = 0;
+    bool ok = false;
+    for (k = 0; k < prm.max_iter; ++k) {
+        JointCS<T, N> q;
+        joint_cs(rb, th, q);
+        double Tc[16], V[6];
+        fk_jacobian<T, N>(rb, q, Tc, J);
+        ik_error(Tc, Td, V, rot, trans);
+        cur = rot + trans;
+        if (rot < prm.eomg && trans < prm.ev) {
+            ok = true;
+            break;
+        }
+        if (cur < best_err) {
+            best_err = cur;
+#pragma unroll
+            for (int j = 0; j < N; ++j) best[j] = th[j];
+            stall = 0;
+        } else {
+            ++stall;
+        }
+        if (stall > 20) {
+            // stagnation restart around the best iterate (ik.py:206-213)
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const T x = best[j] + 0.1 * ik_normal(seed, target, (unsigned long long)k * N + j);
+                th[j] = fmin(fmax(x, prm.lo[j]), prm.hi[j]);
+            }
+            stall = 0;
+            continue;
+        }
+        // (J J^T + mu 1) y = W e ;  dtheta = J^T y
+        T A[6][6], y[6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            y[r] = V[r] * (r < 3 ? prm.w_rot : prm.w_pos);
+#pragma unroll
+            for (int c = 0; c <= r; ++c) {
+                T s = r == c ? prm.mu : T(0);
+#pragma unroll
+                for (int i = 0; i < N; ++i) s += J[r * N + i] * J[c * N + i];
+                A[r][c] = s;
+            }
+        }
+        ldlt_solve<T, 6>(A, y);
+        T d[N], nrm = T(0);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T s = T(0);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) s += J[r * N + i] * y[r];
+            d[i] = s;
+            nrm += s * s;
+        }
+        nrm = sqrt(nrm);
+        const T scale = nrm > prm.step_cap ? prm.step_cap / nrm : T(1);
+#pragma unroll
+        for (int j = 0; j < N; ++j) th[j] = fmin(fmax(th[j] + scale * d[j], prm.lo[j]), prm.hi[j]);
+    }
+    if (!ok && best_err < cur) {
+        // max_iterations reached (ik.py:264-275): fall back to the best iterate if it is better
+#pragma unroll
+        for (int j = 0; j < N; ++j) th[j] = best[j];
+        JointCS<T, N> q;
+        joint_cs(rb, th, q);
+        double Tc[16], V[6];
+        fk_jacobian<T, N>(rb, q, Tc, (T *)nullptr);
+        ik_error(Tc, Td, V, rot, trans);
+        ok = rot < prm.eomg && trans < prm.ev;
+    }
+    iterations = k + 1;
+    return ok;
 }
 
 // ---- time scaling (planning/trajectory.py:15-75) -------------------------------

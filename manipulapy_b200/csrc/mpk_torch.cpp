@@ -268,6 +268,34 @@ std::tuple<Tensor, Tensor, Tensor> forward_dynamics_trajectory(
     return {pos, vel, acc};
 }
 
+std::tuple<Tensor, Tensor, Tensor> inverse_kinematics_dls(
+    int64_t h, const Tensor &T_desired, const Tensor &theta0, double eomg, double ev, int64_t max_iterations,
+    double damping, double step_cap, double weight_orientation, double weight_position, const OptT &limits,
+    int64_t seed) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th0 = dev_rows(theta0, n, "thetalist0", false);
+    const int64_t P = th0.numel() / n;
+    TORCH_CHECK(T_desired.is_cuda() && T_desired.numel() == P * 16, "mpk: T_desired must be a CUDA (P, 4, 4) tensor");
+    Tensor Td = T_desired.to(at::kDouble).contiguous();
+    std::vector<double> lim;
+    if (limits.has_value()) {
+        Tensor l = limits->to(at::kCPU, at::kDouble).contiguous();
+        TORCH_CHECK(l.numel() == n * 2, "mpk: joint_limits must be (n, 2)");
+        lim.assign(l.data_ptr<double>(), l.data_ptr<double>() + n * 2);
+    }
+    c10::cuda::CUDAGuard guard(th0.device());
+    Tensor theta = at::empty({P, n}, th0.options());
+    Tensor iters = at::empty({P}, th0.options().dtype(at::kInt));
+    Tensor ok = at::empty({P}, th0.options().dtype(at::kByte));
+    check(mpk_inverse_kinematics_dls(rb, P, Td.data_ptr<double>(), th0.data_ptr<double>(), eomg, ev,
+                                     (int)max_iterations, damping, step_cap, weight_orientation, weight_position,
+                                     lim.empty() ? nullptr : lim.data(), (uint64_t)seed, theta.data_ptr<double>(),
+                                     iters.data_ptr<int32_t>(), ok.data_ptr<uint8_t>(), stream_of(th0)),
+          "inverse_kinematics_dls");
+    return {theta, ok, iters};
+}
+
 void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads, int64_t iters) {
     TORCH_CHECK(sink.is_cuda() && sink.scalar_type() == at::kDouble && sink.numel() >= 1,
                 "mpk: sink must be a CUDA float64 tensor");
@@ -304,5 +332,9 @@ TORCH_LIBRARY(mpk, m) {
     m.def("forward_dynamics_trajectory(int robot, Tensor theta0, Tensor dtheta0, Tensor taumat, float[] g, "
           "Tensor? Ftipmat, float dt, int intRes, Tensor? joint_limits) -> (Tensor, Tensor, Tensor)",
           &forward_dynamics_trajectory);
+    m.def("inverse_kinematics_dls(int robot, Tensor T_desired, Tensor theta0, float eomg, float ev, "
+          "int max_iterations, float damping, float step_cap, float weight_orientation, float weight_position, "
+          "Tensor? joint_limits, int seed) -> (Tensor, Tensor, Tensor)",
+          &inverse_kinematics_dls);
     m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
 }

@@ -5,7 +5,9 @@
 (kinematics/jacobian.py:39-93) accept a single ``(n,)`` configuration (reference behaviour:
 returns ``(4, 4)`` / ``(6, n)`` float64) or a batch ``(P, n)`` (returns ``(P, 4, 4)`` /
 ``(P, 6, n)``), in the space or the body frame.  Both run in hand-written CUDA kernels; there
-is no CPU path.  The IK solvers are out of scope.
+is no CPU path.  ``iterative_inverse_kinematics`` (kinematics/ik.py:39-311, default mode) runs
+one target per thread in a batched damped-least-squares kernel; the other IK front ends
+(smart / robust / trac_ik) are out of scope.
 """
 
 from __future__ import annotations
@@ -171,6 +173,49 @@ class SerialManipulator:
         rb = self.robot_body if body else self.robot
         _, J = _native.ops().fk_jacobian(rb.handle, th, False, True, _host.is_f32(precision), body)
         return self._finish(J, single, on_dev)
+
+    def iterative_inverse_kinematics(self, T_desired, thetalist0, eomg: float = 1e-6, ev: float = 1e-6,
+                                     max_iterations: int = 10000, plot_residuals: bool = False,
+                                     damping: float = 2e-2, step_cap: float = 0.3,
+                                     png_name: str = "ik_residuals.png", weight_orientation: float = 1.0,
+                                     weight_position: float = 1.0, adaptive_tuning: bool = False,
+                                     backtracking: bool = False, *, seed: int = 0):
+        """Damped-least-squares IK with step cap, joint-limit projection, best-iterate tracking
+        and stagnation restart (kinematics/ik.py:39-311, default mode).
+
+        Reference call: ``T_desired (4, 4)``, ``thetalist0 (n,)`` -> ``(theta (n,), success, iterations)``.
+        Batched extension: ``(P, 4, 4)``, ``(P, n)`` -> ``(theta (P, n), success (P,) bool,
+        iterations (P,) int32)``, one target per GPU thread.  ``adaptive_tuning``, ``backtracking``
+        and ``plot_residuals`` are not part of the kernel.  ``seed`` keys the noise of the
+        stagnation restart (the reference draws it from NumPy's global generator)."""
+        if adaptive_tuning or backtracking or plot_residuals:
+            raise NotImplementedError(
+                "adaptive_tuning / backtracking / plot_residuals are outside the B200 hot path; the batched "
+                "kernel implements the default mode of iterative_inverse_kinematics")
+        on_dev = _host.any_device(T_desired, thetalist0)
+        dev = (thetalist0.device if _host.is_device_tensor(thetalist0)
+               else T_desired.device if _host.is_device_tensor(T_desired) else self.device)
+        th0 = _host.to_device(thetalist0, dev)
+        single = th0.dim() == 1
+        n = self.num_joints
+        th0 = th0.reshape(-1, n)
+        Td = _host.to_device(T_desired, dev).reshape(-1, 4, 4)
+        if Td.shape[0] != th0.shape[0]:
+            raise ValueError(f"{Td.shape[0]} target poses for {th0.shape[0]} initial guesses")
+        lim = np.empty((n, 2))
+        for i in range(n):
+            mn, mx = (self.joint_limits[i] if i < len(self.joint_limits) else (None, None))
+            lim[i] = (-np.inf if mn is None else mn, np.inf if mx is None else mx)
+        theta, ok, it = _native.ops().inverse_kinematics_dls(
+            self.robot.handle, Td, th0, float(eomg), float(ev), int(max_iterations), float(damping), float(step_cap),
+            float(weight_orientation), float(weight_position), torch.from_numpy(lim), int(seed))
+        ok = ok.bool()
+        if single:
+            th1 = theta[0] if on_dev else _host.to_host(theta[0])
+            return th1, bool(ok[0].item()), int(it[0].item())
+        if on_dev:
+            return theta, ok, it
+        return _host.to_host(theta), ok.cpu().numpy(), it.cpu().numpy()
 
     def forward_kinematics_and_jacobian(self, thetalist, precision=None, frame: str = "space"):
         """Both outputs from one fused kernel launch (batched extension)."""

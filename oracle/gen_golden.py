@@ -17,6 +17,7 @@ Writes
                                        forward_dynamics outputs computed here by the reference.
   tests/golden/trajectory.npz          joint_trajectory / batch_joint_trajectory (float32).
   tests/golden/body_kinematics.npz     forward_kinematics / jacobian with frame="body".
+  tests/golden/inverse_kinematics.npz  iterative_inverse_kinematics (theta, success, iterations).
   tests/golden/registry_trajectory.npz the registry launcher seam (linear method, N <= 1 / Tf <= 0 guards).
   tests/golden/id_trajectory.npz       inverse_dynamics_trajectory (float32, clipped).
   tests/golden/fd_trajectory.npz       forward_dynamics_trajectory rollouts (float32).
@@ -188,6 +189,43 @@ def trajectory_golden() -> None:
     print("trajectory golden written")
 
 
+def ik_golden() -> None:
+    """iterative_inverse_kinematics of the unmodified reference (default mode): reachable
+    targets T = FK(theta*) from seeds at increasing distance, an unreachable target that
+    exhausts its iteration budget, and non-default damping / weights / step cap."""
+    out = {}
+    for robot, count in (("ur5", 10), ("iiwa14", 8)):
+        proc, sm, dyn = load(robot)
+        n = sm.S_list.shape[1]
+        lims = limits_array(proc, n)
+        rng = np.random.default_rng(12)
+        tgt = rng.uniform(0.6 * lims[:, 0], 0.6 * lims[:, 1], (count, n))
+        seeds = tgt + rng.uniform(-1, 1, (count, n)) * np.linspace(0.05, 0.9, count)[:, None]
+        Td = np.stack([np.asarray(sm.forward_kinematics(t)) for t in tgt])
+        Td[-1, :3, 3] += np.array([5.0, 0.0, 0.0])  # out of reach
+        kw = [dict(max_iterations=300)] * count
+        kw[1] = dict(max_iterations=300, damping=5e-2, step_cap=0.15)
+        kw[2] = dict(max_iterations=300, weight_orientation=0.5, weight_position=2.0)
+        kw[-1] = dict(max_iterations=60)
+        th, ok, it = [], [], []
+        for i in range(count):
+            np.random.seed(100 + i)
+            r = sm.iterative_inverse_kinematics(Td[i], seeds[i], **kw[i])
+            th.append(np.asarray(r[0], np.float64))
+            ok.append(bool(r[1]))
+            it.append(int(r[2]))
+        par = np.array([[k.get("max_iterations"), k.get("damping", 2e-2), k.get("step_cap", 0.3),
+                         k.get("weight_orientation", 1.0), k.get("weight_position", 1.0)] for k in kw])
+        # (self-contained: the reference's URDF loader picks the end-effector link from a set, so
+        # M depends on PYTHONHASHSEED -- for the UR5 either the tool frame or the base link)
+        out.update({f"{robot}_M": np.asarray(sm.M_list, np.float64), f"{robot}_S": np.asarray(sm.S_list, np.float64),
+                    f"{robot}_T": Td, f"{robot}_seed": seeds, f"{robot}_params": par, f"{robot}_theta": np.stack(th),
+                    f"{robot}_success": np.array(ok), f"{robot}_iterations": np.array(it),
+                    f"{robot}_limits": lims})
+    np.savez(GOLD_DIR / "inverse_kinematics.npz", **out)
+    print("inverse kinematics golden written", {k: out[k] for k in out if k.endswith("iterations") or k.endswith("success")})
+
+
 def body_kinematics_golden() -> None:
     """forward_kinematics / jacobian with frame="body" of the unmodified reference: the UR5 as
     loaded from its URDF, and a chain whose B_list is NOT Ad(M^-1) S_list (the reference takes
@@ -321,6 +359,7 @@ def main() -> None:
         dynamics_golden(robot)
     trajectory_golden()
     body_kinematics_golden()
+    ik_golden()
     registry_trajectory_golden()
     id_trajectory_golden()
     fd_trajectory_golden()

@@ -210,6 +210,73 @@ class Oracle:
             pos, vel, acc = pos[0], vel[0], acc[0]
         return {"positions": pos, "velocities": vel, "accelerations": acc}
 
+    # -- inverse kinematics (numpy restatement; small cases only) -------------------------------
+    def iterative_inverse_kinematics(self, T_desired, thetalist0, eomg=1e-6, ev=1e-6, max_iterations=10000,
+                                     damping=2e-2, step_cap=0.3, weight_orientation=1.0, weight_position=1.0,
+                                     joint_limits=None):
+        """``iterative_inverse_kinematics`` in its default mode (adaptive_tuning = backtracking =
+        False), restated from kinematics/ik.py:39-311: geometric error (:88-140), SVD damped
+        least squares (:142-162), step cap and limit projection (:164-176, :253-262), best-iterate
+        tracking and the stagnation restart drawn from NumPy's global generator (:196-213).
+        Returns (theta, success, iterations) like the reference."""
+        theta = _d(thetalist0).copy()
+        Td = _d(T_desired).reshape(4, 4)
+        n = theta.shape[0]
+        lo, hi = np.full(n, -np.inf), np.full(n, np.inf)
+        if joint_limits is not None:
+            for i, (mn, mx) in enumerate(list(joint_limits)[:n]):
+                if mn is not None:
+                    lo[i] = mn
+                if mx is not None:
+                    hi[i] = mx
+
+        def err(T):
+            pos = Td[:3, 3] - T[:3, 3]
+            R = T[:3, :3]
+            E = R.T @ Td[:3, :3]
+            ang = np.arccos(np.clip((np.trace(E) - 1) / 2, -1, 1))
+            vee = np.array([E[2, 1] - E[1, 2], E[0, 2] - E[2, 0], E[1, 0] - E[0, 1]])
+            if ang < 1e-6:
+                w = vee / 2
+            elif abs(ang - np.pi) < 1e-6:
+                w = ang * np.eye(3)[int(np.argmax(np.diag(E)))]
+            else:
+                w = ang * (vee / (2 * np.sin(ang) + 1e-10))
+            return np.concatenate((R @ w, pos)), abs(ang), float(np.linalg.norm(pos))
+
+        best_theta, best_error, stall, success = theta.copy(), np.inf, 0, False
+        cur = np.inf
+        k = 0
+        for k in range(max_iterations):
+            V, rot, trans = err(self.forward_kinematics(theta)[0])
+            cur = rot + trans
+            if rot < eomg and trans < ev:
+                success = True
+                break
+            if cur < best_error:
+                best_error, best_theta, stall = cur, theta.copy(), 0
+            else:
+                stall += 1
+            if stall > 20:
+                theta = np.minimum(np.maximum(best_theta + 0.1 * np.random.randn(n), lo), hi)
+                stall = 0
+                continue
+            J = self.jacobian(theta)[0]
+            Vw = V * np.array([weight_orientation] * 3 + [weight_position] * 3)
+            U, sv, Vt = np.linalg.svd(J, full_matrices=False)
+            d = Vt.T @ ((sv / (sv**2 + damping**2 + 1e-12)) * (U.T @ Vw))
+            nd = np.linalg.norm(d)
+            if nd > step_cap:
+                d = d * (step_cap / nd)
+            theta = np.minimum(np.maximum(theta + d, lo), hi)
+        else:
+            k += 1 if max_iterations > 0 else 0
+        if not success and best_error < cur:
+            theta = best_theta
+            _, rot, trans = err(self.forward_kinematics(theta)[0])
+            success = bool(rot < eomg and trans < ev)
+        return theta, success, k + 1
+
     # -- body frame (numpy restatement; small cases only) --------------------------------------
     @staticmethod
     def _exp_twist(S, th):

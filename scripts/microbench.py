@@ -114,6 +114,18 @@ def main():
         rec(f"fk_jacobian_f32_{name}", Pk, timeit(lambda: ops.fk_jacobian(h, th, True, True, True)), 8 * n + 64 + 24 * n, 170 * n, "configs")
         rec(f"fk_only_{name}", Pk, timeit(lambda: ops.fk_jacobian(h, th, True, False)), 8 * n + 128, 110 * n, "configs")
         rec(f"mass_matrix_{name}", Pk, timeit(lambda: ops.mass_matrix(h, th)), 8 * n + 8 * n * n, 64 * n + 100 * n + 53 * n * (n + 1) // 2, "configs")
+        if name == "iiwa14":
+            # batched DLS inverse kinematics: targets = FK of random configurations, seeds 0.3 rad away
+            Pi = 200_000
+            tgt = 0.5 * th[:Pi]
+            Td = ops.fk_jacobian(h, tgt, True, False)[0]
+            seed = tgt + 0.6 * (torch.rand(Pi, n, dtype=torch.float64, device=dev, generator=gen) - 0.5)
+            lim = torch.from_numpy(rb.joint_limits.astype(np.float64))
+            sol = ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0)
+            res["ik_dls_iiwa14_success_rate"] = float(sol[1].float().mean())
+            res["ik_dls_iiwa14_mean_iterations"] = float(sol[2].float().mean())
+            rec("ik_dls_iiwa14", Pi, timeit(lambda: ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0), 3, 1),
+                128 + 8 * n + 8 * n + 5, 1400 * float(sol[2].float().mean()), "targets")
         dth, tau = rand(Pk, n), rand(Pk, n, lo=-20, hi=20)
         rec(f"forward_dynamics_{name}", Pk, timeit(lambda: ops.forward_dynamics(h, th, dth, tau, g, None, None)), 32 * n, 5300, "points")
 

@@ -212,6 +212,29 @@ extern "C" int hc_fk_f32(const mpk_robot *rb, int64_t P, const double *th, doubl
     HC_DISPATCH(rb->n, fk32_n<N_>(rb, P, th, T, J));
     return 0;
 }
+template <int N>
+static void ik_n(const mpk_robot *rb, int64_t P, const double *Td, const double *th0,
+                 const IkParams<double, MPK_MAX_DOF> &prm, unsigned long long seed, double *theta, int *iters,
+                 unsigned char *ok) {
+    const RobotPack<double, N> pk = narrow<N>(rb);
+    for (int64_t p = 0; p < P; ++p) {
+        double th[N], J[6 * N + 1];
+        for (int j = 0; j < N; ++j) th[j] = th0[p * N + j];
+        int it = 0;
+        ok[p] = ik_dls<double, N>(pk, Td + 16 * p, th, prm, seed, (unsigned long long)p, J, it) ? 1 : 0;
+        iters[p] = it;
+        for (int j = 0; j < N; ++j) theta[p * N + j] = th[j];
+    }
+}
+extern "C" int hc_ik(const mpk_robot *rb, int64_t P, const double *Td, const double *th0, double eomg, double ev,
+                     int max_iterations, double damping, double step_cap, double w_rot, double w_pos,
+                     const double *limits, unsigned long long seed, double *theta, int *iters,
+                     unsigned char *ok) {
+    const IkParams<double, MPK_MAX_DOF> prm =
+        make_ik_params(rb->n, eomg, ev, max_iterations, damping, step_cap, w_rot, w_pos, limits);
+    HC_DISPATCH(rb->n, ik_n<N_>(rb, P, Td, th0, prm, seed, theta, iters, ok));
+    return 0;
+}
 extern "C" int hc_sincos(int64_t P, const double *x, double *sn, double *cs) {
     double tab[17];
     fill_trig_table(tab);

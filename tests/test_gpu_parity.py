@@ -339,6 +339,42 @@ def test_body_frame_kinematics(robots):
         rb.dynamics.jacobian(th[0], frame="tool")
 
 
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_batched_inverse_kinematics(robot):
+    """iterative_inverse_kinematics: the reference's goldens (success, iteration counts, solutions),
+    then 20,000 targets in one launch: every converged solution reproduces its target pose."""
+    from manipulapy_b200 import SerialManipulator
+
+    g = load_golden("inverse_kinematics")
+    lim = [tuple(r) for r in g[f"{robot}_limits"]]
+    sm = SerialManipulator(M_list=g[f"{robot}_M"], S_list=g[f"{robot}_S"], joint_limits=lim)
+    n = sm.num_joints
+    for i, (Td, seed, par) in enumerate(zip(g[f"{robot}_T"], g[f"{robot}_seed"], g[f"{robot}_params"])):
+        th, ok, it = sm.iterative_inverse_kinematics(Td, seed, max_iterations=int(par[0]), damping=par[1],
+                                                     step_cap=par[2], weight_orientation=par[3], weight_position=par[4])
+        assert th.shape == (n,) and isinstance(ok, bool) and isinstance(it, int)
+        assert ok == bool(g[f"{robot}_success"][i]), i
+        if ok:
+            assert it == int(g[f"{robot}_iterations"][i]), i
+            np.testing.assert_allclose(th, g[f"{robot}_theta"][i], rtol=0, atol=1e-7)
+        else:
+            assert it == int(par[0]) + 1
+    rng = np.random.default_rng(2)
+    P = 20001
+    lo, hi = g[f"{robot}_limits"][:, 0], g[f"{robot}_limits"][:, 1]
+    tgt = rng.uniform(0.5 * lo, 0.5 * hi, (P, n))
+    Td = sm.forward_kinematics(tgt)
+    th, ok, it = sm.iterative_inverse_kinematics(Td, tgt + rng.uniform(-0.3, 0.3, (P, n)), max_iterations=400)
+    assert th.shape == (P, n) and ok.dtype == bool and it.dtype == np.int32
+    assert ok.mean() > 0.95  # (the method itself stalls on a few per cent of random 7-DOF targets)
+    T = sm.forward_kinematics(th)
+    assert np.abs(T[ok] - Td[ok])[:, :3, 3].max() < 2e-6 and np.abs(T[ok] - Td[ok])[:, :3, :3].max() < 2e-6
+    assert (it[ok] <= 400).all() and (it[~ok] == 401).all()
+    assert (th >= lo - 1e-12).all() and (th <= hi + 1e-12).all()
+    with pytest.raises(NotImplementedError):
+        sm.iterative_inverse_kinematics(Td[0], tgt[0], backtracking=True)
+
+
 def test_registry_launcher_contract_vs_reference_golden():
     """`trajectory.*` registry launchers: the reference's registry contract (linear for other
     methods, N <= 1 / Tf <= 0 guards) against outputs of the reference's own launcher."""

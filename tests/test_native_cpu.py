@@ -318,6 +318,32 @@ def test_time_scaling_bit_exact_vs_golden(hostcheck):
     assert np.array_equal(np.isnan(got[0]), np.isnan(ref["positions"]))
 
 
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_kinematics_kernel_vs_reference_golden(hostcheck, robot):
+    """The kernel's per-target DLS solver (csrc/mpk_device.cuh ik_dls) against the unmodified
+    reference: same success flags and iteration counts, solutions to 1e-7, for every run that
+    does not reach the stagnation restart (whose noise comes from a different generator);
+    exhausted runs report max_iterations + 1 and failure like the reference."""
+    g = load_golden("inverse_kinematics")
+    rb = hostcheck.kin_robot(g[f"{robot}_S"], g[f"{robot}_M"])
+    lim = g[f"{robot}_limits"]
+    for i, (Td, seed, par) in enumerate(zip(g[f"{robot}_T"], g[f"{robot}_seed"], g[f"{robot}_params"])):
+        th, ok, it = hostcheck.ik(rb, Td, seed, max_iterations=int(par[0]), damping=par[1], step_cap=par[2],
+                                  weight_orientation=par[3], weight_position=par[4], limits=lim)
+        assert bool(ok[0]) == bool(g[f"{robot}_success"][i]), i
+        if g[f"{robot}_success"][i]:
+            assert int(it[0]) == int(g[f"{robot}_iterations"][i]), i
+            np.testing.assert_allclose(th[0], g[f"{robot}_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
+        else:
+            assert int(it[0]) == int(par[0]) + 1
+    # batch call = per-target calls; zero iterations allowed
+    Tds, seeds = g[f"{robot}_T"][[0, 3, 4]], g[f"{robot}_seed"][[0, 3, 4]]
+    th, ok, it = hostcheck.ik(rb, Tds, seeds, max_iterations=300, limits=lim)
+    assert ok.all() and np.array_equal(it, g[f"{robot}_iterations"][[0, 3, 4]])
+    th0, ok0, it0 = hostcheck.ik(rb, Tds, seeds, max_iterations=0, limits=lim)
+    assert not ok0.any() and np.array_equal(th0, seeds) and (it0 == 1).all()
+
+
 def test_body_frame_kinematics_vs_reference_golden(hostcheck):
     """frame="body": the kernel template with screws S' = Ad(M) B and the Ad(T^-1) column
     transform against the unmodified reference (tests/golden/body_kinematics.npz)."""

@@ -196,3 +196,24 @@ def test_body_frame_restatement_vs_reference():
         J = Oracle.body_jacobian(g[f"{k}_B"], g[f"{k}_theta"])
         np.testing.assert_allclose(T, g[f"{k}_T"], rtol=0, atol=1e-13)
         np.testing.assert_allclose(J, g[f"{k}_J"], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_kinematics_restatement_vs_reference(robot):
+    """Oracle.iterative_inverse_kinematics against the unmodified reference
+    (tests/golden/inverse_kinematics.npz): same iterates, success flags and iteration counts --
+    including the runs that go through the stagnation restart, because both draw it from
+    NumPy's global generator seeded alike."""
+    from oracle import Oracle
+
+    g = load_golden("inverse_kinematics")
+    pack = load_pack(robot)
+    o = Oracle(g[f"{robot}_S"], g[f"{robot}_M"], pack["Glist"], pack["Mlist_per_link"])  # the golden's own M
+    lim = [tuple(r) for r in g[f"{robot}_limits"]]
+    for i, (Td, seed, par) in enumerate(zip(g[f"{robot}_T"], g[f"{robot}_seed"], g[f"{robot}_params"])):
+        np.random.seed(100 + i)
+        th, ok, it = o.iterative_inverse_kinematics(Td, seed, max_iterations=int(par[0]), damping=par[1], step_cap=par[2],
+                                                    weight_orientation=par[3], weight_position=par[4], joint_limits=lim)
+        assert ok == bool(g[f"{robot}_success"][i]), i
+        assert it == int(g[f"{robot}_iterations"][i]), i
+        np.testing.assert_allclose(th, g[f"{robot}_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
