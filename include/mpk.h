@@ -94,6 +94,17 @@ int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const
                          int inputs_f32, double Tf, int method, const float *limits, float *pos,
                          float *vel, float *acc, double *ts_scratch, void *stream);
 
+/* cartesian_trajectory (planning/trajectory.py:504-594, 676-740) for B start / end pose pairs:
+ * orientation Rstart exp(log(Rstart^T Rend) s), position s pend + (1 - s) pstart, linear velocity /
+ * acceleration ds (pend - pstart), dds (pend - pstart); s cubic for method 3, quintic otherwise;
+ * ds = dds = 0 for a method other than 3 / 5 (the reference's CPU path).  float64 arithmetic,
+ * one rounding to float32.
+ *   Xstart, Xend dev (B, 4, 4) float64;  pos / vel / acc dev (B, N, 3) float32 or NULL;
+ *   orientations dev (B, N, 3, 3) float32 or NULL */
+int mpk_cartesian_trajectory(int64_t B, int64_t N, const double *Xstart, const double *Xend, double Tf,
+                             int method, float *pos, float *vel, float *acc, float *orientations,
+                             void *stream);
+
 /* SerialManipulator.forward_kinematics(theta, "space") (kinematics/fk.py:39-86) and
  * SerialManipulator.jacobian(theta, "space") (kinematics/jacobian.py:39-93), batched.
  *   theta dev (P, n) theta_dtype;  T dev (P, 4, 4) float64 or NULL;  J dev (P, 6, n) float64 or NULL */

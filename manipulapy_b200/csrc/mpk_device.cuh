@@ -101,6 +101,14 @@ MPK_HD double bits_f64(int64_t b) {
 #endif
 }
 
+MPK_HD double ld_ro(const double *p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 // Coefficient table of sincos_pack: [0] 2/pi, [1] 1.5 * 2^52, [2..4] -(pi/2) split in three
 // (fdlibm's pio2_1, pio2_2, pio2_2t), [5..10] fdlibm __kernel_sin S1..S6, [11..16]
 // __kernel_cos C1..C6.
@@ -1018,6 +1026,111 @@ MPK_HD void fk_jacobian(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T *To
     }
 }
 
+// ---- Cartesian straight-line trajectory (planning/trajectory.py:504-594, 676-740) ----------
+// Rotation vector of E = Rstart^T Rend as utils/so3.py:172-191 (MatrixLog3) computes it: angle
+// from atan2(|vee|/2, cos) (:150-169), the generic 0.5 (theta / sin theta) vee with its Taylor
+// band near the identity (:114-147), and across (pi - 1e-2, pi] the half-turn form theta * n
+// with n from the symmetric part (:33-79).
+MPK_HD void so3_log_vec(const double (&E)[9], double (&w)[3]) {
+    double c = ((E[0] + E[4] + E[8]) - 1.0) / 2.0;
+    c = c < -1.0 ? -1.0 : (c > 1.0 ? 1.0 : c);
+    const double vee[3] = {E[7] - E[5], E[2] - E[6], E[3] - E[1]};
+    const double vv = vee[0] * vee[0] + vee[1] * vee[1] + vee[2] * vee[2];
+    const double sin_t = sqrt(vv > 1e-300 ? vv : 1e-300) / 2.0;
+    const double theta = atan2(sin_t, c);
+    if (theta > 3.141592653589793 - 1e-2) {
+        // columns of (E + E^T)/2 - cos(theta) 1 = (1 - cos theta) n n^T are parallel to the axis
+        const double s00 = E[0] - c, s11 = E[4] - c, s22 = E[8] - c;
+        const double s01 = 0.5 * (E[1] + E[3]), s02 = 0.5 * (E[2] + E[6]), s12 = 0.5 * (E[5] + E[7]);
+        double cx, cy, cz, ref;
+        if (s22 >= 1e-6) {
+            cx = s02; cy = s12; cz = s22; ref = vee[2];
+        } else if (s11 >= 1e-6) {
+            cx = s01; cy = s11; cz = s12; ref = vee[1];
+        } else {
+            cx = s00; cy = s01; cz = s02; ref = vee[0];
+        }
+        const double n2 = cx * cx + cy * cy + cz * cz;
+        const double k = (ref >= 0.0 ? theta : -theta) / sqrt(n2 > 1e-24 ? n2 : 1e-24);
+        w[0] = k * cx;
+        w[1] = k * cy;
+        w[2] = k * cz;
+        return;
+    }
+    double coef;
+    if (c > 1.0 - 5e-5) {
+        const double u = 1.0 - c;
+        coef = 1.0 + u / 3.0 + u * u * (4.0 / 45.0);
+    } else {
+        const double cs = c < -1.0 + 1e-7 ? -1.0 + 1e-7 : (c > 1.0 - 1e-7 ? 1.0 - 1e-7 : c);
+        const double d = 1.0 - cs * cs;
+        coef = acos(cs) / sqrt(d > 1e-30 ? d : 1e-30);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) w[k] = 0.5 * coef * vee[k];
+}
+
+// Step `idx` of the straight-line motion from Xs to Xe (row-major 4x4):
+//   R = Rs exp([w] s), p = s pe + (1 - s) ps (trajectory.py:541-556), v = ds (pe - ps),
+//   a = dds (pe - ps) (:700-721); s is cubic for method 3 and QUINTIC for anything else (:544-547),
+//   ds / dds vanish for a method other than 3 / 5 (:716-717).  float64, one rounding to float32.
+MPK_HD void cartesian_point(const double *Xs, const double *Xe, int64_t idx, int64_t N, double Tf, int method,
+                            float (&pos)[3], float (&vel)[3], float (&acc)[3], float (&R)[9]) {
+    double Rs[9], E[9], w[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Rs[3 * r + c] = ld_ro(Xs + 4 * r + c);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            E[3 * i + j] = Rs[i] * ld_ro(Xe + j) + Rs[3 + i] * ld_ro(Xe + 4 + j) + Rs[6 + i] * ld_ro(Xe + 8 + j);
+    so3_log_vec(E, w);
+    // time scaling of the orientation / position: utils/time_scaling.py:28-53 at t = timegap * i
+    const double tq = rn_div(rn_mul(rn_div(Tf, (double)N - 1.0), (double)idx), Tf);
+    double s;
+    if (method == 3) s = 3.0 * (tq * tq) - 2.0 * (tq * tq * tq);
+    else s = 10.0 * (tq * tq * tq) - 15.0 * (tq * tq * tq * tq) + 6.0 * (tq * tq * tq * tq * tq);
+    // ... and of the linear velocity / acceleration (trajectory.py:703-717)
+    const double tau = rn_div(rn_mul((double)idx, rn_div(Tf, (double)(N - 1))), Tf);
+    double sd = 0.0, sdd = 0.0;
+    if (method == 3) {
+        sd = 6.0 * tau * (1.0 - tau) / Tf;
+        sdd = 6.0 / (Tf * Tf) * (1.0 - 2.0 * tau);
+    } else if (method == 5) {
+        const double t2 = tau * tau, t3 = t2 * tau, t4 = t2 * t2;
+        sd = (30.0 * t2 - 60.0 * t3 + 30.0 * t4) / Tf;
+        sdd = (60.0 * tau - 180.0 * t2 + 120.0 * t3) / (Tf * Tf);
+    }
+    // Rodrigues with the Taylor-safe coefficients of utils/so3.py:199-219
+    const double kx = w[0] * s, ky = w[1] * s, kz = w[2] * s;
+    const double th2 = kx * kx + ky * ky + kz * kz;
+    double A, B;
+    if (th2 < 1e-4) {
+        A = 1.0 - th2 / 6.0 + th2 * th2 / 120.0;
+        B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
+    } else {
+        const double th = sqrt(th2 > 1e-12 ? th2 : 1e-12);
+        A = sin(th) / th;
+        B = (1.0 - cos(th)) / (th * th);
+    }
+    // exp = 1 + A K + B K^2,  K = [k]x,  K^2 = k k^T - |k|^2 1
+    const double X[9] = {1.0 + B * (kx * kx - th2), -A * kz + B * kx * ky, A * ky + B * kx * kz,
+                         A * kz + B * kx * ky, 1.0 + B * (ky * ky - th2), -A * kx + B * ky * kz,
+                         -A * ky + B * kx * kz, A * kx + B * ky * kz, 1.0 + B * (kz * kz - th2)};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            R[3 * r + c] = (float)(Rs[3 * r] * X[c] + Rs[3 * r + 1] * X[3 + c] + Rs[3 * r + 2] * X[6 + c]);
+        const double ps = ld_ro(Xs + 4 * r + 3), pe = ld_ro(Xe + 4 * r + 3);
+        pos[r] = (float)(s * pe + (1.0 - s) * ps);
+        vel[r] = (float)(sd * (pe - ps));
+        acc[r] = (float)(sdd * (pe - ps));
+    }
+}
+
 // ---- damped-least-squares inverse kinematics (kinematics/ik.py:39-311) -------------------
 template <typename T, int NMAX>
 struct IkParams {
@@ -1057,14 +1170,6 @@ MPK_HD double ik_normal(unsigned long long seed, unsigned long long a, unsigned 
     y ^= y >> 32;
     const double u2 = (double)(y >> 11) * (1.0 / 9007199254740992.0);
     return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
-}
-
-MPK_HD double ld_ro(const double *p) {
-#ifdef __CUDA_ARCH__
-    return __ldg(p);
-#else
-    return *p;
-#endif
 }
 
 // Geometric pose error of ik.py:88-140: V = [R_c w; p_d - p_c], rot = |angle|, trans = |p_d - p_c|;

@@ -296,6 +296,24 @@ std::tuple<Tensor, Tensor, Tensor> inverse_kinematics_dls(
     return {theta, ok, iters};
 }
 
+std::tuple<Tensor, Tensor, Tensor, Tensor> cartesian_trajectory(const Tensor &Xstart, const Tensor &Xend, double Tf,
+                                                                int64_t N, int64_t method) {
+    TORCH_CHECK(Xstart.is_cuda() && Xend.is_cuda(), "mpk: Xstart / Xend must be CUDA tensors");
+    Tensor xs = Xstart.to(at::kDouble).contiguous(), xe = Xend.to(at::kDouble).contiguous();
+    TORCH_CHECK(xs.numel() % 16 == 0 && xe.numel() == xs.numel(), "mpk: Xstart / Xend must be (B, 4, 4)");
+    TORCH_CHECK(N >= 0, "mpk: N must be >= 0");
+    const int64_t B = xs.numel() / 16;
+    c10::cuda::CUDAGuard guard(xs.device());
+    auto opt = xs.options().dtype(at::kFloat);
+    Tensor pos = at::empty({B, N, 3}, opt), vel = at::empty({B, N, 3}, opt), acc = at::empty({B, N, 3}, opt);
+    Tensor ori = at::empty({B, N, 3, 3}, opt);
+    check(mpk_cartesian_trajectory(B, N, xs.data_ptr<double>(), xe.data_ptr<double>(), Tf, (int)method,
+                                   pos.data_ptr<float>(), vel.data_ptr<float>(), acc.data_ptr<float>(),
+                                   ori.data_ptr<float>(), stream_of(xs)),
+          "cartesian_trajectory");
+    return {pos, vel, acc, ori};
+}
+
 void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads, int64_t iters) {
     TORCH_CHECK(sink.is_cuda() && sink.scalar_type() == at::kDouble && sink.numel() >= 1,
                 "mpk: sink must be a CUDA float64 tensor");
@@ -336,5 +354,8 @@ TORCH_LIBRARY(mpk, m) {
           "int max_iterations, float damping, float step_cap, float weight_orientation, float weight_position, "
           "Tensor? joint_limits, int seed) -> (Tensor, Tensor, Tensor)",
           &inverse_kinematics_dls);
+    m.def("cartesian_trajectory(Tensor Xstart, Tensor Xend, float Tf, int N, int method) -> "
+          "(Tensor, Tensor, Tensor, Tensor)",
+          &cartesian_trajectory);
     m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
 }

@@ -127,9 +127,84 @@ int launch_joint_trajectory(int n, int64_t B, int64_t N, const double *start, co
     return check_launch("joint_trajectory");
 }
 
+// ---- Cartesian straight-line trajectories ------------------------------------------------
+struct CartArgs {
+    int64_t B, N, P;
+    FastDiv div;
+    const double *Xs, *Xe;
+    double Tf;
+    int method;
+    float *pos, *vel, *acc, *orient;
+};
+
+// One thread = one (trajectory, step): 3 + 3 + 3 + 9 float32 out, staged per warp and flushed
+// with coalesced stores like the joint-space kernel.
+__global__ void __launch_bounds__(kTrajThreads) cartesian_kernel(const CartArgs a) {
+    __shared__ __align__(16) float sm[kTrajThreads / 32][32 * 9];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t pw = (int64_t)blockIdx.x * kTrajThreads + warp * 32;
+    if (pw >= a.P) return;
+    const int64_t p = pw + lane;
+    float pos[3], vel[3], acc[3], R[9];
+    if (p < a.P) {
+        int64_t b, t;
+        point_coords(a.div, a.N, p, b, t);
+        cartesian_point(a.Xs + 16 * b, a.Xe + 16 * b, t, a.N, a.Tf, a.method, pos, vel, acc, R);
+    }
+    const int64_t rem = a.P - pw;
+    const int rows = (int)(rem < 32 ? rem : 32);
+    float *buf = sm[warp];
+    const float *src3[3] = {pos, vel, acc};
+    float *dst3[3] = {a.pos, a.vel, a.acc};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (!dst3[k]) continue;
+        if (lane < rows) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) buf[lane * 3 + j] = src3[k][j];
+        }
+        __syncwarp();
+        for (int e = lane; e < rows * 3; e += 32) __stcs(dst3[k] + pw * 3 + e, buf[e]);
+        __syncwarp();
+    }
+    if (a.orient) {
+        if (lane < rows) {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) buf[lane * 9 + j] = R[j];
+        }
+        __syncwarp();
+        for (int e = lane; e < rows * 9; e += 32) __stcs(a.orient + pw * 9 + e, buf[e]);
+    }
+}
+
 }  // namespace mpk
 
 using namespace mpk;
+
+extern "C" int mpk_cartesian_trajectory(int64_t B, int64_t N, const double *Xstart, const double *Xend,
+                                        double Tf, int method, float *pos, float *vel, float *acc,
+                                        float *orientations, void *stream) {
+    if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
+    if (B == 0 || N == 0) return MPK_OK;
+    if (!Xstart || !Xend) return fail(MPK_EINVAL, "Xstart / Xend are NULL");
+    CartArgs a;
+    a.B = B;
+    a.N = N;
+    a.P = B * N;
+    a.div = make_fastdiv(N, a.P);
+    a.Xs = Xstart;
+    a.Xe = Xend;
+    a.Tf = Tf;
+    a.method = method;
+    a.pos = pos;
+    a.vel = vel;
+    a.acc = acc;
+    a.orient = orientations;
+    const int64_t blocks = (a.P + kTrajThreads - 1) / kTrajThreads;
+    if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B*N exceeds the grid limit");
+    cartesian_kernel<<<(unsigned)blocks, kTrajThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+    return check_launch("cartesian_trajectory");
+}
 
 extern "C" int mpk_joint_trajectory(int n, int64_t B, int64_t N, const double *start,
                                     const double *end, int inputs_f32, double Tf, int method,

@@ -209,6 +209,36 @@ class OptimizedTrajectoryPlanning:
             return outs[0], {"positions": outs[1], "velocities": outs[2], "accelerations": outs[3]}
         return outs[0]
 
+    def cartesian_trajectory(self, Xstart, Xend, Tf, N, method) -> Dict[str, Any]:
+        """Straight-line Cartesian trajectory (planning/trajectory.py:504-594): orientation
+        ``Rstart exp(log(Rstart^T Rend) s)``, position ``s pend + (1 - s) pstart`` and the linear
+        velocity / acceleration, float32.  Reference call: ``(4, 4)`` poses -> ``(N, 3)`` /
+        ``(N, 3, 3)`` arrays; batched extension: ``(B, 4, 4)`` -> ``(B, N, 3)`` / ``(B, N, 3, 3)``."""
+        t0 = time.perf_counter()
+        N = int(N)
+        if N < 0:
+            raise ValueError("negative dimensions are not allowed")
+        if N == 1:
+            raise ZeroDivisionError("float division by zero")  # Tf / (N - 1.0), trajectory.py:525
+        on_dev = _host.any_device(Xstart, Xend)
+        dev = Xstart.device if _host.is_device_tensor(Xstart) else (
+            Xend.device if _host.is_device_tensor(Xend) else self.device)
+        xs, xe = _host.to_device(Xstart, dev), _host.to_device(Xend, dev)
+        single = xs.dim() == 2
+        xs, xe = xs.reshape(-1, 4, 4), xe.reshape(-1, 4, 4)
+        if xs.shape != xe.shape:
+            raise ValueError("Xstart and Xend must have the same shape")
+        pos, vel, acc, ori = _native.ops().cartesian_trajectory(xs, xe, float(Tf), N, int(method))
+        outs = [pos, vel, acc, ori]
+        if single:
+            outs = [o[0] for o in outs]
+            if N == 0:
+                outs[0] = outs[0].reshape(0)  # the reference's empty positions array is (0,)
+        if not on_dev:
+            outs = [_host.to_host(o) for o in outs]
+        self._tick(t0, transfers=0 if on_dev else 6, kernel="cartesian_trajectory")
+        return {"positions": outs[0], "velocities": outs[1], "accelerations": outs[2], "orientations": outs[3]}
+
     def forward_dynamics_trajectory(self, thetalist, dthetalist, taumat, g, Ftipmat, dt, intRes) -> Dict[str, Any]:
         """Single rollout (reference call: ``thetalist (n,)``, ``taumat (N, n)``, ``Ftipmat (N, 6)``)
         or ``B`` independent rollouts (``(B, n)``, ``(B, N, n)``, ``(B, N, 6)`` or ``None``)."""

@@ -17,6 +17,7 @@ Writes
                                        forward_dynamics outputs computed here by the reference.
   tests/golden/trajectory.npz          joint_trajectory / batch_joint_trajectory (float32).
   tests/golden/body_kinematics.npz     forward_kinematics / jacobian with frame="body".
+  tests/golden/cartesian_trajectory.npz cartesian_trajectory (positions, velocities, accelerations, orientations).
   tests/golden/inverse_kinematics.npz  iterative_inverse_kinematics (theta, success, iterations).
   tests/golden/registry_trajectory.npz the registry launcher seam (linear method, N <= 1 / Tf <= 0 guards).
   tests/golden/id_trajectory.npz       inverse_dynamics_trajectory (float32, clipped).
@@ -189,6 +190,48 @@ def trajectory_golden() -> None:
     print("trajectory golden written")
 
 
+def cartesian_golden() -> None:
+    """cartesian_trajectory of the unmodified reference: a generic pose pair (quintic, cubic and
+    a method that is neither), equal orientations, a tiny rotation, and rotations just below
+    and inside the half-turn band of MatrixLog3."""
+    planner, dyn, lims = make_planner("ur5")
+    rng = np.random.default_rng(8)
+
+    def rot(axis, ang):
+        a = np.asarray(axis, float) / np.linalg.norm(axis)
+        K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+    def pose(R, p):
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = p
+        return T
+
+    R0 = rot(rng.normal(size=3), 0.7)
+    ax = rng.normal(size=3)
+    cases = {
+        "generic5": (pose(R0, rng.uniform(-1, 1, 3)), pose(rot(rng.normal(size=3), 1.9), rng.uniform(-1, 1, 3)), 2.0, 40, 5),
+        "generic3": (pose(R0, rng.uniform(-1, 1, 3)), pose(rot(rng.normal(size=3), 2.4), rng.uniform(-1, 1, 3)), 1.3, 25, 3),
+        "method1": (pose(R0, rng.uniform(-1, 1, 3)), pose(rot(rng.normal(size=3), 0.9), rng.uniform(-1, 1, 3)), 2.0, 12, 1),
+        "same_R": (pose(R0, rng.uniform(-1, 1, 3)), pose(R0, rng.uniform(-1, 1, 3)), 0.8, 9, 5),
+        "tiny": (pose(R0, rng.uniform(-1, 1, 3)), pose(R0 @ rot(ax, 3e-4), rng.uniform(-1, 1, 3)), 1.0, 9, 5),
+        "near_pi": (pose(R0, rng.uniform(-1, 1, 3)), pose(R0 @ rot(ax, np.pi - 0.05), rng.uniform(-1, 1, 3)), 1.0, 21, 5),
+        "pi_band": (pose(R0, rng.uniform(-1, 1, 3)), pose(R0 @ rot(ax, np.pi - 2e-3), rng.uniform(-1, 1, 3)), 1.0, 21, 3),
+        "pi_exact": (pose(np.eye(3), np.zeros(3)), pose(np.diag([1.0, -1.0, -1.0]), np.ones(3)), 1.0, 11, 5),
+    }
+    out = {}
+    for name, (Xs, Xe, Tf, N, method) in cases.items():
+        r = planner.cartesian_trajectory(Xs, Xe, Tf, N, method)
+        out.update({f"{name}_Xstart": Xs, f"{name}_Xend": Xe, f"{name}_args": np.array([Tf, N, method], np.float64)})
+        for k in ("positions", "velocities", "accelerations", "orientations"):
+            a = np.asarray(r[k])
+            assert a.dtype == np.float32, (name, k, a.dtype)
+            out[f"{name}_{k}"] = a
+    np.savez(GOLD_DIR / "cartesian_trajectory.npz", **out)
+    print("cartesian trajectory golden written")
+
+
 def ik_golden() -> None:
     """iterative_inverse_kinematics of the unmodified reference (default mode): reachable
     targets T = FK(theta*) from seeds at increasing distance, an unreachable target that
@@ -359,6 +402,7 @@ def main() -> None:
         dynamics_golden(robot)
     trajectory_golden()
     body_kinematics_golden()
+    cartesian_golden()
     ik_golden()
     registry_trajectory_golden()
     id_trajectory_golden()

@@ -210,6 +210,67 @@ class Oracle:
             pos, vel, acc = pos[0], vel[0], acc[0]
         return {"positions": pos, "velocities": vel, "accelerations": acc}
 
+    # -- Cartesian straight-line trajectory (numpy restatement) ---------------------------------
+    @staticmethod
+    def _log3_vec(E):
+        """Rotation vector of utils/so3.py:172-191 (MatrixLog3): atan2 angle (:150-169), Taylor-safe
+        theta / sin theta (:114-147), half-turn axis from the symmetric part (:33-79)."""
+        c = float(np.clip((np.trace(E) - 1) / 2, -1.0, 1.0))
+        vee = np.array([E[2, 1] - E[1, 2], E[0, 2] - E[2, 0], E[1, 0] - E[0, 1]])
+        theta = np.arctan2(np.sqrt(max(float(vee @ vee), 1e-300)) / 2, c)
+        if theta > np.pi - 1e-2:
+            sym = 0.5 * (E + E.T) - c * np.eye(3)
+            j = 2 if sym[2, 2] >= 1e-6 else (1 if sym[1, 1] >= 1e-6 else 0)
+            cand = sym[:, j]
+            axis = cand / np.sqrt(max(float(cand @ cand), 1e-24))
+            return theta * (1.0 if vee[j] >= 0 else -1.0) * axis
+        if c > 1 - 5e-5:
+            u = 1.0 - c
+            coef = 1.0 + u / 3.0 + u * u * (4.0 / 45.0)
+        else:
+            cs = float(np.clip(c, -1.0 + 1e-7, 1.0 - 1e-7))
+            coef = np.arccos(cs) / np.sqrt(max(1 - cs * cs, 1e-30))
+        return 0.5 * coef * vee
+
+    @staticmethod
+    def cartesian_trajectory(Xstart, Xend, Tf, N, method):
+        """``cartesian_trajectory`` restated from planning/trajectory.py:504-594 (orientation /
+        position assembly) and :676-740 (linear velocity / acceleration), utils/so3.py:199-237
+        (MatrixExp3) and utils/time_scaling.py:28-53.  float32 outputs like the reference."""
+        Xs, Xe = _d(Xstart).reshape(4, 4), _d(Xend).reshape(4, 4)
+        N = int(N)
+        Rs, ps, pe = Xs[:3, :3], Xs[:3, 3], Xe[:3, 3]
+        w = Oracle._log3_vec(Rs.T @ Xe[:3, :3])
+        timegap = Tf / (N - 1.0)
+        ori, pos, vel, acc = [], [], [], []
+        for i in range(N):
+            t = timegap * i
+            s = 3 * (t / Tf) ** 2 - 2 * (t / Tf) ** 3 if method == 3 else \
+                10 * (t / Tf) ** 3 - 15 * (t / Tf) ** 4 + 6 * (t / Tf) ** 5
+            k = w * s
+            th2 = float(k @ k)
+            if th2 < 1e-4:
+                A, B = 1.0 - th2 / 6.0 + th2 * th2 / 120.0, 0.5 - th2 / 24.0 + th2 * th2 / 720.0
+            else:
+                th = np.sqrt(max(th2, 1e-12))
+                A, B = np.sin(th) / th, (1 - np.cos(th)) / (th * th)
+            K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+            ori.append(Rs @ (np.eye(3) + A * K + B * (K @ K)))
+            pos.append(s * pe + (1 - s) * ps)
+            tau = (i * (Tf / (N - 1))) / Tf
+            if method == 3:
+                sd, sdd = 6.0 * tau * (1.0 - tau) / Tf, 6.0 / (Tf * Tf) * (1.0 - 2.0 * tau)
+            elif method == 5:
+                t2, t3, t4 = tau * tau, tau * tau * tau, tau * tau * tau * tau
+                sd, sdd = (30.0 * t2 - 60.0 * t3 + 30.0 * t4) / Tf, (60.0 * tau - 180.0 * t2 + 120.0 * t3) / (Tf * Tf)
+            else:
+                sd = sdd = 0.0
+            vel.append(sd * (pe - ps))
+            acc.append(sdd * (pe - ps))
+        f = lambda a, tail: np.asarray(a, np.float32).reshape((N,) + tail)
+        return {"positions": f(pos, (3,)), "velocities": f(vel, (3,)), "accelerations": f(acc, (3,)),
+                "orientations": f(ori, (3, 3))}
+
     # -- inverse kinematics (numpy restatement; small cases only) -------------------------------
     def iterative_inverse_kinematics(self, T_desired, thetalist0, eomg=1e-6, ev=1e-6, max_iterations=10000,
                                      damping=2e-2, step_cap=0.3, weight_orientation=1.0, weight_position=1.0,

@@ -168,6 +168,15 @@ class HostCheck:
                      _C.c_double(weight_position), _ptr(lim), _C.c_uint64(seed), _ptr(th), _ptr(it), _ptr(ok))
         return th, ok.astype(bool), it
 
+    def cartesian(self, Xs, Xe, Tf, N, method):
+        Xs = np.ascontiguousarray(Xs, dtype=np.float64).reshape(4, 4)
+        Xe = np.ascontiguousarray(Xe, dtype=np.float64).reshape(4, 4)
+        pos, vel, acc = (np.empty((N, 3), np.float32) for _ in range(3))
+        ori = np.empty((N, 3, 3), np.float32)
+        self.H.hc_cartesian(_C.c_int64(N), _ptr(Xs), _ptr(Xe), _C.c_double(Tf), int(method), _ptr(pos), _ptr(vel),
+                            _ptr(acc), _ptr(ori))
+        return {"positions": pos, "velocities": vel, "accelerations": acc, "orientations": ori}
+
     def sincos(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).ravel()
         s, c = np.empty_like(x), np.empty_like(x)

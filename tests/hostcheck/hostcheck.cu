@@ -235,6 +235,20 @@ extern "C" int hc_ik(const mpk_robot *rb, int64_t P, const double *Td, const dou
     HC_DISPATCH(rb->n, ik_n<N_>(rb, P, Td, th0, prm, seed, theta, iters, ok));
     return 0;
 }
+extern "C" int hc_cartesian(int64_t N, const double *Xs, const double *Xe, double Tf, int method, float *pos,
+                            float *vel, float *acc, float *orient) {
+    for (int64_t t = 0; t < N; ++t) {
+        float p[3], v[3], a[3], R[9];
+        cartesian_point(Xs, Xe, t, N, Tf, method, p, v, a, R);
+        for (int k = 0; k < 3; ++k) {
+            pos[3 * t + k] = p[k];
+            vel[3 * t + k] = v[k];
+            acc[3 * t + k] = a[k];
+        }
+        for (int k = 0; k < 9; ++k) orient[9 * t + k] = R[k];
+    }
+    return 0;
+}
 extern "C" int hc_sincos(int64_t P, const double *x, double *sn, double *cs) {
     double tab[17];
     fill_trig_table(tab);

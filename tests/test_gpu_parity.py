@@ -375,6 +375,45 @@ def test_batched_inverse_kinematics(robot):
         sm.iterative_inverse_kinematics(Td[0], tgt[0], backtracking=True)
 
 
+def test_cartesian_trajectory(robots):
+    """cartesian_trajectory against the reference goldens (float32 rounding), batched = per-pair,
+    R R^T = 1 along 1,000,000 interpolated poses, exact end points."""
+    from oracle import Oracle
+
+    planner = robots["ur5"].planner()
+    g = load_golden("cartesian_trajectory")
+    names = ("generic5", "generic3", "method1", "same_R", "tiny", "near_pi", "pi_band", "pi_exact")
+    for name in names:
+        Tf, N, method = g[f"{name}_args"]
+        got = planner.cartesian_trajectory(g[f"{name}_Xstart"], g[f"{name}_Xend"], float(Tf), int(N), int(method))
+        for k in ("positions", "velocities", "accelerations", "orientations"):
+            assert got[k].dtype == np.float32 and got[k].shape == g[f"{name}_{k}"].shape
+            np.testing.assert_allclose(got[k], g[f"{name}_{k}"], rtol=3e-7, atol=1e-7, err_msg=f"{name} {k}")
+    rng = np.random.default_rng(3)
+    B, N = 1000, 1000
+    def poses(B):
+        Q, _ = np.linalg.qr(rng.normal(size=(B, 3, 3)))
+        Q[:, :, 0] *= np.sign(np.linalg.det(Q))[:, None]
+        T = np.tile(np.eye(4), (B, 1, 1))
+        T[:, :3, :3] = Q
+        T[:, :3, 3] = rng.uniform(-1, 1, (B, 3))
+        return T
+    Xs, Xe = poses(B), poses(B)
+    r = planner.cartesian_trajectory(Xs, Xe, 2.0, N, 5)
+    assert r["orientations"].shape == (B, N, 3, 3) and r["positions"].shape == (B, N, 3)
+    R = r["orientations"].astype(np.float64)
+    assert np.abs(np.einsum("bnij,bnkj->bnik", R, R) - np.eye(3)).max() < 1e-6
+    np.testing.assert_allclose(R[:, 0], Xs[:, :3, :3], atol=1e-6)
+    np.testing.assert_allclose(R[:, -1], Xe[:, :3, :3], atol=1e-6)
+    np.testing.assert_allclose(r["positions"][:, -1], Xe[:, :3, 3], atol=1e-6)
+    for b in (0, 499, 999):
+        ref = Oracle.cartesian_trajectory(Xs[b], Xe[b], 2.0, N, 5)
+        for k in ref:
+            np.testing.assert_allclose(r[k][b], ref[k], rtol=3e-7, atol=1e-7)
+    with pytest.raises(ZeroDivisionError):
+        planner.cartesian_trajectory(Xs[0], Xe[0], 2.0, 1, 5)
+
+
 def test_registry_launcher_contract_vs_reference_golden():
     """`trajectory.*` registry launchers: the reference's registry contract (linear for other
     methods, N <= 1 / Tf <= 0 guards) against outputs of the reference's own launcher."""

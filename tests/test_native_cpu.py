@@ -344,6 +344,17 @@ def test_inverse_kinematics_kernel_vs_reference_golden(hostcheck, robot):
     assert not ok0.any() and np.array_equal(th0, seeds) and (it0 == 1).all()
 
 
+def test_cartesian_trajectory_kernel_vs_reference_golden(hostcheck):
+    """The kernel's per-step Cartesian interpolation (csrc/mpk_device.cuh cartesian_point) against
+    the unmodified reference, to float32 rounding."""
+    g = load_golden("cartesian_trajectory")
+    for name in ("generic5", "generic3", "method1", "same_R", "tiny", "near_pi", "pi_band", "pi_exact"):
+        Tf, N, method = g[f"{name}_args"]
+        got = hostcheck.cartesian(g[f"{name}_Xstart"], g[f"{name}_Xend"], float(Tf), int(N), int(method))
+        for k in ("positions", "velocities", "accelerations", "orientations"):
+            np.testing.assert_allclose(got[k], g[f"{name}_{k}"], rtol=3e-7, atol=1e-7, err_msg=f"{name} {k}")
+
+
 def test_body_frame_kinematics_vs_reference_golden(hostcheck):
     """frame="body": the kernel template with screws S' = Ad(M) B and the Ad(T^-1) column
     transform against the unmodified reference (tests/golden/body_kinematics.npz)."""

@@ -217,3 +217,21 @@ def test_inverse_kinematics_restatement_vs_reference(robot):
         assert ok == bool(g[f"{robot}_success"][i]), i
         assert it == int(g[f"{robot}_iterations"][i]), i
         np.testing.assert_allclose(th, g[f"{robot}_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
+
+
+CART_CASES = ("generic5", "generic3", "method1", "same_R", "tiny", "near_pi", "pi_band", "pi_exact")
+
+
+def test_cartesian_trajectory_restatement_vs_reference():
+    """Oracle.cartesian_trajectory against the unmodified reference
+    (tests/golden/cartesian_trajectory.npz): float32 outputs equal to one float32 rounding,
+    including rotations inside MatrixLog3's half-turn band."""
+    from oracle import Oracle
+
+    g = load_golden("cartesian_trajectory")
+    for name in CART_CASES:
+        Tf, N, method = g[f"{name}_args"]
+        got = Oracle.cartesian_trajectory(g[f"{name}_Xstart"], g[f"{name}_Xend"], float(Tf), int(N), int(method))
+        for k in ("positions", "velocities", "accelerations", "orientations"):
+            assert got[k].dtype == np.float32 and got[k].shape == g[f"{name}_{k}"].shape
+            np.testing.assert_allclose(got[k], g[f"{name}_{k}"], rtol=3e-7, atol=1e-7, err_msg=f"{name} {k}")
