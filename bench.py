@@ -186,6 +186,10 @@ def run_ours(args) -> None:
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: stay on the CPU cores (and NUMA node) next to this GPU so the pinned
+    # result buffers of the end-to-end path do not cross the socket link
+    from manipulapy_b200 import bind_host_to_device
+    numa_cpus = bind_host_to_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ops = _native.ops()
@@ -355,7 +359,7 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "e2e": {"value": world * P * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * 6 * 8),
                 "d2h_bytes_per_step": int(P * 6 * 4), "api": "OptimizedTrajectoryPlanning.trajectory_inverse_dynamics",
-                "pcie_d2h_gbs_measured": d2h_gbs,
+                "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound_to": numa_cpus,
                 "pcie_bound_points_per_s": world * d2h_gbs * 1e9 / (6 * 4)},
         "gpu_launches": launches_per_step * args.steps,  # in the timed region of `value`
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",

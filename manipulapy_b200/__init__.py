@@ -17,11 +17,12 @@ from .kinematics import SerialManipulator
 from .path_planning import OptimizedTrajectoryPlanning, TrajectoryPlanning
 from .robots import RobotBundle, available_robots, load_robot
 from .sharding import gather_rows, shard_range
+from ._host import bind_host_to_device
 
 __version__ = "0.1.0"
 
 __all__ = [
     "KERNEL_REGISTRY", "KernelRegistration", "KernelRegistry", "execute_registered_kernel",
     "ManipulatorDynamics", "SerialManipulator", "OptimizedTrajectoryPlanning", "TrajectoryPlanning",
-    "RobotBundle", "available_robots", "load_robot", "gather_rows", "shard_range",
+    "RobotBundle", "available_robots", "load_robot", "gather_rows", "shard_range", "bind_host_to_device",
 ]

@@ -107,6 +107,34 @@ def chunked_to_host(launch, rows: int, tail: Sequence[int], dtype: torch.dtype, 
     return out.numpy()
 
 
+def bind_host_to_device(device: Optional[Any] = None) -> Optional[str]:
+    """Pin this process to the CPU cores next to ``device`` (its PCIe root's ``local_cpulist``),
+    so that pinned result buffers are first-touched on the GPU's own NUMA node.  With one
+    process per GPU on a two-socket box this keeps every device->host stream off the
+    inter-socket link.  Returns the CPU list applied, or ``None`` when sysfs does not say."""
+    import os
+
+    try:
+        d = default_device(device)
+        pr = torch.cuda.get_device_properties(d)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        text = open(f"/sys/bus/pci/devices/{bdf}/local_cpulist").read().strip()
+        cpus = set()
+        for part in text.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return text
+    except Exception:
+        return None
+
+
 def limits_tensor(limits: Any) -> Optional[torch.Tensor]:
     """(n, 2) float32 host tensor, or None when every bound is infinite (clip is a no-op)."""
     if limits is None:
