@@ -414,6 +414,99 @@ def test_cartesian_trajectory(robots):
         planner.cartesian_trajectory(Xs[0], Xe[0], 2.0, 1, 5)
 
 
+def test_reference_planner_unit_cases():
+    """The cases of the reference's tests/test_path_planning_unit.py:52-160, on a 2-joint planner:
+    end points respected, batch = per-trajectory generator, positions clipped to the joint
+    limits, torques clipped to the torque limits, shapes of the rollout and Cartesian outputs."""
+    from manipulapy_b200 import ManipulatorDynamics, OptimizedTrajectoryPlanning
+    from oracle import Oracle
+
+    p = planar_2r_pack()
+    dyn = ManipulatorDynamics(p["M"], S_list=p["S_list"], Glist=p["Glist"], Mlist_per_link=p["Mlist_per_link"])
+    planner = OptimizedTrajectoryPlanning(dyn, "nonexistent.urdf", dyn, [(-1.0, 1.0), (-2.0, 2.0)])
+    r = planner.joint_trajectory(thetastart=[0.0, 0.5], thetaend=[1.0, -0.5], Tf=1.0, N=4, method=3)
+    assert r["positions"].shape == (4, 2)
+    assert np.allclose(r["positions"][0], [0.0, 0.5]) and np.allclose(r["positions"][-1], [1.0, -0.5])
+    sb = np.array([[0.0, 0.0], [0.5, -0.5]], dtype=np.float32)
+    eb = np.array([[1.0, 1.0], [-0.5, 0.5]], dtype=np.float32)
+    res = planner.batch_joint_trajectory(sb, eb, Tf=1.0, N=3, method=3)
+    assert res["positions"].shape == (2, 3, 2)
+    exp = Oracle.joint_trajectory(sb[0], eb[0], 1.0, 3, 3, np.array([[-1.0, 1.0], [-2.0, 2.0]]))
+    assert np.array_equal(res["positions"][0], exp["positions"])
+    planner1 = OptimizedTrajectoryPlanning(dyn, "nonexistent.urdf", dyn, [(-1.0, 1.0), (-1.0, 1.0)])
+    pos = planner1.batch_joint_trajectory(np.zeros((1, 2), np.float32), np.array([[5.0, -5.0]], np.float32),
+                                          Tf=1.0, N=4, method=3)["positions"]
+    assert np.all(pos <= 1.0) and np.all(pos >= -1.0) and pos.max() == 1.0 and pos.min() == -1.0
+    planner2 = OptimizedTrajectoryPlanning(dyn, "nonexistent.urdf", dyn, [(-1.0, 1.0)] * 2, [(-0.2, 0.2)] * 2)
+    q = np.zeros((2, 2), np.float32)
+    tq = planner2.inverse_dynamics_trajectory(q, np.zeros_like(q), np.ones_like(q) * 5.0)
+    assert tq.dtype == np.float32 and np.all(tq <= np.float32(0.2)) and np.all(tq >= np.float32(-0.2))
+    res = planner.forward_dynamics_trajectory(np.zeros(2, np.float32), np.zeros(2, np.float32), np.zeros((3, 2), np.float32),
+                                              np.array([0, 0, -9.81], np.float32), np.zeros((3, 6), np.float32),
+                                              dt=0.1, intRes=1)
+    assert all(res[k].shape == (3, 2) and res[k].dtype == np.float32 for k in ("positions", "velocities", "accelerations"))
+    Xs, Xe = np.eye(4, dtype=np.float32), np.eye(4, dtype=np.float32)
+    Xe[:3, 3] = [1.0, 0.0, 0.0]
+    res = planner.cartesian_trajectory(Xs, Xe, Tf=1.0, N=5, method=3)
+    assert res["positions"].shape == (5, 3) and res["orientations"].shape == (5, 3, 3)
+    assert np.allclose(res["positions"][0], 0) and np.allclose(res["positions"][-1], [1, 0, 0])
+    assert np.allclose(res["orientations"], np.eye(3))
+    with pytest.raises(IndexError):  # zero steps (planning/trajectory_dynamics.py:612-615)
+        planner.forward_dynamics_trajectory(np.zeros(2), np.zeros(2), np.zeros((0, 2)), [0, 0, -9.81], None, 0.1, 1)
+
+
+def test_return_types_match_reference_api_contract(robots):
+    """Return type / dtype / shape of every mirrored method on a 6-DOF robot, as pinned by the
+    reference's tests/data/api_contract_golden.json (hot-path subset, tests/golden/api_contract.json)."""
+    import json
+    from pathlib import Path
+
+    contract = json.loads((Path(__file__).resolve().parent / "golden" / "api_contract.json").read_text())
+    rb = robots["ur5"]
+    dyn, planner = rb.dynamics, rb.planner()
+    rng = np.random.default_rng(0)
+    th, dth, dd = rng.uniform(-1, 1, 6), rng.uniform(-1, 1, 6), rng.uniform(-1, 1, 6)
+    g, ft = np.array([0, 0, -9.81]), np.zeros(6)
+    N = 8
+    traj = planner.joint_trajectory(th, th + 0.5, 2.0, N, 5)
+    X0, X1 = dyn.forward_kinematics(th), dyn.forward_kinematics(th + 0.3)
+    got = {
+        "ManipulatorDynamics.forward_dynamics": dyn.forward_dynamics(th, dth, dd, g, ft),
+        "ManipulatorDynamics.gravity_forces": dyn.gravity_forces(th),
+        "ManipulatorDynamics.inverse_dynamics": dyn.inverse_dynamics(th, dth, dd, g, ft),
+        "ManipulatorDynamics.mass_matrix": dyn.mass_matrix(th),
+        "ManipulatorDynamics.velocity_quadratic_forces": dyn.velocity_quadratic_forces(th, dth),
+        "OptimizedTrajectoryPlanning.cartesian_trajectory": planner.cartesian_trajectory(X0, X1, 2.0, N, 5),
+        "OptimizedTrajectoryPlanning.forward_dynamics_trajectory":
+            planner.forward_dynamics_trajectory(th, dth, rng.uniform(-5, 5, (N, 6)), g, np.zeros((N, 6)), 0.01, 1),
+        "OptimizedTrajectoryPlanning.inverse_dynamics_trajectory":
+            planner.inverse_dynamics_trajectory(traj["positions"], traj["velocities"], traj["accelerations"]),
+        "OptimizedTrajectoryPlanning.joint_trajectory": traj,
+        "SerialManipulator.forward_kinematics": dyn.forward_kinematics(th),
+        "SerialManipulator.iterative_inverse_kinematics": dyn.iterative_inverse_kinematics(X1, th),
+        "SerialManipulator.jacobian": dyn.jacobian(th),
+    }
+
+    def check(value, spec, where):
+        if spec["type"] == "numpy.ndarray":
+            assert isinstance(value, np.ndarray), where
+            assert str(value.dtype) == spec["dtype"] and list(value.shape) == spec["shape"], (where, value.dtype, value.shape)
+        elif spec["type"] == "dict":
+            assert isinstance(value, dict) and set(value) == set(spec["items"]), where
+            for k, sub in spec["items"].items():
+                check(value[k], sub, f"{where}[{k}]")
+        elif spec["type"] == "tuple":
+            assert isinstance(value, tuple) and len(value) == len(spec["elements"]), where
+            for i, sub in enumerate(spec["elements"]):
+                check(value[i], sub, f"{where}[{i}]")
+        else:
+            assert type(value).__name__ == spec["type"], (where, type(value))
+
+    for key, spec in contract.items():
+        if not key.startswith("_"):
+            check(got[key], spec["return"], key)
+
+
 def test_registry_launcher_contract_vs_reference_golden():
     """`trajectory.*` registry launchers: the reference's registry contract (linear for other
     methods, N <= 1 / Tf <= 0 guards) against outputs of the reference's own launcher."""

@@ -17,6 +17,10 @@ import sys
 import numpy as np
 import pytest
 
+from pathlib import Path as _Path
+
+GOLDEN_DIR = _Path(__file__).resolve().parent / "golden"
+
 from conftest import REPO, load_golden, load_pack, planar_2r_pack, random_general_pack
 
 ROBOTS = ["ur5", "panda", "iiwa14", "xarm6"]
@@ -386,6 +390,32 @@ def test_registry_trajectory_contract_vs_golden(hostcheck):
     # the planner contract is untouched: other methods -> zero scaling
     got = hostcheck.traj(np.zeros(3), np.ones(3), 2.0, 5, 1, None)
     assert np.all(got[0] == 0) and np.all(got[1] == 0)
+
+
+def test_public_signatures_match_reference_api_contract():
+    """tests/data/api_contract_golden.json of the reference, hot-path subset: every mirrored
+    method takes the reference's parameters, same names, same order; parameters that are optional
+    in the reference are optional here (extension keywords may follow)."""
+    import inspect
+    import json
+
+    import manipulapy_b200 as mp
+
+    contract = json.loads((GOLDEN_DIR / "api_contract.json").read_text())
+    for key, spec in contract.items():
+        if key.startswith("_"):
+            continue
+        cls, meth = key.split(".")
+        params = [p for p in inspect.signature(getattr(getattr(mp, cls), meth)).parameters.values()
+                  if p.name != "self"]
+        want = spec["parameters"]
+        assert [p.name for p in params[:len(want)]] == [w["name"] for w in want], key
+        for p, w in zip(params, want):
+            assert p.kind in (p.POSITIONAL_OR_KEYWORD,), (key, p.name)
+            if w["has_default"]:
+                assert p.default is not inspect.Parameter.empty, (key, p.name)
+        for p in params[len(want):]:  # extensions never become required
+            assert p.default is not inspect.Parameter.empty or p.kind == p.KEYWORD_ONLY, (key, p.name)
 
 
 def test_registry_contract():
