@@ -12,8 +12,9 @@
 // Every kernel exists in three FLAVOURS, each compiled in its own translation unit
 // (dyn_flavour.cu / fd_flavour.cu with -DMPK_FLAVOUR=k) so that the build parallelises:
 //   0  rigid link inertias, all joints revolute, plain D-H links   (UR5, iiwa, ...: most URDF arms)
-//   1  rigid link inertias, a prismatic joint or a Hayati link    (the reference's 8-DOF Panda)
-//   2  general symmetric 6x6 link inertias
+//   1  rigid link inertias, a prismatic joint or a Hayati link past a revolute first joint
+//      (the reference's 8-DOF Panda)
+//   2  general symmetric 6x6 link inertias (and the rare rigid chain whose first joint is prismatic)
 #pragma once
 #include "mpk_common.cuh"
 
@@ -27,7 +28,9 @@ constexpr int kRneaMinBlocks = 4;
 
 constexpr bool flavour_gen(int f) { return f == 2; }
 constexpr bool flavour_rev(int f) { return f == 0; }
-inline int flavour_of(const mpk_robot *rb) { return !rb->rigid ? 2 : (rb->plain ? 0 : 1); }
+inline int flavour_of(const mpk_robot *rb) {
+    return (!rb->rigid || !rb->first_revolute) ? 2 : (rb->plain ? 0 : 1);
+}
 
 struct TipArgs {
     double g0[3];  // -g in frame-0 coordinates (base_gravity)

@@ -12,6 +12,7 @@ struct mpk_robot {
     int rigid;         // every link inertia is a rigid body at its centre of mass
     int all_revolute;  // no prismatic joint
     int plain;         // all revolute and every link plain Denavit-Hartenberg (beta = 0): flavour 0
+    int first_revolute;  // joint 0 is revolute (required by the rigid kernel flavours)
     int has_dynamics;
     mpk::RobotPack<double, MPK_MAX_DOF> pack;  // host copy, frames 0..n-1 valid
 };

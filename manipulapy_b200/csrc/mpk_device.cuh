@@ -539,8 +539,9 @@ struct RegStore {
     }
 };
 // Whether rnea() takes the shortcut for link 0 (only the z moment about its own axis is
-// stored for it): a rigid, plain all-revolute chain of at least two links.
-constexpr bool rnea_fast0(bool GEN, bool REV, int N) { return REV && !GEN && N >= 2; }
+// stored for it): rigid inertias, revolute first joint, at least two links.
+// (the rigid kernel flavours are only used for chains whose FIRST joint is revolute)
+constexpr bool rnea_fast0(bool GEN, bool REV, int N) { return (void)REV, !GEN && N >= 2; }
 
 template <typename T, int N, int THREADS, bool FAST0 = false>
 struct SmemStore {
@@ -679,17 +680,19 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                 if (!NOACC) dw[2] += qdd;
                 dv[0] += qd * v[1];
                 dv[1] -= qd * v[0];
-            } else {
-                const T sr = rb.sr[i], st = rb.st[i];
-                w[2] += sr * qd;
-                v[2] += st * qd;
-                const T a = sr * qd, b = st * qd;
-                dw[0] += a * w[1];
-                dw[1] -= a * w[0];
-                dw[2] += sr * qdd;
-                dv[0] = dv[0] + a * v[1] + b * w[1];
-                dv[1] = dv[1] - a * v[0] - b * w[0];
-                dv[2] += st * qdd;
+            } else if (rb.sr[i] != T(0)) {  // revolute joint of a mixed chain (warp-uniform test)
+                w[2] += qd;
+                dw[0] += qd * w[1];
+                dw[1] -= qd * w[0];
+                if (!NOACC) dw[2] += qdd;
+                dv[0] += qd * v[1];
+                dv[1] -= qd * v[0];
+            } else {  // prismatic: A = [0; 0, 0, st]
+                const T b = rb.st[i] * qd;
+                v[2] += b;
+                dv[0] += b * w[1];
+                dv[1] -= b * w[0];
+                dv[2] += rb.st[i] * qdd;
             }
         }
         T Fn[3], Ff[3];
@@ -737,7 +740,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
             T cj = c, sj = s, dj = dz;
 #pragma unroll
             for (int j = N - 1; j >= 1; --j) {
-                tau[j] = REV ? an[2] : rb.sr[j] * an[2] + rb.st[j] * af[2];
+                tau[j] = (REV || rb.sr[j] != T(0)) ? an[2] : rb.st[j] * af[2];
                 // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
                 if (j < N - 1) st_.template get_cs<REV>(rb, j, cj, sj, dj);
                 if (FAST0 && j == 1) {
@@ -753,7 +756,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                     }
                 }
             }
-            tau[0] = REV ? an[2] : rb.sr[0] * an[2] + rb.st[0] * af[2];
+            tau[0] = (REV || FAST0 || rb.sr[0] != T(0)) ? an[2] : rb.st[0] * af[2];
         }
     }
 }
@@ -819,7 +822,7 @@ MPK_HD void inertia_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, 
 }
 
 // M[i][j] for j <= i is written to Mm[i][j] AND Mm[j][i].  Matches the reference's
-// sym(sum_k J_k^T G_k J_k) (dynamics/mass_matrix.py:62-96).
+// sym(sum_k J_k^T G_k J_k) (dynamics/mass_matrix.py:62-96).  Rigid inertias, first joint revolute.
 template <typename T, int N, bool REV>
 MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T (&Mm)[N][N]) {
     // composite inertia of links i..N-1 in frame i
@@ -837,24 +840,29 @@ MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T (&Mm)[N][N
             n[0] = I[2]; n[1] = I[4]; n[2] = I[5];
             f[0] = -h[1]; f[1] = h[0]; f[2] = T(0);
             Mm[i][i] = n[2];
+        } else if (rb.sr[i] != T(0)) {
+            n[0] = I[2]; n[1] = I[4]; n[2] = I[5];
+            f[0] = -h[1]; f[1] = h[0]; f[2] = T(0);
+            Mm[i][i] = n[2];
         } else {
-            const T sr = rb.sr[i], st = rb.st[i];
-            n[0] = sr * I[2] + st * h[1];
-            n[1] = sr * I[4] - st * h[0];
-            n[2] = sr * I[5];
-            f[0] = -sr * h[1];
-            f[1] = sr * h[0];
+            const T st = rb.st[i];
+            n[0] = st * h[1];
+            n[1] = -(st * h[0]);
+            n[2] = T(0);
+            f[0] = T(0);
+            f[1] = T(0);
             f[2] = st * m;
-            Mm[i][i] = sr * n[2] + st * f[2];
+            Mm[i][i] = st * f[2];
         }
 #pragma unroll
         for (int j = i; j > 0; --j) {
             T mij;
-            if (REV && j == 1) {
+            if (j == 1) {
+                // the first joint of a chain routed here is revolute: only the z moment is needed
                 mij = wrench_to_parent_nz<T, N, !REV>(rb, 1, q.c[1], q.s[1], q.d[1], n, f, T(0));
             } else {
                 wrench_to_parent<T, N, !REV>(rb, j, q.c[j], q.s[j], q.d[j], n, f);
-                mij = REV ? n[2] : rb.sr[j - 1] * n[2] + rb.st[j - 1] * f[2];
+                mij = (REV || rb.sr[j - 1] != T(0)) ? n[2] : rb.st[j - 1] * f[2];
             }
             Mm[i][j - 1] = mij;
             Mm[j - 1][i] = mij;

@@ -372,6 +372,7 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
     }
     rb->all_revolute = all_rev ? 1 : 0;
     rb->plain = rb->all_revolute;
+    rb->first_revolute = rb->pack.sr[0] != 0.0;
     for (int i = 0; i < n; ++i)
         if (rb->pack.sb[i] != 0.0) rb->plain = 0;
 

@@ -11,7 +11,7 @@ using namespace mpk;
 
 // flavour of the kernels this robot is routed to (csrc/dyn_kernels.cuh): 0 rigid + all
 // revolute, 1 rigid, 2 general inertias
-static int flavour(const mpk_robot *rb) { return !rb->rigid ? 2 : (rb->plain ? 0 : 1); }
+static int flavour(const mpk_robot *rb) { return (!rb->rigid || !rb->first_revolute) ? 2 : (rb->plain ? 0 : 1); }
 
 template <int N, bool GEN, bool REV>
 static void rnea_nf(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
