@@ -36,10 +36,14 @@ ncu)
   tail -2 $OUT/${TAG}_ncu.log ;;
 ncu_micro)
   # full captures of the other kernels (one launch each) while running the micro-benchmark
-  timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:'traj_kernel|fk_jacobian_kernel|fd_rollout_kernel|mass_matrix_kernel|rnea_kernel' -c 14 \
+  # (no --import-source here: 24 full captures with source exceed gpurun's 64 MiB return limit)
+  timeout 1200 ncu --set full --clock-control none \
+      -k regex:'traj_kernel|fk_jacobian_kernel|fd_rollout_kernel|mass_matrix_kernel|rnea_kernel|ik_dls_kernel|forward_dynamics_kernel' -c 24 \
       -f -o $OUT/${TAG}_micro python scripts/microbench.py --quick > $OUT/${TAG}_ncu_micro.log 2>&1
-  tail -2 $OUT/${TAG}_ncu_micro.log ;;
+  tail -2 $OUT/${TAG}_ncu_micro.log
+  # summarise on the box and drop the report: 24 full captures are ~90 MB, gpurun returns <= 64 MiB
+  python scripts/ncu_summary.py $OUT/${TAG}_micro.ncu-rep --md $OUT/${TAG}_ncu_kernels_micro.md > /dev/null 2>&1
+  rm -f $OUT/${TAG}_micro.ncu-rep ;;
 micro)
   timeout 900 python scripts/microbench.py > $OUT/${TAG}_micro.json 2> $OUT/${TAG}_micro.err
   cat $OUT/${TAG}_micro.json; tail -3 $OUT/${TAG}_micro.err ;;
