@@ -103,14 +103,18 @@ for _name, _sym, _src in (
     ("dynamics.trajectory_inverse", "mpk_trajectory_inverse_dynamics", "csrc/dyn.cu"),
     ("dynamics.mass_matrix", "mpk_mass_matrix", "csrc/dyn.cu"),
     ("dynamics.forward", "mpk_forward_dynamics", "csrc/dyn.cu"),
-    ("dynamics.forward_rollout", "mpk_forward_dynamics_trajectory", "csrc/fd.cu"),
+    ("dynamics.forward_rollout", "mpk_forward_dynamics_trajectory", "csrc/fd_flavour.cu"),
+    ("kinematics.inverse_dls", "mpk_inverse_kinematics_dls", "csrc/ik.cu"),
+    ("trajectory.cartesian", "mpk_cartesian_trajectory", "csrc/traj.cu"),
 ):
     def _make(sym):
         def _launch(*args, **kwargs):
             op = {"mpk_fk_jacobian_space": "fk_jacobian", "mpk_inverse_dynamics": "inverse_dynamics",
                   "mpk_trajectory_inverse_dynamics": "trajectory_inverse_dynamics",
                   "mpk_mass_matrix": "mass_matrix", "mpk_forward_dynamics": "forward_dynamics",
-                  "mpk_forward_dynamics_trajectory": "forward_dynamics_trajectory"}[sym]
+                  "mpk_forward_dynamics_trajectory": "forward_dynamics_trajectory",
+                  "mpk_inverse_kinematics_dls": "inverse_kinematics_dls",
+                  "mpk_cartesian_trajectory": "cartesian_trajectory"}[sym]
             return getattr(_native.ops(), op)(*args, **kwargs)
         return _launch
 
