@@ -26,6 +26,7 @@
 #ifndef MPK_H
 #define MPK_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -140,7 +141,13 @@ int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const double *T_d
                                const double *theta0, double eomg, double ev, int max_iterations,
                                double damping, double step_cap, double weight_orientation,
                                double weight_position, const double *joint_limits, uint64_t seed,
-                               double *theta, int32_t *iterations, uint8_t *success, void *stream);
+                               double *theta, int32_t *iterations, uint8_t *success, void *workspace,
+                               size_t workspace_bytes, void *stream);
+/*   workspace  dev scratch of mpk_inverse_kinematics_workspace_bytes(n, P) bytes, or NULL.  With
+ *              it, targets still running after 64 iterations are queued and finished by a second,
+ *              densely packed launch (a warp otherwise lives as long as its slowest target);
+ *              results are identical either way. */
+size_t mpk_inverse_kinematics_workspace_bytes(int n, int64_t P);
 
 /* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
  * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).

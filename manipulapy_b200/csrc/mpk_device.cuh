@@ -1220,19 +1220,38 @@ MPK_HD void ik_error(const double (&Tc)[16], const double *Td, double (&V)[6], d
     for (int r = 0; r < 3; ++r) V[r] = Tc[4 * r] * w[0] + Tc[4 * r + 1] * w[1] + Tc[4 * r + 2] * w[2];
 }
 
-// One target.  th: initial guess in, solution out; J: scratch for the 6 x N Jacobian of the
-// current iterate (the kernel passes the thread's shared-memory row); returns success and the
-// reference's iteration count (k + 1; max_iter + 1 when exhausted).
+// Solver state of one target between iteration windows.
 template <typename T, int N>
-MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], const IkParams<T, MPK_MAX_DOF_> &prm,
-                   unsigned long long seed, unsigned long long target, T *J, int &iterations) {
-    T best[N];
+struct IkState {
+    T th[N], best[N];
+    double best_err;
+    int stall, k;
+};
+
+template <typename T, int N>
+MPK_HD void ik_state_init(IkState<T, N> &st, const T (&th0)[N]) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) best[j] = th[j];
-    double best_err = INFINITY, cur = INFINITY, rot = 0.0, trans = 0.0;
-    int stall = 0, k = 0;
-    bool ok = false;
-    for (k = 0; k < prm.max_iter; ++k) {
+    for (int j = 0; j < N; ++j) st.best[j] = st.th[j] = th0[j];
+    st.best_err = INFINITY;
+    st.stall = 0;
+    st.k = 0;
+}
+
+// Iterations st.k .. k_stop-1 of one target (k_stop <= max_iter).  J: scratch for the 6 x N
+// Jacobian of the current iterate (the kernel passes the thread's shared-memory row).
+// Returns true when the target is FINISHED -- converged, or max_iter reached (then the
+// best-iterate fall-back of ik.py:264-275 has been applied): st.th is the answer, `ok` the
+// success flag, `iterations` the reference's count (k + 1; max_iter + 1 when exhausted).
+// Returns false when k_stop was reached first: st carries everything the next window needs.
+template <typename T, int N>
+MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T, N> &st,
+                          const IkParams<T, MPK_MAX_DOF_> &prm, unsigned long long seed,
+                          unsigned long long target, T *J, int k_stop, bool &ok, int &iterations) {
+    T (&th)[N] = st.th;
+    double cur = INFINITY, rot = 0.0, trans = 0.0;
+    int k = st.k;
+    ok = false;
+    for (; k < k_stop; ++k) {
         JointCS<T, N> q;
         joint_cs(rb, th, q);
         double Tc[16], V[6];
@@ -1243,22 +1262,22 @@ MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], cons
             ok = true;
             break;
         }
-        if (cur < best_err) {
-            best_err = cur;
+        if (cur < st.best_err) {
+            st.best_err = cur;
 #pragma unroll
-            for (int j = 0; j < N; ++j) best[j] = th[j];
-            stall = 0;
+            for (int j = 0; j < N; ++j) st.best[j] = th[j];
+            st.stall = 0;
         } else {
-            ++stall;
+            ++st.stall;
         }
-        if (stall > 20) {
+        if (st.stall > 20) {
             // stagnation restart around the best iterate (ik.py:206-213)
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const T x = best[j] + 0.1 * ik_normal(seed, target, (unsigned long long)k * N + j);
+                const T x = st.best[j] + 0.1 * ik_normal(seed, target, (unsigned long long)k * N + j);
                 th[j] = fmin(fmax(x, prm.lo[j]), prm.hi[j]);
             }
-            stall = 0;
+            st.stall = 0;
             continue;
         }
         // (J J^T + mu 1) y = W e ;  dtheta = J^T y
@@ -1289,10 +1308,12 @@ MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], cons
 #pragma unroll
         for (int j = 0; j < N; ++j) th[j] = fmin(fmax(th[j] + scale * d[j], prm.lo[j]), prm.hi[j]);
     }
-    if (!ok && best_err < cur) {
+    st.k = k;
+    if (!ok && k < prm.max_iter) return false;  // window exhausted, budget not
+    if (!ok && st.best_err < cur) {
         // max_iterations reached (ik.py:264-275): fall back to the best iterate if it is better
 #pragma unroll
-        for (int j = 0; j < N; ++j) th[j] = best[j];
+        for (int j = 0; j < N; ++j) th[j] = st.best[j];
         JointCS<T, N> q;
         joint_cs(rb, th, q);
         double Tc[16], V[6];
@@ -1301,6 +1322,19 @@ MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], cons
         ok = rot < prm.eomg && trans < prm.ev;
     }
     iterations = k + 1;
+    return true;
+}
+
+// One target, whole iteration budget.  th: initial guess in, solution out.
+template <typename T, int N>
+MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], const IkParams<T, MPK_MAX_DOF_> &prm,
+                   unsigned long long seed, unsigned long long target, T *J, int &iterations) {
+    IkState<T, N> st;
+    ik_state_init(st, th);
+    bool ok;
+    ik_dls_window(rb, Td, st, prm, seed, target, J, prm.max_iter, ok, iterations);
+#pragma unroll
+    for (int j = 0; j < N; ++j) th[j] = st.th[j];
     return ok;
 }
 

@@ -126,6 +126,8 @@ def main():
             res["ik_dls_iiwa14_mean_iterations"] = float(sol[2].float().mean())
             rec("ik_dls_iiwa14", Pi, timeit(lambda: ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0), 3, 1),
                 128 + 8 * n + 8 * n + 5, 1400 * float(sol[2].float().mean()), "targets")
+            rec("ik_dls_one_phase_iiwa14", Pi, timeit(lambda: ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0, False), 3, 1),
+                128 + 8 * n + 8 * n + 5, 1400 * float(sol[2].float().mean()), "targets")
         dth, tau = rand(Pk, n), rand(Pk, n, lo=-20, hi=20)
         rec(f"forward_dynamics_{name}", Pk, timeit(lambda: ops.forward_dynamics(h, th, dth, tau, g, None, None)), 32 * n, 5300, "points")
 

@@ -371,6 +371,15 @@ def test_batched_inverse_kinematics(robot):
     assert np.abs(T[ok] - Td[ok])[:, :3, 3].max() < 2e-6 and np.abs(T[ok] - Td[ok])[:, :3, :3].max() < 2e-6
     assert (it[ok] <= 400).all() and (it[~ok] == 401).all()
     assert (th >= lo - 1e-12).all() and (th <= hi + 1e-12).all()
+    # the two-phase schedule (stragglers re-packed after 64 iterations) changes no iterate
+    from manipulapy_b200 import _native
+    dev = torch.device("cuda")
+    args = (sm.robot.handle, torch.from_numpy(Td).to(dev), torch.from_numpy(tgt + 0.25).to(dev), 1e-6, 1e-6, 400, 2e-2,
+            0.3, 1.0, 1.0, torch.from_numpy(np.ascontiguousarray(g[f"{robot}_limits"], dtype=np.float64)), 7)
+    one = _native.ops().inverse_kinematics_dls(*args, False)
+    two = _native.ops().inverse_kinematics_dls(*args, True)
+    assert all(bool(torch.equal(x, y)) for x, y in zip(one, two))
+    assert 0 < int((two[2] > 64).sum()) < P  # some targets did go through the second phase
     with pytest.raises(NotImplementedError):
         sm.iterative_inverse_kinematics(Td[0], tgt[0], backtracking=True)
 
