@@ -423,6 +423,43 @@ def test_cartesian_trajectory(robots):
         planner.cartesian_trajectory(Xs[0], Xe[0], 2.0, 1, 5)
 
 
+@pytest.mark.parametrize("robot", ROBOTS)
+def test_reference_property_tests(robots, robot):
+    """The property tests of the reference's suite on batches: M symmetric positive definite and
+    inverse dynamics at rest = gravity forces (tests/test_dynamics_golden.py:236-272); c(theta, 0) = 0
+    and the inverse -> forward dynamics round trip (tests/test_dynamics.py:23-144, there atol 1e-3);
+    FK(0) = M, R R^T = 1, det R = 1 (tests/test_kinematics.py:147-212); quintic trajectories start
+    and end with zero velocity and acceleration (tests/test_v132_regressions.py:516-541)."""
+    rb = robots[robot]
+    dyn, n = rb.dynamics, rb.num_joints
+    rng = np.random.default_rng(13)
+    lo, hi = rb.joint_limits[:, 0], rb.joint_limits[:, 1]
+    P = 3000
+    th = rng.uniform(lo, hi, (P, n))
+    dth, dd = rng.uniform(-2, 2, (P, n)), rng.uniform(-5, 5, (P, n))
+    M = dyn.mass_matrix(th)
+    assert np.array_equal(M, np.swapaxes(M, 1, 2))
+    assert np.linalg.eigvalsh(M).min() > 0
+    zero = np.zeros_like(th)
+    grav = dyn.gravity_forces(th)
+    assert np.abs(dyn.inverse_dynamics(th, zero, zero, [0, 0, -9.81], None) - grav).max() == 0.0
+    assert np.abs(dyn.velocity_quadratic_forces(th, zero)).max() == 0.0
+    ft = rng.uniform(-5, 5, (P, 6))
+    tau = dyn.inverse_dynamics(th, dth, dd, [0, 0, -9.81], ft)
+    back = dyn.forward_dynamics(th, dth, tau, [0, 0, -9.81], ft)
+    assert _rel_rows(back, dd) < 1e-9  # round trip through M^-1 (cond(M) up to ~3e4)
+    T0 = dyn.forward_kinematics(np.zeros(n))
+    np.testing.assert_allclose(T0, rb.M, rtol=0, atol=1e-13)
+    T = dyn.forward_kinematics(th)
+    R = T[:, :3, :3]
+    assert np.abs(np.einsum("pij,pkj->pik", R, R) - np.eye(3)).max() < 1e-13
+    assert np.abs(np.linalg.det(R) - 1).max() < 1e-13
+    tr = rb.planner().batch_joint_trajectory(th[:50], rng.uniform(lo, hi, (50, n)), 2.0, 101, 5)
+    for k in ("velocities", "accelerations"):
+        assert np.abs(tr[k][:, 0]).max() == 0.0 and np.abs(tr[k][:, -1]).max() < 1e-4
+    np.testing.assert_array_equal(tr["positions"][:, 0], th[:50].astype(np.float32))
+
+
 def test_reference_planner_unit_cases():
     """The cases of the reference's tests/test_path_planning_unit.py:52-160, on a 2-joint planner:
     end points respected, batch = per-trajectory generator, positions clipped to the joint
