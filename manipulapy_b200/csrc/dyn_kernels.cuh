@@ -181,30 +181,72 @@ __device__ __forceinline__ const double *load_tip(const TipArgs &tip, int64_t p,
     return nullptr;
 }
 
-// Joint values of row p read from global memory when the recursion reaches the link.  Each
-// thread walks its own contiguous row, rows of neighbouring threads are adjacent, so every
-// fetched sector is fully consumed (through L1) although the individual loads are strided.
+// Joint values of row p.  float64 rows are read from global memory when the recursion reaches
+// the link, one joint ahead (each thread walks its own contiguous row, rows of neighbouring
+// threads are adjacent, so every fetched sector is consumed through L1 -- the launcher leaves
+// L1 room for that).  float32 rows (the trajectory-level API: 3 x 4 N bytes per point) are
+// fetched whole up front with 8 / 16-byte vector loads and wait in 3 N 32-bit registers: all
+// loads of a row are in flight together and every sector is requested at most twice.
 template <int N, typename T>
 struct RowIn {
     const void *th, *dth, *ddth;
     int dtype;
     int64_t row;          // p * N
-    T nx[3];              // joint i's values, loaded while link i - 1 was being processed
+    T nx[3];              // float64 rows: joint i's values, loaded while link i - 1 was being processed
+    float r32[3][N];      // float32 rows
     __device__ __forceinline__ T at(const void *base, int i) const {
         if (base == nullptr) return T(0);
-        return dtype == MPK_F64 ? (T)__ldg(static_cast<const double *>(base) + row + i)
-                                : (T)__ldg(static_cast<const float *>(base) + row + i);
+        return (T)__ldg(static_cast<const double *>(base) + row + i);
     }
     __device__ __forceinline__ void prefetch(int i) {
         nx[0] = at(th, i);
         nx[1] = at(dth, i);
         nx[2] = at(ddth, i);
     }
+    __device__ __forceinline__ void load_f32(const void *base, float (&dst)[N], bool vec) {
+        if (base == nullptr) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) dst[j] = 0.f;
+            return;
+        }
+        const float *g = static_cast<const float *>(base) + row;
+        if (vec && N % 4 == 0) {
+#pragma unroll
+            for (int j = 0; j < N / 4; ++j) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(g) + j);
+                dst[4 * j] = v.x; dst[4 * j + 1] = v.y; dst[4 * j + 2] = v.z; dst[4 * j + 3] = v.w;
+            }
+        } else if (vec && N % 2 == 0) {
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(g) + j);
+                dst[2 * j] = v.x; dst[2 * j + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) dst[j] = __ldg(g + j);
+        }
+    }
+    __device__ __forceinline__ void begin(bool vec) {
+        if (dtype == MPK_F64) {
+            prefetch(0);
+        } else {
+            load_f32(th, r32[0], vec);
+            load_f32(dth, r32[1], vec);
+            load_f32(ddth, r32[2], vec);
+        }
+    }
     __device__ __forceinline__ void joint(int i, T &a, T &b, T &c) {
-        a = nx[0];
-        b = nx[1];
-        c = nx[2];
-        if (i + 1 < N) prefetch(i + 1);  // overlaps the load latency with link i's arithmetic
+        if (dtype == MPK_F64) {
+            a = nx[0];
+            b = nx[1];
+            c = nx[2];
+            if (i + 1 < N) prefetch(i + 1);  // overlaps the load latency with link i's arithmetic
+        } else {
+            a = (T)r32[0][i];
+            b = (T)r32[1][i];
+            c = (T)r32[2][i];
+        }
     }
 };
 
@@ -235,8 +277,8 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const double *ftp = load_tip(a.tip, p, ft);
     TipT<T> tt;
     const T *ftt = tip_to<T>(a.tip, ftp, tt);
-    RowIn<N, T> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {T(0), T(0), T(0)}};
-    in.prefetch(0);
+    RowIn<N, T> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {T(0), T(0), T(0)}, {}};
+    in.begin(a.vec_in != 0);
     SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
     T tau[N];
     rnea<T, N, GEN, REV>(rb, in, tt.g0, ftt, tau, st);
