@@ -680,6 +680,38 @@ def test_full_size_cfg3_ur5_trajectory_rnea(robots, oracle_factory):
     assert float((lhs - rhs).abs().max()) < 1e-9 * max(1.0, float(rhs.abs().max()))
 
 
+def test_full_size_cfg5_billion_points(robots, oracle_factory):
+    """BASELINE config 5 at its largest size on ONE GPU: 409,600 UR5 trajectories x 2441 steps =
+    1.0e9 points (24 GB of float32 torques; element offsets beyond 2^32).  Size-independent checks:
+    any slice of the big run is bit-identical to the same trajectories run as a small batch, the
+    last trajectories (highest addresses) match the oracle, nothing is left unwritten."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    rb, o = robots["ur5"], oracle_factory("ur5")
+    planner = rb.planner()
+    B, N = 409_600, 2441
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    s = (torch.rand(B, 6, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1) * np.pi
+    e = (torch.rand(B, 6, dtype=torch.float64, device="cuda", generator=gen) * 2 - 1) * np.pi
+    tau = planner.trajectory_inverse_dynamics(s, e, 2.0, N, 5)
+    assert tau.shape == (B, N, 6) and tau.numel() > 2**32
+    for lo in (0, 123_457, B - 1000):
+        small = planner.trajectory_inverse_dynamics(s[lo:lo + 1000], e[lo:lo + 1000], 2.0, N, 5)
+        assert bool(torch.equal(small.view(torch.int32), tau[lo:lo + 1000].view(torch.int32))), lo
+        del small
+    from oracle import Oracle
+    for b in (B - 1, B // 2):
+        ref = Oracle.joint_trajectory(s[b].cpu().numpy()[None], e[b].cpu().numpy()[None], 2.0, N, 5, rb.joint_limits)
+        rt = o.inverse_dynamics_trajectory(ref["positions"][0], ref["velocities"][0], ref["accelerations"][0], analytic=True)
+        np.testing.assert_allclose(tau[b].cpu().numpy(), rt, rtol=3e-7, atol=1e-7)
+    # every chunk of the output was written with finite values
+    for lo in range(0, B, 51_200):
+        assert bool(torch.isfinite(tau[lo:lo + 51_200]).all())
+    del tau
+    torch.cuda.empty_cache()
+
+
 def test_full_size_cfg2_million_fk_jacobian(robots, oracle_factory):
     """iiwa14 (true 7-DOF) and the reference's 8-DOF Panda: 1,000,000 random configurations."""
     for robot in ("iiwa14", "panda"):
