@@ -30,7 +30,9 @@
 // Template flags used throughout:
 //   GEN  general symmetric 6x6 link inertias (else rigid bodies: I about the origin, m c, m)
 //   REV  a "plain" chain: every joint revolute (sr = 1, st = 0) and every link plain
-//        Denavit-Hartenberg (beta = 0); drops the prismatic and Hayati terms at compile time
+//        Denavit-Hartenberg (beta = 0); drops the prismatic and Hayati terms at compile time.
+//        Without it joints are told apart by warp-uniform tests on rb.sr / rb.st / rb.sb.
+//   The rigid (non-GEN) paths assume a revolute FIRST joint; other chains take the GEN path.
 //   HAY  (transform helpers) keep the warp-uniform Ry(beta) step; kernels pass HAY = !REV
 #pragma once
 #include <cuda_runtime.h>
@@ -616,8 +618,8 @@ struct zero_acc_of<In, decltype((void)In::kZeroAcc)> {
 template <typename T, int N, bool GEN, bool REV, typename In, typename St>
 MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *ftip, T (&tau)[N],
                  St &st_) {
-    // a rigid all-revolute chain: link 0 only contributes the z moment about its own axis, and
-    // link 1 receives a twist with known zeros
+    // rigid inertias and a revolute first joint (guaranteed by the flavour selection): link 0 only
+    // contributes the z moment about its own axis, and link 1 receives a twist with known zeros
     constexpr bool FAST0 = rnea_fast0(GEN, REV, N);
     constexpr bool NOACC = zero_acc_of<In>::value;  // ddtheta == 0
     T w[3], v[3], dw[3], dv[3];
