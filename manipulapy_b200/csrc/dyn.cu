@@ -109,17 +109,23 @@ static int trajectory_inverse_dynamics_impl(const mpk_robot *rb, int64_t B, int6
     a.tlim = make_limits(tau_limits, rb->n);
     a.tip = make_tip(rb, g, Ftip, nullptr);
     a.tau = tau;
+    a.pos = a.vel = a.acc = nullptr;
     a.compute_f32 = compute_f32;
     unsigned grid;
     if (int rc = grid_for(a.P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     a.ts_table = prepare_time_scaling(ts_scratch, B, N, Tf, method, s);
     if (pos || vel || acc) {
-        // optional materialisation of the trajectory rows: the store-bound trajectory kernel
-        // does it at the write-bandwidth ceiling; the fused kernel then only writes torques
-        if (int rc = launch_joint_trajectory(rb->n, B, N, start, end, inputs_f32, Tf, method, joint_limits,
-                                             pos, vel, acc, a.ts_table, s))
-            return rc;
+        // optional materialisation of the trajectory rows
+        if (!compute_f32 && !a.tip.has_ftip) {
+            // the fused kernel stores them itself, hidden under its arithmetic
+            a.pos = pos;
+            a.vel = vel;
+            a.acc = acc;
+        } else if (int rc = launch_joint_trajectory(rb->n, B, N, start, end, inputs_f32, Tf, method,
+                                                    joint_limits, pos, vel, acc, a.ts_table, s)) {
+            return rc;  // (other variants: the store-bound trajectory kernel writes them first)
+        }
     }
     MPK_DISPATCH_FLAVOUR(rb, launch_traj_rnea<F_>(rb, a, grid, s));
     return check_launch("trajectory_inverse_dynamics");

@@ -43,6 +43,11 @@ void launch_traj_rnea(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid,
     } else if (a.compute_f32) {
         MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<float, N_, GEN, REV, false>, grid, kDynThreads,
                                               wrench_smem<float, N_, GEN, REV>(), s, narrow<N_, float>(rb), a));
+    } else if (a.pos || a.vel || a.acc) {
+        // (float64, no tip wrench: the launcher only asks for this variant then)
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<double, N_, GEN, REV, false, true>, grid, kDynThreads,
+                                              wrench_smem<double, N_, GEN, REV>() + 3 * sizeof(float) * kDynThreads * N_,
+                                              s, narrow<N_>(rb), a));
     } else if (a.tip.has_ftip) {
         MPK_DISPATCH_DOF_V(rb->n, launch_smem(traj_rnea_kernel<double, N_, GEN, REV, true>, grid, kDynThreads,
                                               wrench_smem<double, N_, GEN, REV>(), s, narrow<N_>(rb), a));

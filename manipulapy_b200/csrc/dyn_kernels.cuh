@@ -59,6 +59,7 @@ struct TrajRneaArgs {
     Limits jlim, tlim;
     TipArgs tip;
     float *tau;
+    float *pos, *vel, *acc;  // only read by the WRITE variant of the fused kernel
     const double *ts_table;
     FastDiv div;
     int compute_f32;
@@ -288,30 +289,43 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
 // ---- fused trajectory + inverse dynamics ----------------------------------------
 // Joint values produced from the time scaling when the recursion reaches the link: the
 // float32-rounded, clipped trajectory row entries the two-call sequence would have stored.
+// `stage` (WRITE variant): the thread's row in the block's shared-memory tiles of positions,
+// velocities and accelerations, from where the rows go to HBM with coalesced stores.
 template <int N, typename T>
 struct TrajIn {
     const TrajRneaArgs &a;
     TimeScale ts;
-    int64_t row;  // b * N
+    int64_t row;   // b * N
+    float *stage;  // or nullptr
     __device__ __forceinline__ void joint(int i, T &th, T &qd, T &qdd) {
         double st, dth;
         endpoint(a.start, a.end, a.inputs_f32, row + i, st, dth);
         float p, v, ac;
         traj_point(ts, st, dth, a.jlim.lo[i], a.jlim.hi[i], a.jlim.on, p, v, ac);
+        if (stage) {
+            stage[i] = p;
+            stage[kDynThreads * N + i] = v;
+            stage[2 * kDynThreads * N + i] = ac;
+        }
         th = (T)p;
         qd = (T)v;
         qdd = (T)ac;
     }
 };
 
-template <typename T, int N, bool GEN, bool REV, bool TIP>
+// WRITE: also materialise the trajectory rows (positions, velocities, accelerations).  The
+// kernel is bound by the fp64 pipe with HBM at 6 %, so the extra 12 N bytes per point ride
+// along at a fraction of their stand-alone cost (0.65 ms against 0.17 + 0.57 ms for the two launches).
+template <typename T, int N, bool GEN, bool REV, bool TIP, bool WRITE = false>
 __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     traj_rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const TrajRneaArgs a) {
     // dynamic shared memory: the per-thread link state of the recursion, then (same bytes) the
-    // block's output rows staged for coalesced stores
+    // block's output rows staged for coalesced stores; WRITE: + three trajectory tiles behind it
     extern __shared__ __align__(16) double wsm_raw[];
     T *wsm = reinterpret_cast<T *>(wsm_raw);
     float *sm = reinterpret_cast<float *>(wsm_raw);
+    float *traj_sm = reinterpret_cast<float *>(
+        reinterpret_cast<char *>(wsm_raw) + wrench_smem<T, N, GEN, REV>());
     const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
     const bool live = p0 + threadIdx.x < a.P;
     int64_t b, t;
@@ -321,7 +335,8 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const int64_t off = p0 * N;
     // (tail threads of the last block recompute point 0: they take part in the barriers and
     // their staged rows are never stored)
-    TrajIn<N, T> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N};
+    TrajIn<N, T> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N,
+                    WRITE ? traj_sm + threadIdx.x * N : nullptr};
     float out[N];
     {
         T g0[3], ft[6];
@@ -346,6 +361,11 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     for (int j = 0; j < N; ++j) sm[threadIdx.x * N + j] = out[j];
     __syncthreads();
     tile_store(a.tau + off, sm, cnt);
+    if (WRITE) {
+        if (a.pos) tile_store(a.pos + off, traj_sm, cnt);
+        if (a.vel) tile_store(a.vel + off, traj_sm + kDynThreads * N, cnt);
+        if (a.acc) tile_store(a.acc + off, traj_sm + 2 * kDynThreads * N, cnt);
+    }
 }
 
 // ---- mass matrix -------------------------------------------------------------------
