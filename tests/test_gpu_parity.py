@@ -644,6 +644,29 @@ def test_float32_fused_trajectory_inverse_dynamics(robots, oracle_factory, robot
         assert not _bits_equal(tau32, tau64)
 
 
+def test_cfg1_reference_case(robots, oracle_factory):
+    """BASELINE config 1, the reference's own CPU-runnable case: UR5, seed 1, U(-1, 1)^6 end points,
+    Tf = 2, N = 1000, quintic joint_trajectory followed by inverse_dynamics_trajectory.  Rows
+    bit-exact against the reference golden; all 1000 torque rows against the oracle's LITERAL
+    restatement of the reference algorithm (finite-difference Coriolis) at the reference's own
+    golden tolerance, and against the analytic one to float32 rounding."""
+    rb, o = robots["ur5"], oracle_factory("ur5")
+    g = load_golden("trajectory")
+    planner = rb.planner()
+    tr = planner.joint_trajectory(g["cfg1_start"], g["cfg1_end"], 2.0, 1000, 5)
+    for k in ("positions", "velocities", "accelerations"):
+        assert _bits_equal(tr[k], g[f"cfg1_{k}"]), k
+    tau = planner.inverse_dynamics_trajectory(tr["positions"], tr["velocities"], tr["accelerations"])
+    assert tau.shape == (1000, 6) and tau.dtype == np.float32
+    th, dth, dd = (tr[k].astype(np.float64) for k in ("positions", "velocities", "accelerations"))
+    lit = o.inverse_dynamics_trajectory(th, dth, dd, analytic=False)
+    np.testing.assert_allclose(tau, lit, rtol=1e-6, atol=1e-6)
+    ana = o.inverse_dynamics_trajectory(th, dth, dd, analytic=True)
+    np.testing.assert_allclose(tau, ana, rtol=3e-7, atol=1e-7)
+    fused = planner.trajectory_inverse_dynamics(g["cfg1_start"], g["cfg1_end"], 2.0, 1000, 5)
+    assert _bits_equal(fused, tau)
+
+
 def test_full_size_cfg3_ur5_trajectory_rnea(robots, oracle_factory):
     """UR5, 4096 trajectories x 2441 steps (9,998,336 points), quintic, fused."""
     from oracle import Oracle
@@ -713,9 +736,20 @@ def test_full_size_cfg5_billion_points(robots, oracle_factory):
 
 
 def test_full_size_cfg2_million_fk_jacobian(robots, oracle_factory):
-    """iiwa14 (true 7-DOF) and the reference's 8-DOF Panda: 1,000,000 random configurations."""
-    for robot in ("iiwa14", "panda"):
-        rb, o = robots[robot], oracle_factory(robot)
+    """iiwa14 (true 7-DOF), the reference's 8-DOF Panda, and the 7-DOF Panda arm (its first seven
+    screws; BASELINE config 2 says "Franka Panda 7-DOF"): 1,000,000 random configurations."""
+    from manipulapy_b200 import load_robot
+    from manipulapy_b200.robots import RobotBundle
+    from oracle import Oracle
+
+    p8 = load_robot("panda")
+    panda7 = RobotBundle("panda7", p8.S_list[:, :7].copy(), p8.M, p8.Glist[:7], p8.Mlist_per_link[:7],
+                         p8.joint_limits[:7])
+    for robot in ("iiwa14", "panda", "panda7"):
+        if robot == "panda7":
+            rb, o = panda7, Oracle(panda7.S_list, panda7.M, panda7.Glist, panda7.Mlist_per_link)
+        else:
+            rb, o = robots[robot], oracle_factory(robot)
         n = rb.num_joints
         rng = np.random.default_rng(2)
         P = 1_000_000
