@@ -32,7 +32,10 @@ NVCC_FLAGS = [
 # so that the build uses every core.
 CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", []), ("kin.cu", "kin", []), ("ik.cu", "ik", []),
             ("dyn.cu", "dyn", [])]
-CU_UNITS += [(f"{base}_flavour.cu", f"{base}_flavour{k}", [f"-DMPK_FLAVOUR={k}"])
+# MPK_FD_DEFINES / MPK_DYN_DEFINES (environment, e.g. "-DMPK_FD_MINBLOCKS=16"): extra defines for
+# the forward-dynamics / inverse-dynamics flavour units, for tuning sweeps on the GPU box.
+CU_UNITS += [(f"{base}_flavour.cu", f"{base}_flavour{k}",
+              [f"-DMPK_FLAVOUR={k}", *os.environ.get(f"MPK_{base.upper()}_DEFINES", "").split()])
              for base in ("dyn", "fd") for k in (0, 1, 2)]
 HEADERS = [CSRC / "mpk_device.cuh", CSRC / "mpk_common.cuh", CSRC / "dyn_kernels.cuh", INCLUDE / "mpk.h"]
 

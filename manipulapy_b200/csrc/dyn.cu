@@ -226,13 +226,8 @@ extern "C" int mpk_forward_dynamics_trajectory(const mpk_robot *rb, int64_t B, i
     a.pos = pos;
     a.vel = vel;
     a.acc = acc;
-    // One warp per block: the kernel needs no block-level cooperation, and single-warp blocks
-    // spread a small batch over all SMs (8,192 rollouts: 4.96 ms against 5.7 ms with 128-thread
-    // blocks; 65,536 rollouts: no difference, 12.5-12.8 ms).
-    const int threads = 32;
-    const int64_t blocks = (B + threads - 1) / threads;
-    if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B exceeds the grid limit");
+    if ((B + 31) / 32 > 0x7fffffffLL) return fail(MPK_EINVAL, "B exceeds the grid limit");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    MPK_DISPATCH_FLAVOUR(rb, launch_rollout<F_>(rb, a, (unsigned)blocks, threads, s));
+    MPK_DISPATCH_FLAVOUR(rb, launch_rollout<F_>(rb, a, s));
     return check_launch("forward_dynamics_trajectory");
 }

@@ -94,11 +94,25 @@ struct RolloutArgs {
 };
 
 // Flavour launchers: defined and explicitly instantiated in dyn_flavour.cu / fd_flavour.cu.
+// Rollout kernel launch shape (tuning knobs, profiles/r1_variants.md E): MPK_FD_THREADS threads per
+// block, MPK_FD_MINBLOCKS resident blocks per SM (the register cap: 16,384 / (32 x warps per
+// scheduler) registers per thread), MPK_FD_PHASES block barriers per Euler step.
+#ifndef MPK_FD_THREADS
+#define MPK_FD_THREADS 32
+#endif
+#ifndef MPK_FD_MINBLOCKS
+#define MPK_FD_MINBLOCKS (256 / MPK_FD_THREADS)
+#endif
+#ifndef MPK_FD_PHASES
+#define MPK_FD_PHASES 0
+#endif
+constexpr int kRolloutThreads = MPK_FD_THREADS;
+
 template <int FLAVOUR> void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s);
 template <int FLAVOUR> void launch_traj_rnea(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s);
 template <int FLAVOUR> void launch_mass(const mpk_robot *rb, const MassArgs &a, unsigned grid, cudaStream_t s);
 template <int FLAVOUR> void launch_fd_point(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaStream_t s);
-template <int FLAVOUR> void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, unsigned grid, int threads, cudaStream_t s);
+template <int FLAVOUR> void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s);
 
 #define MPK_DISPATCH_FLAVOUR(rb, CALL)                 \
     switch (flavour_of(rb)) {                          \
@@ -464,20 +478,25 @@ __device__ __forceinline__ void tau_row_take(const double *stage, int dtype, dou
     }
 }
 
-// shared memory per warp: two torque-row stages + one word per lane for the rollout's row base
+// shared memory per warp: two torque-row stages + two words per lane for the loop state (the
+// rollout's row base and its step counter)
 template <int N>
 constexpr size_t rollout_smem_per_warp() {
-    return sizeof(double) * 32 * (N * 2 + 1);
+    return sizeof(double) * 32 * (N * 2 + 2);
 }
 
 // TIP: rows of Ftipmat are applied (else every tip-wrench term is compiled out).
 template <int N, bool GEN, bool REV, bool TIP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kRolloutThreads, MPK_FD_MINBLOCKS)
     fd_rollout_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
     extern __shared__ __align__(16) double fsm[];
-    double *stage = fsm + (threadIdx.x >> 5) * (32 * (N * 2 + 1)) + (threadIdx.x & 31);  // + (step & 1) * 32 * N
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    double *stage = fsm + (threadIdx.x >> 5) * (32 * (N * 2 + 2)) + (threadIdx.x & 31);  // + (step & 1) * 32 * N
+    // (with block barriers in the step every thread must stay: surplus threads of the last block
+    // recompute the last rollout and store nothing)
+    const int64_t b_ = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = b_ < a.B;
+    if (MPK_FD_PHASES == 0 && !live) return;
+    const int64_t b = live ? b_ : a.B - 1;
     double th[N], dth[N], last[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
@@ -485,20 +504,30 @@ __global__ void __launch_bounds__(128)
         dth[j] = a.dth0[b * N + j];
         last[j] = 0.0;
     }
-    // The step body needs every register; what the loop keeps per thread besides the state is
-    // this one row index, parked in shared memory and re-read each step.  (Left to the compiler,
-    // the four row pointers derived from it are spilled to LOCAL memory, whose reloads miss L1
-    // behind the torque stream and stall the top of every step: ncu long_scoreboard 21 %.)
+    // The step body needs every register; what the loop carries per thread besides the state --
+    // the rollout's row base and the step counter -- is parked in shared memory and re-read at
+    // the top of each step.  (Left to the compiler, the row pointers derived from the base, and
+    // then the 64-bit counter itself, are spilled to LOCAL memory, whose reloads miss L1 behind
+    // the torque stream: ncu long_scoreboard 21 % of the samples, all on the reload at the loop
+    // head, profiles/r1_variants.md E.)
     volatile int64_t *base_slot = reinterpret_cast<volatile int64_t *>(stage + 32 * N * 2);
+    volatile int64_t *step_slot = reinterpret_cast<volatile int64_t *>(stage + 32 * (N * 2 + 1));
     {
         const int64_t base = b * a.N;
         *base_slot = base;
-        store_state<N>(a.pos, base, th);
-        store_state<N>(a.vel, base, dth);
-        store_state<N>(a.acc, base, last);
+        *step_slot = 1;
+        if (MPK_FD_PHASES == 0 || live) {
+            store_state<N>(a.pos, base, th);
+            store_state<N>(a.vel, base, dth);
+            store_state<N>(a.acc, base, last);
+        }
         if (a.N > 1) tau_row_async<N>(stage + 32 * N, a.taumat, a.tau_dtype, base + 1);
     }
-    for (int64_t i = 1; i < a.N; ++i) {
+    for (;;) {
+        const int64_t i = *step_slot;
+        if (i >= a.N) break;
+        *step_slot = i + 1;
+        if (MPK_FD_PHASES >= 1) __syncthreads();
         const int64_t base = *base_slot;
         double tau[N];
         tau_row_take<N>(stage + (i & 1) * 32 * N, a.tau_dtype, tau);
@@ -514,7 +543,7 @@ __global__ void __launch_bounds__(128)
         for (int j = 0; j < N; ++j) last[j] = 0.0;
         for (int r = 0; r < a.intRes; ++r) {
             double dd[N];
-            forward_dynamics<double, N, GEN, REV>(rb, th, dth, tau, a.g0, ftp, dd);
+            forward_dynamics<double, N, GEN, REV, MPK_FD_PHASES>(rb, th, dth, tau, a.g0, ftp, dd);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 dth[j] = rn_add(dth[j], rn_mul(dd[j], a.dts));
@@ -527,9 +556,12 @@ __global__ void __launch_bounds__(128)
                 last[j] = dd[j];
             }
         }
-        store_state<N>(a.pos, base + i, th);
-        store_state<N>(a.vel, base + i, dth);
-        store_state<N>(a.acc, base + i, last);
+        const int64_t row = *base_slot + *step_slot - 1;
+        if (MPK_FD_PHASES == 0 || live) {
+            store_state<N>(a.pos, row, th);
+            store_state<N>(a.vel, row, dth);
+            store_state<N>(a.acc, row, last);
+        }
     }
 }
 #endif  // MPK_FLAVOUR_KERNELS

@@ -28,9 +28,14 @@ void launch_fd_point(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaSt
     MPK_DISPATCH_DOF_V(rb->n, (forward_dynamics_kernel<N_, GEN, REV><<<grid, kDynThreads, 0, s>>>(narrow<N_>(rb), a)));
 }
 
+// One warp per block by default: the kernel needs no block-level cooperation, and single-warp
+// blocks spread a small batch over all SMs (8,192 rollouts: 4.96 ms against 5.7 ms with 128-thread
+// blocks; 65,536 rollouts: no difference).
 template <int F>
-void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, unsigned grid, int threads, cudaStream_t s) {
+void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    constexpr int threads = kRolloutThreads;
+    const unsigned grid = (unsigned)((a.B + threads - 1) / threads);
     if (a.ftipmat) {
         MPK_DISPATCH_DOF_V(rb->n, launch_smem(fd_rollout_kernel<N_, GEN, REV, true>, grid, threads,
                                               rollout_smem_per_warp<N_>() * (threads / 32), s, narrow<N_>(rb), a));
@@ -41,6 +46,6 @@ void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, unsigned grid, in
 }
 
 template void launch_fd_point<MPK_FLAVOUR>(const mpk_robot *, const FdArgs &, unsigned, cudaStream_t);
-template void launch_rollout<MPK_FLAVOUR>(const mpk_robot *, const RolloutArgs &, unsigned, int, cudaStream_t);
+template void launch_rollout<MPK_FLAVOUR>(const mpk_robot *, const RolloutArgs &, cudaStream_t);
 
 }  // namespace mpk

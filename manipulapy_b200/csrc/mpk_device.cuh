@@ -170,14 +170,10 @@ __host__ __device__ __noinline__ inline SinCos sincos_far(double x) {
     return r;
 }
 
+// The reduction + kernels alone, valid for |x| < 1e5 (no branch: several calls in a row form
+// one basic block whose independent dependency chains the scheduler interleaves).
 template <typename T>
-MPK_HD void sincos_pack(const T *tc, double x, double *sn, double *cs) {
-    if (!(fabs(x) < 1e5)) {  // also NaN / inf
-        const SinCos far = sincos_far(x);  // (by value: the outputs never have their address taken)
-        *sn = far.s;
-        *cs = far.c;
-        return;
-    }
+MPK_HD void sincos_near(const T *tc, double x, double *sn, double *cs) {
     const double t = fma(x, (double)tc[0], (double)tc[1]);
     const int k = (int)(uint32_t)f64_bits(t);  // round(x * 2/pi) sits in the low mantissa bits
     const double kd = t - (double)tc[1];
@@ -205,6 +201,20 @@ MPK_HD void sincos_pack(const T *tc, double x, double *sn, double *cs) {
     *sn = bits_f64(f64_bits(s0) ^ ss);
     *cs = bits_f64(f64_bits(c0) ^ sc);
 }
+MPK_HD bool sincos_is_near(double x) { return fabs(x) < 1e5; }  // false for NaN / inf too
+MPK_HD bool sincos_is_near(float) { return false; }
+
+template <typename T>
+MPK_HD void sincos_pack(const T *tc, double x, double *sn, double *cs) {
+    if (!sincos_is_near(x)) {
+        const SinCos far = sincos_far(x);  // (by value: the outputs never have their address taken)
+        *sn = far.s;
+        *cs = far.c;
+        return;
+    }
+    sincos_near(tc, x, sn, cs);
+}
+MPK_HD void sincos_near(const float *, float x, float *s, float *c) { sincos_t(x, s, c); }
 MPK_HD void sincos_pack(const float *, float x, float *s, float *c) { sincos_t(x, s, c); }
 
 // Planar rotation of the pair (p, q) by the angle whose cosine / sine are (c, s):
@@ -249,6 +259,34 @@ template <typename T, int N, bool REV = false>
 MPK_HD void joint_cs(const RobotPack<T, N> &rb, const T (&th)[N], JointCS<T, N> &q) {
 #pragma unroll
     for (int i = 0; i < N; ++i) joint_rot<T, N, REV>(rb, i, th[i], q.c[i], q.s[i], q.d[i]);
+}
+
+// All joint rotations up front with ONE range test for the whole chain: the N sin / cos
+// evaluations then sit in a single basic block (N independent ~35-instruction dependency chains)
+// instead of N blocks each behind its own branch.  Same values as joint_cs().  Used where few
+// warps are resident and instruction-level parallelism is what hides the fp64 latency (the
+// forward-dynamics rollouts: 2 warps per scheduler).
+template <typename T, int N, bool REV>
+MPK_HD void joint_cs_all(const RobotPack<T, N> &rb, const T (&th)[N], JointCS<T, N> &q) {
+    bool near = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        if (REV || rb.sr[i] != T(0)) near = near && sincos_is_near(rb.phi[i] + th[i]);
+    if (near) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (REV || rb.sr[i] != T(0)) {
+                sincos_near(rb.trig, rb.phi[i] + th[i], &q.s[i], &q.c[i]);
+                q.d[i] = rb.d[i];
+            } else {
+                q.c[i] = rb.cphi[i];
+                q.s[i] = rb.sphi[i];
+                q.d[i] = rb.d[i] + rb.st[i] * th[i];
+            }
+        }
+    } else {
+        joint_cs<T, N, REV>(rb, th, q);
+    }
 }
 
 // -g expressed in frame 0 at theta_0 = 0 (uniform over a batch: launchers compute it once on
@@ -523,6 +561,7 @@ MPK_HD void rigid_wrench(const RobotPack<T, N> &rb, int i, const T (&w)[3], cons
 // z offset in the s slot instead.
 template <typename T, int N>
 struct RegStore {
+    static constexpr bool kPrecomputedCS = false;
     T x[N][6];
     JointCS<T, N> q;
     MPK_HD void put(int i, int k, T v) { x[i][k] = v; }
@@ -540,6 +579,12 @@ struct RegStore {
         d = q.d[i];
     }
 };
+// ... with the joint rotations q already filled in by the caller (joint_cs_all): rnea() reads
+// them instead of evaluating sin / cos link by link.
+template <typename T, int N>
+struct RegStorePre : RegStore<T, N> {
+    static constexpr bool kPrecomputedCS = true;
+};
 // Whether rnea() takes the shortcut for link 0 (only the z moment about its own axis is
 // stored for it): rigid inertias, revolute first joint, at least two links.
 // (the rigid kernel flavours are only used for chains whose FIRST joint is revolute)
@@ -547,6 +592,7 @@ constexpr bool rnea_fast0(bool GEN, bool REV, int N) { return (void)REV, !GEN &&
 
 template <typename T, int N, int THREADS, bool FAST0 = false>
 struct SmemStore {
+    static constexpr bool kPrecomputedCS = false;
     T *base;  // shared memory + threadIdx.x; slot l = wrench of link l, (c, s) of link l + 1
     // values per thread: 8 per link 0..N-2; with FAST0 link 0 keeps 3 (its z moment and (c, s) of link 1)
     static constexpr int kValues = N > 1 ? (FAST0 ? 3 + (N - 2) * 8 : (N - 1) * 8) : 0;
@@ -635,8 +681,12 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
     for (int i = 0; i < N; ++i) {
         T th_i, qd, qdd, c, s, dz;
         in.joint(i, th_i, qd, qdd);
-        joint_rot<T, N, REV>(rb, i, th_i, c, s, dz);
-        st_.template put_cs<REV>(rb, i, c, s, dz);
+        if constexpr (St::kPrecomputedCS) {
+            st_.template get_cs<REV>(rb, i, c, s, dz);
+        } else {
+            joint_rot<T, N, REV>(rb, i, th_i, c, s, dz);
+            st_.template put_cs<REV>(rb, i, c, s, dz);
+        }
         if (i == 0) {
             // base twist is zero and the base acceleration is [0; -g]: V_0 = A_0 qd,
             // dV_0 = [0; Rz^T g0] + A_0 qdd  (ad(V_0) A_0 = 0)
@@ -907,9 +957,30 @@ MPK_HD void mass_matrix(const RobotPack<T, N> &rb, const T (&th)[N], const Joint
     else crba<T, N, REV>(rb, q, Mm);
 }
 
+// Reciprocal of an LDL^T pivot without the division's special-case branch: hardware seed
+// (MUFU.RCP64H, ~2^-20) and two Newton steps, <= 1 ulp for normal, finite arguments (pivots of a
+// mass matrix are).  Branch-free, so the N pivots do not cut the factorisation into N basic
+// blocks and the seed's latency overlaps the column updates.
+MPK_HD double rcp_pivot(double d) {
+#ifdef __CUDA_ARCH__
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    e = fma(e, e, e);  // e + e^2: third-order last step
+    return fma(x, e, x);
+#else
+    return 1.0 / d;
+#endif
+}
+MPK_HD float rcp_pivot(float d) { return 1.0f / d; }
+
 // Solve M x = b in place (b <- x) with an unrolled LDL^T; M symmetric positive definite
 // (only the lower triangle is read; it is overwritten).
-template <typename T, int N>
+// FASTRCP: pivots inverted by rcp_pivot (forward dynamics) instead of an IEEE division (the
+// inverse kinematics, whose iterates are compared step by step with the reference's).
+template <typename T, int N, bool FASTRCP = false>
 MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
     T dinv[N];
 #pragma unroll
@@ -918,7 +989,7 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
 #pragma unroll
         for (int k = 0; k < j; ++k) dj -= Mm[j][k] * Mm[j][k] * Mm[k][k];
         Mm[j][j] = dj;
-        dinv[j] = T(1) / dj;
+        dinv[j] = FASTRCP ? rcp_pivot(dj) : T(1) / dj;
 #pragma unroll
         for (int i = j + 1; i < N; ++i) {
             T l = Mm[i][j];
@@ -940,18 +1011,30 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
 }
 
 // ddtheta = M(theta)^-1 (tau - rnea(theta, dtheta, 0, g, Ftip))  (dynamics/id_fd.py:50-83).
-template <typename T, int N, bool GEN, bool REV>
+// PHASES > 0: the block's warps meet at a barrier between the phases (joint rotations | bias
+// forces | mass matrix | solve), so that they walk through the ~45 KB of straight-line code
+// together and share its instruction-cache lines (every thread of the block must call).
+MPK_HD void phase_barrier() {
+#ifdef __CUDA_ARCH__
+    __syncthreads();
+#endif
+}
+template <typename T, int N, bool GEN, bool REV, int PHASES = 0>
 MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N],
                              const T (&tau)[N], const T (&g0)[3], const T *ftip, T (&dd)[N]) {
     T bias[N];
-    RegStore<T, N> st_;
+    RegStorePre<T, N> st_;
+    joint_cs_all<T, N, REV>(rb, th, st_.q);
+    if (PHASES >= 4) phase_barrier();
     ArrayInNoAcc<T, N> in{th, dth};
     rnea<T, N, GEN, REV>(rb, in, g0, ftip, bias, st_);
 #pragma unroll
     for (int i = 0; i < N; ++i) dd[i] = tau[i] - bias[i];
+    if (PHASES >= 2) phase_barrier();
     T Mm[N][N];
     mass_matrix<T, N, GEN, REV>(rb, th, st_.q, Mm);
-    ldlt_solve<T, N>(Mm, dd);
+    if (PHASES >= 3) phase_barrier();
+    ldlt_solve<T, N, true>(Mm, dd);
 }
 
 // ---- kinematics ---------------------------------------------------------------
