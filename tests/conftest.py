@@ -28,6 +28,43 @@ def load_golden(name: str) -> dict:
         return {k: d[k] for k in d.files}
 
 
+def load_zoo() -> dict:
+    """Robots of the reference's whole bundled database (oracle/gen_robot_zoo.py): name -> dict
+    with the constant pack and the reference's outputs at a few configurations."""
+    with np.load(GOLDEN / "robot_zoo.npz") as d:
+        zoo = {str(r): {} for r in d["robots"]}
+        for k in d.files:
+            if "/" in k:
+                r, f = k.split("/", 1)
+                zoo[r][f] = d[k]
+        for r in zoo:
+            zoo[r]["g"] = d["g"]
+    return zoo
+
+
+ZOO_ROBOTS = sorted(load_zoo())
+
+
+def _zoo_rel(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    sc = np.maximum(1.0, np.abs(ref).reshape(ref.shape[0], -1).max(1))
+    return float((np.abs(np.asarray(got) - ref).reshape(ref.shape[0], -1).max(1) / sc).max())
+
+
+def check_zoo_outputs(z, fk, jac, M, grav, cor, tau, dd):
+    """The reference's own golden tolerances (tests/test_dynamics_golden.py:77-83) for M, g, c and
+    inverse dynamics; 1e-13 for FK / Jacobian; forward dynamics per vector."""
+    np.testing.assert_allclose(fk, z["fk"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(jac, z["jac"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(M, z["mass"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(grav, z["g_forces"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(cor, z["c"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(tau, z["id"], rtol=1e-7, atol=1e-8)
+    # the reference's finite-difference Coriolis noise (~1e-9 abs) is amplified by cond(M)
+    # (up to ~1e5 for the grippers' gram-scale links), hence per vector at 1e-6
+    assert _zoo_rel(dd, z["fd"]) < 1e-6
+
+
 @pytest.fixture(scope="session")
 def oracle_factory():
     from oracle import Oracle

@@ -821,3 +821,29 @@ def test_full_size_cfg4_iiwa_rollouts(robots, oracle_factory):
     # the first 50 steps agree to float32 rounding
     for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
         assert _rel_rows(got[sel, :50].cpu().numpy().reshape(-1, n), ref[k][:, :50].reshape(-1, n)) < 1e-6, k
+
+
+# ---------------------------------------------------------------------------------------------
+# every robot of the reference's bundled database (oracle/gen_robot_zoo.py)
+# ---------------------------------------------------------------------------------------------
+from conftest import ZOO_ROBOTS, check_zoo_outputs, load_zoo  # noqa: E402
+
+
+@pytest.mark.parametrize("robot", ZOO_ROBOTS)
+def test_robot_zoo_vs_reference(robot):
+    """26 URDF-derived chains (1 to 8 joints): FK, Jacobian, mass matrix, gravity / Coriolis forces,
+    inverse and forward dynamics against outputs of the unmodified reference."""
+    from manipulapy_b200 import ManipulatorDynamics
+
+    z = load_zoo()[robot]
+    dyn = ManipulatorDynamics(z["M"], None, None, None, z["S_list"], None, z["Glist"], z["Mlist_per_link"])
+    th, dth, ddth, ft, g = z["thetas"], z["dthetas"], z["ddthetas"], z["ftips"], z["g"]
+    check_zoo_outputs(
+        z, dyn.forward_kinematics(th), dyn.jacobian(th), dyn.mass_matrix(th), dyn.gravity_forces(th, g),
+        dyn.velocity_quadratic_forces(th, dth), dyn.inverse_dynamics(th, dth, ddth, g, ft),
+        dyn.forward_dynamics(th, dth, z["taus"], g, ft))
+    # a batch much larger than the golden rows gives the same bits for those rows
+    rng = np.random.default_rng(1)
+    n = th.shape[1]
+    big = np.concatenate([th, rng.uniform(-1, 1, (997, n))])
+    assert np.array_equal(dyn.mass_matrix(big)[: th.shape[0]], dyn.mass_matrix(th))

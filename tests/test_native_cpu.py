@@ -502,3 +502,23 @@ def test_gather_rows_gloo_world2(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+
+
+# ---------------------------------------------------------------------------------------------
+# every robot of the reference's bundled database (oracle/gen_robot_zoo.py): the kernels' link
+# frame construction (Denavit-Hartenberg / Hayati) on 26 different axis arrangements
+# ---------------------------------------------------------------------------------------------
+from conftest import ZOO_ROBOTS, check_zoo_outputs, load_zoo  # noqa: E402
+
+
+@pytest.mark.parametrize("robot", ZOO_ROBOTS)
+def test_robot_zoo_kernel_algebra_vs_reference(hostcheck, robot):
+    z = load_zoo()[robot]
+    th, dth, ddth, ft, g = z["thetas"], z["dthetas"], z["ddthetas"], z["ftips"], z["g"]
+    for flags in (0, 1):
+        rb = hostcheck.robot(z, flags)
+        T, J = hostcheck.fk(rb, th)
+        check_zoo_outputs(
+            z, T, J, hostcheck.mass(rb, th), hostcheck.rnea(rb, th, g=g),
+            hostcheck.rnea(rb, th, dth, g=(0, 0, 0)), hostcheck.rnea(rb, th, dth, ddth, g, ft),
+            hostcheck.fd(rb, th, dth, z["taus"], g, ft))

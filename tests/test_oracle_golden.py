@@ -235,3 +235,24 @@ def test_cartesian_trajectory_restatement_vs_reference():
         for k in ("positions", "velocities", "accelerations", "orientations"):
             assert got[k].dtype == np.float32 and got[k].shape == g[f"{name}_{k}"].shape
             np.testing.assert_allclose(got[k], g[f"{name}_{k}"], rtol=3e-7, atol=1e-7, err_msg=f"{name} {k}")
+
+
+# ---------------------------------------------------------------------------------------------
+# every robot of the reference's bundled database (oracle/gen_robot_zoo.py)
+# ---------------------------------------------------------------------------------------------
+from conftest import ZOO_ROBOTS, check_zoo_outputs, load_zoo  # noqa: E402
+
+
+@pytest.mark.parametrize("analytic", [False, True], ids=["literal", "analytic"])
+@pytest.mark.parametrize("robot", ZOO_ROBOTS)
+def test_robot_zoo_vs_reference(robot, analytic):
+    from oracle import Oracle
+
+    z = load_zoo()[robot]
+    o = Oracle(z["S_list"], z["M"], z["Glist"], z["Mlist_per_link"])
+    th, dth, ddth, ft, g = z["thetas"], z["dthetas"], z["ddthetas"], z["ftips"], z["g"]
+    check_zoo_outputs(
+        z, o.forward_kinematics(th), o.jacobian(th), o.mass_matrix(th, analytic),
+        o.gravity_forces(th, g, analytic), o.velocity_quadratic_forces(th, dth, analytic),
+        o.inverse_dynamics(th, dth, ddth, g, ft, analytic),
+        o.forward_dynamics(th, dth, z["taus"], g, ft, analytic))
