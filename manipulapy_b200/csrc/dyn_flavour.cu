@@ -28,6 +28,10 @@ void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStre
     if (a.compute_f32) {
         MPK_DISPATCH_DOF_V(rb->n, launch_smem_l1(rnea_kernel<float, N_, GEN, REV>, grid, kDynThreads,
                                                  wrench_smem<float, N_, GEN, REV>(), 7, s, narrow<N_, float>(rb), a));
+    } else if (!GEN && !a.dth && !a.ddth && !a.tip.has_ftip) {
+        // gravity forces: theta rows only, at-rest recursion (HBM-bound)
+        MPK_DISPATCH_DOF_V(rb->n, launch_smem_l1(rnea_kernel<double, N_, GEN, REV, true>, grid, kDynThreads,
+                                                 wrench_smem<double, N_, GEN, REV>(), 5, s, narrow<N_>(rb), a));
     } else {
         MPK_DISPATCH_DOF_V(rb->n, launch_smem_l1(rnea_kernel<double, N_, GEN, REV>, grid, kDynThreads,
                                                  wrench_smem<double, N_, GEN, REV>(), 5, s, narrow<N_>(rb), a));

@@ -202,8 +202,12 @@ __device__ __forceinline__ const double *load_tip(const TipArgs &tip, int64_t p,
 // L1 room for that).  float32 rows (the trajectory-level API: 3 x 4 N bytes per point) are
 // fetched whole up front with 8 / 16-byte vector loads and wait in 3 N 32-bit registers: all
 // loads of a row are in flight together and every sector is requested at most twice.
-template <int N, typename T>
+// REST: the rows of dtheta and ddtheta are absent (gravity forces) -- only theta is read and the
+// recursion takes its at-rest form.
+template <int N, typename T, bool REST = false>
 struct RowIn {
+    static constexpr bool kZeroAcc = REST;
+    static constexpr bool kZeroVel = REST;
     const void *th, *dth, *ddth;
     int dtype;
     int64_t row;          // p * N
@@ -215,8 +219,10 @@ struct RowIn {
     }
     __device__ __forceinline__ void prefetch(int i) {
         nx[0] = at(th, i);
-        nx[1] = at(dth, i);
-        nx[2] = at(ddth, i);
+        if (!REST) {
+            nx[1] = at(dth, i);
+            nx[2] = at(ddth, i);
+        }
     }
     __device__ __forceinline__ void load_f32(const void *base, float (&dst)[N], bool vec) {
         if (base == nullptr) {
@@ -247,20 +253,22 @@ struct RowIn {
             prefetch(0);
         } else {
             load_f32(th, r32[0], vec);
-            load_f32(dth, r32[1], vec);
-            load_f32(ddth, r32[2], vec);
+            if (!REST) {
+                load_f32(dth, r32[1], vec);
+                load_f32(ddth, r32[2], vec);
+            }
         }
     }
     __device__ __forceinline__ void joint(int i, T &a, T &b, T &c) {
         if (dtype == MPK_F64) {
             a = nx[0];
-            b = nx[1];
-            c = nx[2];
+            b = REST ? T(0) : nx[1];
+            c = REST ? T(0) : nx[2];
             if (i + 1 < N) prefetch(i + 1);  // overlaps the load latency with link i's arithmetic
         } else {
             a = (T)r32[0][i];
-            b = (T)r32[1][i];
-            c = (T)r32[2][i];
+            b = REST ? T(0) : (T)r32[1][i];
+            c = REST ? T(0) : (T)r32[2][i];
         }
     }
 };
@@ -281,7 +289,7 @@ __device__ __forceinline__ const T *tip_to(const TipArgs &tip, const double *ftp
     return o.ft;
 }
 
-template <typename T, int N, bool GEN, bool REV>
+template <typename T, int N, bool GEN, bool REV, bool REST = false>
 __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const RneaArgs a) {
     extern __shared__ __align__(16) double wsm_raw[];
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const double *ftp = load_tip(a.tip, p, ft);
     TipT<T> tt;
     const T *ftt = tip_to<T>(a.tip, ftp, tt);
-    RowIn<N, T> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {T(0), T(0), T(0)}, {}};
+    RowIn<N, T, REST> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {T(0), T(0), T(0)}, {}};
     in.begin(a.vec_in != 0);
     SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
     T tau[N];

@@ -27,7 +27,14 @@ static void rnea_nf(const mpk_robot *rb, int64_t P, const double *th, const doub
             b[j] = dth ? dth[p * N + j] : 0.0;
             c[j] = ddth ? ddth[p * N + j] : 0.0;
         }
-        if (use_smem_store) {
+        if (!GEN && !dth && !ddth && !ftip) {
+            // gravity forces: the at-rest form of the recursion, as launch_rnea routes them
+            using Store = SmemStore<double, N, 1, rnea_fast0(GEN, REV, N)>;
+            double buf[Store::kValues + 1];
+            Store st{buf};
+            ArrayInAtRest<double, N> in{a};
+            rnea<double, N, GEN, REV>(pk, in, g0, ftip, t, st);
+        } else if (use_smem_store) {
             // the shared-memory state store of the kernels, exercised with a one-thread "block"
             using Store = SmemStore<double, N, 1, rnea_fast0(GEN, REV, N)>;
             double buf[Store::kValues + 1];
