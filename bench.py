@@ -307,6 +307,22 @@ def run_ours(args) -> None:
     b.record()
     torch.cuda.synchronize()
     d2h_gbs = pin.numel() / (a.elapsed_time(b) / 1e3) / 1e9
+    # ... and with every rank copying at the same time: the GPUs of one box share PCIe uplinks, so
+    # the per-GPU rate drops (8 GPUs: 57 -> 12-18 GB/s, profiles/r1_d2h_n8.json), and the e2e time
+    # is the slowest rank's
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(4):
+        pin.copy_(src, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    d2h_conc = torch.tensor([4 * pin.numel() / (a.elapsed_time(b) / 1e3) / 1e9], dtype=torch.float64, device=dev)
+    d2h_conc_sum = d2h_conc.clone()
+    if world > 1:
+        dist.all_reduce(d2h_conc, op=dist.ReduceOp.MIN)
+        dist.all_reduce(d2h_conc_sum, op=dist.ReduceOp.SUM)
+    d2h_conc_min, d2h_conc_sum = float(d2h_conc), float(d2h_conc_sum)
     del pin, src
 
     # second metric of BASELINE.json: forward-dynamics rollout steps/s (configs[3]: iiwa14, 65,536
@@ -359,8 +375,11 @@ def run_ours(args) -> None:
         "clocks": clocks,
         "e2e": {"value": world * P * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(2 * B * 6 * 8),
                 "d2h_bytes_per_step": int(P * 6 * 4), "api": "OptimizedTrajectoryPlanning.trajectory_inverse_dynamics",
-                "pcie_d2h_gbs_measured": d2h_gbs, "host_cpus_bound_to": numa_cpus,
-                "pcie_bound_points_per_s": world * d2h_gbs * 1e9 / (6 * 4)},
+                "pcie_d2h_gbs_measured": d2h_gbs, "pcie_d2h_gbs_all_ranks_together_min": d2h_conc_min,
+                "pcie_d2h_gbs_all_ranks_together_sum": d2h_conc_sum, "host_cpus_bound_to": numa_cpus,
+                # ceiling of the e2e number: every rank's 240 MB result crosses PCIe at the
+                # slowest rank's share of the box's uplinks
+                "pcie_bound_points_per_s": world * d2h_conc_min * 1e9 / (6 * 4)},
         "gpu_launches": launches_per_step * args.steps,  # in the timed region of `value`
         "roofline": {"bound": "hbm", "kernel": dom_kernel, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": _traffic(dom_kernel), "peak_source": peak_src,
