@@ -149,6 +149,20 @@ int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const double *T_d
  *              results are identical either way. */
 size_t mpk_inverse_kinematics_workspace_bytes(int n, int64_t P);
 
+/* The same solver with the reference's optional modes (kinematics/ik.py:215-229, 253-276), which
+ * smart_inverse_kinematics / robust_inverse_kinematics (ik.py:327-598) switch on:
+ *   MPK_IK_ADAPTIVE_TUNING  Levenberg-Marquardt adaptation of the damping and of the step cap
+ *   MPK_IK_BACKTRACKING     line search over the scales 1, 1/2, 1/4, 1/8, 3/4 of the capped step
+ * flags = 0 is mpk_inverse_kinematics_dls. */
+#define MPK_IK_ADAPTIVE_TUNING 1
+#define MPK_IK_BACKTRACKING 2
+int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, const double *T_desired,
+                                     const double *theta0, double eomg, double ev, int max_iterations,
+                                     double damping, double step_cap, double weight_orientation,
+                                     double weight_position, const double *joint_limits, int flags,
+                                     uint64_t seed, double *theta, int32_t *iterations, uint8_t *success,
+                                     void *workspace, size_t workspace_bytes, void *stream);
+
 /* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
  * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).
  *   theta/dtheta/ddtheta  dev (P, n) in_dtype; dtheta / ddtheta may be NULL (= 0), which gives

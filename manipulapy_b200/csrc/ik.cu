@@ -1,7 +1,9 @@
 // ik.cu -- batched damped-least-squares inverse kinematics.
 //
 // Replaces the per-target Python loop of SerialManipulator.iterative_inverse_kinematics
-// (kinematics/ik.py:39-311) in its default mode (adaptive_tuning = backtracking = False): per
+// (kinematics/ik.py:39-311), including its optional modes -- adaptive_tuning (Levenberg-Marquardt
+// adaptation of the damping and the step cap, :215-229) and backtracking (five-scale line search,
+// five more forward kinematics per iteration, :253-276): per
 // iteration one forward kinematics + space Jacobian (kinematics/fk.py:61-70,
 // jacobian.py:62-73), the geometric pose error (ik.py:88-140), the damped least-squares step
 //   dtheta = V diag(s / (s^2 + lambda^2 + 1e-12)) U^T e = J^T (J J^T + (lambda^2 + 1e-12) 1)^-1 e
@@ -33,10 +35,11 @@ struct IkArgs {
 };
 
 // Queue of unfinished targets between the two phases (device workspace supplied by the caller):
-// [count (8 bytes) | entries of (2 N + 3) 8-byte words: target index, best_err, (stall, k), th, best].
+// [count (8 bytes) | entries of (2 N + 7) 8-byte words: target index, best_err, (stall, k), the four
+// adaptive-tuning scalars, th, best].
 template <int N>
 struct IkQueue {
-    static constexpr int kWords = 2 * N + 3;
+    static constexpr int kWords = 2 * N + 7;
     unsigned long long *count;
     double *entries;
     __device__ __forceinline__ explicit IkQueue(void *ws)
@@ -46,10 +49,14 @@ struct IkQueue {
         e[0] = __longlong_as_double(target);
         e[1] = st.best_err;
         e[2] = __longlong_as_double(((long long)st.stall << 32) | (unsigned)st.k);
+        e[3] = st.damping;
+        e[4] = st.step_cap;
+        e[5] = st.prev_err;
+        e[6] = st.nu;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            e[3 + j] = st.th[j];
-            e[3 + N + j] = st.best[j];
+            e[7 + j] = st.th[j];
+            e[7 + N + j] = st.best[j];
         }
     }
     __device__ __forceinline__ int64_t pop(unsigned long long slot, IkState<double, N> &st) const {
@@ -58,10 +65,14 @@ struct IkQueue {
         const long long w = __double_as_longlong(e[2]);
         st.stall = (int)(w >> 32);
         st.k = (int)(w & 0xffffffffLL);
+        st.damping = e[3];
+        st.step_cap = e[4];
+        st.prev_err = e[5];
+        st.nu = e[6];
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            st.th[j] = e[3 + j];
-            st.best[j] = e[3 + N + j];
+            st.th[j] = e[7 + j];
+            st.best[j] = e[7 + N + j];
         }
         return __double_as_longlong(e[0]);
     }
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(kIkThreads)
         double th0[N];
 #pragma unroll
         for (int j = 0; j < N; ++j) th0[j] = a.th0[p * N + j];
-        ik_state_init(st, th0);
+        ik_state_init(st, th0, a.prm);
     } else {
         IkQueue<N> q(a.workspace);
         if ((unsigned long long)t >= *q.count) return;
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(kIkThreads)
 using namespace mpk;
 
 extern "C" size_t mpk_inverse_kinematics_workspace_bytes(int n, int64_t P) {
-    return 16 + (size_t)(P > 0 ? P : 0) * (size_t)(2 * n + 3) * sizeof(double);
+    return 16 + (size_t)(P > 0 ? P : 0) * (size_t)(2 * n + 7) * sizeof(double);
 }
 
 extern "C" int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const double *T_desired,
@@ -125,7 +136,20 @@ extern "C" int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const 
                                           uint64_t seed, double *theta, int32_t *iterations,
                                           uint8_t *success, void *workspace, size_t workspace_bytes,
                                           void *stream) {
+    return mpk_inverse_kinematics_dls_modes(rb, P, T_desired, theta0, eomg, ev, max_iterations, damping, step_cap,
+                                            weight_orientation, weight_position, joint_limits, 0, seed, theta,
+                                            iterations, success, workspace, workspace_bytes, stream);
+}
+
+extern "C" int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, const double *T_desired,
+                                                const double *theta0, double eomg, double ev,
+                                                int max_iterations, double damping, double step_cap,
+                                                double weight_orientation, double weight_position,
+                                                const double *joint_limits, int flags, uint64_t seed,
+                                                double *theta, int32_t *iterations, uint8_t *success,
+                                                void *workspace, size_t workspace_bytes, void *stream) {
     if (!rb) return fail(MPK_EINVAL, "robot is NULL");
+    if (flags & ~(MPK_IK_ADAPTIVE_TUNING | MPK_IK_BACKTRACKING)) return fail(MPK_EINVAL, "unknown flags");
     if (P < 0 || max_iterations < 0) return fail(MPK_EINVAL, "negative size");
     if (P == 0) return MPK_OK;
     if (!T_desired || !theta0 || !theta || !iterations || !success)
@@ -135,7 +159,7 @@ extern "C" int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const 
     a.Td = T_desired;
     a.th0 = theta0;
     a.prm = make_ik_params(rb->n, eomg, ev, max_iterations, damping, step_cap, weight_orientation,
-                           weight_position, joint_limits);
+                           weight_position, joint_limits, flags);
     a.seed = seed;
     a.theta = theta;
     a.iters = iterations;

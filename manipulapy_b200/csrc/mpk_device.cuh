@@ -1266,18 +1266,24 @@ MPK_HD void cartesian_point(const double *Xs, const double *Xe, int64_t idx, int
 template <typename T, int NMAX>
 struct IkParams {
     T eomg, ev, mu, step_cap, w_rot, w_pos;
+    T damping;          // lambda (mu = lambda^2 + 1e-12 unless adaptive_tuning moves lambda)
     int max_iter;
+    int adaptive;       // adaptive_tuning: Levenberg-Marquardt damping / step-cap adaptation (ik.py:215-229)
+    int backtracking;   // five-scale line search (ik.py:253-276)
     T lo[NMAX], hi[NMAX];
 };
 
 template <int NMAX = 8>
 inline IkParams<double, NMAX> make_ik_params(int n, double eomg, double ev, int max_iterations, double damping,
                                              double step_cap, double w_rot, double w_pos,
-                                             const double *joint_limits) {
+                                             const double *joint_limits, int flags = 0) {
     IkParams<double, NMAX> p;
     p.eomg = eomg;
     p.ev = ev;
     p.mu = damping * damping + 1e-12;  // sigma / (sigma^2 + lambda^2 + 1e-12), ik.py:151
+    p.damping = damping;
+    p.adaptive = flags & 1;
+    p.backtracking = (flags >> 1) & 1;
     p.step_cap = step_cap;
     p.w_rot = w_rot;
     p.w_pos = w_pos;
@@ -1349,15 +1355,32 @@ struct IkState {
     T th[N], best[N];
     double best_err;
     int stall, k;
+    // adaptive_tuning (unused otherwise): current lambda and step cap, last error, growth factor
+    double damping, step_cap, prev_err, nu;
 };
 
 template <typename T, int N>
-MPK_HD void ik_state_init(IkState<T, N> &st, const T (&th0)[N]) {
+MPK_HD void ik_state_init(IkState<T, N> &st, const T (&th0)[N], const IkParams<T, MPK_MAX_DOF_> &prm) {
 #pragma unroll
     for (int j = 0; j < N; ++j) st.best[j] = st.th[j] = th0[j];
     st.best_err = INFINITY;
     st.stall = 0;
     st.k = 0;
+    st.damping = prm.damping;
+    st.step_cap = prm.step_cap;
+    st.prev_err = INFINITY;
+    st.nu = 2.0;
+}
+
+// rot + trans of the pose reached at joint values th (the line search's trial points)
+template <typename T, int N>
+MPK_HD double ik_pose_error(const RobotPack<T, N> &rb, const T (&th)[N], const double *Td) {
+    JointCS<T, N> q;
+    joint_cs(rb, th, q);
+    double Tc[16], V[6], rot, trans;
+    fk_jacobian<T, N>(rb, q, Tc, (T *)nullptr);
+    ik_error(Tc, Td, V, rot, trans);
+    return rot + trans;
 }
 
 // Iterations st.k .. k_stop-1 of one target (k_stop <= max_iter).  J: scratch for the 6 x N
@@ -1401,7 +1424,29 @@ MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T
                 th[j] = fmin(fmax(x, prm.lo[j]), prm.hi[j]);
             }
             st.stall = 0;
+            st.damping = prm.damping;
+            st.nu = 2.0;
             continue;
+        }
+        T mu = prm.mu, cap = prm.step_cap;
+        if (prm.adaptive) {
+            // Levenberg-Marquardt adaptation of lambda and of the step cap (ik.py:215-229)
+            if (k > 0) {
+                if (cur < st.prev_err * 0.75) {
+                    st.damping = fmax(1e-6, st.damping / 3);
+                    st.step_cap = fmin(prm.step_cap * 1.5, st.step_cap * 1.2);
+                    st.nu = 2.0;
+                } else if (cur < st.prev_err * 0.95) {
+                    st.damping = fmax(1e-6, st.damping / 1.5);
+                } else if (cur > st.prev_err) {
+                    st.damping = fmin(5e-1, st.damping * st.nu);
+                    st.nu = fmin(st.nu * 1.5, 8.0);
+                    st.step_cap = fmax(0.01, st.step_cap * 0.7);
+                }
+            }
+            st.prev_err = cur;
+            mu = (T)(st.damping * st.damping + 1e-12);
+            cap = (T)st.step_cap;
         }
         // (J J^T + mu 1) y = W e ;  dtheta = J^T y
         T A[6][6], y[6];
@@ -1410,7 +1455,7 @@ MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T
             y[r] = V[r] * (r < 3 ? prm.w_rot : prm.w_pos);
 #pragma unroll
             for (int c = 0; c <= r; ++c) {
-                T s = r == c ? prm.mu : T(0);
+                T s = r == c ? mu : T(0);
 #pragma unroll
                 for (int i = 0; i < N; ++i) s += J[r * N + i] * J[c * N + i];
                 A[r][c] = s;
@@ -1427,9 +1472,39 @@ MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T
             nrm += s * s;
         }
         nrm = sqrt(nrm);
-        const T scale = nrm > prm.step_cap ? prm.step_cap / nrm : T(1);
+        const T scale = nrm > cap ? cap / nrm : T(1);
+        if (prm.backtracking) {
+            // line search over five scales of the (capped) step (ik.py:253-276): the best trial
+            // point replaces theta when it is not worse than 1.1 x the current error
 #pragma unroll
-        for (int j = 0; j < N; ++j) th[j] = fmin(fmax(th[j] + scale * d[j], prm.lo[j]), prm.hi[j]);
+            for (int j = 0; j < N; ++j) d[j] *= scale;
+            T bst[N];
+            double bst_err = cur;
+#pragma unroll
+            for (int j = 0; j < N; ++j) bst[j] = th[j];
+            for (int t = 0; t < 5; ++t) {
+                const T sc = t == 0 ? T(1) : t == 1 ? T(0.5) : t == 2 ? T(0.25) : t == 3 ? T(0.125) : T(0.75);
+                T cand[N];
+#pragma unroll
+                for (int j = 0; j < N; ++j) cand[j] = fmin(fmax(th[j] + sc * d[j], prm.lo[j]), prm.hi[j]);
+                const double e = ik_pose_error<T, N>(rb, cand, Td);
+                if (e < bst_err) {
+                    bst_err = e;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) bst[j] = cand[j];
+                }
+            }
+            if (bst_err < cur * 1.1) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) th[j] = bst[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < N; ++j) th[j] = fmin(fmax(th[j] + T(0.1) * d[j], prm.lo[j]), prm.hi[j]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; ++j) th[j] = fmin(fmax(th[j] + scale * d[j], prm.lo[j]), prm.hi[j]);
+        }
     }
     st.k = k;
     if (!ok && k < prm.max_iter) return false;  // window exhausted, budget not
@@ -1453,7 +1528,7 @@ template <typename T, int N>
 MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], const IkParams<T, MPK_MAX_DOF_> &prm,
                    unsigned long long seed, unsigned long long target, T *J, int &iterations) {
     IkState<T, N> st;
-    ik_state_init(st, th);
+    ik_state_init(st, th, prm);
     bool ok;
     ik_dls_window(rb, Td, st, prm, seed, target, J, prm.max_iter, ok, iterations);
 #pragma unroll

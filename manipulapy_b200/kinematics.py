@@ -181,17 +181,17 @@ class SerialManipulator:
                                      weight_position: float = 1.0, adaptive_tuning: bool = False,
                                      backtracking: bool = False, *, seed: int = 0):
         """Damped-least-squares IK with step cap, joint-limit projection, best-iterate tracking
-        and stagnation restart (kinematics/ik.py:39-311, default mode).
+        and stagnation restart (kinematics/ik.py:39-311), optionally with the reference's
+        Levenberg-Marquardt adaptation (``adaptive_tuning``) and line search (``backtracking``).
 
         Reference call: ``T_desired (4, 4)``, ``thetalist0 (n,)`` -> ``(theta (n,), success, iterations)``.
         Batched extension: ``(P, 4, 4)``, ``(P, n)`` -> ``(theta (P, n), success (P,) bool,
-        iterations (P,) int32)``, one target per GPU thread.  ``adaptive_tuning``, ``backtracking``
-        and ``plot_residuals`` are not part of the kernel.  ``seed`` keys the noise of the
-        stagnation restart (the reference draws it from NumPy's global generator)."""
-        if adaptive_tuning or backtracking or plot_residuals:
-            raise NotImplementedError(
-                "adaptive_tuning / backtracking / plot_residuals are outside the B200 hot path; the batched "
-                "kernel implements the default mode of iterative_inverse_kinematics")
+        iterations (P,) int32)``, one target per GPU thread.  ``plot_residuals`` is not part of the
+        kernel.  ``seed`` keys the noise of the stagnation restart (the reference draws it from
+        NumPy's global generator)."""
+        if plot_residuals:
+            raise NotImplementedError("plot_residuals is outside the B200 hot path (no plotting)")
+        flags = (1 if adaptive_tuning else 0) | (2 if backtracking else 0)
         on_dev = _host.any_device(T_desired, thetalist0)
         dev = (thetalist0.device if _host.is_device_tensor(thetalist0)
                else T_desired.device if _host.is_device_tensor(T_desired) else self.device)
@@ -208,7 +208,7 @@ class SerialManipulator:
             lim[i] = (-np.inf if mn is None else mn, np.inf if mx is None else mx)
         theta, ok, it = _native.ops().inverse_kinematics_dls(
             self.robot.handle, Td, th0, float(eomg), float(ev), int(max_iterations), float(damping), float(step_cap),
-            float(weight_orientation), float(weight_position), torch.from_numpy(lim), int(seed))
+            float(weight_orientation), float(weight_position), torch.from_numpy(lim), int(seed), True, flags)
         ok = ok.bool()
         if single:
             th1 = theta[0] if on_dev else _host.to_host(theta[0])
@@ -216,6 +216,78 @@ class SerialManipulator:
         if on_dev:
             return theta, ok, it
         return _host.to_host(theta), ok.cpu().numpy(), it.cpu().numpy()
+
+    # -- IK front ends (kinematics/ik.py:327-598): initial-guess strategies + restarts around the kernel --
+    def _ik_limits(self):
+        n = self.num_joints
+        lim = list(self.joint_limits)[:n]
+        return lim + [(None, None)] * (n - len(lim))
+
+    def _ik_batch(self, T_desired):
+        if _host.is_device_tensor(T_desired):
+            T_desired = T_desired.detach().cpu().numpy()
+        Td = np.asarray(T_desired, dtype=np.float64)
+        return Td.reshape(-1, 4, 4), Td.ndim == 2
+
+    def smart_inverse_kinematics(self, T_desired, strategy: str = "workspace_heuristic", theta_current=None,
+                                 T_current=None, cache=None, eomg: float = 1e-6, ev: float = 1e-6,
+                                 max_iterations: int = 10000, plot_residuals: bool = False, damping: float = 2e-2,
+                                 step_cap: float = 0.3, png_name: str = "ik_residuals.png",
+                                 weight_orientation: float = 1.0, weight_position: float = 1.0,
+                                 adaptive_tuning: bool = True, backtracking: bool = True,
+                                 auto_fallback: bool = True, *, seed: int = 0):
+        """Initial guess by ``strategy`` (workspace_heuristic, midpoint, random), then
+        ``iterative_inverse_kinematics``; with ``auto_fallback`` up to four more starts (midpoint,
+        3 x random) for targets that failed, keeping the best iterate (kinematics/ik.py:327-475).
+        ``T_desired (4, 4)`` -> ``(theta, success, iterations)`` like the reference; batched
+        extension ``(P, 4, 4)`` -> arrays, each fall-back round one launch over the failed targets.
+        The 'extrapolate' and 'cached' strategies are host-side bookkeeping outside the hot path."""
+        from . import ik_helpers
+
+        valid = ["workspace_heuristic", "extrapolate", "cached", "random", "midpoint"]
+        if strategy not in valid:
+            raise ValueError(f"Unknown strategy '{strategy}'. Choose from: {valid}")
+        if strategy == "extrapolate" and theta_current is not None and T_current is not None:
+            raise NotImplementedError("strategy 'extrapolate' is outside the B200 hot path")
+        if strategy == "cached" and cache is not None:
+            raise NotImplementedError("strategy 'cached' is outside the B200 hot path")
+        if strategy in ("extrapolate", "cached"):
+            strategy = "workspace_heuristic"  # the reference's fall-back when the inputs are missing (:431-434)
+        Td, single = self._ik_batch(T_desired)
+
+        def solve(Tds, th0):
+            return self.iterative_inverse_kinematics(Tds, th0, eomg, ev, max_iterations, plot_residuals, damping,
+                                                     step_cap, png_name, weight_orientation, weight_position,
+                                                     adaptive_tuning, backtracking, seed=seed)
+
+        theta, ok, it = ik_helpers.smart_driver(solve, self.forward_kinematics, Td, self.num_joints,
+                                                self._ik_limits(), strategy, auto_fallback)
+        if single:
+            return theta[0], bool(ok[0]), int(it[0])
+        return theta, ok, it
+
+    def robust_inverse_kinematics(self, T_desired, max_attempts: int = 10, eomg: float = 2e-3, ev: float = 2e-3,
+                                  max_iterations: int = 5000, verbose: bool = False, *, seed: int = 0):
+        """Multi-start IK (kinematics/ik.py:477-598): up to ``max_attempts`` of ten (guess, damping,
+        step cap) combinations with adaptive tuning and the line search on, tracking the best
+        iterate.  Returns ``(theta, success, total_iterations, winning_strategy)``; batched
+        extension ``(P, 4, 4)`` -> arrays (``winning_strategy`` an object array of names)."""
+        from . import ik_helpers
+
+        Td, single = self._ik_batch(T_desired)
+
+        def solve(Tds, th0, damping, step_cap):
+            return self.iterative_inverse_kinematics(Tds, th0, eomg, ev, max_iterations, damping=damping,
+                                                     step_cap=step_cap, adaptive_tuning=True, backtracking=True,
+                                                     seed=seed)
+
+        theta, ok, it, win = ik_helpers.robust_driver(solve, self.forward_kinematics, Td, self.num_joints,
+                                                      self._ik_limits(), max_attempts)
+        if verbose:
+            print(f"robust_inverse_kinematics: {int(ok.sum())} of {ok.size} targets solved")
+        if single:
+            return theta[0], bool(ok[0]), int(it[0]), str(win[0])
+        return theta, ok, it, win
 
     def forward_kinematics_and_jacobian(self, thetalist, precision=None, frame: str = "space"):
         """Both outputs from one fused kernel launch (batched extension)."""

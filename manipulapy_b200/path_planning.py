@@ -79,6 +79,8 @@ class OptimizedTrajectoryPlanning:
         }
         self._jl = _host.limits_tensor(self.joint_limits)
         self._tl = _host.limits_tensor(self.torque_limits)
+        # host results of the fused path leave the device in this many pipelined chunks
+        self.host_chunks = 8
 
     # -- bookkeeping ------------------------------------------------------------------------------
     def _should_use_gpu(self, N: int, num_joints: int) -> bool:
@@ -193,8 +195,9 @@ class OptimizedTrajectoryPlanning:
                                                        int(method), self._jl, g, ftip, self._tl, False, f32c)[0]
 
             B = int(s.shape[0])
-            out = _host.chunked_to_host(launch, B, (int(N), n), torch.float32, dev)
-            self._tick(t0, launches=2 * min(8, B), transfers=2 + min(8, B), kernel="trajectory_inverse_dynamics")
+            out = _host.chunked_to_host(launch, B, (int(N), n), torch.float32, dev, chunks=self.host_chunks)
+            self._tick(t0, launches=2 * min(self.host_chunks, B), transfers=2 + min(self.host_chunks, B),
+                       kernel="trajectory_inverse_dynamics")
             return out
         tau, pos, vel, acc = ops.trajectory_inverse_dynamics(
             handle, s, e, f32, float(Tf), int(N), int(method), self._jl, g, ftip, self._tl,

@@ -269,6 +269,93 @@ def ik_golden() -> None:
     print("inverse kinematics golden written", {k: out[k] for k in out if k.endswith("iterations") or k.endswith("success")})
 
 
+def ik_modes_golden() -> None:
+    """iterative_inverse_kinematics of the unmodified reference with ``adaptive_tuning`` and / or
+    ``backtracking`` (the modes smart_ / robust_inverse_kinematics switch on), same targets as
+    ik_golden: (theta, success, iterations) per mode."""
+    out = {}
+    modes = {"adaptive": dict(adaptive_tuning=True), "backtracking": dict(backtracking=True),
+             "both": dict(adaptive_tuning=True, backtracking=True)}
+    for robot, count in (("ur5", 8), ("iiwa14", 8)):
+        proc, sm, dyn = load(robot)
+        n = sm.S_list.shape[1]
+        lims = limits_array(proc, n)
+        rng = np.random.default_rng(21)
+        tgt = rng.uniform(0.6 * lims[:, 0], 0.6 * lims[:, 1], (count, n))
+        seeds = tgt + rng.uniform(-1, 1, (count, n)) * np.linspace(0.05, 0.8, count)[:, None]
+        Td = np.stack([np.asarray(sm.forward_kinematics(t)) for t in tgt])
+        Td[-1, :3, 3] += np.array([5.0, 0.0, 0.0])  # out of reach
+        budget = [300] * count
+        budget[-1] = 60
+        out.update({f"{robot}_M": np.asarray(sm.M_list, np.float64), f"{robot}_S": np.asarray(sm.S_list, np.float64),
+                    f"{robot}_T": Td, f"{robot}_seed": seeds, f"{robot}_limits": lims,
+                    f"{robot}_max_iterations": np.array(budget)})
+        for name, kw in modes.items():
+            th, ok, it = [], [], []
+            for i in range(count):
+                np.random.seed(200 + i)
+                r = sm.iterative_inverse_kinematics(Td[i], seeds[i], max_iterations=budget[i], **kw)
+                th.append(np.asarray(r[0], np.float64))
+                ok.append(bool(r[1]))
+                it.append(int(r[2]))
+            out.update({f"{robot}_{name}_theta": np.stack(th), f"{robot}_{name}_success": np.array(ok),
+                        f"{robot}_{name}_iterations": np.array(it)})
+            print(robot, name, ok, it)
+    np.savez(GOLD_DIR / "inverse_kinematics_modes.npz", **out)
+
+
+def ik_front_golden() -> None:
+    """smart_inverse_kinematics / robust_inverse_kinematics of the unmodified reference
+    (kinematics/ik.py:327-598): targets reached from the first guess, targets that need the
+    fall-back starts (NumPy's global generator seeded per call), one out of reach."""
+    out = {}
+    for robot, count in (("ur5", 8), ("iiwa14", 8)):
+        proc, sm, dyn = load(robot)
+        n = sm.S_list.shape[1]
+        lims = limits_array(proc, n)
+        sm.joint_limits = [tuple(r) for r in lims]
+        rng = np.random.default_rng(33)
+        tgt = rng.uniform(0.8 * lims[:, 0], 0.8 * lims[:, 1], (count, n))
+        Td = np.stack([np.asarray(sm.forward_kinematics(t)) for t in tgt])
+        Td[-1, :3, 3] += np.array([5.0, 0.0, 0.0])  # out of reach
+        res = {k: [] for k in ("smart_theta", "smart_success", "smart_iterations", "smart_restarts", "robust_theta",
+                               "robust_success", "robust_iterations", "robust_strategy", "robust_restarts")}
+        # stagnation restarts of each run, counted by wrapping NumPy's randn (the solver's only use
+        # of it): runs without any are the ones a solver with another noise source reproduces
+        calls = {"n": 0}
+        randn = np.random.randn
+
+        def counting_randn(*a):
+            calls["n"] += 1
+            return randn(*a)
+
+        np.random.randn = counting_randn
+        for i in range(count):
+            np.random.seed(300 + i)
+            calls["n"] = 0
+            th, ok, it = sm.smart_inverse_kinematics(Td[i], max_iterations=120)
+            res["smart_theta"].append(np.asarray(th, np.float64))
+            res["smart_success"].append(bool(ok))
+            res["smart_iterations"].append(int(it))
+            res["smart_restarts"].append(calls["n"])
+            np.random.seed(400 + i)
+            calls["n"] = 0
+            th, ok, it, name = sm.robust_inverse_kinematics(Td[i], max_attempts=4, max_iterations=120)
+            res["robust_theta"].append(np.asarray(th, np.float64))
+            res["robust_success"].append(bool(ok))
+            res["robust_iterations"].append(int(it))
+            res["robust_strategy"].append(str(name))
+            res["robust_restarts"].append(calls["n"])
+        np.random.randn = randn
+        out.update({f"{robot}_M": np.asarray(sm.M_list, np.float64), f"{robot}_S": np.asarray(sm.S_list, np.float64),
+                    f"{robot}_T": Td, f"{robot}_limits": lims})
+        for k, v in res.items():
+            out[f"{robot}_{k}"] = np.array(v)
+        print(robot, "smart", res["smart_success"], res["smart_iterations"], res["smart_restarts"])
+        print(robot, "robust", res["robust_success"], res["robust_iterations"], res["robust_strategy"], res["robust_restarts"])
+    np.savez(GOLD_DIR / "inverse_kinematics_front_ends.npz", **out)
+
+
 def body_kinematics_golden() -> None:
     """forward_kinematics / jacobian with frame="body" of the unmodified reference: the UR5 as
     loaded from its URDF, and a chain whose B_list is NOT Ad(M^-1) S_list (the reference takes
@@ -404,6 +491,8 @@ def main() -> None:
     body_kinematics_golden()
     cartesian_golden()
     ik_golden()
+    ik_modes_golden()
+    ik_front_golden()
     registry_trajectory_golden()
     id_trajectory_golden()
     fd_trajectory_golden()

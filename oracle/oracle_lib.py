@@ -274,11 +274,12 @@ class Oracle:
     # -- inverse kinematics (numpy restatement; small cases only) -------------------------------
     def iterative_inverse_kinematics(self, T_desired, thetalist0, eomg=1e-6, ev=1e-6, max_iterations=10000,
                                      damping=2e-2, step_cap=0.3, weight_orientation=1.0, weight_position=1.0,
-                                     joint_limits=None):
-        """``iterative_inverse_kinematics`` in its default mode (adaptive_tuning = backtracking =
-        False), restated from kinematics/ik.py:39-311: geometric error (:88-140), SVD damped
-        least squares (:142-162), step cap and limit projection (:164-176, :253-262), best-iterate
-        tracking and the stagnation restart drawn from NumPy's global generator (:196-213).
+                                     joint_limits=None, adaptive_tuning=False, backtracking=False):
+        """``iterative_inverse_kinematics`` restated from kinematics/ik.py:39-311: geometric error
+        (:88-140), SVD damped least squares (:142-162), step cap and limit projection (:164-176,
+        :253-262), best-iterate tracking and the stagnation restart drawn from NumPy's global
+        generator (:196-213), the Levenberg-Marquardt damping / step-cap adaptation
+        (``adaptive_tuning``, :215-229) and the five-scale line search (``backtracking``, :253-276).
         Returns (theta, success, iterations) like the reference."""
         theta = _d(thetalist0).copy()
         Td = _d(T_desired).reshape(4, 4)
@@ -307,6 +308,8 @@ class Oracle:
 
         best_theta, best_error, stall, success = theta.copy(), np.inf, 0, False
         cur = np.inf
+        damping_local, step_cap_local, prev_error, nu = damping, step_cap, np.inf, 2.0
+        clip = lambda th: np.minimum(np.maximum(th, lo), hi)  # noqa: E731
         k = 0
         for k in range(max_iterations):
             V, rot, trans = err(self.forward_kinematics(theta)[0])
@@ -319,17 +322,38 @@ class Oracle:
             else:
                 stall += 1
             if stall > 20:
-                theta = np.minimum(np.maximum(best_theta + 0.1 * np.random.randn(n), lo), hi)
-                stall = 0
+                theta = clip(best_theta + 0.1 * np.random.randn(n))
+                damping_local, stall, nu = damping, 0, 2.0
                 continue
+            if adaptive_tuning and k > 0:
+                if cur < prev_error * 0.75:
+                    damping_local = max(1e-6, damping_local / 3)
+                    step_cap_local = min(step_cap * 1.5, step_cap_local * 1.2)
+                    nu = 2.0
+                elif cur < prev_error * 0.95:
+                    damping_local = max(1e-6, damping_local / 1.5)
+                elif cur > prev_error:
+                    damping_local = min(5e-1, damping_local * nu)
+                    nu = min(nu * 1.5, 8)
+                    step_cap_local = max(0.01, step_cap_local * 0.7)
+            prev_error = cur
             J = self.jacobian(theta)[0]
             Vw = V * np.array([weight_orientation] * 3 + [weight_position] * 3)
             U, sv, Vt = np.linalg.svd(J, full_matrices=False)
-            d = Vt.T @ ((sv / (sv**2 + damping**2 + 1e-12)) * (U.T @ Vw))
+            d = Vt.T @ ((sv / (sv**2 + damping_local**2 + 1e-12)) * (U.T @ Vw))
             nd = np.linalg.norm(d)
-            if nd > step_cap:
-                d = d * (step_cap / nd)
-            theta = np.minimum(np.maximum(theta + d, lo), hi)
+            if nd > step_cap_local:
+                d = d * (step_cap_local / nd)
+            if backtracking:
+                best_scale_theta, best_scale_error = theta, cur
+                for scale in (1.0, 0.5, 0.25, 0.125, 0.75):
+                    cand = clip(theta + scale * d)
+                    _, rot_t, trans_t = err(self.forward_kinematics(cand)[0])
+                    if rot_t + trans_t < best_scale_error:
+                        best_scale_error, best_scale_theta = rot_t + trans_t, cand
+                theta = best_scale_theta if best_scale_error < cur * 1.1 else clip(theta + 0.1 * d)
+            else:
+                theta = clip(theta + d)
         else:
             k += 1 if max_iterations > 0 else 0
         if not success and best_error < cur:

@@ -236,9 +236,9 @@ static void ik_n(const mpk_robot *rb, int64_t P, const double *Td, const double 
 extern "C" int hc_ik(const mpk_robot *rb, int64_t P, const double *Td, const double *th0, double eomg, double ev,
                      int max_iterations, double damping, double step_cap, double w_rot, double w_pos,
                      const double *limits, unsigned long long seed, double *theta, int *iters,
-                     unsigned char *ok) {
+                     unsigned char *ok, int flags) {
     const IkParams<double, MPK_MAX_DOF> prm =
-        make_ik_params(rb->n, eomg, ev, max_iterations, damping, step_cap, w_rot, w_pos, limits);
+        make_ik_params(rb->n, eomg, ev, max_iterations, damping, step_cap, w_rot, w_pos, limits, flags);
     HC_DISPATCH(rb->n, ik_n<N_>(rb, P, Td, th0, prm, seed, theta, iters, ok));
     return 0;
 }

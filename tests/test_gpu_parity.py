@@ -381,7 +381,67 @@ def test_batched_inverse_kinematics(robot):
     assert all(bool(torch.equal(x, y)) for x, y in zip(one, two))
     assert 0 < int((two[2] > 64).sum()) < P  # some targets did go through the second phase
     with pytest.raises(NotImplementedError):
-        sm.iterative_inverse_kinematics(Td[0], tgt[0], backtracking=True)
+        sm.iterative_inverse_kinematics(Td[0], tgt[0], plot_residuals=True)
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_kinematics_modes_and_front_ends(robot):
+    """adaptive_tuning / backtracking (kinematics/ik.py:215-229, 253-276) and the smart_ / robust_
+    front ends (ik.py:327-598) against goldens generated from the unmodified reference: success,
+    iteration counts, winning strategy and solutions for every run without a stagnation restart;
+    then 5,000 random targets through each front end in batched launches."""
+    from manipulapy_b200 import SerialManipulator, ik_helpers
+
+    g = load_golden("inverse_kinematics_modes")
+    lim = [tuple(r) for r in g[f"{robot}_limits"]]
+    sm = SerialManipulator(M_list=g[f"{robot}_M"], S_list=g[f"{robot}_S"], joint_limits=lim)
+    for mode in ("adaptive", "backtracking", "both"):
+        kw = dict(adaptive_tuning=mode in ("adaptive", "both"), backtracking=mode in ("backtracking", "both"))
+        # all targets of the golden in ONE launch (ragged iteration budgets: the last one separately)
+        Td, seed, budget = g[f"{robot}_T"], g[f"{robot}_seed"], g[f"{robot}_max_iterations"]
+        th, ok, it = sm.iterative_inverse_kinematics(Td[:-1], seed[:-1], max_iterations=int(budget[0]), **kw)
+        assert np.array_equal(ok, g[f"{robot}_{mode}_success"][:-1])
+        assert np.array_equal(it[ok], g[f"{robot}_{mode}_iterations"][:-1][ok])
+        np.testing.assert_allclose(th[ok], g[f"{robot}_{mode}_theta"][:-1][ok], rtol=0, atol=1e-7)
+        th1, ok1, it1 = sm.iterative_inverse_kinematics(Td[-1], seed[-1], max_iterations=int(budget[-1]), **kw)
+        assert ok1 == bool(g[f"{robot}_{mode}_success"][-1]) and it1 == int(budget[-1]) + 1
+
+    g = load_golden("inverse_kinematics_front_ends")
+    lim = [tuple(r) for r in g[f"{robot}_limits"]]
+    sm = SerialManipulator(M_list=g[f"{robot}_M"], S_list=g[f"{robot}_S"], joint_limits=lim)
+    for i, Td in enumerate(g[f"{robot}_T"]):
+        np.random.seed(300 + i)
+        th, ok, it = sm.smart_inverse_kinematics(Td, max_iterations=120)
+        assert isinstance(ok, bool) and isinstance(it, int) and th.shape == (len(lim),)
+        if g[f"{robot}_smart_restarts"][i] == 0:
+            assert ok == bool(g[f"{robot}_smart_success"][i]) and it == int(g[f"{robot}_smart_iterations"][i]), i
+            if ok:
+                np.testing.assert_allclose(th, g[f"{robot}_smart_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
+        np.random.seed(400 + i)
+        th, ok, it, win = sm.robust_inverse_kinematics(Td, max_attempts=4, max_iterations=120)
+        if g[f"{robot}_robust_restarts"][i] == 0:
+            assert ok == bool(g[f"{robot}_robust_success"][i]) and it == int(g[f"{robot}_robust_iterations"][i]), i
+            if ok:
+                assert win == str(g[f"{robot}_robust_strategy"][i])
+                np.testing.assert_allclose(th, g[f"{robot}_robust_theta"][i], rtol=0, atol=1e-6, err_msg=str(i))
+    with pytest.raises(ValueError):
+        sm.smart_inverse_kinematics(g[f"{robot}_T"][0], strategy="nonsense")
+
+    # batched: random reachable targets, no initial guess given
+    rng = np.random.default_rng(5)
+    lo, hi = g[f"{robot}_limits"][:, 0], g[f"{robot}_limits"][:, 1]
+    P = 5000
+    Td = sm.forward_kinematics(rng.uniform(0.8 * lo, 0.8 * hi, (P, len(lim))))
+    np.random.seed(9)
+    th, ok, it = sm.smart_inverse_kinematics(Td, max_iterations=150)
+    assert th.shape == (P, len(lim)) and ok.mean() > 0.9
+    assert ik_helpers.pose_error(sm.forward_kinematics(th[ok]), Td[ok]).max() < 1e-5
+    plain = sm.smart_inverse_kinematics(Td, max_iterations=150, auto_fallback=False)[1]
+    assert ok.sum() >= plain.sum()  # the fall-back starts only add solutions
+    np.random.seed(9)
+    th, ok, it, win = sm.robust_inverse_kinematics(Td, max_attempts=6, max_iterations=150)
+    assert ok.mean() > 0.95 and set(win) <= {"workspace_heuristic", "midpoint", "random", "none"}
+    assert ik_helpers.pose_error(sm.forward_kinematics(th[ok]), Td[ok]).max() < 5e-3
 
 
 def test_cartesian_trajectory(robots):

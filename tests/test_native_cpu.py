@@ -348,6 +348,24 @@ def test_inverse_kinematics_kernel_vs_reference_golden(hostcheck, robot):
     assert not ok0.any() and np.array_equal(th0, seeds) and (it0 == 1).all()
 
 
+@pytest.mark.parametrize("mode", ["adaptive", "backtracking", "both"])
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_kinematics_kernel_modes_vs_reference_golden(hostcheck, robot, mode):
+    """... with adaptive_tuning and / or backtracking (kinematics/ik.py:215-229, 253-276): same
+    success flags and iteration counts as the unmodified reference, solutions to 1e-7."""
+    g = load_golden("inverse_kinematics_modes")
+    rb = hostcheck.kin_robot(g[f"{robot}_S"], g[f"{robot}_M"])
+    kw = dict(adaptive_tuning=mode in ("adaptive", "both"), backtracking=mode in ("backtracking", "both"))
+    for i, (Td, seed, budget) in enumerate(zip(g[f"{robot}_T"], g[f"{robot}_seed"], g[f"{robot}_max_iterations"])):
+        th, ok, it = hostcheck.ik(rb, Td, seed, max_iterations=int(budget), limits=g[f"{robot}_limits"], **kw)
+        assert bool(ok[0]) == bool(g[f"{robot}_{mode}_success"][i]), i
+        if ok[0]:
+            assert int(it[0]) == int(g[f"{robot}_{mode}_iterations"][i]), i
+            np.testing.assert_allclose(th[0], g[f"{robot}_{mode}_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
+        else:
+            assert int(it[0]) == int(budget) + 1
+
+
 def test_cartesian_trajectory_kernel_vs_reference_golden(hostcheck):
     """The kernel's per-step Cartesian interpolation (csrc/mpk_device.cuh cartesian_point) against
     the unmodified reference, to float32 rounding."""
@@ -522,3 +540,69 @@ def test_robot_zoo_kernel_algebra_vs_reference(hostcheck, robot):
             z, T, J, hostcheck.mass(rb, th), hostcheck.rnea(rb, th, g=g),
             hostcheck.rnea(rb, th, dth, g=(0, 0, 0)), hostcheck.rnea(rb, th, dth, ddth, g, ft),
             hostcheck.fd(rb, th, dth, z["taus"], g, ft))
+
+
+def _front_end_cases(hostcheck, robot):
+    g = load_golden("inverse_kinematics_front_ends")
+    rb = hostcheck.kin_robot(g[f"{robot}_S"], g[f"{robot}_M"])
+    lim = g[f"{robot}_limits"]
+    limits = [tuple(r) for r in lim]
+    n = lim.shape[0]
+    fk = lambda th: hostcheck.fk(rb, th)[0]  # noqa: E731
+    return g, rb, lim, limits, n, fk
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_smart_inverse_kinematics_kernel_vs_reference_golden(hostcheck, robot):
+    """smart_inverse_kinematics = ik_helpers.smart_driver around the kernel's solver, against the
+    unmodified reference: same success flags everywhere; same total iteration counts and solutions
+    for every run without a stagnation restart (the kernel draws that noise from its own
+    generator; the driver itself is pinned with the oracle's solver in test_oracle_golden.py)."""
+    from manipulapy_b200 import ik_helpers
+
+    g, rb, lim, limits, n, fk = _front_end_cases(hostcheck, robot)
+
+    def solve(Tds, th0):
+        return hostcheck.ik(rb, Tds, th0, max_iterations=120, limits=lim, adaptive_tuning=True, backtracking=True)
+
+    for i, Td in enumerate(g[f"{robot}_T"]):
+        np.random.seed(300 + i)
+        th, ok, it = ik_helpers.smart_driver(solve, fk, Td[None], n, limits, "workspace_heuristic", True)
+        if g[f"{robot}_smart_restarts"][i] == 0:
+            assert bool(ok[0]) == bool(g[f"{robot}_smart_success"][i]), i
+            assert int(it[0]) == int(g[f"{robot}_smart_iterations"][i]), i
+            if ok[0]:
+                np.testing.assert_allclose(th[0], g[f"{robot}_smart_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
+        elif ok[0]:
+            assert ik_helpers.pose_error(fk(th), Td[None]).max() < 1e-5
+    # the batch driver: every target the per-target calls solve without restarts is solved
+    np.random.seed(1)
+    th, ok, it = ik_helpers.smart_driver(solve, fk, g[f"{robot}_T"], n, limits, "workspace_heuristic", True)
+    easy = g[f"{robot}_smart_success"] & (g[f"{robot}_smart_restarts"] == 0)
+    assert ok[easy].all() and not ok[-1]
+    assert ik_helpers.pose_error(fk(th[ok]), g[f"{robot}_T"][ok]).max() < 1e-5
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_robust_inverse_kinematics_kernel_vs_reference_golden(hostcheck, robot):
+    """robust_inverse_kinematics = ik_helpers.robust_driver around the kernel's solver: success, total
+    iterations, winning strategy and solution as the unmodified reference (runs without restarts)."""
+    from manipulapy_b200 import ik_helpers
+
+    g, rb, lim, limits, n, fk = _front_end_cases(hostcheck, robot)
+
+    def solve(Tds, th0, damping, step_cap):
+        return hostcheck.ik(rb, Tds, th0, eomg=2e-3, ev=2e-3, max_iterations=120, damping=damping,
+                            step_cap=step_cap, limits=lim, adaptive_tuning=True, backtracking=True)
+
+    for i, Td in enumerate(g[f"{robot}_T"]):
+        np.random.seed(400 + i)
+        th, ok, it, win = ik_helpers.robust_driver(solve, fk, Td[None], n, limits, 4)
+        if g[f"{robot}_robust_restarts"][i] == 0:
+            assert bool(ok[0]) == bool(g[f"{robot}_robust_success"][i]), i
+            assert int(it[0]) == int(g[f"{robot}_robust_iterations"][i]), i
+            if ok[0]:
+                assert str(win[0]) == str(g[f"{robot}_robust_strategy"][i]), i
+                np.testing.assert_allclose(th[0], g[f"{robot}_robust_theta"][i], rtol=0, atol=1e-6, err_msg=str(i))
+        elif ok[0]:
+            assert ik_helpers.pose_error(fk(th), Td[None]).max() < 5e-3

@@ -219,6 +219,67 @@ def test_inverse_kinematics_restatement_vs_reference(robot):
         np.testing.assert_allclose(th, g[f"{robot}_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
 
 
+IK_MODES = {"adaptive": dict(adaptive_tuning=True), "backtracking": dict(backtracking=True),
+            "both": dict(adaptive_tuning=True, backtracking=True)}
+
+
+@pytest.mark.parametrize("mode", sorted(IK_MODES))
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_inverse_kinematics_modes_restatement_vs_reference(robot, mode):
+    """... and with the Levenberg-Marquardt adaptation and / or the line search switched on
+    (tests/golden/inverse_kinematics_modes.npz, generated from the unmodified reference)."""
+    from oracle import Oracle
+
+    g = load_golden("inverse_kinematics_modes")
+    pack = load_pack(robot)
+    o = Oracle(g[f"{robot}_S"], g[f"{robot}_M"], pack["Glist"], pack["Mlist_per_link"])
+    lim = [tuple(r) for r in g[f"{robot}_limits"]]
+    for i, (Td, seed, budget) in enumerate(zip(g[f"{robot}_T"], g[f"{robot}_seed"], g[f"{robot}_max_iterations"])):
+        np.random.seed(200 + i)
+        th, ok, it = o.iterative_inverse_kinematics(Td, seed, max_iterations=int(budget), joint_limits=lim,
+                                                    **IK_MODES[mode])
+        assert ok == bool(g[f"{robot}_{mode}_success"][i]), i
+        assert it == int(g[f"{robot}_{mode}_iterations"][i]), i
+        np.testing.assert_allclose(th, g[f"{robot}_{mode}_theta"][i], rtol=0, atol=1e-7, err_msg=str(i))
+
+
+def _oracle_ik_solver(o, lim, **fixed):
+    def solve(Tds, th0, **kw):
+        r = [o.iterative_inverse_kinematics(T, t, joint_limits=lim, adaptive_tuning=True, backtracking=True,
+                                            **fixed, **kw) for T, t in zip(Tds, th0)]
+        return np.stack([x[0] for x in r]), np.array([x[1] for x in r]), np.array([x[2] for x in r])
+    return solve
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_ik_front_end_drivers_vs_reference(robot):
+    """The host-side restart logic of smart_ / robust_inverse_kinematics (manipulapy_b200.ik_helpers:
+    initial guesses, fall-back rounds, best-iterate tracking, NumPy-generator draws) with the oracle's
+    solver plugged in reproduces the unmodified reference on every golden case -- success, total
+    iterations, winning strategy, solution -- including those with fall-back starts and restarts."""
+    from manipulapy_b200 import ik_helpers
+    from oracle import Oracle
+
+    g = load_golden("inverse_kinematics_front_ends")
+    pack = load_pack(robot)
+    o = Oracle(g[f"{robot}_S"], g[f"{robot}_M"], pack["Glist"], pack["Mlist_per_link"])
+    lim = [tuple(r) for r in g[f"{robot}_limits"]]
+    n = len(lim)
+    fk = o.forward_kinematics
+    for i, Td in enumerate(g[f"{robot}_T"]):
+        np.random.seed(300 + i)
+        th, ok, it = ik_helpers.smart_driver(_oracle_ik_solver(o, lim, max_iterations=120), fk, Td[None], n, lim,
+                                             "workspace_heuristic", True)
+        assert bool(ok[0]) == bool(g[f"{robot}_smart_success"][i]) and int(it[0]) == int(g[f"{robot}_smart_iterations"][i]), i
+        np.testing.assert_allclose(th[0], g[f"{robot}_smart_theta"][i], rtol=0, atol=1e-9, err_msg=str(i))
+        np.random.seed(400 + i)
+        th, ok, it, win = ik_helpers.robust_driver(_oracle_ik_solver(o, lim, eomg=2e-3, ev=2e-3, max_iterations=120),
+                                                   fk, Td[None], n, lim, 4)
+        assert bool(ok[0]) == bool(g[f"{robot}_robust_success"][i]) and int(it[0]) == int(g[f"{robot}_robust_iterations"][i]), i
+        assert str(win[0]) == str(g[f"{robot}_robust_strategy"][i]), i
+        np.testing.assert_allclose(th[0], g[f"{robot}_robust_theta"][i], rtol=0, atol=1e-9, err_msg=str(i))
+
+
 CART_CASES = ("generic5", "generic3", "method1", "same_R", "tiny", "near_pi", "pi_band", "pi_exact")
 
 
