@@ -106,6 +106,10 @@ struct RolloutArgs {
 #ifndef MPK_FD_PHASES
 #define MPK_FD_PHASES 0
 #endif
+// MPK_FD_PAIR: plain revolute chains take fd_rollout_pair_kernel (a step split across two warps)
+#ifndef MPK_FD_PAIR
+#define MPK_FD_PAIR 1
+#endif
 constexpr int kRolloutThreads = MPK_FD_THREADS;
 
 template <int FLAVOUR> void launch_rnea(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s);
@@ -569,6 +573,128 @@ __global__ void __launch_bounds__(kRolloutThreads, MPK_FD_MINBLOCKS)
             store_state<N>(a.pos, row, th);
             store_state<N>(a.vel, row, dth);
             store_state<N>(a.acc, row, last);
+        }
+    }
+}
+// ---- the same rollouts with each Euler step split across a PAIR of warps ----------------------
+// A step is a ~1950-instruction fp64 dependency chain; with 8 warps per SM (255 registers) nothing
+// hides its latency.  Here lane l of warp A and lane l of warp B of a 64-thread block own rollout
+// 32 blockIdx.x + l together:
+//   A: joint sin / cos -> (c, s) to shared memory | bias forces (Newton-Euler, ddtheta = 0) -> shared
+//      memory | ... waits for ddtheta | Euler update, limits, row stores
+//   B: torque row (cp.async, one step ahead) | waits for (c, s) | mass matrix (CRBA) + LDL^T
+//      factorisation | waits for the bias forces | ddtheta = M^-1 (tau - bias) -> shared memory
+// so the bias forces and the mass matrix -- the two halves of the chain -- run side by side, and
+// each warp holds about half of the state.  Hand-over by named barriers (bar.arrive on the
+// producer, bar.sync on the consumer, 64 threads each): 1 = (c, s) ready, 2 = bias ready,
+// 3 = ddtheta ready.  Same arithmetic as fd_rollout_kernel.  Plain revolute chains with
+// rigid links and no tip wrench; everything else takes fd_rollout_kernel.
+// (no fence: st.shared; bar.arrive | bar.sync; ld.shared is the PTX ISA's own producer / consumer
+// pattern, and a MEMBAR here would also wait for the row stores and the cp.async in flight)
+__device__ __forceinline__ void pair_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+#ifndef MPK_FD_PAIR_MINBLOCKS
+#define MPK_FD_PAIR_MINBLOCKS 4
+#endif
+constexpr int kRolloutPairBlocksPerSm = MPK_FD_PAIR_MINBLOCKS;
+
+// doubles of shared memory per block: (c, s) 2 N, bias N, ddtheta N, two torque-row stages 2 N
+template <int N>
+constexpr size_t rollout_pair_smem() {
+    return sizeof(double) * 32 * (6 * N);
+}
+
+template <int N>
+__global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
+    fd_rollout_pair_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
+    extern __shared__ __align__(16) double psm[];
+    const int lane = threadIdx.x & 31;
+    double *cs = psm + lane;               // [2 N][32]
+    double *bias_s = cs + 32 * 2 * N;      // [N][32]
+    double *dd_s = bias_s + 32 * N;        // [N][32]
+    double *stage = dd_s + 32 * N;         // [2][N][32]
+    const int64_t b_ = (int64_t)blockIdx.x * 32 + lane;
+    const bool live = b_ < a.B;            // surplus lanes of the last block shadow the last rollout
+    const int64_t b = live ? b_ : a.B - 1;
+    const int64_t base = b * a.N;
+    if (threadIdx.x < 32) {
+        // ---- warp A: state, joint rotations, bias forces, integration, output rows ----
+        double th[N], dth[N], last[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            th[j] = a.th0[b * N + j];
+            dth[j] = a.dth0[b * N + j];
+            last[j] = 0.0;
+        }
+        if (live) {
+            store_state<N>(a.pos, base, th);
+            store_state<N>(a.vel, base, dth);
+            store_state<N>(a.acc, base, last);
+        }
+        for (int64_t i = 1; i < a.N; ++i) {
+            for (int r = 0; r < a.intRes; ++r) {
+                RegStorePre<double, N> st_;
+                joint_cs_all<double, N, true>(rb, th, st_.q);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    cs[32 * j] = st_.q.c[j];
+                    cs[32 * (N + j)] = st_.q.s[j];
+                }
+                pair_arrive(1);
+                double bias[N];
+                ArrayInNoAcc<double, N> in{th, dth};
+                rnea<double, N, false, true>(rb, in, a.g0, nullptr, bias, st_);
+#pragma unroll
+                for (int j = 0; j < N; ++j) bias_s[32 * j] = bias[j];
+                pair_arrive(2);
+                pair_wait(3);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double dd = *(volatile double *)(dd_s + 32 * j);
+                    dth[j] = rn_add(dth[j], rn_mul(dd, a.dts));
+                    double x = rn_add(th[j], rn_mul(dth[j], a.dts));
+                    if (a.lim.on) {
+                        const double lo = (double)a.lim.lo[j], hi = (double)a.lim.hi[j];
+                        x = x < lo ? lo : (x > hi ? hi : x);
+                    }
+                    th[j] = x;
+                    last[j] = dd;
+                }
+            }
+            if (live) {
+                store_state<N>(a.pos, base + i, th);
+                store_state<N>(a.vel, base + i, dth);
+                store_state<N>(a.acc, base + i, last);
+            }
+        }
+    } else {
+        // ---- warp B: torque rows, mass matrix, factorisation, solve ----
+        if (a.N > 1) tau_row_async<N>(stage + 32 * N, a.taumat, a.tau_dtype, base + 1);
+        for (int64_t i = 1; i < a.N; ++i) {
+            double tau[N];
+            tau_row_take<N>(stage + (i & 1) * 32 * N, a.tau_dtype, tau);
+            if (i + 1 < a.N) tau_row_async<N>(stage + ((i + 1) & 1) * 32 * N, a.taumat, a.tau_dtype, base + i + 1);
+            for (int r = 0; r < a.intRes; ++r) {
+                JointCS<double, N> q;
+                pair_wait(1);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    q.c[j] = *(volatile double *)(cs + 32 * j);
+                    q.s[j] = *(volatile double *)(cs + 32 * (N + j));
+                    q.d[j] = rb.d[j];
+                }
+                double Mm[N][N], dinv[N], dd[N];
+                crba<double, N, true>(rb, q, Mm);
+                ldlt_factor<double, N, true>(Mm, dinv);
+                pair_wait(2);
+#pragma unroll
+                for (int j = 0; j < N; ++j) dd[j] = tau[j] - *(volatile double *)(bias_s + 32 * j);
+                ldlt_apply<double, N>(Mm, dinv, dd);
+#pragma unroll
+                for (int j = 0; j < N; ++j) dd_s[32 * j] = dd[j];
+                pair_arrive(3);
+            }
         }
     }
 }

@@ -1018,9 +1018,9 @@ MPK_HD float rcp_pivot(float d) { return 1.0f / d; }
 // (only the lower triangle is read; it is overwritten).
 // FASTRCP: pivots inverted by rcp_pivot (forward dynamics) instead of an IEEE division (the
 // inverse kinematics, whose iterates are compared step by step with the reference's).
+// Factorisation M = L D L^T in place (unit lower L below the diagonal, D on it), 1 / D in dinv ...
 template <typename T, int N, bool FASTRCP = false>
-MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
-    T dinv[N];
+MPK_HD void ldlt_factor(T (&Mm)[N][N], T (&dinv)[N]) {
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         T dj = Mm[j][j];
@@ -1036,6 +1036,10 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
             Mm[i][j] = l * dinv[j];
         }
     }
+}
+// ... and the two triangular solves (b <- M^-1 b).
+template <typename T, int N>
+MPK_HD void ldlt_apply(const T (&Mm)[N][N], const T (&dinv)[N], T (&b)[N]) {
 #pragma unroll
     for (int i = 0; i < N; ++i)
 #pragma unroll
@@ -1046,6 +1050,12 @@ MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
     for (int i = N - 1; i >= 0; --i)
 #pragma unroll
         for (int k = i + 1; k < N; ++k) b[i] -= Mm[k][i] * b[k];
+}
+template <typename T, int N, bool FASTRCP = false>
+MPK_HD void ldlt_solve(T (&Mm)[N][N], T (&b)[N]) {
+    T dinv[N];
+    ldlt_factor<T, N, FASTRCP>(Mm, dinv);
+    ldlt_apply<T, N>(Mm, dinv, b);
 }
 
 // ddtheta = M(theta)^-1 (tau - rnea(theta, dtheta, 0, g, Ftip))  (dynamics/id_fd.py:50-83).

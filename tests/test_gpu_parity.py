@@ -292,6 +292,38 @@ def test_batched_rollouts_vs_oracle(robots, oracle_factory, robot, B, N, intres)
     assert all(_bits_equal(r32[k], r64[k]) for k in r32)
 
 
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_rollout_kernels_agree(robots, oracle_factory, robot):
+    """A batch that fits the GPU in one wave runs each Euler step split across a pair of warps
+    (fd_rollout_pair_kernel); larger batches run one warp per 32 rollouts (fd_rollout_kernel).  The
+    same rollouts through both -- one call of 24,000 against six calls of 4,000 -- give the same
+    float32 rows (to one rounding of the float64 state), ragged last block, intRes = 2, and both
+    agree with the oracle on sampled rollouts."""
+    rb, o = robots[robot], oracle_factory(robot)
+    n = rb.num_joints
+    B, N = 24000, 40
+    assert B > 4 * 32 * torch.cuda.get_device_properties(0).multi_processor_count > 4000
+    rng = np.random.default_rng(77)
+    lo, hi = rb.joint_limits[:, 0], rb.joint_limits[:, 1]
+    th0 = rng.uniform(0.5 * lo, 0.5 * hi, (B, n))
+    dth0 = rng.uniform(-0.5, 0.5, (B, n))
+    tau = rng.uniform(-10, 10, (B, N, n)).astype(np.float32)
+    planner = rb.planner()
+    big = planner.forward_dynamics_trajectory(th0, dth0, tau, [0, 0, -9.81], None, 1e-3, 2)
+    parts = [planner.forward_dynamics_trajectory(th0[i:i + 4000], dth0[i:i + 4000], tau[i:i + 4000], [0, 0, -9.81],
+                                                 None, 1e-3, 2) for i in range(0, B, 4000)]
+    for k in big:
+        small = np.concatenate([p[k] for p in parts])
+        assert _rel_rows(small.reshape(B * N, n), big[k].reshape(B * N, n)) <= 3e-7, k
+    odd = planner.forward_dynamics_trajectory(th0[:1001], dth0[:1001], tau[:1001], [0, 0, -9.81], None, 1e-3, 2)
+    idx = np.array([0, 31, 32, 999, 1000])
+    ref = o.forward_dynamics_trajectory(th0[idx], dth0[idx], tau[idx].astype(np.float64), [0, 0, -9.81], None, 1e-3, 2,
+                                        rb.joint_limits, analytic=True)
+    for k in ref:
+        assert _rel_rows(odd[k][idx].reshape(-1, n), ref[k].reshape(-1, n)) <= 1e-6, k
+        assert _rel_rows(big[k][idx].reshape(-1, n), ref[k].reshape(-1, n)) <= 1e-6, k
+
+
 def test_device_resident_path(robots):
     rb = robots["ur5"]
     planner = rb.planner()
