@@ -38,7 +38,7 @@ ncu_micro)
   # full captures of the other kernels (one launch each) while running the micro-benchmark
   # (no --import-source here: 24 full captures with source exceed gpurun's 64 MiB return limit)
   timeout 1200 ncu --set full --clock-control none \
-      -k regex:'traj_kernel|fk_jacobian_kernel|fd_rollout_kernel|mass_matrix_kernel|rnea_kernel|ik_dls_kernel|forward_dynamics_kernel' -c 24 \
+      -k regex:'traj_kernel|fk_jacobian_kernel|fd_rollout|mass_matrix_kernel|rnea_kernel|ik_dls_kernel|forward_dynamics_kernel' -c 24 \
       -f -o $OUT/${TAG}_micro python scripts/microbench.py --quick > $OUT/${TAG}_ncu_micro.log 2>&1
   tail -2 $OUT/${TAG}_ncu_micro.log
   # summarise on the box and drop the report: 24 full captures are ~90 MB, gpurun returns <= 64 MiB
