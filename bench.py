@@ -164,8 +164,12 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"UR5 {B_TRAJ}x{N_STEPS} quintic trajectory + inverse dynamics (sampled)",
-                   "robot": ROBOT, "trajectories": B_TRAJ, "steps_per_trajectory": N_STEPS},
+        # the same workload as the GPU arm's line (each step a bounded sample of it, see cpu_baseline.sample)
+        "config": {"workload": f"UR5 {B_TRAJ} trajectories x {N_STEPS} steps per GPU, quintic joint_trajectory + "
+                               "inverse_dynamics_trajectory (BASELINE.json configs[2])",
+                   "robot": ROBOT, "trajectories_per_gpu": B_TRAJ, "steps_per_trajectory": N_STEPS,
+                   "points_per_gpu": B_TRAJ * N_STEPS, "mode": "cpu reference algorithm, sampled",
+                   "outputs": "float32 torques (B, N, 6)"},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -327,7 +331,7 @@ def run_ours(args) -> None:
 
     # second metric of BASELINE.json: forward-dynamics rollout steps/s (configs[3]: iiwa14, 65,536
     # shooting trajectories x 1000 Euler steps per GPU, float32 torque rows resident in HBM)
-    t_fd, fd_steps = 0.0, 0
+    t_fd, fd_steps, t_fd_small = 0.0, 0, 0.0
     if not args.no_fd:
         iiwa = load_robot("iiwa14", device=dev)
         h7, jl7 = iiwa.dynamics.robot.handle, iiwa.planner()._jl
@@ -342,6 +346,10 @@ def run_ours(args) -> None:
                 + (torch.rand(Bf, Nf, 7, dtype=torch.float64, device=dev, generator=gen) - 0.5) * amp).float()
         t_fd = timed(lambda: ops.forward_dynamics_trajectory(h7, th0, dth0, taum, g, None, 1e-3, 1, jl7), 3, 1)
         fd_steps = Bf * (Nf - 1) * 3
+        # one GPU's share of the same 65,536 rollouts on 8 GPUs (strong scaling): each step split across a warp pair
+        Bs = Bf // 8
+        t_fd_small = timed(lambda: ops.forward_dynamics_trajectory(h7, th0[:Bs], dth0[:Bs], taum[:Bs], g, None, 1e-3, 1,
+                                                                   jl7), 3, 1) / 3
         del taum
 
     red = torch.tensor([t_dev, t_dom, t_e2e, t_fd], dtype=torch.float64, device=dev)
@@ -401,6 +409,7 @@ def run_ours(args) -> None:
         line["fd_rollout"] = {
             "metric": "fd_rollout_steps_per_s", "value": world * fd_steps / t_fd, "unit": "steps/s",
             "ms_per_launch": t_fd / 3 * 1e3, "gpu_launches": 3,
+            "ms_per_launch_8192_rollouts": t_fd_small * 1e3,  # rank 0's time (not reduced over ranks)
             "config": {"workload": f"iiwa14 {FD_ROLLOUTS} rollouts x {FD_STEPS} Euler steps per GPU, CRBA mass matrix + "
                                    "LDL^T solve per step (BASELINE.json configs[3])", "dt": 1e-3, "intRes": 1,
                        "taumat": "float32 (B, N, 7) resident in HBM", "outputs": "3 x float32 (B, N, 7)"}}
