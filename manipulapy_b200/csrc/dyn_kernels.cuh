@@ -24,7 +24,15 @@ constexpr int kDynThreads = 128;
 // 4 blocks (16 warps) per SM, 127-register cap.  Measured on B200 (profiles/r1_variants.md): 4, 5
 // and 6 resident blocks run the fused 6-DOF kernel within 2 % of each other -- the fp64 pipe, not
 // latency hiding, is the limit -- and the looser register cap gives the shortest code.
-constexpr int kRneaMinBlocks = 4;
+#ifndef MPK_RNEA_MINBLOCKS
+#define MPK_RNEA_MINBLOCKS 4
+#endif
+constexpr int kRneaMinBlocks = MPK_RNEA_MINBLOCKS;
+// MPK_RNEA_REGSTORE (tuning knob): the fused kernel keeps the link wrenches in registers (RegStore)
+// instead of the per-thread shared-memory column.
+#ifndef MPK_RNEA_REGSTORE
+#define MPK_RNEA_REGSTORE 0
+#endif
 
 constexpr bool flavour_gen(int f) { return f == 2; }
 constexpr bool flavour_rev(int f) { return f == 0; }
@@ -373,8 +381,12 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
             for (int k = 0; k < 6; ++k) ft[k] = (T)a.tip.ftip[k];
         }
         const T *ftp = TIP ? ft : nullptr;
-        SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
         T tau[N];
+#if MPK_RNEA_REGSTORE
+        RegStore<T, N> st;
+#else
+        SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
+#endif
         rnea<T, N, GEN, REV>(rb, in, g0, ftp, tau, st);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
