@@ -174,6 +174,22 @@ class SerialManipulator:
         _, J = _native.ops().fk_jacobian(rb.handle, th, False, True, _host.is_f32(precision), body)
         return self._finish(J, single, on_dev)
 
+    def end_effector_velocity(self, thetalist, dthetalist, frame: str = "space"):
+        """End-effector twist ``J(theta) dtheta`` in the space or body frame (kinematics/velocity.py:39-63);
+        ``(n,)`` inputs -> ``(6,)``, batched ``(P, n)`` -> ``(P, 6)``.  The Jacobians come from the
+        FK / Jacobian kernel and stay on the device for the product."""
+        if frame not in ("space", "body"):
+            raise ValueError("Invalid frame specified. Choose 'space' or 'body'.")
+        th, single, on_dev = self._rows(thetalist, "thetalist")
+        dth, _, _ = self._rows(dthetalist, "dthetalist")
+        if dth.shape != th.shape:
+            raise ValueError("thetalist and dthetalist must have the same shape")
+        body = frame == "body"
+        rb = self.robot_body if body else self.robot
+        _, J = _native.ops().fk_jacobian(rb.handle, th, False, True, False, body)
+        V = torch.einsum("prn,pn->pr", J, dth.to(J.dtype))
+        return self._finish(V, single, on_dev or _host.is_device_tensor(dthetalist))
+
     def iterative_inverse_kinematics(self, T_desired, thetalist0, eomg: float = 1e-6, ev: float = 1e-6,
                                      max_iterations: int = 10000, plot_residuals: bool = False,
                                      damping: float = 2e-2, step_cap: float = 0.3,

@@ -356,6 +356,44 @@ def ik_front_golden() -> None:
     np.savez(GOLD_DIR / "inverse_kinematics_front_ends.npz", **out)
 
 
+API_CONTRACT_KEYS = (
+    "ManipulatorDynamics.forward_dynamics", "ManipulatorDynamics.gravity_forces", "ManipulatorDynamics.inverse_dynamics",
+    "ManipulatorDynamics.mass_matrix", "ManipulatorDynamics.velocity_quadratic_forces",
+    "OptimizedTrajectoryPlanning.cartesian_trajectory", "OptimizedTrajectoryPlanning.forward_dynamics_trajectory",
+    "OptimizedTrajectoryPlanning.inverse_dynamics_trajectory", "OptimizedTrajectoryPlanning.joint_trajectory",
+    "SerialManipulator.forward_kinematics", "SerialManipulator.iterative_inverse_kinematics", "SerialManipulator.jacobian",
+    "SerialManipulator.smart_inverse_kinematics", "SerialManipulator.robust_inverse_kinematics",
+    "SerialManipulator.end_effector_velocity",
+)
+
+
+def api_contract_golden() -> None:
+    """Hot-path subset of the reference's tests/data/api_contract_golden.json: per mirrored method
+    the parameter names / optionality (from the reference classes themselves) and the pinned return
+    type, dtype and shape."""
+    import inspect
+    import json
+
+    import ManipulaPy.dynamics as dynamics_mod
+    import ManipulaPy.kinematics as kinematics_mod
+
+    classes = {"ManipulatorDynamics": dynamics_mod.ManipulatorDynamics,
+               "SerialManipulator": kinematics_mod.SerialManipulator,
+               "OptimizedTrajectoryPlanning": OptimizedTrajectoryPlanning}
+    ref = json.loads((REF / "tests" / "data" / "api_contract_golden.json").read_text())
+    out = {"_source": "reference tests/data/api_contract_golden.json (hot-path subset, oracle/gen_golden.py)"}
+    for key in API_CONTRACT_KEYS:
+        cls, meth = key.split(".")
+        sig = inspect.signature(getattr(classes[cls], meth))
+        out[key] = {
+            "parameters": [{"name": q.name, "has_default": q.default is not inspect.Parameter.empty}
+                           for q in sig.parameters.values() if q.name != "self"],
+            "return": ref[key]["return"],
+        }
+    (GOLD_DIR / "api_contract.json").write_text(json.dumps(out, indent=1, sort_keys=True) + "\n")
+    print("api contract subset:", len(out) - 1, "methods")
+
+
 def body_kinematics_golden() -> None:
     """forward_kinematics / jacobian with frame="body" of the unmodified reference: the UR5 as
     loaded from its URDF, and a chain whose B_list is NOT Ad(M^-1) S_list (the reference takes
@@ -493,6 +531,7 @@ def main() -> None:
     ik_golden()
     ik_modes_golden()
     ik_front_golden()
+    api_contract_golden()
     registry_trajectory_golden()
     id_trajectory_golden()
     fd_trajectory_golden()

@@ -626,7 +626,17 @@ def test_return_types_match_reference_api_contract(robots):
         "SerialManipulator.forward_kinematics": dyn.forward_kinematics(th),
         "SerialManipulator.iterative_inverse_kinematics": dyn.iterative_inverse_kinematics(X1, th),
         "SerialManipulator.jacobian": dyn.jacobian(th),
+        "SerialManipulator.smart_inverse_kinematics": dyn.smart_inverse_kinematics(X1, max_iterations=200),
+        "SerialManipulator.robust_inverse_kinematics": dyn.robust_inverse_kinematics(X1, max_attempts=3, max_iterations=200),
+        "SerialManipulator.end_effector_velocity": dyn.end_effector_velocity(th, dth),
     }
+    # end_effector_velocity = J dtheta in either frame, batched = per row
+    for frame in ("space", "body"):
+        V = dyn.end_effector_velocity(np.stack([th, dd]), np.stack([dth, th]), frame)
+        np.testing.assert_allclose(V[0], dyn.jacobian(th, frame) @ dth, rtol=0, atol=1e-14)
+        np.testing.assert_allclose(V[1], dyn.jacobian(dd, frame) @ th, rtol=0, atol=1e-14)
+    with pytest.raises(ValueError):
+        dyn.end_effector_velocity(th, dth, "tool")
 
     def check(value, spec, where):
         if spec["type"] == "numpy.ndarray":
