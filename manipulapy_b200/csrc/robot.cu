@@ -501,6 +501,19 @@ __global__ void fma_peak_kernel(int64_t iters, double *sink, const __grid_consta
             } else if (MODE == 2) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) x[k] = x[k + 1] * T(pc.k[k]) - x[k + 3];
+            } else if (MODE == 4) {
+                // half of the instructions with a uniform-register operand, half with three registers
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    x[k] = (k & 1) ? x[k + 1] * x[k + 2] - x[k + 3] : x[k + 1] * T(pc.k[k]) - x[k + 3];
+            } else if (MODE == 5) {
+                // three registers, but consecutive instructions share their middle operand (.reuse)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = x[k + 1] * x[(k < 4) ? 10 : 11] - x[k + 3];
+            } else if (MODE == 6) {
+                // three registers, consecutive instructions share TWO operands pairwise (a*b - c, a*b' - c)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = x[(k & ~1) + 1] * x[k + 2] - x[(k & ~1) + 3];
             } else {
                 // 4 x (t = c*p (DMUL); p' = t - s*q (DFMA)): 8 instructions, 12 flops (counted as 16)
 #pragma unroll
@@ -533,6 +546,9 @@ extern "C" int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, d
     else if (dtype == MPK_F64 && mode == 1) fma_peak_kernel<double, 1><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F64 && mode == 2) fma_peak_kernel<double, 2><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F64 && mode == 3) fma_peak_kernel<double, 3><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 4) fma_peak_kernel<double, 4><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 5) fma_peak_kernel<double, 5><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 6) fma_peak_kernel<double, 6><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F32 && mode == 0) fma_peak_kernel<float, 0><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F32 && mode == 1) fma_peak_kernel<float, 1><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else return fail(MPK_EINVAL, "bad dtype / mode");

@@ -72,7 +72,8 @@ def main():
     # fp64 issue rate under the operand patterns of the real kernels (csrc/robot.cu fma_peak modes):
     # instructions per clock per SM, against the 32 (= 64 lanes / 2) of the FMA pipe
     for mode, label in ((0, "shared_operands"), (1, "three_distinct_registers"), (2, "constant_bank_operand"),
-                        (3, "dmul_dfma_pairs")):
+                        (3, "dmul_dfma_pairs"), (4, "half_uniform_half_three_registers"),
+                        (5, "three_registers_shared_middle_operand"), (6, "three_registers_two_shared_operands")):
         blocks, threads, iters = 148 * 8, 256, 1 << 14
         sec = timeit(lambda: ops.fma_peak(sink, mode << 8, blocks, threads, iters), 5, 2)
         res[f"fp64_pattern_{label}_ginstr_per_s"] = blocks * threads * iters * 8 / sec[1] / 1e9
