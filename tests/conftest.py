@@ -18,6 +18,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_libraries():
+    """A fresh checkout has no built libraries (they are git-ignored): build them once, in-tree,
+    like ``__graft_entry__.build()`` does.  Nothing is rebuilt when they are there."""
+    from manipulapy_b200 import _build, _native
+
+    if not (_native.LIB_PATH.exists() and _native.OPS_PATH.exists()):
+        _build.build_all()
+
+
 def load_pack(name: str) -> dict:
     with np.load(ROBOTS / f"{name}.npz") as d:
         return {k: d[k] for k in d.files}
