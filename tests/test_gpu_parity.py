@@ -470,6 +470,16 @@ def test_inverse_kinematics_modes_and_front_ends(robot):
     assert ik_helpers.pose_error(sm.forward_kinematics(th[ok]), Td[ok]).max() < 1e-5
     plain = sm.smart_inverse_kinematics(Td, max_iterations=150, auto_fallback=False)[1]
     assert ok.sum() >= plain.sum()  # the fall-back starts only add solutions
+    # the two-phase schedule carries the adaptive-tuning state of the stragglers through its queue
+    from manipulapy_b200 import _native
+    dev = torch.device("cuda")
+    th0 = ik_helpers.workspace_heuristic_guess(Td, len(lim), lim)
+    args = (sm.robot.handle, torch.from_numpy(Td).to(dev), torch.from_numpy(th0).to(dev), 1e-6, 1e-6, 300, 2e-2, 0.3,
+            1.0, 1.0, torch.from_numpy(np.ascontiguousarray(g[f"{robot}_limits"], dtype=np.float64)), 3)
+    one = _native.ops().inverse_kinematics_dls(*args, False, 3)
+    two = _native.ops().inverse_kinematics_dls(*args, True, 3)
+    assert all(bool(torch.equal(x, y)) for x, y in zip(one, two))
+    assert 0 < int((two[2] > 64).sum()) < P
     np.random.seed(9)
     th, ok, it, win = sm.robust_inverse_kinematics(Td, max_attempts=6, max_iterations=150)
     assert ok.mean() > 0.95 and set(win) <= {"workspace_heuristic", "midpoint", "random", "none"}
