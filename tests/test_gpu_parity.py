@@ -891,10 +891,12 @@ def test_full_size_cfg2_million_fk_jacobian(robots, oracle_factory):
         assert float((dp - pred).abs().max()) < 1e-8
 
 
-def test_full_size_cfg4_iiwa_rollouts(robots, oracle_factory):
-    """iiwa14, 65,536 rollouts x 1000 Euler steps; sampled rollouts against the oracle."""
+@pytest.mark.parametrize("B", [65536, 8192], ids=["one_gpu", "eighth_share"])
+def test_full_size_cfg4_iiwa_rollouts(robots, oracle_factory, B):
+    """iiwa14, 65,536 rollouts x 1000 Euler steps (one warp per 32 rollouts), and one GPU's share of
+    them on 8 GPUs (8,192: each step split across a warp pair); sampled rollouts against the oracle."""
     rb, o = robots["iiwa14"], oracle_factory("iiwa14")
-    B, N, n = 65536, 1000, 7
+    N, n = 1000, 7
     gen = torch.Generator(device="cuda").manual_seed(4)
     lo = torch.from_numpy(rb.joint_limits[:, 0]).cuda()
     hi = torch.from_numpy(rb.joint_limits[:, 1]).cuda()
@@ -927,7 +929,7 @@ def test_full_size_cfg4_iiwa_rollouts(robots, oracle_factory):
     lo32, hi32 = lo.float(), hi.float()
     ok = torch.isfinite(pos)
     assert bool(((pos >= lo32) | ~ok).all()) and bool(((pos <= hi32) | ~ok).all())
-    sel = [0, 1, 4097, 65535]
+    sel = [0, 1, 4097, B - 1]
     ref = o.forward_dynamics_trajectory(th0[sel].cpu().numpy(), dth0[sel].cpu().numpy(), tau[sel].double().cpu().numpy(),
                                         [0, 0, -9.81], None, 1e-3, 1, rb.joint_limits, analytic=True)
     # 1000 chaotic steps amplify rounding differences between LDL^T and the oracle's LU: 1e-5 per row
