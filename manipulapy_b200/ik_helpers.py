@@ -76,6 +76,17 @@ def random_in_limits(joint_limits: Limits) -> np.ndarray:
     return np.asarray(angles, dtype=np.float64)
 
 
+def random_in_limits_batch(joint_limits: Limits, count: int) -> np.ndarray:
+    """``count`` configurations, the same values and the same use of NumPy's global generator as
+    ``count`` calls of random_in_limits (one vectorised draw when every joint has both limits)."""
+    lim = list(joint_limits)
+    if count and all(mn is not None and mx is not None for mn, mx in lim):
+        lo = np.array([mn for mn, _ in lim], dtype=np.float64)
+        hi = np.array([mx for _, mx in lim], dtype=np.float64)
+        return np.random.uniform(lo, hi, (count, len(lim)))
+    return np.stack([random_in_limits(lim) for _ in range(count)]) if count else np.empty((0, len(lim)))
+
+
 def midpoint_of_limits(joint_limits: Limits) -> np.ndarray:
     """(ik_helpers.py:215-246)"""
     return np.asarray([(mn + mx) / 2.0 if mn is not None and mx is not None else 0.0 for mn, mx in joint_limits],
@@ -96,7 +107,7 @@ def _guess(strategy: str, Td: np.ndarray, n: int, limits: Limits) -> np.ndarray:
     if strategy == "midpoint":
         return np.tile(midpoint_of_limits(limits)[:n], (Td.shape[0], 1))
     if strategy == "random":
-        return np.stack([random_in_limits(limits)[:n] for _ in range(Td.shape[0])]) if Td.shape[0] else np.empty((0, n))
+        return random_in_limits_batch(limits, Td.shape[0])[:, :n]
     raise NotImplementedError(
         f"initial-guess strategy '{strategy}' is not part of the batched front end "
         "(workspace_heuristic, midpoint and random are)")

@@ -606,3 +606,30 @@ def test_robust_inverse_kinematics_kernel_vs_reference_golden(hostcheck, robot):
                 np.testing.assert_allclose(th[0], g[f"{robot}_robust_theta"][i], rtol=0, atol=1e-6, err_msg=str(i))
         elif ok[0]:
             assert ik_helpers.pose_error(fk(th), Td[None]).max() < 5e-3
+
+
+def test_ik_guess_helpers_match_reference_formulas():
+    """The vectorised random guesses consume NumPy's global generator exactly like the reference's
+    joint-by-joint draws (kinematics/ik_helpers.py:179-212); midpoint and clip as the reference."""
+    from manipulapy_b200 import ik_helpers
+
+    lim = [(-1.0, 2.0), (-3.0, 0.5), (0.1, 0.2), (-np.pi, np.pi)]
+    np.random.seed(5)
+    a = ik_helpers.random_in_limits_batch(lim, 7)
+    np.random.seed(5)
+    b = np.stack([ik_helpers.random_in_limits(lim) for _ in range(7)])
+    assert np.array_equal(a, b)
+    assert np.random.uniform() == np.random.RandomState(5).uniform(size=7 * 4 + 1)[-1]  # same stream position
+    open_lim = [(-1.0, None), (None, 2.0), (None, None), (0.0, 1.0)]
+    np.random.seed(6)
+    c = ik_helpers.random_in_limits_batch(open_lim, 3)
+    np.random.seed(6)
+    d = np.stack([ik_helpers.random_in_limits(open_lim) for _ in range(3)])
+    assert np.array_equal(c, d) and (c[:, 0] >= -1).all() and (c[:, 1] <= 2).all()
+    assert np.array_equal(ik_helpers.midpoint_of_limits(open_lim), [0.0, 0.0, 0.0, 0.5])
+    assert ik_helpers.random_in_limits_batch(lim, 0).shape == (0, 4)
+    T = np.eye(4)
+    T[:3, 3] = [0.3, 0.2, 0.4]
+    g1 = ik_helpers.workspace_heuristic_guess(T, 6, [(-3, 3)] * 6)
+    gb = ik_helpers.workspace_heuristic_guess(np.stack([T, T]), 6, [(-3, 3)] * 6)
+    assert g1.shape == (6,) and np.array_equal(gb[0], g1) and np.isclose(g1[0], np.arctan2(0.2, 0.3))
