@@ -17,6 +17,7 @@ from .kinematics import SerialManipulator
 from .path_planning import OptimizedTrajectoryPlanning, TrajectoryPlanning
 from .robots import RobotBundle, available_robots, load_robot
 from .sharding import gather_rows, shard_range
+from .singularity import Singularity
 from ._host import bind_host_to_device
 from . import ik_helpers
 
@@ -26,5 +27,5 @@ __all__ = [
     "KERNEL_REGISTRY", "KernelRegistration", "KernelRegistry", "execute_registered_kernel",
     "ManipulatorDynamics", "SerialManipulator", "OptimizedTrajectoryPlanning", "TrajectoryPlanning",
     "RobotBundle", "available_robots", "load_robot", "gather_rows", "shard_range", "bind_host_to_device",
-    "ik_helpers",
+    "ik_helpers", "Singularity",
 ]

@@ -394,6 +394,32 @@ def api_contract_golden() -> None:
     print("api contract subset:", len(out) - 1, "methods")
 
 
+def singularity_golden() -> None:
+    """Singularity.condition_number / singularity_analysis / near_singularity_detection of the
+    unmodified reference (singularity/singularity_analysis.py:52-74, 246-305) at random and at
+    singular configurations (stretched-out arm)."""
+    import importlib
+
+    sing_mod = importlib.import_module("ManipulaPy.singularity")
+    out = {}
+    for robot in ("ur5", "iiwa14"):
+        proc, sm, dyn = load(robot)
+        n = sm.S_list.shape[1]
+        lims = limits_array(proc, n)
+        rng = np.random.default_rng(44)
+        th = rng.uniform(0.7 * lims[:, 0], 0.7 * lims[:, 1], (10, n))
+        th[0] = 0.0  # home pose: singular for both arms
+        th[1, 2:] = 0.0
+        sg = sing_mod.Singularity(sm)
+        out.update({f"{robot}_M": np.asarray(sm.M_list, np.float64), f"{robot}_S": np.asarray(sm.S_list, np.float64),
+                    f"{robot}_thetas": th,
+                    f"{robot}_condition_number": np.array([float(sg.condition_number(t)) for t in th]),
+                    f"{robot}_singular": np.array([bool(sg.singularity_analysis(t)) for t in th]),
+                    f"{robot}_near": np.array([bool(sg.near_singularity_detection(t)) for t in th])})
+        print(robot, out[f"{robot}_condition_number"], out[f"{robot}_singular"])
+    np.savez(GOLD_DIR / "singularity.npz", **out)
+
+
 def body_kinematics_golden() -> None:
     """forward_kinematics / jacobian with frame="body" of the unmodified reference: the UR5 as
     loaded from its URDF, and a chain whose B_list is NOT Ad(M^-1) S_list (the reference takes
@@ -532,6 +558,7 @@ def main() -> None:
     ik_modes_golden()
     ik_front_golden()
     api_contract_golden()
+    singularity_golden()
     registry_trajectory_golden()
     id_trajectory_golden()
     fd_trajectory_golden()

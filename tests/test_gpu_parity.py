@@ -964,3 +964,30 @@ def test_robot_zoo_vs_reference(robot):
     n = th.shape[1]
     big = np.concatenate([th, rng.uniform(-1, 1, (997, n))])
     assert np.array_equal(dyn.mass_matrix(big)[: th.shape[0]], dyn.mass_matrix(th))
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_singularity_callers(robot):
+    """Singularity.condition_number / singularity_analysis / near_singularity_detection
+    (singularity/singularity_analysis.py:52-74, 246-305) against the unmodified reference, one
+    configuration at a time and batched; workspace_points = forward kinematics of the samples."""
+    from manipulapy_b200 import SerialManipulator, Singularity
+
+    g = load_golden("singularity")
+    sm = SerialManipulator(M_list=g[f"{robot}_M"], S_list=g[f"{robot}_S"])
+    sg = Singularity(sm)
+    th, ref = g[f"{robot}_thetas"], g[f"{robot}_condition_number"]
+    cond = sg.condition_number(th)
+    reg = ref < 1e8  # regular configurations; the singular ones are rounding noise over ~1e-16
+    np.testing.assert_allclose(cond[reg], ref[reg], rtol=1e-9)
+    assert (cond[~reg] > 1e12).all() and (~reg).sum() == 2
+    assert np.array_equal(sg.singularity_analysis(th), g[f"{robot}_singular"])
+    assert np.array_equal(sg.near_singularity_detection(th), g[f"{robot}_near"])
+    c3 = sg.condition_number(th[3])
+    assert isinstance(c3, float) and abs(c3 - ref[3]) <= 1e-9 * ref[3]
+    assert sg.singularity_analysis(th[0]) is True and sg.singularity_analysis(th[3]) is False
+    lim = [(-1.0, 1.0)] * sm.num_joints
+    pts, samples, hull = sg.workspace_points(lim, 20000, return_samples=True, return_hull=True)
+    assert pts.shape == (20000, 3) and samples.dtype == np.float32 and np.abs(samples).max() <= 1.0
+    np.testing.assert_allclose(pts, sm.forward_kinematics(samples.astype(np.float64))[:, :3, 3], rtol=0, atol=1e-12)
+    assert hull.volume > 0 and np.array_equal(pts, sg.workspace_points(lim, 20000))  # seeded: reproducible
