@@ -277,6 +277,27 @@ class OptimizedTrajectoryPlanning:
         return {"positions": outs[0], "velocities": outs[1], "accelerations": outs[2]}
 
 
+    # -- small planner utilities kept for drop-in use -------------------------------------------------------
+    def calculate_derivatives(self, positions, dt):
+        """First, second and third finite differences of a sampled trajectory
+        (planning/trajectory_dynamics.py:710-731): ``(v, a, j)`` with one row less each.  A few
+        subtractions per row: done where the data lives (NumPy on the host, torch on the device)."""
+        if _host.is_device_tensor(positions):
+            v = (positions[1:] - positions[:-1]) / dt
+            a = (v[1:] - v[:-1]) / dt
+            return v, a, (a[1:] - a[:-1]) / dt
+        x = np.asarray(positions)
+        v = (x[1:] - x[:-1]) / dt
+        a = (v[1:] - v[:-1]) / dt
+        return v, a, (a[1:] - a[:-1]) / dt
+
+    def cleanup_gpu_memory(self) -> None:
+        """The reference frees its per-instance device arrays and memory pool
+        (planning/trajectory_planning.py:502-530); here device buffers live only for the duration
+        of a call, so this just returns torch's cached blocks to the driver."""
+        torch.cuda.empty_cache()
+
+
 def _input_is_f32(x) -> bool:
     if isinstance(x, torch.Tensor):
         return x.dtype == torch.float32

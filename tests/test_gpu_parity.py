@@ -565,6 +565,18 @@ def test_reference_property_tests(robots, robot):
     np.testing.assert_array_equal(tr["positions"][:, 0], th[:50].astype(np.float32))
 
 
+def test_planner_utilities(robots):
+    """calculate_derivatives (planning/trajectory_dynamics.py:710-731) and cleanup_gpu_memory."""
+    planner = robots["ur5"].planner()
+    x = np.random.default_rng(0).normal(size=(9, 6))
+    v, a, j = planner.calculate_derivatives(x, 0.1)
+    assert v.shape == (8, 6) and a.shape == (7, 6) and j.shape == (6, 6)
+    assert np.array_equal(v, np.diff(x, axis=0) / 0.1) and np.array_equal(j, (a[1:] - a[:-1]) / 0.1)
+    vd, ad, jd = planner.calculate_derivatives(torch.from_numpy(x).cuda(), 0.1)
+    assert vd.is_cuda and np.allclose(jd.cpu().numpy(), j, rtol=0, atol=1e-9)
+    planner.cleanup_gpu_memory()
+
+
 def test_reference_planner_unit_cases():
     """The cases of the reference's tests/test_path_planning_unit.py:52-160, on a 2-joint planner:
     end points respected, batch = per-trajectory generator, positions clipped to the joint
