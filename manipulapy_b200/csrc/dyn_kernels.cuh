@@ -599,7 +599,8 @@ __global__ void __launch_bounds__(kRolloutThreads, MPK_FD_MINBLOCKS)
 // so the bias forces and the mass matrix -- the two halves of the chain -- run side by side, and
 // each warp holds about half of the state.  Hand-over by named barriers (bar.arrive on the
 // producer, bar.sync on the consumer, 64 threads each): 1 = (c, s) ready, 2 = bias ready,
-// 3 = ddtheta ready.  Same arithmetic as fd_rollout_kernel.  Plain revolute chains with
+// 3 = ddtheta ready.  Same arithmetic as fd_rollout_kernel (the same bits: test_rollout_kernels_agree).
+// Plain revolute chains with
 // rigid links and no tip wrench; everything else takes fd_rollout_kernel.
 // (no fence: st.shared; bar.arrive | bar.sync; ld.shared is the PTX ISA's own producer / consumer
 // pattern, and a MEMBAR here would also wait for the row stores and the cp.async in flight)
