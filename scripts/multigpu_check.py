@@ -48,7 +48,7 @@ def main():
         ok &= on0 is None and everyone.shape == (B, N, 6)
     # rollouts
     iiwa = load_robot("iiwa14", device=dev)
-    Bf, Nf = 515, 40
+    Bf, Nf = 20011, 24  # whole batch: one warp per 32 rollouts; shards: warp-pair kernel (same bits)
     th0 = rng.uniform(-1, 1, (Bf, 7)); dth0 = rng.uniform(-0.5, 0.5, (Bf, 7)); tm = rng.uniform(-5, 5, (Bf, Nf, 7)).astype(np.float32)
     lo, hi = shard_range(Bf, world, rank)
     pl7 = iiwa.planner()
