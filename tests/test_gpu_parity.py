@@ -1003,3 +1003,38 @@ def test_singularity_callers(robot):
     assert pts.shape == (20000, 3) and samples.dtype == np.float32 and np.abs(samples).max() <= 1.0
     np.testing.assert_allclose(pts, sm.forward_kinematics(samples.astype(np.float64))[:, :3, 3], rtol=0, atol=1e-12)
     assert hull.volume > 0 and np.array_equal(pts, sg.workspace_points(lim, 20000))  # seeded: reproducible
+
+
+def test_widened_rows_edge_cases(robots):
+    """Empty and single-row batches through the widened rows (IK modes and front ends, singularity
+    callers, end-effector velocity), device-resident inputs, unknown options."""
+    from manipulapy_b200 import Singularity
+
+    from manipulapy_b200 import SerialManipulator
+
+    rb = robots["ur5"]
+    n = rb.num_joints
+    sm = SerialManipulator(M_list=rb.M, S_list=rb.S_list, joint_limits=[tuple(r) for r in rb.joint_limits])
+    none_T, none_th = np.empty((0, 4, 4)), np.empty((0, n))
+    th, ok, it = sm.iterative_inverse_kinematics(none_T, none_th, adaptive_tuning=True, backtracking=True)
+    assert th.shape == (0, n) and ok.shape == (0,) and it.shape == (0,)
+    th, ok, it = sm.smart_inverse_kinematics(none_T)
+    assert th.shape == (0, n) and ok.shape == (0,)
+    th, ok, it, win = sm.robust_inverse_kinematics(none_T)
+    assert th.shape == (0, n) and win.shape == (0,)
+    assert sm.end_effector_velocity(none_th, none_th).shape == (0, 6)
+    # one target as a batch of one keeps the batch axis
+    T1 = sm.forward_kinematics(np.full((1, n), 0.3))
+    th, ok, it = sm.smart_inverse_kinematics(T1, max_iterations=200)
+    assert th.shape == (1, n) and ok.shape == (1,) and bool(ok[0])
+    # device-resident targets
+    thd, okd, itd = sm.iterative_inverse_kinematics(torch.from_numpy(T1).cuda(), torch.full((1, n), 0.25, dtype=torch.float64).cuda(),
+                                                    backtracking=True)
+    assert thd.is_cuda and okd.dtype == torch.bool and bool(okd[0])
+    sg = Singularity(sm)
+    c = sg.condition_number(torch.full((3, n), 0.3, dtype=torch.float64).cuda())
+    assert c.is_cuda and c.shape == (3,) and bool((c > 1).all())
+    assert sg.singularity_analysis(np.empty((0, n))).shape == (0,)
+    assert sg.workspace_points([(-1, 1)] * n, 0).shape == (0, 3)
+    with pytest.raises(NotImplementedError):
+        sm.smart_inverse_kinematics(T1[0], strategy="cached", cache=object())
