@@ -153,15 +153,22 @@ size_t mpk_inverse_kinematics_workspace_bytes(int n, int64_t P);
  * smart_inverse_kinematics / robust_inverse_kinematics (ik.py:327-598) switch on:
  *   MPK_IK_ADAPTIVE_TUNING  Levenberg-Marquardt adaptation of the damping and of the step cap
  *   MPK_IK_BACKTRACKING     line search over the scales 1, 1/2, 1/4, 1/8, 3/4 of the capped step
- * flags = 0 is mpk_inverse_kinematics_dls. */
+ * flags = 0 is mpk_inverse_kinematics_dls.
+ *   restart_noise  dev (P, noise_rows, n) float64 standard normals, or NULL: restart r of target p adds
+ *                  0.1 x row (p, r) to the best iterate (ik.py:206-213).  A caller that draws the rows from
+ *                  NumPy's global generator reproduces the reference's restarts draw for draw; beyond
+ *                  noise_rows, or with NULL, the counter-based generator keyed by `seed` is used.
+ *   restarts       dev (P) int32: restarts taken per target (how many rows were consumed), or NULL */
 #define MPK_IK_ADAPTIVE_TUNING 1
 #define MPK_IK_BACKTRACKING 2
 int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, const double *T_desired,
                                      const double *theta0, double eomg, double ev, int max_iterations,
                                      double damping, double step_cap, double weight_orientation,
                                      double weight_position, const double *joint_limits, int flags,
-                                     uint64_t seed, double *theta, int32_t *iterations, uint8_t *success,
-                                     void *workspace, size_t workspace_bytes, void *stream);
+                                     uint64_t seed, const double *restart_noise, int noise_rows,
+                                     double *theta, int32_t *iterations, uint8_t *success,
+                                     int32_t *restarts, void *workspace, size_t workspace_bytes,
+                                     void *stream);
 
 /* ManipulatorDynamics.inverse_dynamics (dynamics/id_fd.py:16-48) batched, and
  * inverse_dynamics_trajectory (planning/trajectory_dynamics.py:308-380).

@@ -13,9 +13,11 @@
 // iterate lives in the thread's shared-memory row (odd stride, conflict free), the 6 x 6
 // system is solved by LDL^T in registers.  Lanes of a warp leave the loop as they converge.
 //
-// Deviation: the stagnation restart adds 0.1 * N(0, 1) noise; the reference draws it from
-// NumPy's global generator, this kernel from a counter-based generator keyed by (seed, target,
-// iteration).  Runs that never stagnate for 20 iterations -- the usual case -- do not touch it.
+// Stagnation restart noise (0.1 * N(0, 1) per joint): the reference draws it from NumPy's global
+// generator.  The caller may pass a table of standard normals per target (restart r uses row r) and
+// read back the number of restarts taken -- the Python mirror fills it from NumPy's generator for
+// single-target calls, which reproduces the reference draw for draw; without a table (batches) the
+// noise comes from a counter-based generator keyed by (seed, target, iteration).
 #include "mpk_common.cuh"
 
 namespace mpk {
@@ -32,14 +34,17 @@ struct IkArgs {
     unsigned char *success;
     void *workspace;  // IkQueue, or nullptr: one phase
     int k_split;      // iterations of phase 0
+    const double *noise;  // (P, noise_rows, n) standard normals for the stagnation restarts, or nullptr
+    int noise_rows;
+    int *restarts;        // (P) restarts taken, or nullptr
 };
 
 // Queue of unfinished targets between the two phases (device workspace supplied by the caller):
-// [count (8 bytes) | entries of (2 N + 7) 8-byte words: target index, best_err, (stall, k), the four
-// adaptive-tuning scalars, th, best].
+// [count (8 bytes) | entries of (2 N + 8) 8-byte words: target index, best_err, (stall, k), the four
+// adaptive-tuning scalars, the restart count, th, best].
 template <int N>
 struct IkQueue {
-    static constexpr int kWords = 2 * N + 7;
+    static constexpr int kWords = 2 * N + 8;
     unsigned long long *count;
     double *entries;
     __device__ __forceinline__ explicit IkQueue(void *ws)
@@ -53,10 +58,11 @@ struct IkQueue {
         e[4] = st.step_cap;
         e[5] = st.prev_err;
         e[6] = st.nu;
+        e[7] = __longlong_as_double((long long)st.restarts);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            e[7 + j] = st.th[j];
-            e[7 + N + j] = st.best[j];
+            e[8 + j] = st.th[j];
+            e[8 + N + j] = st.best[j];
         }
     }
     __device__ __forceinline__ int64_t pop(unsigned long long slot, IkState<double, N> &st) const {
@@ -69,10 +75,11 @@ struct IkQueue {
         st.step_cap = e[4];
         st.prev_err = e[5];
         st.nu = e[6];
+        st.restarts = (int)__double_as_longlong(e[7]);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            st.th[j] = e[7 + j];
-            st.best[j] = e[7 + N + j];
+            st.th[j] = e[8 + j];
+            st.best[j] = e[8 + N + j];
         }
         return __double_as_longlong(e[0]);
     }
@@ -110,7 +117,8 @@ __global__ void __launch_bounds__(kIkThreads)
     bool ok;
     int iters;
     const bool done = ik_dls_window<double, N>(rb, a.Td + p * 16, st, a.prm, a.seed, (unsigned long long)p,
-                                               jsm + threadIdx.x * S, k_stop, ok, iters);
+                                               jsm + threadIdx.x * S, k_stop, ok, iters,
+                                               a.noise ? a.noise + p * a.noise_rows * N : nullptr, a.noise_rows);
     if (!done) {
         IkQueue<N>(a.workspace).push(p, st);
         return;
@@ -119,6 +127,7 @@ __global__ void __launch_bounds__(kIkThreads)
     for (int j = 0; j < N; ++j) a.theta[p * N + j] = st.th[j];
     a.iters[p] = iters;
     a.success[p] = ok ? 1 : 0;
+    if (a.restarts) a.restarts[p] = st.restarts;
 }
 
 }  // namespace mpk
@@ -126,7 +135,7 @@ __global__ void __launch_bounds__(kIkThreads)
 using namespace mpk;
 
 extern "C" size_t mpk_inverse_kinematics_workspace_bytes(int n, int64_t P) {
-    return 16 + (size_t)(P > 0 ? P : 0) * (size_t)(2 * n + 7) * sizeof(double);
+    return 16 + (size_t)(P > 0 ? P : 0) * (size_t)(2 * n + 8) * sizeof(double);
 }
 
 extern "C" int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const double *T_desired,
@@ -137,8 +146,8 @@ extern "C" int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const 
                                           uint8_t *success, void *workspace, size_t workspace_bytes,
                                           void *stream) {
     return mpk_inverse_kinematics_dls_modes(rb, P, T_desired, theta0, eomg, ev, max_iterations, damping, step_cap,
-                                            weight_orientation, weight_position, joint_limits, 0, seed, theta,
-                                            iterations, success, workspace, workspace_bytes, stream);
+                                            weight_orientation, weight_position, joint_limits, 0, seed, nullptr, 0,
+                                            theta, iterations, success, nullptr, workspace, workspace_bytes, stream);
 }
 
 extern "C" int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, const double *T_desired,
@@ -146,8 +155,10 @@ extern "C" int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, 
                                                 int max_iterations, double damping, double step_cap,
                                                 double weight_orientation, double weight_position,
                                                 const double *joint_limits, int flags, uint64_t seed,
+                                                const double *restart_noise, int noise_rows,
                                                 double *theta, int32_t *iterations, uint8_t *success,
-                                                void *workspace, size_t workspace_bytes, void *stream) {
+                                                int32_t *restarts, void *workspace, size_t workspace_bytes,
+                                                void *stream) {
     if (!rb) return fail(MPK_EINVAL, "robot is NULL");
     if (flags & ~(MPK_IK_ADAPTIVE_TUNING | MPK_IK_BACKTRACKING)) return fail(MPK_EINVAL, "unknown flags");
     if (P < 0 || max_iterations < 0) return fail(MPK_EINVAL, "negative size");
@@ -161,6 +172,9 @@ extern "C" int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, 
     a.prm = make_ik_params(rb->n, eomg, ev, max_iterations, damping, step_cap, weight_orientation,
                            weight_position, joint_limits, flags);
     a.seed = seed;
+    a.noise = noise_rows > 0 ? restart_noise : nullptr;
+    a.noise_rows = a.noise ? noise_rows : 0;
+    a.restarts = restarts;
     a.theta = theta;
     a.iters = iterations;
     a.success = success;

@@ -1365,6 +1365,7 @@ struct IkState {
     T th[N], best[N];
     double best_err;
     int stall, k;
+    int restarts;  // stagnation restarts taken so far (row of the caller's noise table to use next)
     // adaptive_tuning (unused otherwise): current lambda and step cap, last error, growth factor
     double damping, step_cap, prev_err, nu;
 };
@@ -1376,6 +1377,7 @@ MPK_HD void ik_state_init(IkState<T, N> &st, const T (&th0)[N], const IkParams<T
     st.best_err = INFINITY;
     st.stall = 0;
     st.k = 0;
+    st.restarts = 0;
     st.damping = prm.damping;
     st.step_cap = prm.step_cap;
     st.prev_err = INFINITY;
@@ -1399,10 +1401,15 @@ MPK_HD double ik_pose_error(const RobotPack<T, N> &rb, const T (&th)[N], const d
 // best-iterate fall-back of ik.py:264-275 has been applied): st.th is the answer, `ok` the
 // success flag, `iterations` the reference's count (k + 1; max_iter + 1 when exhausted).
 // Returns false when k_stop was reached first: st carries everything the next window needs.
+// noise: this target's table of standard normals for the stagnation restarts, `noise_rows` rows of
+// N (restart r uses row r), or nullptr / exhausted: the counter-based generator keyed by (seed,
+// target, iteration).  A caller that fills the table from NumPy's global generator reproduces the
+// reference's restarts draw for draw (Python mirror: single-target calls).
 template <typename T, int N>
 MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T, N> &st,
                           const IkParams<T, MPK_MAX_DOF_> &prm, unsigned long long seed,
-                          unsigned long long target, T *J, int k_stop, bool &ok, int &iterations) {
+                          unsigned long long target, T *J, int k_stop, bool &ok, int &iterations,
+                          const double *noise = nullptr, int noise_rows = 0) {
     T (&th)[N] = st.th;
     double cur = INFINITY, rot = 0.0, trans = 0.0;
     int k = st.k;
@@ -1428,11 +1435,15 @@ MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T
         }
         if (st.stall > 20) {
             // stagnation restart around the best iterate (ik.py:206-213)
+            const bool tabled = noise != nullptr && st.restarts < noise_rows;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const T x = st.best[j] + 0.1 * ik_normal(seed, target, (unsigned long long)k * N + j);
+                const double z = tabled ? ld_ro(noise + (int64_t)st.restarts * N + j)
+                                        : ik_normal(seed, target, (unsigned long long)k * N + j);
+                const T x = st.best[j] + 0.1 * z;
                 th[j] = fmin(fmax(x, prm.lo[j]), prm.hi[j]);
             }
+            ++st.restarts;
             st.stall = 0;
             st.damping = prm.damping;
             st.nu = 2.0;
@@ -1536,11 +1547,13 @@ MPK_HD bool ik_dls_window(const RobotPack<T, N> &rb, const double *Td, IkState<T
 // One target, whole iteration budget.  th: initial guess in, solution out.
 template <typename T, int N>
 MPK_HD bool ik_dls(const RobotPack<T, N> &rb, const double *Td, T (&th)[N], const IkParams<T, MPK_MAX_DOF_> &prm,
-                   unsigned long long seed, unsigned long long target, T *J, int &iterations) {
+                   unsigned long long seed, unsigned long long target, T *J, int &iterations,
+                   const double *noise = nullptr, int noise_rows = 0, int *restarts = nullptr) {
     IkState<T, N> st;
     ik_state_init(st, th, prm);
     bool ok;
-    ik_dls_window(rb, Td, st, prm, seed, target, J, prm.max_iter, ok, iterations);
+    ik_dls_window(rb, Td, st, prm, seed, target, J, prm.max_iter, ok, iterations, noise, noise_rows);
+    if (restarts) *restarts = st.restarts;
 #pragma unroll
     for (int j = 0; j < N; ++j) th[j] = st.th[j];
     return ok;

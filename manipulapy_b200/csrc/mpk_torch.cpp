@@ -268,10 +268,10 @@ std::tuple<Tensor, Tensor, Tensor> forward_dynamics_trajectory(
     return {pos, vel, acc};
 }
 
-std::tuple<Tensor, Tensor, Tensor> inverse_kinematics_dls(
+std::tuple<Tensor, Tensor, Tensor, Tensor> inverse_kinematics_dls(
     int64_t h, const Tensor &T_desired, const Tensor &theta0, double eomg, double ev, int64_t max_iterations,
     double damping, double step_cap, double weight_orientation, double weight_position, const OptT &limits,
-    int64_t seed, bool two_phase, int64_t flags) {
+    int64_t seed, bool two_phase, int64_t flags, const OptT &restart_noise) {
     mpk_robot *rb = robot(h);
     const int64_t n = mpk_robot_dof(rb);
     Tensor th0 = dev_rows(theta0, n, "thetalist0", false);
@@ -288,16 +288,26 @@ std::tuple<Tensor, Tensor, Tensor> inverse_kinematics_dls(
     Tensor theta = at::empty({P, n}, th0.options());
     Tensor iters = at::empty({P}, th0.options().dtype(at::kInt));
     Tensor ok = at::empty({P}, th0.options().dtype(at::kByte));
+    Tensor restarts = at::empty({P}, th0.options().dtype(at::kInt));
+    Tensor noise;
+    int noise_rows = 0;
+    if (restart_noise.has_value() && P > 0) {
+        TORCH_CHECK(restart_noise->is_cuda() && restart_noise->numel() % (P * n) == 0,
+                    "mpk: restart_noise must be a CUDA (P, rows, n) tensor");
+        noise = restart_noise->to(at::kDouble).contiguous();
+        noise_rows = (int)(noise.numel() / (P * n));
+    }
     const size_t ws_bytes = two_phase ? mpk_inverse_kinematics_workspace_bytes((int)n, P) : 0;
     Tensor ws = at::empty({(int64_t)(ws_bytes / 8) + 1}, th0.options());
     check(mpk_inverse_kinematics_dls_modes(rb, P, Td.data_ptr<double>(), th0.data_ptr<double>(), eomg, ev,
                                            (int)max_iterations, damping, step_cap, weight_orientation,
                                            weight_position, lim.empty() ? nullptr : lim.data(), (int)flags,
-                                           (uint64_t)seed, theta.data_ptr<double>(), iters.data_ptr<int32_t>(),
-                                           ok.data_ptr<uint8_t>(), two_phase ? ws.data_ptr() : nullptr, ws_bytes,
-                                           stream_of(th0)),
+                                           (uint64_t)seed, noise_rows ? noise.data_ptr<double>() : nullptr, noise_rows,
+                                           theta.data_ptr<double>(), iters.data_ptr<int32_t>(),
+                                           ok.data_ptr<uint8_t>(), restarts.data_ptr<int32_t>(),
+                                           two_phase ? ws.data_ptr() : nullptr, ws_bytes, stream_of(th0)),
           "inverse_kinematics_dls");
-    return {theta, ok, iters};
+    return {theta, ok, iters, restarts};
 }
 
 std::tuple<Tensor, Tensor, Tensor, Tensor> cartesian_trajectory(const Tensor &Xstart, const Tensor &Xend, double Tf,
@@ -356,7 +366,8 @@ TORCH_LIBRARY(mpk, m) {
           &forward_dynamics_trajectory);
     m.def("inverse_kinematics_dls(int robot, Tensor T_desired, Tensor theta0, float eomg, float ev, "
           "int max_iterations, float damping, float step_cap, float weight_orientation, float weight_position, "
-          "Tensor? joint_limits, int seed, bool two_phase=True, int flags=0) -> (Tensor, Tensor, Tensor)",
+          "Tensor? joint_limits, int seed, bool two_phase=True, int flags=0, Tensor? restart_noise=None) -> "
+          "(Tensor, Tensor, Tensor, Tensor)",
           &inverse_kinematics_dls);
     m.def("cartesian_trajectory(Tensor Xstart, Tensor Xend, float Tf, int N, int method) -> "
           "(Tensor, Tensor, Tensor, Tensor)",

@@ -73,6 +73,23 @@ class RobotHandle:
                 pass
 
 
+def restart_noise_table(n: int, max_iterations: int):
+    """Standard normals for the stagnation restarts of ONE iterative_inverse_kinematics run, drawn
+    from NumPy's global generator exactly as the reference would draw them (``np.random.randn(n)``
+    per restart, kinematics/ik.py:208), for as many restarts as the iteration budget allows (one
+    per 21 iterations).  Returns ``(table (rows, n), generator state before the draws)``."""
+    state = np.random.get_state()
+    rows = max(1, int(max_iterations) // 21 + 1)
+    return np.stack([np.random.randn(n) for _ in range(rows)]), state
+
+
+def settle_generator(state, n: int, restarts: int) -> None:
+    """Leave NumPy's global generator where the reference would: advanced by ``restarts`` draws."""
+    np.random.set_state(state)
+    for _ in range(int(restarts)):
+        np.random.randn(n)
+
+
 class SerialManipulator:
     """Kinematic model of a serial manipulator (space-frame product of exponentials)."""
 
@@ -203,8 +220,10 @@ class SerialManipulator:
         Reference call: ``T_desired (4, 4)``, ``thetalist0 (n,)`` -> ``(theta (n,), success, iterations)``.
         Batched extension: ``(P, 4, 4)``, ``(P, n)`` -> ``(theta (P, n), success (P,) bool,
         iterations (P,) int32)``, one target per GPU thread.  ``plot_residuals`` is not part of the
-        kernel.  ``seed`` keys the noise of the stagnation restart (the reference draws it from
-        NumPy's global generator)."""
+        kernel.  Stagnation restarts (a 0.1 sigma kick off the best iterate after 20 iterations
+        without progress): a single-target call on host arrays takes that noise from NumPy's global
+        generator draw for draw like the reference, and leaves the generator where the reference
+        would; batched and device-resident calls use a counter-based generator keyed by ``seed``."""
         if plot_residuals:
             raise NotImplementedError("plot_residuals is outside the B200 hot path (no plotting)")
         flags = (1 if adaptive_tuning else 0) | (2 if backtracking else 0)
@@ -222,9 +241,15 @@ class SerialManipulator:
         for i in range(n):
             mn, mx = (self.joint_limits[i] if i < len(self.joint_limits) else (None, None))
             lim[i] = (-np.inf if mn is None else mn, np.inf if mx is None else mx)
-        theta, ok, it = _native.ops().inverse_kinematics_dls(
+        noise = state = None
+        if single and not on_dev and int(max_iterations) > 20:
+            table, state = restart_noise_table(n, int(max_iterations))
+            noise = torch.from_numpy(table).to(dev).reshape(1, -1, n)
+        theta, ok, it, restarts = _native.ops().inverse_kinematics_dls(
             self.robot.handle, Td, th0, float(eomg), float(ev), int(max_iterations), float(damping), float(step_cap),
-            float(weight_orientation), float(weight_position), torch.from_numpy(lim), int(seed), True, flags)
+            float(weight_orientation), float(weight_position), torch.from_numpy(lim), int(seed), True, flags, noise)
+        if state is not None:
+            settle_generator(state, n, int(restarts[0].item()))
         ok = ok.bool()
         if single:
             th1 = theta[0] if on_dev else _host.to_host(theta[0])
@@ -272,9 +297,12 @@ class SerialManipulator:
         Td, single = self._ik_batch(T_desired)
 
         def solve(Tds, th0):
-            return self.iterative_inverse_kinematics(Tds, th0, eomg, ev, max_iterations, plot_residuals, damping,
-                                                     step_cap, png_name, weight_orientation, weight_position,
-                                                     adaptive_tuning, backtracking, seed=seed)
+            args = (eomg, ev, max_iterations, plot_residuals, damping, step_cap, png_name, weight_orientation,
+                    weight_position, adaptive_tuning, backtracking)
+            if single:  # the reference's call: restart noise from NumPy's generator, like the guesses
+                th, ok, it = self.iterative_inverse_kinematics(Tds[0], th0[0], *args)
+                return th[None], np.array([ok]), np.array([it])
+            return self.iterative_inverse_kinematics(Tds, th0, *args, seed=seed)
 
         theta, ok, it = ik_helpers.smart_driver(solve, self.forward_kinematics, Td, self.num_joints,
                                                 self._ik_limits(), strategy, auto_fallback)
@@ -293,9 +321,11 @@ class SerialManipulator:
         Td, single = self._ik_batch(T_desired)
 
         def solve(Tds, th0, damping, step_cap):
-            return self.iterative_inverse_kinematics(Tds, th0, eomg, ev, max_iterations, damping=damping,
-                                                     step_cap=step_cap, adaptive_tuning=True, backtracking=True,
-                                                     seed=seed)
+            kw = dict(damping=damping, step_cap=step_cap, adaptive_tuning=True, backtracking=True)
+            if single:
+                th, ok, it = self.iterative_inverse_kinematics(Tds[0], th0[0], eomg, ev, max_iterations, **kw)
+                return th[None], np.array([ok]), np.array([it])
+            return self.iterative_inverse_kinematics(Tds, th0, eomg, ev, max_iterations, seed=seed, **kw)
 
         theta, ok, it, win = ik_helpers.robust_driver(solve, self.forward_kinematics, Td, self.num_joints,
                                                       self._ik_limits(), max_attempts)

@@ -204,17 +204,32 @@ class HostCheck:
 
     def ik(self, rb, Td, th0, eomg=1e-6, ev=1e-6, max_iterations=10000, damping=2e-2, step_cap=0.3,
            weight_orientation=1.0, weight_position=1.0, limits=None, seed=0, adaptive_tuning=False,
-           backtracking=False):
+           backtracking=False, numpy_restarts=False):
         h, n = rb
         Td = np.ascontiguousarray(Td, dtype=np.float64).reshape(-1, 4, 4)
         th0 = np.ascontiguousarray(th0, dtype=np.float64).reshape(-1, n)
         P = Td.shape[0]
         lim = None if limits is None else np.ascontiguousarray(limits, dtype=np.float64).reshape(n, 2)
         th, it, ok = np.empty((P, n)), np.empty(P, np.int32), np.empty(P, np.uint8)
+        if numpy_restarts:
+            # the Python mirror's protocol for single-target calls (kinematics.py): restart noise drawn
+            # from NumPy's global generator, which is then left where the reference would leave it
+            from manipulapy_b200.kinematics import restart_noise_table, settle_generator
+
+            assert P == 1
+            noise, state = restart_noise_table(n, int(max_iterations))
+            rs = np.zeros(1, np.int32)
+            self.H.hc_ik(h, _C.c_int64(P), _ptr(Td), _ptr(th0), _C.c_double(eomg), _C.c_double(ev),
+                         int(max_iterations), _C.c_double(damping), _C.c_double(step_cap),
+                         _C.c_double(weight_orientation), _C.c_double(weight_position), _ptr(lim), _C.c_uint64(seed),
+                         _ptr(th), _ptr(it), _ptr(ok), (1 if adaptive_tuning else 0) | (2 if backtracking else 0),
+                         _ptr(noise), int(noise.shape[0]), _ptr(rs))
+            settle_generator(state, n, int(rs[0]))
+            return th, ok.astype(bool), it
         self.H.hc_ik(h, _C.c_int64(P), _ptr(Td), _ptr(th0), _C.c_double(eomg), _C.c_double(ev), int(max_iterations),
                      _C.c_double(damping), _C.c_double(step_cap), _C.c_double(weight_orientation),
                      _C.c_double(weight_position), _ptr(lim), _C.c_uint64(seed), _ptr(th), _ptr(it), _ptr(ok),
-                     (1 if adaptive_tuning else 0) | (2 if backtracking else 0))
+                     (1 if adaptive_tuning else 0) | (2 if backtracking else 0), None, 0, None)
         return th, ok.astype(bool), it
 
     def cartesian(self, Xs, Xe, Tf, N, method):

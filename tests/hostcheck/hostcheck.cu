@@ -222,13 +222,16 @@ extern "C" int hc_fk_f32(const mpk_robot *rb, int64_t P, const double *th, doubl
 template <int N>
 static void ik_n(const mpk_robot *rb, int64_t P, const double *Td, const double *th0,
                  const IkParams<double, MPK_MAX_DOF> &prm, unsigned long long seed, double *theta, int *iters,
-                 unsigned char *ok) {
+                 unsigned char *ok, const double *noise, int noise_rows, int *restarts) {
     const RobotPack<double, N> pk = narrow<N>(rb);
     for (int64_t p = 0; p < P; ++p) {
         double th[N], J[6 * N + 1];
         for (int j = 0; j < N; ++j) th[j] = th0[p * N + j];
         int it = 0;
-        ok[p] = ik_dls<double, N>(pk, Td + 16 * p, th, prm, seed, (unsigned long long)p, J, it) ? 1 : 0;
+        int rs = 0;
+        ok[p] = ik_dls<double, N>(pk, Td + 16 * p, th, prm, seed, (unsigned long long)p, J, it,
+                                  noise ? noise + p * noise_rows * N : nullptr, noise_rows, &rs) ? 1 : 0;
+        if (restarts) restarts[p] = rs;
         iters[p] = it;
         for (int j = 0; j < N; ++j) theta[p * N + j] = th[j];
     }
@@ -236,10 +239,10 @@ static void ik_n(const mpk_robot *rb, int64_t P, const double *Td, const double 
 extern "C" int hc_ik(const mpk_robot *rb, int64_t P, const double *Td, const double *th0, double eomg, double ev,
                      int max_iterations, double damping, double step_cap, double w_rot, double w_pos,
                      const double *limits, unsigned long long seed, double *theta, int *iters,
-                     unsigned char *ok, int flags) {
+                     unsigned char *ok, int flags, const double *noise, int noise_rows, int *restarts) {
     const IkParams<double, MPK_MAX_DOF> prm =
         make_ik_params(rb->n, eomg, ev, max_iterations, damping, step_cap, w_rot, w_pos, limits, flags);
-    HC_DISPATCH(rb->n, ik_n<N_>(rb, P, Td, th0, prm, seed, theta, iters, ok));
+    HC_DISPATCH(rb->n, ik_n<N_>(rb, P, Td, th0, prm, seed, theta, iters, ok, noise, noise_rows, restarts));
     return 0;
 }
 extern "C" int hc_cartesian(int64_t N, const double *Xs, const double *Xe, double Tf, int method, float *pos,
