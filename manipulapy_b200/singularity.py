@@ -11,7 +11,7 @@ end-effector positions (and their convex hull on request) instead of drawing the
 
 from __future__ import annotations
 
-from typing import Any, List, Optional, Sequence, Tuple
+from typing import Any, List, Sequence, Tuple
 
 import numpy as np
 import torch

@@ -6,7 +6,6 @@ TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.
 from __future__ import annotations
 
 import ctypes as C
-import os
 import subprocess
 from pathlib import Path
 from typing import Optional

@@ -1,7 +1,11 @@
-import sys, json
+"""Fused trajectory + inverse-dynamics kernel across the bundled robots (device time per launch)."""
+import sys
 from pathlib import Path
-import numpy as np, torch
-sys.path.insert(0, "/root/repo")
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from manipulapy_b200 import _native, load_robot
 dev = torch.device("cuda", 0)
 ops = _native.ops()
