@@ -144,9 +144,9 @@ int mpk_inverse_kinematics_dls(const mpk_robot *rb, int64_t P, const double *T_d
                                double *theta, int32_t *iterations, uint8_t *success, void *workspace,
                                size_t workspace_bytes, void *stream);
 /*   workspace  dev scratch of mpk_inverse_kinematics_workspace_bytes(n, P) bytes, or NULL.  With
- *              it, targets still running after 64 iterations are queued and finished by a second,
- *              densely packed launch (a warp otherwise lives as long as its slowest target);
- *              results are identical either way. */
+ *              it, targets still running after 16, 32, 64, ... iterations are queued and continued by
+ *              further, densely packed launches (a warp otherwise lives as long as its slowest
+ *              target); results are identical either way. */
 size_t mpk_inverse_kinematics_workspace_bytes(int n, int64_t P);
 
 /* The same solver with the reference's optional modes (kinematics/ik.py:215-229, 253-276), which

@@ -129,6 +129,12 @@ def main():
                 128 + 8 * n + 8 * n + 5, 1400 * float(sol[2].float().mean()), "targets")
             rec("ik_dls_one_phase_iiwa14", Pi, timeit(lambda: ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0, False), 3, 1),
                 128 + 8 * n + 8 * n + 5, 1400 * float(sol[2].float().mean()), "targets")
+            # the same targets with adaptive tuning + line search (flags 3), as smart_ / robust_inverse_kinematics run it
+            solm = ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0, True, 3)
+            res["ik_dls_modes_iiwa14_success_rate"] = float(solm[1].float().mean())
+            res["ik_dls_modes_iiwa14_mean_iterations"] = float(solm[2].float().mean())
+            rec("ik_dls_modes_iiwa14", Pi, timeit(lambda: ops.inverse_kinematics_dls(h, Td, seed, 1e-6, 1e-6, 400, 2e-2, 0.3, 1.0, 1.0, lim, 0, True, 3), 3, 1),
+                128 + 8 * n + 8 * n + 5, (1400 + 5 * 350) * float(solm[2].float().mean()), "targets")
         dth, tau = rand(Pk, n), rand(Pk, n, lo=-20, hi=20)
         rec(f"forward_dynamics_{name}", Pk, timeit(lambda: ops.forward_dynamics(h, th, dth, tau, g, None, None)), 32 * n, 5300, "points")
 

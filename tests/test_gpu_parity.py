@@ -402,7 +402,7 @@ def test_batched_inverse_kinematics(robot):
     assert np.abs(T[ok] - Td[ok])[:, :3, 3].max() < 2e-6 and np.abs(T[ok] - Td[ok])[:, :3, :3].max() < 2e-6
     assert (it[ok] <= 400).all() and (it[~ok] == 401).all()
     assert (th >= lo - 1e-12).all() and (th <= hi + 1e-12).all()
-    # the two-phase schedule (stragglers re-packed after 64 iterations) changes no iterate
+    # the re-packing ladder (stragglers re-packed after 16, 32, 64, ... iterations) changes no iterate
     from manipulapy_b200 import _native
     dev = torch.device("cuda")
     args = (sm.robot.handle, torch.from_numpy(Td).to(dev), torch.from_numpy(tgt + 0.25).to(dev), 1e-6, 1e-6, 400, 2e-2,
@@ -469,7 +469,7 @@ def test_inverse_kinematics_modes_and_front_ends(robot):
     assert ik_helpers.pose_error(sm.forward_kinematics(th[ok]), Td[ok]).max() < 1e-5
     plain = sm.smart_inverse_kinematics(Td, max_iterations=150, auto_fallback=False)[1]
     assert ok.sum() >= plain.sum()  # the fall-back starts only add solutions
-    # the two-phase schedule carries the adaptive-tuning state of the stragglers through its queue
+    # the re-packing ladder carries the adaptive-tuning state of the stragglers through its queues
     from manipulapy_b200 import _native
     dev = torch.device("cuda")
     th0 = ik_helpers.workspace_heuristic_guess(Td, len(lim), lim)
