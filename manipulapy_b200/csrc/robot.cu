@@ -302,7 +302,7 @@ double build_frames(int n, Line *L, RobotPack<double, MPK_MAX_DOF> &pk, SE3 *F) 
 
 using namespace mpk;
 
-extern "C" int mpk_version(void) { return 100; }
+extern "C" int mpk_version(void) { return 110; }  // 110: + mpk_inverse_kinematics_dls_modes
 extern "C" const char *mpk_last_error(void) { return g_err.c_str(); }
 
 extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, const double *Glist,
