@@ -239,6 +239,12 @@ int mpk_forward_dynamics_trajectory(const mpk_robot *rb, int64_t B, int64_t N, c
  * Runs `iters` dependent-chain FMAs x 8 chains per thread; flops = grid*block*iters*8*2. */
 int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, double *sink_dev, void *stream);
 
+/* Store-bandwidth micro-benchmark: `blocks` x 256 threads write `bytes` (a multiple of 16) to
+ * dst_dev with 16-byte vector stores, grid-strided.  mode 0 st.global, 1 st.global.cs (what the
+ * row-writing kernels use), 2 .cg, 3 .wt.  bench.py / scripts/microbench.py time it with CUDA
+ * events to get the write-only HBM ceiling the trajectory kernel's roofline is quoted against. */
+int mpk_store_peak(void *dst_dev, int64_t bytes, int mode, int blocks, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,15 @@ def to_device(x: Any, device: torch.device, dtype: Optional[torch.dtype] = torch
     return t.to(device).to(want).contiguous()
 
 
+def promote_rows(*ts: Optional[torch.Tensor]):
+    """Common storage type of the row inputs of one call: float32 only when EVERY row array is
+    float32 (then the rows stay float32 in HBM and are upcast exactly in registers); any float64
+    input promotes all of them to float64, as NumPy promotion does in the reference."""
+    live = [t for t in ts if t is not None]
+    want = torch.float32 if live and all(t.dtype == torch.float32 for t in live) else torch.float64
+    return tuple(None if t is None else (t if t.dtype == want else t.to(want)) for t in ts)
+
+
 def to_host(t: torch.Tensor) -> np.ndarray:
     """CUDA tensor -> fresh NumPy array (through pinned memory for large results)."""
     if t.numel() >= (1 << 16):

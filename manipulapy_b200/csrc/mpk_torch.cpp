@@ -336,6 +336,12 @@ void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads
           "fma_peak");
 }
 
+void store_peak(const Tensor &dst, int64_t mode, int64_t blocks) {
+    TORCH_CHECK(dst.is_cuda() && dst.is_contiguous(), "mpk: dst must be a contiguous CUDA tensor");
+    c10::cuda::CUDAGuard guard(dst.device());
+    check(mpk_store_peak(dst.data_ptr(), (int64_t)dst.nbytes(), (int)mode, (int)blocks, stream_of(dst)), "store_peak");
+}
+
 }  // namespace
 
 TORCH_LIBRARY(mpk, m) {
@@ -373,4 +379,5 @@ TORCH_LIBRARY(mpk, m) {
           "(Tensor, Tensor, Tensor, Tensor)",
           &cartesian_trajectory);
     m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
+    m.def("store_peak(Tensor dst, int mode, int blocks) -> ()", &store_peak);
 }

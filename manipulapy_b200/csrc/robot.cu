@@ -471,7 +471,8 @@ extern "C" int mpk_robot_all_revolute(const mpk_robot *rb) { return rb ? rb->all
 // mode 1: 12 registers rotating, x_k = fma(x_{k+1}, x_{k+2}, x_{k+3}): three DISTINCT register
 //         operands per instruction, like the rigid-body algebra of the kernels;
 // mode 2: mode 1 with one operand taken from the constant bank (a kernel parameter);
-// mode 3: the planar-rotation pattern of the kernels: DMUL + DFMA pairs on distinct registers.
+// mode 3: the planar-rotation pattern of the kernels: DMUL + DFMA pairs on distinct registers
+//         (two dependent rotations per iteration; every operand is rewritten in the loop).
 // All modes execute 16 flops per loop iteration per chain slot so the callers' flop count
 // (blocks * threads * iters * 16) holds: modes 1-3 run 8 instructions per iteration too.
 struct PeakConsts {
@@ -492,6 +493,7 @@ __global__ void fma_peak_kernel(int64_t iters, double *sink, const __grid_consta
         if (s == T(-1.2345)) sink[0] = (double)s;  // never true; keeps the chains alive
     } else {
         T x[12];
+        unsigned iq[4] = {threadIdx.x, threadIdx.x * 3u + 1u, threadIdx.x * 5u + 2u, threadIdx.x * 7u + 3u};
 #pragma unroll
         for (int k = 0; k < 12; ++k) x[k] = T(0.5) + T(threadIdx.x + k) * T(1e-4);
         for (int64_t i = 0; i < iters; ++i) {
@@ -510,17 +512,45 @@ __global__ void fma_peak_kernel(int64_t iters, double *sink, const __grid_consta
                 // three registers, but consecutive instructions share their middle operand (.reuse)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) x[k] = x[k + 1] * x[(k < 4) ? 10 : 11] - x[k + 3];
+            } else if (MODE == 7 || MODE == 8) {
+                // each DFMA (7: three registers; 8: one constant-bank operand) followed by one 32-bit
+                // integer multiply-add on three registers: does instruction issue / register-file
+                // bandwidth taken by the non-fp64 half of a kernel slow the fp64 pipe down?
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    x[k] = MODE == 7 ? x[k + 1] * x[k + 2] - x[k + 3] : x[k + 1] * T(pc.k[k]) - x[k + 3];
+                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(iq[k & 3]) : "r"(iq[(k + 1) & 3]), "r"(iq[(k + 2) & 3]));
+                }
             } else if (MODE == 6) {
                 // three registers, consecutive instructions share TWO operands pairwise (a*b - c, a*b' - c)
 #pragma unroll
                 for (int k = 0; k < 8; ++k) x[k] = x[(k & ~1) + 1] * x[k + 2] - x[(k & ~1) + 3];
             } else {
-                // 4 x (t = c*p (DMUL); p' = t - s*q (DFMA)): 8 instructions, 12 flops (counted as 16)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const T t = x[2 * k + 1] * x[2 * k + 2];
-                    x[2 * k] = t - x[2 * k + 3] * x[(2 * k + 5) % 12];
+                // the planar-rotation pattern of the kernels, p' = c p - s q, q' = s p + c q: two DMUL +
+                // two DFMA on distinct registers per rotation, two rotations per iteration (8
+                // instructions, 12 flops -- counted as 16).  Every register the loop reads is also
+                // written by it, so nothing is loop-invariant.  (The round-1 version of this mode left
+                // x[1], x[3], x[5], x[7] unwritten: ptxas hoisted two of its four DMULs out of the loop,
+                // the loop body had 6 instructions where the caller counted 8, and the reported rate came
+                // out 8/6 above the pipe's peak -- profiles/r2_fp64_operand_patterns.md.)
+                {
+                    const T p = x[0], q = x[1], c = x[2], sn = x[3];
+                    const T t0 = sn * q, t1 = sn * p;
+                    x[0] = c * p - t0;
+                    x[1] = c * q + t1;
                 }
+                {
+                    const T p = x[2], q = x[3], c = x[0], sn = x[1];
+                    const T t0 = sn * q, t1 = sn * p;
+                    x[2] = c * p - t0;
+                    x[3] = c * q + t1;
+                }
+                // keep the values bounded (the rotation scales by |(c, s)|): renormalising would add
+                // instructions, so the chains are re-seeded from the untouched registers instead
+                if ((i & 63) == 63) {
+                    x[0] = x[4]; x[1] = x[5]; x[2] = x[6]; x[3] = x[7];
+                }
+                continue;
             }
             // rotate so that the next iteration's operands are other registers
             const T t0 = x[8];
@@ -529,7 +559,24 @@ __global__ void fma_peak_kernel(int64_t iters, double *sink, const __grid_consta
         T s = T(0);
 #pragma unroll
         for (int k = 0; k < 12; ++k) s += x[k];
-        if (s == T(-1.2345)) sink[0] = (double)s;
+        if (s == T(-1.2345) || (iq[0] ^ iq[1] ^ iq[2] ^ iq[3]) == 0x12345u) sink[0] = (double)s;
+    }
+}
+
+// ---- store-bandwidth micro-benchmark ---------------------------------------------------
+// The write-only ceiling of this GPU's HBM for the roofline of the store-bound kernels (trajectory
+// rows): every thread writes 16-byte vectors, a warp 512 contiguous bytes per instruction.
+//   mode 0: st.global (default, write-back)   mode 1: st.global.cs (streaming, what the kernels use)
+//   mode 2: st.global.cg                      mode 3: st.global.wt
+template <int MODE>
+__global__ void __launch_bounds__(256) store_peak_kernel(float4 *dst, int64_t n16) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float4 v = make_float4(1.f, 2.f, 3.f, (float)blockIdx.x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+        if (MODE == 0) dst[i] = v;
+        else if (MODE == 1) __stcs(dst + i, v);
+        else if (MODE == 2) __stcg(dst + i, v);
+        else __stwt(dst + i, v);
     }
 }
 
@@ -549,8 +596,23 @@ extern "C" int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, d
     else if (dtype == MPK_F64 && mode == 4) fma_peak_kernel<double, 4><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F64 && mode == 5) fma_peak_kernel<double, 5><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F64 && mode == 6) fma_peak_kernel<double, 6><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 7) fma_peak_kernel<double, 7><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
+    else if (dtype == MPK_F64 && mode == 8) fma_peak_kernel<double, 8><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F32 && mode == 0) fma_peak_kernel<float, 0><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else if (dtype == MPK_F32 && mode == 1) fma_peak_kernel<float, 1><<<blocks, threads, 0, s>>>(iters, sink_dev, pc);
     else return fail(MPK_EINVAL, "bad dtype / mode");
     return check_launch("fma_peak");
+}
+
+extern "C" int mpk_store_peak(void *dst_dev, int64_t bytes, int mode, int blocks, void *stream) {
+    if (!dst_dev || bytes < 16 || !aligned16(dst_dev) || blocks <= 0 || mode < 0 || mode > 3)
+        return fail(MPK_EINVAL, "bad store_peak arguments");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    float4 *d = static_cast<float4 *>(dst_dev);
+    const int64_t n16 = bytes / 16;
+    if (mode == 0) store_peak_kernel<0><<<blocks, 256, 0, s>>>(d, n16);
+    else if (mode == 1) store_peak_kernel<1><<<blocks, 256, 0, s>>>(d, n16);
+    else if (mode == 2) store_peak_kernel<2><<<blocks, 256, 0, s>>>(d, n16);
+    else store_peak_kernel<3><<<blocks, 256, 0, s>>>(d, n16);
+    return check_launch("store_peak");
 }

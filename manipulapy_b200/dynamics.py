@@ -93,7 +93,8 @@ class ManipulatorDynamics(SerialManipulator):
     def velocity_quadratic_forces(self, thetalist, dthetalist, precision=None):
         th, single, on_dev = self._rows(thetalist, "thetalist")
         dth, _, _ = self._rows(dthetalist, "dthetalist")
-        c = self._id(th, dth.to(th.dtype), None, [0.0, 0.0, 0.0], None, precision=precision)
+        th, dth = _host.promote_rows(th, dth)
+        c = self._id(th, dth, None, [0.0, 0.0, 0.0], None, precision=precision)
         return self._finish(c, single, on_dev)
 
     def gravity_forces(self, thetalist, g=None, precision=None):
@@ -106,7 +107,8 @@ class ManipulatorDynamics(SerialManipulator):
         th, single, on_dev = self._rows(thetalist, "thetalist")
         dth, _, _ = self._rows(dthetalist, "dthetalist")
         ddth, _, _ = self._rows(ddthetalist, "ddthetalist")
-        tau = self._id(th, dth.to(th.dtype), ddth.to(th.dtype), _host.gravity(g), Ftip, precision=precision)
+        th, dth, ddth = _host.promote_rows(th, dth, ddth)
+        tau = self._id(th, dth, ddth, _host.gravity(g), Ftip, precision=precision)
         return self._finish(tau, single, on_dev)
 
     def forward_dynamics(self, thetalist, dthetalist, taulist, g=None, Ftip=None):

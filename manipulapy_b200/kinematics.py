@@ -5,9 +5,13 @@
 (kinematics/jacobian.py:39-93) accept a single ``(n,)`` configuration (reference behaviour:
 returns ``(4, 4)`` / ``(6, n)`` float64) or a batch ``(P, n)`` (returns ``(P, 4, 4)`` /
 ``(P, 6, n)``), in the space or the body frame.  Both run in hand-written CUDA kernels; there
-is no CPU path.  ``iterative_inverse_kinematics`` (kinematics/ik.py:39-311, default mode) runs
-one target per thread in a batched damped-least-squares kernel; the other IK front ends
-(smart / robust / trac_ik) are out of scope.
+is no CPU path.  ``iterative_inverse_kinematics`` (kinematics/ik.py:39-311, all modes) runs
+one target per thread in a batched damped-least-squares kernel; ``smart_`` / ``robust_inverse_kinematics``
+(:327-598) are host restart logic around it (``ik_helpers``); ``trac_ik`` is out of scope.
+
+Not a blanket drop-in for the reference classes: ``OptimizedTrajectoryPlanning`` needs THIS
+package's ``ManipulatorDynamics`` (a reference object is wrapped automatically through
+``ManipulatorDynamics.from_reference``) and raises on ``use_cuda=False``.
 """
 
 from __future__ import annotations

@@ -156,8 +156,9 @@ class OptimizedTrajectoryPlanning:
         th = _host.to_device(thetalist_trajectory, dev, keep_f32=True)
         shape = tuple(th.shape)
         th = th.reshape(-1, n)
-        dth = _host.to_device(dthetalist_trajectory, dev, keep_f32=True).reshape(-1, n).to(th.dtype)
-        ddth = _host.to_device(ddthetalist_trajectory, dev, keep_f32=True).reshape(-1, n).to(th.dtype)
+        dth = _host.to_device(dthetalist_trajectory, dev, keep_f32=True).reshape(-1, n)
+        ddth = _host.to_device(ddthetalist_trajectory, dev, keep_f32=True).reshape(-1, n)
+        th, dth, ddth = _host.promote_rows(th, dth, ddth)
         ftip = None if Ftip is None else _host.vec(Ftip, 6, "Ftip")
         tau = _native.ops().inverse_dynamics(dyn.robot.handle, th, dth, ddth, _host.gravity(gravity_vector),
                                              ftip, None, self._tl, True, _host.is_f32(precision)).reshape(shape)

@@ -44,6 +44,9 @@ class RobotBundle:
         if self._dyn is None:
             self._dyn = ManipulatorDynamics(self.M, None, None, None, self.S_list, None, self.Glist,
                                             self.Mlist_per_link, device=self.device)
+            # the reference hands the URDF's joint limits to its SerialManipulator (urdf/core.py:794):
+            # the inverse-kinematics front ends clip to them and draw their guesses inside them
+            self._dyn.joint_limits = [(float(lo), float(hi)) for lo, hi in np.asarray(self.joint_limits)]
         return self._dyn
 
     @property

@@ -16,6 +16,7 @@ REPO = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(REPO))
 
 from manipulapy_b200 import _native, load_robot  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (nvidia-smi clocks / throttle reasons during the timed regions)
 
 HBM = json.loads((REPO / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (REPO / "MEASURED_PEAKS.json").exists() else 6650.0
 
@@ -47,6 +48,7 @@ def main():
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     timeit.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    main.sampler = ClockSampler(0).start()
     ops = _native.ops()
     res = {"hbm_peak_gbs": HBM, "device": torch.cuda.get_device_name(0)}
     g = [0.0, 0.0, -9.81]
@@ -73,12 +75,29 @@ def main():
     # instructions per clock per SM, against the 32 (= 64 lanes / 2) of the FMA pipe
     for mode, label in ((0, "shared_operands"), (1, "three_distinct_registers"), (2, "constant_bank_operand"),
                         (3, "dmul_dfma_pairs"), (4, "half_uniform_half_three_registers"),
-                        (5, "three_registers_shared_middle_operand"), (6, "three_registers_two_shared_operands")):
+                        (5, "three_registers_shared_middle_operand"), (6, "three_registers_two_shared_operands"),
+                        (7, "three_registers_plus_one_imad_each"), (8, "constant_bank_operand_plus_one_imad_each")):
         blocks, threads, iters = 148 * 8, 256, 1 << 14
         sec = timeit(lambda: ops.fma_peak(sink, mode << 8, blocks, threads, iters), 5, 2)
         res[f"fp64_pattern_{label}_ginstr_per_s"] = blocks * threads * iters * 8 / sec[1] / 1e9
 
+    # write-only HBM ceiling: hand-written 16-byte vector stores over 256 MiB .. 4 GiB (the round-1 figure
+    # came from torch's memset on a buffer that half fits the 126 MB L2)
+    stores = {}
+    for gib in (0.25, 1, 2, 4):
+        buf = torch.empty(int(gib * (1 << 30)), dtype=torch.uint8, device=dev)
+        for mode, label in ((0, "st"), (1, "st.cs"), (2, "st.cg"), (3, "st.wt")):
+            for blocks in (148 * 8, 148 * 32):
+                sec = timeit(lambda: ops.store_peak(buf, mode, blocks), 5, 2)
+                stores[f"{label}_{gib}GiB_{blocks}blocks"] = buf.numel() / sec[0] / 1e9
+        sec = timeit(lambda: buf.zero_(), 5, 2)
+        stores[f"torch_memset_{gib}GiB"] = buf.numel() / sec[0] / 1e9
+        del buf
+    res["store_gbs"] = stores
+    res["store_peak_gbs"] = max(stores.values())
+
     if "--peaks-only" in sys.argv:
+        res["clocks"] = main.sampler.stop()
         print(json.dumps(res, indent=1))
         return
 
@@ -162,6 +181,7 @@ def main():
             timeit(lambda: ops.forward_dynamics_trajectory(h7, th0, dth0, taum, g, None, 1e-3, 1, jl7), 3, 1),
             28 + 84, 5300, "steps")
         del taum
+    res["clocks"] = main.sampler.stop()
     print(json.dumps(res, indent=1))
 
 
