@@ -245,6 +245,19 @@ int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, double *sink
  * events to get the write-only HBM ceiling the trajectory kernel's roofline is quoted against. */
 int mpk_store_peak(void *dst_dev, int64_t bytes, int mode, int blocks, void *stream);
 
+/* Result buffers shared by the processes of one box (one process per GPU), SURVEY.md 8e: the
+ * rank that collects a sharded result allocates it with mpk_peer_alloc and hands the 64-byte handle
+ * to the other ranks (any channel: torch.distributed's object broadcast in the Python host); they
+ * map it with mpk_peer_open -- the driver enables peer access over NVLink -- and pass the mapped
+ * pointer (plus their row offset) as the OUTPUT pointer of the launchers above.  The kernels' row
+ * stores then go straight into the collecting GPU's HBM: no gather step after the kernel.
+ * All four act on the CURRENT CUDA device. */
+#define MPK_PEER_HANDLE_BYTES 64
+int mpk_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle /* [MPK_PEER_HANDLE_BYTES] out */);
+int mpk_peer_free(void *dev_ptr);
+int mpk_peer_open(const unsigned char *handle /* [MPK_PEER_HANDLE_BYTES] */, void **dev_ptr);
+int mpk_peer_close(void *dev_ptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,14 +90,31 @@ def _copy_stream(device: torch.device) -> torch.cuda.Stream:
     return _copy_streams[key]
 
 
+def host_out(out: Any, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
+    """Caller-owned host destination (``out=`` of the API mirrors): a NumPy array or a CPU torch
+    tensor of the result's shape and dtype, C-contiguous.  Pinned memory (``torch.empty(...,
+    pin_memory=True)``, or its ``.numpy()`` view) receives the rows at PCIe speed; pageable memory
+    works too, through the driver's staging copy."""
+    t = out if isinstance(out, torch.Tensor) else torch.from_numpy(out)
+    if t.is_cuda or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous():
+        raise ValueError(f"out must be a C-contiguous host array of shape {tuple(shape)} and dtype {dtype}")
+    return t
+
+
 def chunked_to_host(launch, rows: int, tail: Sequence[int], dtype: torch.dtype, device: torch.device,
-                    chunks: int = 8, min_rows: int = 64) -> np.ndarray:
+                    chunks: int = 8, min_rows: int = 64, out: Any = None):
     """Run ``launch(lo, hi) -> CUDA tensor (hi - lo, *tail)`` over contiguous row chunks and
     stream every finished chunk to pinned host memory on a second stream, so the PCIe copy of
-    chunk k overlaps the kernel of chunk k + 1.  Returns a fresh host array ``(rows, *tail)``."""
-    out = torch.empty((rows, *tail), dtype=dtype, pin_memory=True)
+    chunk k overlaps the kernel of chunk k + 1.  Returns a fresh host array ``(rows, *tail)`` --
+    or fills and returns the caller's ``out`` (no pinned allocation per call: a caller that keeps
+    its results would otherwise pin host memory without bound, ~100 ms of ``cudaHostAlloc`` each)."""
+    ret = None
+    if out is not None:
+        ret, out = out, host_out(out, (rows, *tail), dtype)
+    else:
+        out = torch.empty((rows, *tail), dtype=dtype, pin_memory=True)
     if rows == 0:
-        return out.numpy()
+        return ret if ret is not None else out.numpy()
     per = max(min_rows, -(-rows // max(1, chunks)))
     compute = torch.cuda.current_stream(device)
     side = _copy_stream(device)
@@ -113,7 +130,7 @@ def chunked_to_host(launch, rows: int, tail: Sequence[int], dtype: torch.dtype, 
         t.record_stream(side)
         keep.append(t)
     side.synchronize()
-    return out.numpy()
+    return ret if ret is not None else out.numpy()
 
 
 def bind_host_to_device(device: Optional[Any] = None) -> Optional[str]:

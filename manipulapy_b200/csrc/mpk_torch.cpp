@@ -160,7 +160,8 @@ Tensor inverse_dynamics(int64_t h, const Tensor &theta, const OptT &dtheta, cons
 std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
     int64_t h, const Tensor &start, const Tensor &end, bool inputs_f32, double Tf, int64_t N,
     int64_t method, const OptT &joint_limits, c10::ArrayRef<double> g,
-    std::optional<c10::ArrayRef<double>> ftip, const OptT &tau_limits, bool want_traj, bool compute_f32) {
+    std::optional<c10::ArrayRef<double>> ftip, const OptT &tau_limits, bool want_traj, bool compute_f32,
+    const OptT &out) {
     mpk_robot *rb = robot(h);
     const int64_t n = mpk_robot_dof(rb);
     TORCH_CHECK(start.dim() == 2, "mpk: start must be (B, n)");
@@ -175,7 +176,18 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
     auto tl = host_limits(tau_limits, n, "torque_limits");
     c10::cuda::CUDAGuard guard(s.device());
     auto opt = s.options().dtype(at::kFloat);
-    Tensor tau = at::empty({B, N, n}, opt);
+    // `out`: caller-owned float32 (B, N, n) destination.  It may live in ANOTHER GPU's memory (a
+    // peer-mapped buffer of the rank that collects the result): the kernel's coalesced row stores then
+    // travel over NVLink as they are produced -- the gather is fused into the kernel, tile by tile.
+    Tensor tau;
+    if (out.has_value()) {
+        TORCH_CHECK(out->is_cuda() && out->scalar_type() == at::kFloat && out->is_contiguous() &&
+                        out->numel() == B * N * n,
+                    "mpk: out must be a contiguous CUDA float32 tensor of B * N * n elements");
+        tau = *out;
+    } else {
+        tau = at::empty({B, N, n}, opt);
+    }
     Tensor pos, vel, acc;
     float *pp = nullptr, *vp = nullptr, *ap = nullptr;
     if (want_traj) {
@@ -194,6 +206,7 @@ std::tuple<Tensor, Tensor, Tensor, Tensor> trajectory_inverse_dynamics(
               gv.data(), fv.empty() ? nullptr : fv.data(), ptr_or_null(tl), tau.data_ptr<float>(), pp, vp, ap,
               scratch.data_ptr<double>(), stream_of(s)),
           "trajectory_inverse_dynamics");
+    if (out.has_value()) tau = at::empty({0}, opt);  // (the schema declares no aliasing: the caller keeps `out`)
     return {tau, pos, vel, acc};
 }
 
@@ -336,6 +349,44 @@ void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads
           "fma_peak");
 }
 
+// ---- peer-shared result buffers (csrc/peer.cu) ----------------------------------------------
+// -> (float32 tensor of `numel` elements on `like`'s device, owning the cudaMalloc'd buffer; 64-byte handle)
+std::tuple<Tensor, Tensor> peer_alloc(int64_t numel, const Tensor &like) {
+    TORCH_CHECK(like.is_cuda() && numel > 0, "mpk: peer_alloc needs a CUDA device and a positive size");
+    c10::cuda::CUDAGuard guard(like.device());
+    void *p = nullptr;
+    Tensor handle = at::empty({MPK_PEER_HANDLE_BYTES}, at::TensorOptions().dtype(at::kByte));
+    check(mpk_peer_alloc((size_t)numel * 4, &p, handle.data_ptr<uint8_t>()), "peer_alloc");
+    const int dev = like.get_device();
+    Tensor t = at::from_blob(
+        p, {numel},
+        [dev](void *q) {
+            c10::cuda::CUDAGuard g((c10::DeviceIndex)dev);
+            mpk_peer_free(q);
+        },
+        at::TensorOptions().dtype(at::kFloat).device(like.device()), like.device());
+    return {t, handle};
+}
+
+// Map another rank's buffer: a float32 tensor labelled with `like`'s device (the pointer is valid in
+// this device's address space; the bytes live in the exporting GPU's HBM).
+Tensor peer_open(const Tensor &handle, int64_t numel, const Tensor &like) {
+    TORCH_CHECK(like.is_cuda() && numel > 0, "mpk: peer_open needs a CUDA device and a positive size");
+    Tensor h = handle.to(at::kCPU, at::kByte).contiguous();
+    TORCH_CHECK(h.numel() == MPK_PEER_HANDLE_BYTES, "mpk: handle must be ", MPK_PEER_HANDLE_BYTES, " bytes");
+    c10::cuda::CUDAGuard guard(like.device());
+    void *p = nullptr;
+    check(mpk_peer_open(h.data_ptr<uint8_t>(), &p), "peer_open");
+    const int dev = like.get_device();
+    return at::from_blob(
+        p, {numel},
+        [dev](void *q) {
+            c10::cuda::CUDAGuard g((c10::DeviceIndex)dev);
+            mpk_peer_close(q);
+        },
+        at::TensorOptions().dtype(at::kFloat).device(like.device()), like.device());
+}
+
 void store_peak(const Tensor &dst, int64_t mode, int64_t blocks) {
     TORCH_CHECK(dst.is_cuda() && dst.is_contiguous(), "mpk: dst must be a contiguous CUDA tensor");
     c10::cuda::CUDAGuard guard(dst.device());
@@ -361,7 +412,7 @@ TORCH_LIBRARY(mpk, m) {
           &inverse_dynamics);
     m.def("trajectory_inverse_dynamics(int robot, Tensor start, Tensor end, bool inputs_f32, float Tf, "
           "int N, int method, Tensor? joint_limits, float[] g, float[]? Ftip, Tensor? torque_limits, "
-          "bool want_traj, bool compute_f32=False) -> (Tensor, Tensor, Tensor, Tensor)",
+          "bool want_traj, bool compute_f32=False, Tensor? out=None) -> (Tensor, Tensor, Tensor, Tensor)",
           &trajectory_inverse_dynamics);
     m.def("mass_matrix(int robot, Tensor theta) -> Tensor", &mass_matrix);
     m.def("forward_dynamics(int robot, Tensor theta, Tensor dtheta, Tensor tau, float[] g, float[]? Ftip, "
@@ -380,4 +431,6 @@ TORCH_LIBRARY(mpk, m) {
           &cartesian_trajectory);
     m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
     m.def("store_peak(Tensor dst, int mode, int blocks) -> ()", &store_peak);
+    m.def("peer_alloc(int numel, Tensor like) -> (Tensor, Tensor)", &peer_alloc);
+    m.def("peer_open(Tensor handle, int numel, Tensor like) -> Tensor", &peer_open);
 }

@@ -168,7 +168,7 @@ class OptimizedTrajectoryPlanning:
 
     def trajectory_inverse_dynamics(self, thetastart_batch, thetaend_batch, Tf, N, method,
                                     gravity_vector=None, Ftip=None, return_trajectory: bool = False,
-                                    precision=None):
+                                    precision=None, out=None):
         """``batch_joint_trajectory`` followed by ``inverse_dynamics_trajectory`` in ONE kernel.
 
         Identical results to the two calls (the trajectory rows are rounded to float32 and
@@ -176,6 +176,13 @@ class OptimizedTrajectoryPlanning:
         of HBM round trip.  Returns ``(B, N, n)`` float32 torques (and the trajectory dict
         when ``return_trajectory``).  ``precision="float32"``: the trajectory rows are unchanged
         (bit-exact), the inverse dynamics runs in float32 arithmetic (1e-4 relative on torques).
+
+        ``out`` (extension): caller-owned destination of the torques.  Host inputs: a ``(B, N, n)``
+        float32 NumPy array / CPU tensor, ideally pinned, filled chunk by chunk (host results
+        otherwise come back in freshly pinned memory, which a caller that keeps them accumulates).
+        Device inputs: a contiguous float32 CUDA tensor of ``B * N * n`` elements -- it may be another
+        GPU's peer-mapped memory (``sharding.PeerRows``): the kernel then stores straight over
+        NVLink and the multi-GPU gather costs no extra pass.
         """
         f32c = _host.is_f32(precision)
         t0 = time.perf_counter()
@@ -189,20 +196,27 @@ class OptimizedTrajectoryPlanning:
         e = _host.to_device(thetaend_batch, dev).reshape(-1, n)
         ftip = None if Ftip is None else _host.vec(Ftip, 6, "Ftip")
         ops, handle, g = _native.ops(), self.dynamics.robot.handle, _host.gravity(gravity_vector)
-        if not on_dev and not return_trajectory and s.shape[0] >= 64:
+        if out is not None and (return_trajectory or (on_dev != _host.is_device_tensor(out))):
+            raise ValueError("out= needs return_trajectory=False and must live where the inputs live "
+                             "(host array for host inputs, CUDA tensor for device inputs)")
+        if not on_dev and not return_trajectory and (s.shape[0] >= 64 or out is not None):
             # host result: pipeline the kernel with the device->host copy, chunk by chunk
             def launch(lo, hi):
                 return ops.trajectory_inverse_dynamics(handle, s[lo:hi], e[lo:hi], f32, float(Tf), int(N),
                                                        int(method), self._jl, g, ftip, self._tl, False, f32c)[0]
 
             B = int(s.shape[0])
-            out = _host.chunked_to_host(launch, B, (int(N), n), torch.float32, dev, chunks=self.host_chunks)
+            res = _host.chunked_to_host(launch, B, (int(N), n), torch.float32, dev, chunks=self.host_chunks,
+                                        min_rows=64 if B >= 64 else 1, out=out)
             self._tick(t0, launches=2 * min(self.host_chunks, B), transfers=2 + min(self.host_chunks, B),
                        kernel="trajectory_inverse_dynamics")
-            return out
+            return res
         tau, pos, vel, acc = ops.trajectory_inverse_dynamics(
             handle, s, e, f32, float(Tf), int(N), int(method), self._jl, g, ftip, self._tl,
-            bool(return_trajectory), f32c)
+            bool(return_trajectory), f32c, out)
+        if out is not None:
+            self._tick(t0, launches=2, kernel="trajectory_inverse_dynamics")
+            return out
         outs = [tau] + ([pos, vel, acc] if return_trajectory else [])
         if single:
             outs = [o[0] for o in outs]

@@ -516,9 +516,40 @@ out = gather_rows(full[lo:hi].clone(), units)
 assert torch.equal(out, full), out
 out = gather_rows(full[lo:hi].clone(), units, dst=0)
 assert (out is None) if rank else torch.equal(out, full)
+# chunked gather that overlaps the transfer of chunk k with the computation of chunk k + 1
+from manipulapy_b200.sharding import gather_rows_pipelined
+calls = []
+def launch(a, b, dest):
+    calls.append((a, b))
+    dest.copy_(full[a:b] * 2)
+for units2, chunks in ((11, 3), (11, 1), (2, 8), (1, 4), (0, 2)):
+    f2 = full[:units2]
+    calls.clear()
+    out = gather_rows_pipelined(launch, units2, (3,), torch.float32, "cpu", dst=0, chunks=chunks)
+    lo2, hi2 = shard_range(units2, 2, rank)
+    assert sorted(calls) == calls and sum(b - a for a, b in calls) == hi2 - lo2, calls
+    assert (out is None) if rank else torch.equal(out, f2 * 2), (units2, chunks, out)
 dist.destroy_process_group()
 print("ok", rank)
 """
+
+
+def test_shard_bounds_weighted():
+    from manipulapy_b200.sharding import shard_bounds, shard_range
+
+    assert shard_bounds(10, 4) == [0, 3, 6, 9, 10]
+    assert shard_bounds(0, 3) == [0, 0, 0, 0]
+    assert shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+    # device->host rates of an 8-GPU box whose GPUs 0-3 share slower uplinks (profiles/r1_d2h_n8.json)
+    w = [11.7] * 4 + [18.5] * 4
+    b = shard_bounds(32768, 8, w)
+    assert b[0] == 0 and b[-1] == 32768 and all(y >= x for x, y in zip(b, b[1:]))
+    sizes = [y - x for x, y in zip(b, b[1:])]
+    assert abs(sizes[0] / sizes[7] - 11.7 / 18.5) < 0.01 and sum(sizes) == 32768
+    assert shard_range(32768, 8, 3, w) == (b[3], b[4])
+    for bad in ([1.0] * 7, [1.0] * 7 + [0.0], [1.0] * 7 + [float("nan")]):
+        with pytest.raises(ValueError):
+            shard_bounds(10, 8, bad)
 
 
 def test_gather_rows_gloo_world2(tmp_path):
