@@ -587,10 +587,23 @@ def run_ours(args) -> None:
             entry["compute_ms"] = t_c * 1e3
             entry["points_per_s_compute_only"] = Bt * N_STEPS / t_c
             if world > 1:
-                # (b) fused: the kernel stores its rows into rank 0's buffer over NVLink (PeerRows)
+                # (b) fused: the kernel stores its rows into rank 0's buffer over NVLink (PeerRows).  Whether the
+                # mapping and a first launch work is decided by all ranks together: a rank must never part ways
+                pr, perr = None, None
                 try:
                     pr = PeerRows(Bt, (N_STEPS, 6), torch.float32, dev, dst=0)
-
+                except RuntimeError as ex:  # (raised on every rank: agreed inside PeerRows)
+                    perr = f"{type(ex).__name__}: {ex}"[:200]
+                if pr is not None:
+                    try:
+                        launch_into(pr.rows())
+                    except Exception as ex:
+                        perr = f"{type(ex).__name__}: {ex}"[:200]
+                    okf = torch.tensor([0 if perr else 1], dtype=torch.int32, device=dev)
+                    dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+                    if int(okf) == 0:
+                        perr = perr or "the first launch into the peer-mapped buffer failed on another rank"
+                if pr is not None and perr is None:
                     def fused():
                         launch_into(pr.rows())
                         pr.commit()
@@ -607,10 +620,11 @@ def run_ours(args) -> None:
                                                         None, False, False, ref)
                         entry["gathered_equals_single_gpu_bits"] = bool(torch.equal(ref, pr.full))
                         del ref
+                if pr is not None:
                     pr.close()
                     del pr
-                except Exception as ex:  # no peer mapping on this box: the NCCL pipeline below is the gather
-                    entry["peer_store_error"] = f"{type(ex).__name__}: {ex}"[:200]
+                if perr:
+                    entry["peer_store_error"] = perr
                 # (c) NCCL baseline: chunked isend / irecv on a second stream while the next chunk computes
                 full = torch.empty((Bt, N_STEPS, 6), dtype=torch.float32, device=dev) if rank == 0 else None
 

@@ -93,8 +93,10 @@ static int trajectory_inverse_dynamics_impl(const mpk_robot *rb, int64_t B, int6
     if (B < 0 || N < 0) return fail(MPK_EINVAL, "negative size");
     if (B == 0 || N == 0) return MPK_OK;
     if (!start || !end || !tau || !g) return fail(MPK_EINVAL, "start, end, g and tau are required");
-    for (float *o : {tau, pos, vel, acc})
-        if (o && !aligned16(o)) return fail(MPK_EINVAL, "outputs must be 16-byte aligned");
+    // (tau may be a row-offset view of a larger, e.g. peer-mapped, buffer: any float alignment)
+    if (reinterpret_cast<uintptr_t>(tau) & 3u) return fail(MPK_EINVAL, "tau must be 4-byte aligned");
+    for (float *o : {pos, vel, acc})
+        if (o && !aligned16(o)) return fail(MPK_EINVAL, "trajectory outputs must be 16-byte aligned");
     TrajRneaArgs a;
     a.B = B;
     a.N = N;

@@ -274,13 +274,28 @@ __device__ __forceinline__ void endpoint(const double *start, const double *end,
     }
 }
 
-// Coalesced copy-out of a block's staged rows: cnt floats from shared memory to o.
+// Coalesced copy-out of a block's staged rows: cnt floats from shared memory (16-byte aligned) to o.
+// The vector width follows the alignment of the destination (block-uniform): 16-byte vectors for the
+// usual freshly allocated result, 8-byte or scalar stores when the caller passed a row-offset view of
+// a larger buffer (e.g. its shard of another GPU's peer-mapped result, sharding.PeerRows) whose
+// first byte is only 8- or 4-byte aligned.
 __device__ __forceinline__ void tile_store(float *o, const float *sm, int cnt) {
-    const int n4 = cnt >> 2;
-    const float4 *s4 = reinterpret_cast<const float4 *>(sm);
-    float4 *o4 = reinterpret_cast<float4 *>(o);
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, s4[i]);
-    for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) o[i] = sm[i];
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
+    if ((addr & 15u) == 0) {
+        const int n4 = cnt >> 2;
+        const float4 *s4 = reinterpret_cast<const float4 *>(sm);
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, s4[i]);
+        for (int i = (n4 << 2) + threadIdx.x; i < cnt; i += blockDim.x) o[i] = sm[i];
+    } else if ((addr & 7u) == 0) {
+        const int n2 = cnt >> 1;
+        const float2 *s2 = reinterpret_cast<const float2 *>(sm);
+        float2 *o2 = reinterpret_cast<float2 *>(o);
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) __stcs(o2 + i, s2[i]);
+        for (int i = (n2 << 1) + threadIdx.x; i < cnt; i += blockDim.x) o[i] = sm[i];
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) __stcs(o + i, sm[i]);
+    }
 }
 
 }  // namespace mpk

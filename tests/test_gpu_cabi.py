@@ -244,3 +244,35 @@ def test_bad_arguments_return_status_codes(lib):
     lib.mpk_robot_destroy(hk)
     lib.mpk_robot_destroy(h)
     torch.cuda.synchronize()
+
+
+def test_fused_kernel_stores_into_row_offset_views():
+    """The multi-GPU gather has every rank's kernel store its rows into a slice of the collecting
+    rank's buffer (sharding.PeerRows): the destination's first byte is then only 8- or 4-byte aligned
+    (2441 x 6 x 4 B per trajectory is not a multiple of 16).  Same bits as a fresh 16-byte-aligned result."""
+    from manipulapy_b200 import _native, load_robot
+    from manipulapy_b200.sharding import PeerRows
+
+    ops = _native.ops()
+    rb = load_robot("ur5")
+    h, jl = rb.dynamics.robot.handle, rb.planner()._jl
+    rng = np.random.default_rng(21)
+    B, N = 9, 2441
+    s = torch.from_numpy(rng.uniform(-3, 3, (B, 6))).cuda()
+    e = torch.from_numpy(rng.uniform(-3, 3, (B, 6))).cuda()
+    g = [0.0, 0.0, -9.81]
+    ref = ops.trajectory_inverse_dynamics(h, s, e, False, 2.0, N, 5, jl, g, None, None, False)[0]
+    big = torch.full((B + 2, N, 6), float("nan"), dtype=torch.float32, device="cuda")
+    for lo in (0, 1, 2, 3):  # byte offsets 0, 8 (mod 16), 0, 8
+        ops.trajectory_inverse_dynamics(h, s[lo:], e[lo:], False, 2.0, N, 5, jl, g, None, None, False, False, big[lo:B])
+        assert torch.equal(big[lo:B], ref[lo:]) and bool(torch.isnan(big[B:]).all())
+    # 4-byte-aligned destination: a flat buffer entered one float in
+    flat = torch.full((B * N * 6 + 1,), float("nan"), dtype=torch.float32, device="cuda")
+    ops.trajectory_inverse_dynamics(h, s, e, False, 2.0, N, 5, jl, g, None, None, False, False, flat[1:])
+    assert torch.equal(flat[1:].view(B, N, 6), ref)
+    # the single-rank PeerRows is the same code path with an ordinary buffer
+    pr = PeerRows(B, (N, 6), torch.float32, torch.device("cuda", torch.cuda.current_device()))
+    ops.trajectory_inverse_dynamics(h, s, e, False, 2.0, N, 5, jl, g, None, None, False, False, pr.rows())
+    pr.commit()
+    assert torch.equal(pr.full, ref)
+    pr.close()
