@@ -569,7 +569,10 @@ def run_ours(args) -> None:
             # (every rank draws the same global endpoint table and keeps its rows: cheap, 48 B per 58 KB of output)
             ends = (torch.rand(2, Bt, 6, dtype=torch.float64, device=dev, generator=gen5) * 2 - 1) * np.pi
             s5, e5 = ends[0, blo:bhi].contiguous(), ends[1, blo:bhi].contiguous()
-            steps5 = 5 if Ptot <= 10 ** 8 else 3
+            # launches per timing: the same on every rank (a function of the sizes only), enough of them that
+            # the entry's clock record has several NVML samples
+            est = Bt * N_STEPS / world / 1.7e10 + 1.2e-4
+            steps5 = int(min(400, max(3, -(-0.12 // est))))
             tw0 = time.time()
 
             def launch_into(dest, a_=0, b_=None):
