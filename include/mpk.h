@@ -74,6 +74,16 @@ int mpk_robot_dof(const mpk_robot *rb);
 /* 1 if every link inertia is a rigid body expressed at its centre of mass
  * (block-diagonal [I, m*1]); 0 if the general symmetric-6x6 kernels are used. */
 int mpk_robot_is_rigid(const mpk_robot *rb);
+/* The joint-aligned link frames the pack was re-expressed in (diagnostics, tests, docs):
+ * out (n, 8) float64 rows [a, cos alpha, sin alpha, cos beta, sin beta, phi, d, revolute?] of
+ * X_i = Tx(a) Rx(alpha) Ry(beta) Rz(phi) Tz(d), the home pose of frame i in frame i-1 (row 0: the
+ * base frame's own offsets, a = 0, alpha = beta = 0). */
+int mpk_robot_link_geometry(const mpk_robot *rb, double *out);
+/* Link geometry classes of a plain revolute chain, 4 bits per link i >= 1 at bit 4 i: 1 consecutive
+ * axes perpendicular (sin alpha == 1), 2 parallel (alpha == 0), 4 a_i == 0, 8 d_i == 0.  The arm
+ * families of the reference's robot database (UR, iiwa, CRX, LR Mate / M-16, IRB 2400, Gen3) have
+ * kernels compiled for their signature; every other robot runs the general code (same results). */
+unsigned mpk_robot_geometry_signature(const mpk_robot *rb);
 /* 1 if no joint is prismatic (the kernels then drop the prismatic terms at compile time). */
 int mpk_robot_all_revolute(const mpk_robot *rb);
 

@@ -37,6 +37,13 @@ CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", []), ("kin.cu", "kin"
 CU_UNITS += [(f"{base}_flavour.cu", f"{base}_flavour{k}",
               [f"-DMPK_FLAVOUR={k}", *os.environ.get(f"MPK_{base.upper()}_DEFINES", "").split()])
              for base in ("dyn", "fd") for k in (0, 1, 2)]
+# one translation unit pair per link-geometry signature that has its own kernels (MPK_GEO_LIST)
+import re as _re
+
+GEO_LIST = [(int(n), g) for n, g in _re.findall(r"X\((\d+), (0x[0-9a-f]+)u\)", (CSRC / "mpk_common.cuh").read_text())]
+CU_UNITS += [(f"{base}_geo.cu", f"{base}_geo_{n}_{g[2:]}", [f"-DMPK_GEO_N={n}", f"-DMPK_GEO_SIG={g}u",
+                                                        *os.environ.get(f"MPK_{base.upper()}_DEFINES", "").split()])
+             for base in ("dyn", "fd") for n, g in GEO_LIST]
 HEADERS = [CSRC / "mpk_device.cuh", CSRC / "mpk_common.cuh", CSRC / "dyn_kernels.cuh", INCLUDE / "mpk.h"]
 
 
@@ -84,7 +91,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
         return True
 
     # the heavy flavour units first so that they overlap with each other
-    units = sorted(CU_UNITS, key=lambda u: "flavour" not in u[0])
+    units = sorted(CU_UNITS, key=lambda u: "flavour" not in u[0] and "geo" not in u[0])
     with ThreadPoolExecutor(max_workers=min(len(units), os.cpu_count() or 1)) as ex:
         rebuilt = list(ex.map(compile_one, units))
     if any(rebuilt) or not LIB.exists():

@@ -126,6 +126,14 @@ template <int FLAVOUR> void launch_mass(const mpk_robot *rb, const MassArgs &a, 
 template <int FLAVOUR> void launch_fd_point(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaStream_t s);
 template <int FLAVOUR> void launch_rollout(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s);
 
+// per joint count (and geometry signature): defined under MPK_FLAVOUR_KERNELS below, instantiated by
+// the flavour units (GEO = 0, N = 1..8) and the geometry units (flavour 0, one (N, GEO) each)
+template <int F, int N, unsigned GEO> void launch_rnea_n(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s);
+template <int F, int N, unsigned GEO> void launch_traj_rnea_n(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s);
+template <int F, int N, unsigned GEO> void launch_mass_n(const mpk_robot *rb, const MassArgs &a, unsigned grid, cudaStream_t s);
+template <int F, int N, unsigned GEO> void launch_fd_point_n(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaStream_t s);
+template <int F, int N, unsigned GEO> void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s);
+
 #define MPK_DISPATCH_FLAVOUR(rb, CALL)                 \
     switch (flavour_of(rb)) {                          \
         case 0: { constexpr int F_ = 0; CALL; } break; \
@@ -301,7 +309,7 @@ __device__ __forceinline__ const T *tip_to(const TipArgs &tip, const double *ftp
     return o.ft;
 }
 
-template <typename T, int N, bool GEN, bool REV, bool REST = false>
+template <typename T, int N, bool GEN, bool REV, bool REST = false, unsigned GEO = 0>
 __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const RneaArgs a) {
     extern __shared__ __align__(16) double wsm_raw[];
@@ -316,7 +324,7 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     in.begin(a.vec_in != 0);
     SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
     T tau[N];
-    rnea<T, N, GEN, REV>(rb, in, tt.g0, ftt, tau, st);
+    rnea<T, N, GEN, REV, GEO>(rb, in, tt.g0, ftt, tau, st);
     store_tau<N, T>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
 }
 
@@ -350,7 +358,7 @@ struct TrajIn {
 // WRITE: also materialise the trajectory rows (positions, velocities, accelerations).  The
 // kernel is bound by the fp64 pipe with HBM at 6 %, so the extra 12 N bytes per point ride
 // along at a fraction of their stand-alone cost (0.65 ms against 0.17 + 0.57 ms for the two launches).
-template <typename T, int N, bool GEN, bool REV, bool TIP, bool WRITE = false>
+template <typename T, int N, bool GEN, bool REV, bool TIP, bool WRITE = false, unsigned GEO = 0>
 __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     traj_rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const TrajRneaArgs a) {
     // dynamic shared memory: the per-thread link state of the recursion, then (same bytes) the
@@ -387,7 +395,7 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
 #else
         SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
 #endif
-        rnea<T, N, GEN, REV>(rb, in, g0, ftp, tau, st);
+        rnea<T, N, GEN, REV, GEO>(rb, in, g0, ftp, tau, st);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             out[j] = (float)tau[j];
@@ -407,7 +415,7 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
 }
 
 // ---- mass matrix -------------------------------------------------------------------
-template <int N, bool GEN, bool REV>
+template <int N, bool GEN, bool REV, unsigned GEO = 0>
 __global__ void __launch_bounds__(kDynThreads)
     mass_matrix_kernel(const __grid_constant__ RobotPack<double, N> rb, const MassArgs a) {
     // N^2 doubles per configuration: staged per warp and flushed coalesced (one thread writing
@@ -425,7 +433,7 @@ __global__ void __launch_bounds__(kDynThreads)
         JointCS<double, N> q;
         joint_cs<double, N, REV>(rb, th, q);
         double Mm[N][N];
-        mass_matrix<double, N, GEN, REV>(rb, th, q, Mm);
+        mass_matrix<double, N, GEN, REV, GEO>(rb, th, q, Mm);
         double *row = buf + lane * WarpStage<N * N>::S;
 #pragma unroll
         for (int i = 0; i < N; ++i)
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(kDynThreads)
 }
 
 // ---- per-point forward dynamics --------------------------------------------------------
-template <int N, bool GEN, bool REV>
+template <int N, bool GEN, bool REV, unsigned GEO = 0>
 __global__ void __launch_bounds__(kDynThreads)
     forward_dynamics_kernel(const __grid_constant__ RobotPack<double, N> rb, const FdArgs a) {
     const int64_t p = (int64_t)blockIdx.x * kDynThreads + threadIdx.x;
@@ -447,7 +455,7 @@ __global__ void __launch_bounds__(kDynThreads)
     load_row<N>(a.tau, MPK_F64, a.vec, p, tau);
     double ft[6];
     const double *ftp = load_tip(a.tip, p, ft);
-    forward_dynamics<double, N, GEN, REV>(rb, th, dth, tau, a.tip.g0, ftp, dd);
+    forward_dynamics<double, N, GEN, REV, 0, GEO>(rb, th, dth, tau, a.tip.g0, ftp, dd);
     store_row_f64<N>(a.out, a.vec, p, dd);
 }
 
@@ -510,7 +518,7 @@ constexpr size_t rollout_smem_per_warp() {
 }
 
 // TIP: rows of Ftipmat are applied (else every tip-wrench term is compiled out).
-template <int N, bool GEN, bool REV, bool TIP>
+template <int N, bool GEN, bool REV, bool TIP, unsigned GEO = 0>
 __global__ void __launch_bounds__(kRolloutThreads, MPK_FD_MINBLOCKS)
     fd_rollout_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
     extern __shared__ __align__(16) double fsm[];
@@ -567,7 +575,7 @@ __global__ void __launch_bounds__(kRolloutThreads, MPK_FD_MINBLOCKS)
         for (int j = 0; j < N; ++j) last[j] = 0.0;
         for (int r = 0; r < a.intRes; ++r) {
             double dd[N];
-            forward_dynamics<double, N, GEN, REV, MPK_FD_PHASES>(rb, th, dth, tau, a.g0, ftp, dd);
+            forward_dynamics<double, N, GEN, REV, MPK_FD_PHASES, GEO>(rb, th, dth, tau, a.g0, ftp, dd);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 dth[j] = rn_add(dth[j], rn_mul(dd[j], a.dts));
@@ -618,7 +626,7 @@ constexpr size_t rollout_pair_smem() {
     return sizeof(double) * 32 * (6 * N);
 }
 
-template <int N>
+template <int N, unsigned GEO = 0>
 __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
     fd_rollout_pair_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
     extern __shared__ __align__(16) double psm[];
@@ -657,7 +665,7 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
                 pair_arrive(1);
                 double bias[N];
                 ArrayInNoAcc<double, N> in{th, dth};
-                rnea<double, N, false, true>(rb, in, a.g0, nullptr, bias, st_);
+                rnea<double, N, false, true, GEO>(rb, in, a.g0, nullptr, bias, st_);
 #pragma unroll
                 for (int j = 0; j < N; ++j) bias_s[32 * j] = bias[j];
                 pair_arrive(2);
@@ -698,7 +706,7 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
                     q.d[j] = rb.d[j];
                 }
                 double Mm[N][N], dinv[N], dd[N];
-                crba<double, N, true>(rb, q, Mm);
+                crba<double, N, true, GEO>(rb, q, Mm);
                 ldlt_factor<double, N, true>(Mm, dinv);
                 pair_wait(2);
 #pragma unroll
@@ -711,6 +719,129 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
         }
     }
 }
+
+// ======================================================================================
+// launchers per (flavour, joint count, geometry signature)
+// ======================================================================================
+template <int F, int N, unsigned GEO>
+void launch_rnea_n(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    if (a.compute_f32) {
+        launch_smem_l1(rnea_kernel<float, N, GEN, REV, false, GEO>, grid, kDynThreads, wrench_smem<float, N, GEN, REV>(), 7,
+                       s, narrow<N, float>(rb), a);
+    } else if (!GEN && !a.dth && !a.ddth && !a.tip.has_ftip) {
+        // gravity forces: theta rows only, at-rest recursion (HBM-bound)
+        launch_smem_l1(rnea_kernel<double, N, GEN, REV, true, GEO>, grid, kDynThreads, wrench_smem<double, N, GEN, REV>(), 5,
+                       s, narrow<N>(rb), a);
+    } else {
+        launch_smem_l1(rnea_kernel<double, N, GEN, REV, false, GEO>, grid, kDynThreads, wrench_smem<double, N, GEN, REV>(),
+                       5, s, narrow<N>(rb), a);
+    }
+}
+
+template <int F, int N, unsigned GEO>
+void launch_traj_rnea_n(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    if (a.compute_f32 && a.tip.has_ftip) {
+        launch_smem(traj_rnea_kernel<float, N, GEN, REV, true, false, GEO>, grid, kDynThreads,
+                    wrench_smem<float, N, GEN, REV>(), s, narrow<N, float>(rb), a);
+    } else if (a.compute_f32) {
+        launch_smem(traj_rnea_kernel<float, N, GEN, REV, false, false, GEO>, grid, kDynThreads,
+                    wrench_smem<float, N, GEN, REV>(), s, narrow<N, float>(rb), a);
+    } else if (a.pos || a.vel || a.acc) {
+        // (float64, no tip wrench: the launcher only asks for this variant then)
+        launch_smem(traj_rnea_kernel<double, N, GEN, REV, false, true, GEO>, grid, kDynThreads,
+                    wrench_smem<double, N, GEN, REV>() + 3 * sizeof(float) * kDynThreads * N, s, narrow<N>(rb), a);
+    } else if (a.tip.has_ftip) {
+        launch_smem(traj_rnea_kernel<double, N, GEN, REV, true, false, GEO>, grid, kDynThreads,
+                    wrench_smem<double, N, GEN, REV>(), s, narrow<N>(rb), a);
+    } else {
+        launch_smem(traj_rnea_kernel<double, N, GEN, REV, false, false, GEO>, grid, kDynThreads,
+                    wrench_smem<double, N, GEN, REV>(), s, narrow<N>(rb), a);
+    }
+}
+
+template <int F, int N, unsigned GEO>
+void launch_mass_n(const mpk_robot *rb, const MassArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    launch_smem(mass_matrix_kernel<N, GEN, REV, GEO>, grid, kDynThreads,
+                sizeof(double) * WarpStage<N * N>::kDoubles * (kDynThreads / 32), s, narrow<N>(rb), a);
+}
+
+template <int F, int N, unsigned GEO>
+void launch_fd_point_n(const mpk_robot *rb, const FdArgs &a, unsigned grid, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    forward_dynamics_kernel<N, GEN, REV, GEO><<<grid, kDynThreads, 0, s>>>(narrow<N>(rb), a);
+}
+
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev] = n > 0 ? n : 1;
+    }
+    return cached[dev];
+}
+
+// One warp per block by default: the kernel needs no block-level cooperation, and single-warp
+// blocks spread a small batch over all SMs (8,192 rollouts: 4.96 ms against 5.7 ms with 128-thread
+// blocks; 65,536 rollouts: no difference).
+template <int F, int N, unsigned GEO>
+void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s) {
+    constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    constexpr int threads = kRolloutThreads;
+    const unsigned grid = (unsigned)((a.B + threads - 1) / threads);
+#if MPK_FD_PAIR
+    // A batch that fits the GPU in one wave of warp pairs (4 blocks x 32 rollouts per SM) runs each
+    // step split across two warps: a lone warp is bound by its own instruction issue (~1950 fp64
+    // instructions at one per two cycles on ONE scheduler's fp64 unit), the pair uses two schedulers.
+    // Measured (iiwa14, 1000 steps): 2,048 rollouts 3.30 -> 2.76 ms, 8,192: 3.95 -> 3.25, 18,944:
+    // 4.71 -> 4.00; beyond one wave the single-warp kernel wins (28,416: 5.60 against 7.13 ms).
+    if constexpr (!GEN && REV && N >= 2) {
+        if (!a.ftipmat && a.B <= (int64_t)kRolloutPairBlocksPerSm * 32 * sm_count()) {
+            // plain revolute chain, rigid links, no tip wrench
+            launch_smem(fd_rollout_pair_kernel<N, GEO>, (unsigned)((a.B + 31) / 32), 64, rollout_pair_smem<N>(), s,
+                        narrow<N>(rb), a);
+            return;
+        }
+    }
+#endif
+    if (a.ftipmat) {
+        launch_smem(fd_rollout_kernel<N, GEN, REV, true, GEO>, grid, threads, rollout_smem_per_warp<N>() * (threads / 32), s,
+                    narrow<N>(rb), a);
+    } else {
+        launch_smem(fd_rollout_kernel<N, GEN, REV, false, GEO>, grid, threads, rollout_smem_per_warp<N>() * (threads / 32), s,
+                    narrow<N>(rb), a);
+    }
+}
+
+// Dispatch of one launcher family over the joint count (general kernels, GEO = 0).
+#define MPK_DISPATCH_N(FN, ...)                      \
+    switch (rb->n) {                                 \
+        case 1: FN<F, 1, 0>(__VA_ARGS__); break;     \
+        case 2: FN<F, 2, 0>(__VA_ARGS__); break;     \
+        case 3: FN<F, 3, 0>(__VA_ARGS__); break;     \
+        case 4: FN<F, 4, 0>(__VA_ARGS__); break;     \
+        case 5: FN<F, 5, 0>(__VA_ARGS__); break;     \
+        case 6: FN<F, 6, 0>(__VA_ARGS__); break;     \
+        case 7: FN<F, 7, 0>(__VA_ARGS__); break;     \
+        case 8: FN<F, 8, 0>(__VA_ARGS__); break;     \
+        default: break;                              \
+    }
+// ... and the kernels of the geometry signatures: the instantiations live in the geometry units
+#define MPK_GEO_EXTERN_(n_, g_)                                                                                     \
+    extern template void launch_rnea_n<0, n_, g_>(const mpk_robot *, const RneaArgs &, unsigned, cudaStream_t);          \
+    extern template void launch_traj_rnea_n<0, n_, g_>(const mpk_robot *, const TrajRneaArgs &, unsigned, cudaStream_t); \
+    extern template void launch_mass_n<0, n_, g_>(const mpk_robot *, const MassArgs &, unsigned, cudaStream_t);          \
+    extern template void launch_fd_point_n<0, n_, g_>(const mpk_robot *, const FdArgs &, unsigned, cudaStream_t);        \
+    extern template void launch_rollout_n<0, n_, g_>(const mpk_robot *, const RolloutArgs &, cudaStream_t);
+#ifndef MPK_GEO_UNIT
+MPK_GEO_LIST(MPK_GEO_EXTERN_)
+#endif
 #endif  // MPK_FLAVOUR_KERNELS
 
 }  // namespace mpk

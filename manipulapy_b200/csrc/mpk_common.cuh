@@ -14,8 +14,22 @@ struct mpk_robot {
     int plain;         // all revolute and every link plain Denavit-Hartenberg (beta = 0): flavour 0
     int first_revolute;  // joint 0 is revolute (required by the rigid kernel flavours)
     int has_dynamics;
+    unsigned geo;      // link geometry classes (mpk_device.cuh kGeo*), 4 bits per link; 0 unless `plain`
     mpk::RobotPack<double, MPK_MAX_DOF> pack;  // host copy, frames 0..n-1 valid
 };
+
+// Link-geometry signatures (mpk_device.cuh "link geometry classes") that have their own kernels:
+// X(joints, signature).  Each is compiled in its own translation unit (csrc/dyn_geo.cu / fd_geo.cu with
+// -DMPK_GEO_N / -DMPK_GEO_SIG; _build.py reads this list); the flavour-0 launchers pick them by
+// (rb->n, rb->geo) and fall back to the general kernels (GEO = 0) for any other robot.
+#define MPK_GEO_LIST(X)                                   \
+    X(6, 0xd52ad0u)  /* UR3 .. UR16e */                   \
+    X(7, 0xd555150u) /* KUKA iiwa 7 / 14 */               \
+    X(6, 0xd558d0u)  /* Fanuc CRX-5iA .. CRX-30iA */      \
+    X(6, 0xdd1890u)  /* Fanuc LR Mate, M-16iB */          \
+    X(6, 0xdd1a90u)  /* ABB IRB 2400 */                   \
+    X(7, 0xc444440u) /* Kinova Gen3 */
+
 
 namespace mpk {
 

@@ -297,18 +297,66 @@ MPK_HD void base_gravity(const RobotPack<T, N> &rb, const T *g, T (&g0)[3]) {
     for (int k = 0; k < 3; ++k) g0[k] = -(rb.Rb[k] * g[0] + rb.Rb[3 + k] * g[1] + rb.Rb[6 + k] * g[2]);
 }
 
+// ---- link geometry classes -----------------------------------------------------------------
+// Most industrial arms are built from consecutive joint axes that are exactly parallel or
+// perpendicular (to within the digits their URDFs carry), that often intersect (a_i = 0) and whose
+// link frames often need no offset along the axis (d_i = 0).  robot.cu classifies every link once
+// on the host; the signature GEO (4 bits per link i >= 1, at bit 4 i) is a TEMPLATE parameter of the
+// plain-chain kernels, so the products with the known 0 / 1 entries of Rx(alpha_i) and the
+// a_i / d_i shifts are not compiled at all (csrc/dyn_kernels.cuh instantiates the signatures of
+// the arm families found in the reference's robot database; any other robot runs GEO = 0, the
+// general code).  Bits of a link's class:
+//   kGeoPerp  sin(alpha) == 1 exactly (cos(alpha) is whatever the URDF's truncated pi/2 left, ~1e-10):
+//             Rx^T(alpha)(y, z) = (ca y + z, ca z - y): two FMAs instead of two DMUL + two DFMA
+//   kGeoPar   alpha == 0 exactly: Rx(alpha) is the identity
+//   kGeoA0    a_i == 0 (intersecting or coincident axes)     kGeoD0    d_i == 0
+// Skipping a multiplication by an exact 1 or an addition of an exact 0 does not change the result
+// of a finite computation, so a specialised kernel returns the general kernel's values (PERP links:
+// to the last rounding of the ~1e-10 term).
+constexpr unsigned kGeoPerp = 1u, kGeoPar = 2u, kGeoA0 = 4u, kGeoD0 = 8u;
+constexpr MPK_HD unsigned geo_class(unsigned geo, int i) { return (geo >> (4 * i)) & 15u; }
+
+// Rx(alpha_i)^T applied to the pair (y, z) of link i's class
+template <unsigned GEO, typename T, int N>
+MPK_HD void rot_alpha_t(const RobotPack<T, N> &rb, int i, T &y, T &z) {
+    const unsigned cls = geo_class(GEO, i);
+    if (cls & kGeoPar) return;
+    if (cls & kGeoPerp) {
+        const T y1 = rb.ca[i] * y + z;
+        z = rb.ca[i] * z - y;
+        y = y1;
+        return;
+    }
+    rot_t(rb.ca[i], rb.sa[i], y, z);
+}
+
+// Rx(alpha_i) applied to the pair (y, z) of link i's class
+template <unsigned GEO, typename T, int N>
+MPK_HD void rot_alpha(const RobotPack<T, N> &rb, int i, T &y, T &z) {
+    const unsigned cls = geo_class(GEO, i);
+    if (cls & kGeoPar) return;
+    if (cls & kGeoPerp) {
+        const T y1 = rb.ca[i] * y - z;
+        z = rb.ca[i] * z + y;
+        y = y1;
+        return;
+    }
+    rot(rb.ca[i], rb.sa[i], y, z);
+}
+
 // ---- moving twists and wrenches across joint i >= 1 -----------------------------
 // Twist (w, v) of frame i-1 coordinates -> frame i coordinates, Ad(T_{i-1,i}^{-1}); (c, s, dz)
 // from joint_rot.  20 fp64 operations.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void twist_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&w)[3], T (&v)[3]) {
-    const T a = rb.a[i], ca = rb.ca[i], sa = rb.sa[i];
+    const unsigned cls = geo_class(GEO, i);
+    const T a = rb.a[i];
     // Tx(a): the origin moves to a x  =>  v += w x (a, 0, 0)
-    T vy = v[1] + a * w[2];
-    T vz = v[2] - a * w[1];
+    T vy = (cls & kGeoA0) ? v[1] : v[1] + a * w[2];
+    T vz = (cls & kGeoA0) ? v[2] : v[2] - a * w[1];
     T vx = v[0], wx = w[0], wy = w[1], wz = w[2];
-    rot_t(ca, sa, wy, wz);
-    rot_t(ca, sa, vy, vz);
+    rot_alpha_t<GEO>(rb, i, wy, wz);
+    rot_alpha_t<GEO>(rb, i, vy, vz);
     if (HAY && rb.sb[i] != T(0)) {
         rot_t(rb.cb[i], rb.sb[i], wz, wx);
         rot_t(rb.cb[i], rb.sb[i], vz, vx);
@@ -316,8 +364,8 @@ MPK_HD void twist_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (
     rot_t(c, s, wx, wy);
     rot_t(c, s, vx, vy);
     // Tz(dz): v += w x (0, 0, dz)
-    v[0] = vx + wy * dz;
-    v[1] = vy - wx * dz;
+    v[0] = (cls & kGeoD0) ? vx : vx + wy * dz;
+    v[1] = (cls & kGeoD0) ? vy : vy - wx * dz;
     v[2] = vz;
     w[0] = wx;
     w[1] = wy;
@@ -326,7 +374,7 @@ MPK_HD void twist_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (
 
 // The same for the twist of a revolute link 0 at rest in translation: w = (0, 0, wz), v = 0
 // (10 operations; products with the known zeros are not something the compiler may drop).
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void twist_to_child_z(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T wz0, T (&w)[3],
                              T (&v)[3]) {
     if (HAY && rb.sb[i] != T(0)) {
@@ -335,19 +383,35 @@ MPK_HD void twist_to_child_z(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T
         twist_to_child(rb, i, c, s, dz, w, v);
         return;
     }
+    const unsigned cls = geo_class(GEO, i);
     const T a = rb.a[i];
-    const T wy1 = rb.sa[i] * wz0, wz1 = rb.ca[i] * wz0;
-    const T vy1 = a * wz1, vz1 = -(a * wy1);
+    if (cls & kGeoPar) {
+        // parallel axes: the twist keeps its direction, only the origin moves
+        w[0] = T(0); w[1] = T(0); w[2] = wz0;
+        const T vy1 = (cls & kGeoA0) ? T(0) : a * wz0;
+        v[0] = s * vy1;
+        v[1] = c * vy1;
+        v[2] = T(0);
+        return;
+    }
+    const T wy1 = (cls & kGeoPerp) ? wz0 : rb.sa[i] * wz0, wz1 = rb.ca[i] * wz0;
     w[0] = s * wy1;
     w[1] = c * wy1;
     w[2] = wz1;
-    v[0] = s * vy1 + w[1] * dz;
-    v[1] = c * vy1 - w[0] * dz;
+    if (cls & kGeoA0) {
+        v[0] = (cls & kGeoD0) ? T(0) : w[1] * dz;
+        v[1] = (cls & kGeoD0) ? T(0) : -(w[0] * dz);
+        v[2] = T(0);
+        return;
+    }
+    const T vy1 = a * wz1, vz1 = -(a * wy1);
+    v[0] = (cls & kGeoD0) ? s * vy1 : s * vy1 + w[1] * dz;
+    v[1] = (cls & kGeoD0) ? c * vy1 : c * vy1 - w[0] * dz;
     v[2] = vz1;
 }
 
 // ... and for its acceleration: dw = (0, 0, dwz), dv full (15 operations).
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void accel_to_child_z(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T dwz0,
                              const T (&dv0)[3], T (&dw)[3], T (&dv)[3]) {
     if (HAY && rb.sb[i] != T(0)) {
@@ -356,35 +420,45 @@ MPK_HD void accel_to_child_z(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T
         twist_to_child(rb, i, c, s, dz, dw, dv);
         return;
     }
-    const T ca = rb.ca[i], sa = rb.sa[i];
-    const T wy1 = sa * dwz0, wz1 = ca * dwz0;
-    T vy = dv0[1] + rb.a[i] * dwz0, vz = dv0[2];
-    rot_t(ca, sa, vy, vz);
+    const unsigned cls = geo_class(GEO, i);
+    T vy = (cls & kGeoA0) ? dv0[1] : dv0[1] + rb.a[i] * dwz0, vz = dv0[2];
+    rot_alpha_t<GEO>(rb, i, vy, vz);
+    if (cls & kGeoPar) {
+        dw[0] = T(0); dw[1] = T(0); dw[2] = dwz0;
+        dv[0] = c * dv0[0] + s * vy;
+        dv[1] = c * vy - s * dv0[0];
+        dv[2] = vz;
+        return;
+    }
+    const T wy1 = (cls & kGeoPerp) ? dwz0 : rb.sa[i] * dwz0, wz1 = rb.ca[i] * dwz0;
     dw[0] = s * wy1;
     dw[1] = c * wy1;
     dw[2] = wz1;
-    dv[0] = c * dv0[0] + s * vy + dw[1] * dz;
-    dv[1] = c * vy - s * dv0[0] - dw[0] * dz;
+    dv[0] = (cls & kGeoD0) ? c * dv0[0] + s * vy : c * dv0[0] + s * vy + dw[1] * dz;
+    dv[1] = (cls & kGeoD0) ? c * vy - s * dv0[0] : c * vy - s * dv0[0] - dw[0] * dz;
     dv[2] = vz;
 }
 
 // Rotate a free vector from frame i-1 coordinates to frame i coordinates.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void vec_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T (&u)[3]) {
-    rot_t(rb.ca[i], rb.sa[i], u[1], u[2]);
+    rot_alpha_t<GEO>(rb, i, u[1], u[2]);
     if (HAY && rb.sb[i] != T(0)) rot_t(rb.cb[i], rb.sb[i], u[2], u[0]);
     rot_t(c, s, u[0], u[1]);
 }
 
 // Wrench (n, f) of frame i-1 coordinates -> frame i coordinates.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void wrench_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&n)[3], T (&f)[3]) {
+    const unsigned cls = geo_class(GEO, i);
     const T a = rb.a[i];
     // Tx(a): n -= (a, 0, 0) x f
-    n[1] += a * f[2];
-    n[2] -= a * f[1];
-    rot_t(rb.ca[i], rb.sa[i], n[1], n[2]);
-    rot_t(rb.ca[i], rb.sa[i], f[1], f[2]);
+    if (!(cls & kGeoA0)) {
+        n[1] += a * f[2];
+        n[2] -= a * f[1];
+    }
+    rot_alpha_t<GEO>(rb, i, n[1], n[2]);
+    rot_alpha_t<GEO>(rb, i, f[1], f[2]);
     if (HAY && rb.sb[i] != T(0)) {
         rot_t(rb.cb[i], rb.sb[i], n[2], n[0]);
         rot_t(rb.cb[i], rb.sb[i], f[2], f[0]);
@@ -392,8 +466,10 @@ MPK_HD void wrench_to_child(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T 
     rot_t(c, s, n[0], n[1]);
     rot_t(c, s, f[0], f[1]);
     // Tz(dz): n -= (0, 0, dz) x f
-    n[0] += dz * f[1];
-    n[1] -= dz * f[0];
+    if (!(cls & kGeoD0)) {
+        n[0] += dz * f[1];
+        n[1] -= dz * f[0];
+    }
 }
 
 // Space-frame wrench -> frame 0 coordinates (general base pose, then the joint rotation).
@@ -419,13 +495,14 @@ MPK_HD void wrench_to_base(const RobotPack<T, N> &rb, T c, T s, T dz, T (&n)[3],
 
 // Wrench (n, f) of frame i coordinates -> frame i-1 coordinates, Ad(T_{i-1,i}^{-1})^T, ADDED to
 // (an, af).  22 operations; the rotated terms are links of FMA chains seeded by an / af.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void wrench_to_parent_acc(const RobotPack<T, N> &rb, int i, T c, T s, T dz, const T (&n)[3],
                                  const T (&f)[3], T (&an)[3], T (&af)[3]) {
+    const unsigned cls = geo_class(GEO, i);
     const T a = rb.a[i], ca = rb.ca[i], sa = rb.sa[i];
     // Tz(dz): n += (0, 0, dz) x f
-    T nx = n[0] - dz * f[1];
-    T ny = n[1] + dz * f[0];
+    T nx = (cls & kGeoD0) ? n[0] : n[0] - dz * f[1];
+    T ny = (cls & kGeoD0) ? n[1] : n[1] + dz * f[0];
     T nz = n[2], fx = f[0], fy = f[1], fz = f[2];
     rot(c, s, nx, ny);
     rot(c, s, fx, fy);
@@ -434,18 +511,32 @@ MPK_HD void wrench_to_parent_acc(const RobotPack<T, N> &rb, int i, T c, T s, T d
         rot(rb.cb[i], rb.sb[i], fz, fx);
     }
     // Rx(alpha), then Tx(a): n += (a, 0, 0) x f -- with Tx applied first (they commute)
-    ny -= a * fz;
-    nz += a * fy;
+    if (!(cls & kGeoA0)) {
+        ny -= a * fz;
+        nz += a * fy;
+    }
     an[0] += nx;
-    an[1] = an[1] + ca * ny - sa * nz;
-    an[2] = an[2] + sa * ny + ca * nz;
     af[0] += fx;
-    af[1] = af[1] + ca * fy - sa * fz;
-    af[2] = af[2] + sa * fy + ca * fz;
+    if (cls & kGeoPar) {
+        an[1] += ny;
+        an[2] += nz;
+        af[1] += fy;
+        af[2] += fz;
+    } else if (cls & kGeoPerp) {
+        an[1] = (an[1] - nz) + ca * ny;
+        an[2] = (an[2] + ny) + ca * nz;
+        af[1] = (af[1] - fz) + ca * fy;
+        af[2] = (af[2] + fy) + ca * fz;
+    } else {
+        an[1] = an[1] + ca * ny - sa * nz;
+        an[2] = an[2] + sa * ny + ca * nz;
+        af[1] = af[1] + ca * fy - sa * fz;
+        af[2] = af[2] + sa * fy + ca * fz;
+    }
 }
 
 // Only the z moment of the moved wrench (all a revolute joint i-1 needs): 10 operations.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD T wrench_to_parent_nz(const RobotPack<T, N> &rb, int i, T c, T s, T dz, const T (&n)[3],
                              const T (&f)[3], T acc) {
     if (HAY && rb.sb[i] != T(0)) {
@@ -453,30 +544,46 @@ MPK_HD T wrench_to_parent_nz(const RobotPack<T, N> &rb, int i, T c, T s, T dz, c
         wrench_to_parent_acc(rb, i, c, s, dz, n, f, an, af);
         return an[2];
     }
-    const T nx = n[0] - dz * f[1];
-    const T ny = n[1] + dz * f[0];
-    const T ny1 = s * nx + c * ny - rb.a[i] * f[2];
-    const T fy1 = s * f[0] + c * f[1];
-    const T nz1 = n[2] + rb.a[i] * fy1;
+    const unsigned cls = geo_class(GEO, i);
+    const T nx = (cls & kGeoD0) ? n[0] : n[0] - dz * f[1];
+    const T ny = (cls & kGeoD0) ? n[1] : n[1] + dz * f[0];
+    if (cls & kGeoPar) {
+        // only z survives Rx(0): n_z + a f_y'
+        if (cls & kGeoA0) return acc + n[2];
+        const T fy1 = s * f[0] + c * f[1];
+        return acc + (n[2] + rb.a[i] * fy1);
+    }
+    const T ny1 = (cls & kGeoA0) ? s * nx + c * ny : s * nx + c * ny - rb.a[i] * f[2];
+    T nz1 = n[2];
+    if (!(cls & kGeoA0)) {
+        const T fy1 = s * f[0] + c * f[1];
+        nz1 = n[2] + rb.a[i] * fy1;
+    }
+    if (cls & kGeoPerp) return (acc + ny1) + rb.ca[i] * nz1;
     return acc + rb.sa[i] * ny1 + rb.ca[i] * nz1;
 }
 
 // Wrench (n, f) of frame i coordinates -> frame i-1 coordinates, in place.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void wrench_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&n)[3], T (&f)[3]) {
+    const unsigned cls = geo_class(GEO, i);
     const T a = rb.a[i];
-    n[0] -= dz * f[1];
-    n[1] += dz * f[0];
+    if (!(cls & kGeoD0)) {
+        n[0] -= dz * f[1];
+        n[1] += dz * f[0];
+    }
     rot(c, s, n[0], n[1]);
     rot(c, s, f[0], f[1]);
     if (HAY && rb.sb[i] != T(0)) {
         rot(rb.cb[i], rb.sb[i], n[2], n[0]);
         rot(rb.cb[i], rb.sb[i], f[2], f[0]);
     }
-    n[1] -= a * f[2];
-    n[2] += a * f[1];
-    rot(rb.ca[i], rb.sa[i], n[1], n[2]);
-    rot(rb.ca[i], rb.sa[i], f[1], f[2]);
+    if (!(cls & kGeoA0)) {
+        n[1] -= a * f[2];
+        n[2] += a * f[1];
+    }
+    rot_alpha<GEO>(rb, i, n[1], n[2]);
+    rot_alpha<GEO>(rb, i, f[1], f[2]);
 }
 
 // Spatial momentum (n, f) = G_i [w; v].
@@ -683,9 +790,10 @@ struct zero_acc_of<In, decltype((void)In::kZeroAcc)> {
 // `in.joint(i, theta, dtheta, ddtheta)` yields joint i's values when link i is reached, so a
 // kernel can produce them lazily (from global memory or from the time scaling) instead of
 // holding 3 N values in registers for the whole recursion.
-template <typename T, int N, bool GEN, bool REV, typename In, typename St>
+template <typename T, int N, bool GEN, bool REV, unsigned GEO = 0, typename In, typename St>
 MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *ftip, T (&tau)[N],
                  St &st_) {
+    static_assert(GEO == 0 || (REV && !GEN), "link geometry classes exist for plain rigid chains only");
     // rigid inertias and a revolute first joint (guaranteed by the flavour selection): link 0 only
     // contributes the z moment about its own axis, and link 1 receives a twist with known zeros
     constexpr bool FAST0 = rnea_fast0(GEN, REV, N);
@@ -740,17 +848,17 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
         } else {
             if (REST) {
                 // no twists: the acceleration of frame i's origin is the rotated base acceleration
-                vec_to_child<T, N, !REV>(rb, i, c, s, dv);
+                vec_to_child<T, N, !REV, GEO>(rb, i, c, s, dv);
             } else if (FAST0 && i == 1) {
                 T dv0[3] = {dv[0], dv[1], dv[2]};
-                twist_to_child_z<T, N, !REV>(rb, 1, c, s, dz, wz0, w, v);
-                accel_to_child_z<T, N, !REV>(rb, 1, c, s, dz, dwz0, dv0, dw, dv);
+                twist_to_child_z<T, N, !REV, GEO>(rb, 1, c, s, dz, wz0, w, v);
+                accel_to_child_z<T, N, !REV, GEO>(rb, 1, c, s, dz, dwz0, dv0, dw, dv);
             } else {
-                twist_to_child<T, N, !REV>(rb, i, c, s, dz, w, v);
-                twist_to_child<T, N, !REV>(rb, i, c, s, dz, dw, dv);
+                twist_to_child<T, N, !REV, GEO>(rb, i, c, s, dz, w, v);
+                twist_to_child<T, N, !REV, GEO>(rb, i, c, s, dz, dw, dv);
             }
-            if (GEN) vec_to_child<T, N, !REV>(rb, i, c, s, ag);
-            if (has_tip) wrench_to_child<T, N, !REV>(rb, i, c, s, dz, tn, tf);
+            if (GEN) vec_to_child<T, N, !REV, GEO>(rb, i, c, s, ag);
+            if (has_tip) wrench_to_child<T, N, !REV, GEO>(rb, i, c, s, dz, tn, tf);
             // V_i += A_i dth_i ;  dV_i += ad(V_i) A_i dth_i + A_i ddth_i
             if (REST) {
             } else if (REV) {
@@ -834,11 +942,11 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                 // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
                 if (j < N - 1) st_.template get_cs<REV>(rb, j, cj, sj, dj);
                 if (FAST0 && j == 1) {
-                    an[2] = wrench_to_parent_nz<T, N, !REV>(rb, 1, cj, sj, dj, an, af, st_.get(0, 2));
+                    an[2] = wrench_to_parent_nz<T, N, !REV, GEO>(rb, 1, cj, sj, dj, an, af, st_.get(0, 2));
                 } else {
                     T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};
                     T bf[3] = {st_.get(j - 1, 3), st_.get(j - 1, 4), st_.get(j - 1, 5)};
-                    wrench_to_parent_acc<T, N, !REV>(rb, j, cj, sj, dj, an, af, bn, bf);
+                    wrench_to_parent_acc<T, N, !REV, GEO>(rb, j, cj, sj, dj, an, af, bn, bf);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
                         an[k] = bn[k];
@@ -852,12 +960,12 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
 }
 
 // Register-resident convenience form over arrays; `q` receives the joint rotations.
-template <typename T, int N, bool GEN, bool REV>
+template <typename T, int N, bool GEN, bool REV, unsigned GEO = 0>
 MPK_HD void rnea(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N], const T (&ddth)[N],
                  const T (&g0)[3], const T *ftip, T (&tau)[N], JointCS<T, N> &q) {
     RegStore<T, N> st_;
     ArrayIn<T, N> in{th, dth, ddth};
-    rnea<T, N, GEN, REV>(rb, in, g0, ftip, tau, st_);
+    rnea<T, N, GEN, REV, GEO>(rb, in, g0, ftip, tau, st_);
     q = st_.q;
 }
 
@@ -879,10 +987,11 @@ MPK_HD void rot_inertia(T c, T s, T &pp, T &qq, T &pq, T &pr, T &qr) {
 // Composite inertia (I about the origin, h = m c, m) of frame i coordinates -> frame i-1
 // coordinates:  Tz(dz), Rz, [Ry], Rx, Tx(a).  A shift of the coordinates by p maps
 // I -> I + 2 (q.p) 1 - (q p^T + p q^T), q = h + m p / 2, and h -> h + m p.
-template <typename T, int N, bool HAY = true>
+template <typename T, int N, bool HAY = true, unsigned GEO = 0>
 MPK_HD void inertia_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, T (&I)[6], T (&h)[3],
                               T m) {
-    {
+    const unsigned cls = geo_class(GEO, i);
+    if (!(cls & kGeoD0)) {
         const T t = m * dz;
         const T e = (T(2) * h[2] + t) * dz;
         I[0] += e;
@@ -897,9 +1006,11 @@ MPK_HD void inertia_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, 
         rot_inertia(rb.cb[i], rb.sb[i], I[5], I[0], I[2], I[4], I[1]);
         rot(rb.cb[i], rb.sb[i], h[2], h[0]);
     }
-    rot_inertia(rb.ca[i], rb.sa[i], I[3], I[5], I[4], I[1], I[2]);
-    rot(rb.ca[i], rb.sa[i], h[1], h[2]);
-    {
+    if (!(cls & kGeoPar)) {
+        rot_inertia(rb.ca[i], rb.sa[i], I[3], I[5], I[4], I[1], I[2]);
+        rot_alpha<GEO>(rb, i, h[1], h[2]);
+    }
+    if (!(cls & kGeoA0)) {
         const T a = rb.a[i];
         const T t = m * a;
         const T e = (T(2) * h[0] + t) * a;
@@ -913,7 +1024,7 @@ MPK_HD void inertia_to_parent(const RobotPack<T, N> &rb, int i, T c, T s, T dz, 
 
 // M[i][j] for j <= i is written to Mm[i][j] AND Mm[j][i].  Matches the reference's
 // sym(sum_k J_k^T G_k J_k) (dynamics/mass_matrix.py:62-96).  Rigid inertias, first joint revolute.
-template <typename T, int N, bool REV>
+template <typename T, int N, bool REV, unsigned GEO = 0>
 MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T (&Mm)[N][N]) {
     // composite inertia of links i..N-1 in frame i
     T I[6] = {T(0), T(0), T(0), T(0), T(0), T(0)}, h[3] = {T(0), T(0), T(0)}, m = T(0);
@@ -949,15 +1060,15 @@ MPK_HD void crba(const RobotPack<T, N> &rb, const JointCS<T, N> &q, T (&Mm)[N][N
             T mij;
             if (j == 1) {
                 // the first joint of a chain routed here is revolute: only the z moment is needed
-                mij = wrench_to_parent_nz<T, N, !REV>(rb, 1, q.c[1], q.s[1], q.d[1], n, f, T(0));
+                mij = wrench_to_parent_nz<T, N, !REV, GEO>(rb, 1, q.c[1], q.s[1], q.d[1], n, f, T(0));
             } else {
-                wrench_to_parent<T, N, !REV>(rb, j, q.c[j], q.s[j], q.d[j], n, f);
+                wrench_to_parent<T, N, !REV, GEO>(rb, j, q.c[j], q.s[j], q.d[j], n, f);
                 mij = (REV || rb.sr[j - 1] != T(0)) ? n[2] : rb.st[j - 1] * f[2];
             }
             Mm[i][j - 1] = mij;
             Mm[j - 1][i] = mij;
         }
-        if (i > 0) inertia_to_parent<T, N, !REV>(rb, i, q.c[i], q.s[i], q.d[i], I, h, m);
+        if (i > 0) inertia_to_parent<T, N, !REV, GEO>(rb, i, q.c[i], q.s[i], q.d[i], I, h, m);
     }
 }
 
@@ -988,11 +1099,11 @@ MPK_HD void mass_matrix_general(const RobotPack<T, N> &rb, const T (&th)[N], T (
         }
 }
 
-template <typename T, int N, bool GEN, bool REV>
+template <typename T, int N, bool GEN, bool REV, unsigned GEO = 0>
 MPK_HD void mass_matrix(const RobotPack<T, N> &rb, const T (&th)[N], const JointCS<T, N> &q,
                         T (&Mm)[N][N]) {
     if (GEN) mass_matrix_general<T, N>(rb, th, Mm);
-    else crba<T, N, REV>(rb, q, Mm);
+    else crba<T, N, REV, GEO>(rb, q, Mm);
 }
 
 // Reciprocal of an LDL^T pivot without the division's special-case branch: hardware seed
@@ -1067,7 +1178,7 @@ MPK_HD void phase_barrier() {
     __syncthreads();
 #endif
 }
-template <typename T, int N, bool GEN, bool REV, int PHASES = 0>
+template <typename T, int N, bool GEN, bool REV, int PHASES = 0, unsigned GEO = 0>
 MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const T (&dth)[N],
                              const T (&tau)[N], const T (&g0)[3], const T *ftip, T (&dd)[N]) {
     T bias[N];
@@ -1075,12 +1186,12 @@ MPK_HD void forward_dynamics(const RobotPack<T, N> &rb, const T (&th)[N], const 
     joint_cs_all<T, N, REV>(rb, th, st_.q);
     if (PHASES >= 4) phase_barrier();
     ArrayInNoAcc<T, N> in{th, dth};
-    rnea<T, N, GEN, REV>(rb, in, g0, ftip, bias, st_);
+    rnea<T, N, GEN, REV, GEO>(rb, in, g0, ftip, bias, st_);
 #pragma unroll
     for (int i = 0; i < N; ++i) dd[i] = tau[i] - bias[i];
     if (PHASES >= 2) phase_barrier();
     T Mm[N][N];
-    mass_matrix<T, N, GEN, REV>(rb, th, st_.q, Mm);
+    mass_matrix<T, N, GEN, REV, GEO>(rb, th, st_.q, Mm);
     if (PHASES >= 3) phase_barrier();
     ldlt_solve<T, N, true>(Mm, dd);
 }

@@ -375,6 +375,21 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
     rb->first_revolute = rb->pack.sr[0] != 0.0;
     for (int i = 0; i < n; ++i)
         if (rb->pack.sb[i] != 0.0) rb->plain = 0;
+    // Offsets that are pure rounding noise of the frame construction (|x| < 1e-15 m, e.g. the 1e-17
+    // common-normal length of two axes that intersect) are exact zeros; then classify the links
+    // (mpk_device.cuh "link geometry classes").
+    rb->geo = 0;
+    for (int i = 1; i < n; ++i) {
+        if (std::fabs(rb->pack.a[i]) < 1e-15) rb->pack.a[i] = 0.0;
+        if (std::fabs(rb->pack.d[i]) < 1e-15 && rb->pack.st[i] == 0.0) rb->pack.d[i] = 0.0;
+        unsigned cls = 0;
+        if (rb->pack.sa[i] == 1.0) cls |= kGeoPerp;
+        else if (rb->pack.sa[i] == 0.0 && rb->pack.ca[i] == 1.0) cls |= kGeoPar;
+        if (rb->pack.a[i] == 0.0) cls |= kGeoA0;
+        if (rb->pack.d[i] == 0.0 && rb->pack.st[i] == 0.0) cls |= kGeoD0;
+        rb->geo |= cls << (4 * i);
+    }
+    if (!rb->plain) rb->geo = 0;
 
     for (int i = 0; i < n; ++i) {
         const SE3 &F = frames[i];
@@ -457,6 +472,18 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
     for (int k = 0; k < 3; ++k) rb->pack.pee[k] = E.p[k];
     rb->rigid = (rigid && !(flags & MPK_ROBOT_FORCE_GENERAL)) ? 1 : 0;
     *out = rb;
+    return MPK_OK;
+}
+
+extern "C" unsigned mpk_robot_geometry_signature(const mpk_robot *rb) { return rb ? rb->geo : 0u; }
+
+extern "C" int mpk_robot_link_geometry(const mpk_robot *rb, double *out) {
+    if (!rb || !out) return fail(MPK_EINVAL, "robot / out is NULL");
+    for (int i = 0; i < rb->n; ++i) {
+        const auto &p = rb->pack;
+        const double row[8] = {p.a[i], p.ca[i], p.sa[i], p.cb[i], p.sb[i], p.phi[i], p.d[i], p.sr[i]};
+        for (int k = 0; k < 8; ++k) out[8 * i + k] = row[k];
+    }
     return MPK_OK;
 }
 

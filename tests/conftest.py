@@ -147,6 +147,15 @@ class HostCheck:
             raise RuntimeError(self.L.mpk_last_error().decode())
         return h, S.shape[1]
 
+    def geo(self, rb):
+        """Link-geometry signature of the robot (0: general kernels)."""
+        self.L.mpk_robot_geometry_signature.restype = _C.c_uint
+        return int(self.L.mpk_robot_geometry_signature(rb[0]))
+
+    def set_geo(self, rb, geo):
+        self.H.hc_set_geo.restype = _C.c_uint
+        return int(self.H.hc_set_geo(rb[0], _C.c_uint(geo)))
+
     def rnea(self, rb, th, dth=None, ddth=None, g=(0, 0, -9.81), ftip=None, smem_store=False, f32=False):
         h, n = rb
         fn = self.H.hc_rnea_f32 if f32 else {0: self.H.hc_rnea, 1: self.H.hc_rnea_smem}[int(smem_store)]

@@ -13,7 +13,7 @@ using namespace mpk;
 // revolute, 1 rigid, 2 general inertias
 static int flavour(const mpk_robot *rb) { return (!rb->rigid || !rb->first_revolute) ? 2 : (rb->plain ? 0 : 1); }
 
-template <int N, bool GEN, bool REV>
+template <int N, bool GEN, bool REV, unsigned GEO = 0>
 static void rnea_nf(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                     const double *ddth, const double *g, const double *ftip, double *tau,
                     int use_smem_store) {
@@ -33,17 +33,17 @@ static void rnea_nf(const mpk_robot *rb, int64_t P, const double *th, const doub
             double buf[Store::kValues + 1];
             Store st{buf};
             ArrayInAtRest<double, N> in{a};
-            rnea<double, N, GEN, REV>(pk, in, g0, ftip, t, st);
+            rnea<double, N, GEN, REV, GEO>(pk, in, g0, ftip, t, st);
         } else if (use_smem_store) {
             // the shared-memory state store of the kernels, exercised with a one-thread "block"
             using Store = SmemStore<double, N, 1, rnea_fast0(GEN, REV, N)>;
             double buf[Store::kValues + 1];
             Store st{buf};
             ArrayIn<double, N> in{a, b, c};
-            rnea<double, N, GEN, REV>(pk, in, g0, ftip, t, st);
+            rnea<double, N, GEN, REV, GEO>(pk, in, g0, ftip, t, st);
         } else {
             JointCS<double, N> q;
-            rnea<double, N, GEN, REV>(pk, a, b, c, g0, ftip, t, q);
+            rnea<double, N, GEN, REV, GEO>(pk, a, b, c, g0, ftip, t, q);
         }
         for (int j = 0; j < N; ++j) tau[p * N + j] = t[j];
     }
@@ -53,6 +53,13 @@ template <int N>
 static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                    const double *ddth, const double *g, const double *ftip, double *tau,
                    int use_smem_store) {
+    // the kernels compiled for this robot's link-geometry signature, exactly as the launchers pick them
+#define X(n_, g_)                                                                                    \
+    if constexpr (N == n_)                                                                           \
+        if (flavour(rb) == 0 && rb->geo == g_)                                                       \
+            return rnea_nf<N, false, true, g_>(rb, P, th, dth, ddth, g, ftip, tau, use_smem_store);
+    MPK_GEO_LIST(X)
+#undef X
     switch (flavour(rb)) {
         case 0: rnea_nf<N, false, true>(rb, P, th, dth, ddth, g, ftip, tau, use_smem_store); break;
         case 1: rnea_nf<N, false, false>(rb, P, th, dth, ddth, g, ftip, tau, use_smem_store); break;
@@ -60,7 +67,7 @@ static void rnea_n(const mpk_robot *rb, int64_t P, const double *th, const doubl
     }
 }
 
-template <int N, bool GEN, bool REV>
+template <int N, bool GEN, bool REV, unsigned GEO = 0>
 static void mass_nf(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
     const RobotPack<double, N> pk = narrow<N>(rb);
     for (int64_t p = 0; p < P; ++p) {
@@ -68,7 +75,7 @@ static void mass_nf(const mpk_robot *rb, int64_t P, const double *th, double *Mo
         for (int j = 0; j < N; ++j) a[j] = th[p * N + j];
         JointCS<double, N> q;
         joint_cs<double, N, REV>(pk, a, q);
-        mass_matrix<double, N, GEN, REV>(pk, a, q, Mm);
+        mass_matrix<double, N, GEN, REV, GEO>(pk, a, q, Mm);
         for (int i = 0; i < N; ++i)
             for (int j = 0; j < N; ++j) Mo[(p * N + i) * N + j] = Mm[i][j];
     }
@@ -76,6 +83,11 @@ static void mass_nf(const mpk_robot *rb, int64_t P, const double *th, double *Mo
 
 template <int N>
 static void mass_n(const mpk_robot *rb, int64_t P, const double *th, double *Mo) {
+#define X(n_, g_)             \
+    if constexpr (N == n_)    \
+        if (flavour(rb) == 0 && rb->geo == g_) return mass_nf<N, false, true, g_>(rb, P, th, Mo);
+    MPK_GEO_LIST(X)
+#undef X
     switch (flavour(rb)) {
         case 0: mass_nf<N, false, true>(rb, P, th, Mo); break;
         case 1: mass_nf<N, false, false>(rb, P, th, Mo); break;
@@ -95,7 +107,7 @@ static void fk_n(const mpk_robot *rb, int64_t P, const double *th, double *T, do
     }
 }
 
-template <int N, bool GEN, bool REV>
+template <int N, bool GEN, bool REV, unsigned GEO = 0>
 static void fd_nf(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                   const double *tau, const double *g, const double *ftip_rows, double *dd) {
     const RobotPack<double, N> pk = narrow<N>(rb);
@@ -109,7 +121,7 @@ static void fd_nf(const mpk_robot *rb, int64_t P, const double *th, const double
             c[j] = tau[p * N + j];
         }
         const double *ft = ftip_rows ? ftip_rows + 6 * p : nullptr;
-        forward_dynamics<double, N, GEN, REV>(pk, a, b, c, g0, ft, o);
+        forward_dynamics<double, N, GEN, REV, 0, GEO>(pk, a, b, c, g0, ft, o);
         for (int j = 0; j < N; ++j) dd[p * N + j] = o[j];
     }
 }
@@ -117,6 +129,12 @@ static void fd_nf(const mpk_robot *rb, int64_t P, const double *th, const double
 template <int N>
 static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                  const double *tau, const double *g, const double *ftip_rows, double *dd) {
+#define X(n_, g_)                                    \
+    if constexpr (N == n_)                           \
+        if (flavour(rb) == 0 && rb->geo == g_)       \
+            return fd_nf<N, false, true, g_>(rb, P, th, dth, tau, g, ftip_rows, dd);
+    MPK_GEO_LIST(X)
+#undef X
     switch (flavour(rb)) {
         case 0: fd_nf<N, false, true>(rb, P, th, dth, tau, g, ftip_rows, dd); break;
         case 1: fd_nf<N, false, false>(rb, P, th, dth, tau, g, ftip_rows, dd); break;
@@ -136,6 +154,14 @@ static void fd_n(const mpk_robot *rb, int64_t P, const double *th, const double 
         case 8: { constexpr int N_ = 8; __VA_ARGS__; } break;    \
         default: return -2;                                      \
     }
+
+// Route a robot through the general kernels (signature 0) or back through the ones of its own
+// link-geometry signature: the tests compare the two.  Returns the previous signature.
+extern "C" unsigned hc_set_geo(mpk_robot *rb, unsigned geo) {
+    const unsigned old = rb->geo;
+    rb->geo = geo;
+    return old;
+}
 
 extern "C" int hc_rnea(const mpk_robot *rb, int64_t P, const double *th, const double *dth,
                        const double *ddth, const double *g, const double *ftip, double *tau) {

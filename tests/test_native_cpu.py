@@ -669,3 +669,42 @@ def test_ik_guess_helpers_match_reference_formulas():
     g1 = ik_helpers.workspace_heuristic_guess(T, 6, [(-3, 3)] * 6)
     gb = ik_helpers.workspace_heuristic_guess(np.stack([T, T]), 6, [(-3, 3)] * 6)
     assert g1.shape == (6,) and np.array_equal(gb[0], g1) and np.isclose(g1[0], np.arctan2(0.2, 0.3))
+
+
+# ---------------------------------------------------------------------------------------------
+# link-geometry signatures: the kernels compiled for an arm family's parallel / perpendicular /
+# intersecting axes return what the general kernels return
+# ---------------------------------------------------------------------------------------------
+def test_link_geometry_signatures_of_the_robot_database(hostcheck):
+    zoo = load_zoo()
+    sig = {r: hostcheck.geo(hostcheck.robot(zoo[r])) for r in ZOO_ROBOTS}
+    assert sig["ur5"] == sig["ur10e"] == sig["ur3"] == 0xD52AD0   # axes 2, 3, 4 parallel; 1, 5, 6 perpendicular
+    assert sig["iiwa14"] == sig["iiwa7"] == 0xD555150             # all perpendicular, all but one intersecting
+    assert sig["crx10ia"] == 0xD558D0 and sig["abb_irb2400"] == 0xDD1A90 and sig["fanuc_lrmate"] == 0xDD1890
+    assert sig["panda"] == 0                                      # not a plain revolute chain: general kernels
+    assert sig["xarm6"] == 0x8402C0                               # alpha = pi/2 only to 1e-6: class bits a = 0 / d = 0 only
+
+
+@pytest.mark.parametrize("robot", ["ur5", "ur10e", "iiwa14", "crx10ia", "fanuc_lrmate", "abb_irb2400", "gen3"])
+def test_geometry_specialised_kernels_equal_general_kernels(hostcheck, robot):
+    z = load_zoo()[robot]
+    rb = hostcheck.robot(z)
+    geo = hostcheck.geo(rb)
+    assert geo != 0
+    rng = np.random.default_rng(8)
+    n = rb[1]
+    th, dth, ddth = rng.uniform(-3, 3, (64, n)), rng.uniform(-2, 2, (64, n)), rng.uniform(-5, 5, (64, n))
+    tau, ft = rng.uniform(-10, 10, (64, n)), rng.uniform(-5, 5, 6)
+
+    def run():
+        return (hostcheck.rnea(rb, th, dth, ddth), hostcheck.rnea(rb, th, dth, ddth, smem_store=True),
+                hostcheck.rnea(rb, th, dth, ddth, ftip=ft), hostcheck.rnea(rb, th), hostcheck.mass(rb, th),
+                hostcheck.fd(rb, th, dth, tau))
+
+    special = run()
+    assert hostcheck.set_geo(rb, 0) == geo
+    general = run()
+    hostcheck.set_geo(rb, geo)
+    for a, b in zip(special, general):
+        sc = np.maximum(1.0, np.abs(b).reshape(64, -1).max(1)).reshape((64,) + (1,) * (b.ndim - 1))
+        assert (np.abs(a - b) / sc).max() < 5e-14
