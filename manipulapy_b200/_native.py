@@ -12,9 +12,14 @@ import ctypes as C
 import re
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "_lib" / "libmpk.so"
-OPS_PATH = PKG / "_lib" / "_mpk_ops.so"
+# MPK_LIB_DIR (tuning sweeps only): load a differently compiled pair of libraries, e.g. one built with
+# other launch bounds (scripts/build_variant.sh)
+_LIB_DIR = Path(os.environ["MPK_LIB_DIR"]).resolve() if os.environ.get("MPK_LIB_DIR") else PKG / "_lib"
+LIB_PATH = _LIB_DIR / "libmpk.so"
+OPS_PATH = _LIB_DIR / "_mpk_ops.so"
 HEADER = PKG.parent / "include" / "mpk.h"
 
 _lib = None

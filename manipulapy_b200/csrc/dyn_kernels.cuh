@@ -28,6 +28,14 @@ constexpr int kDynThreads = 128;
 #define MPK_RNEA_MINBLOCKS 4
 #endif
 constexpr int kRneaMinBlocks = MPK_RNEA_MINBLOCKS;
+// The fused kernel: 6 resident blocks (24 warps) per SM -- what its shared memory allows -- i.e. an
+// 85-register cap.  Its prologue evaluates the sines / cosines of all joints as independent chains,
+// which the compiler would otherwise spread over 120 registers (4 blocks per SM: fp64 pipe 67 % busy,
+// top stalls `wait` and `barrier`; with 6 blocks and no block barrier: see profiles/r2_variants.md).
+#ifndef MPK_FUSED_MINBLOCKS
+#define MPK_FUSED_MINBLOCKS 6
+#endif
+constexpr int kFusedMinBlocks = MPK_FUSED_MINBLOCKS;
 // MPK_RNEA_REGSTORE (tuning knob): the fused kernel keeps the link wrenches in registers (RegStore)
 // instead of the per-thread shared-memory column.
 #ifndef MPK_RNEA_REGSTORE
@@ -329,56 +337,140 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
 }
 
 // ---- fused trajectory + inverse dynamics ----------------------------------------
-// Joint values produced from the time scaling when the recursion reaches the link: the
-// float32-rounded, clipped trajectory row entries the two-call sequence would have stored.
+// The trajectory rows are never read back from HBM: each thread produces the float32-rounded,
+// clipped row entries the two-call sequence would have stored and feeds them to the recursion.
+//
+// Prologue (everything that is not rigid-body algebra, kept as short as it can be -- the kernel is
+// bound by the fp64 pipe AND the register-file bandwidth, which every instruction shares):
+//   1. the block's 128 consecutive points belong to at most 127 / N + 2 trajectories: their
+//      endpoints (start, end - start, in the precision the reference subtracts in) are staged ONCE
+//      per block in shared memory, so a thread's per-joint work is two 8-byte shared loads instead
+//      of two global loads, three conversions and a subtraction;
+//   2. all joint positions first, then all joint sines / cosines behind ONE range test: N
+//      independent dependency chains in one basic block, coefficients fetched once (SmemStorePre);
+//   3. velocities / accelerations of a joint are produced when the recursion reaches its link.
 // `stage` (WRITE variant): the thread's row in the block's shared-memory tiles of positions,
 // velocities and accelerations, from where the rows go to HBM with coalesced stores.
 template <int N, typename T>
-struct TrajIn {
-    const TrajRneaArgs &a;
-    TimeScale ts;
-    int64_t row;   // b * N
-    float *stage;  // or nullptr
+struct TrajInPre {
+    double sd, sdd;
+    const double *tab;  // this thread's trajectory in the block's endpoint table: (start, delta) per joint
+    float *stage;       // or nullptr
     __device__ __forceinline__ void joint(int i, T &th, T &qd, T &qdd) {
-        double st, dth;
-        endpoint(a.start, a.end, a.inputs_f32, row + i, st, dth);
-        float p, v, ac;
-        traj_point(ts, st, dth, a.jlim.lo[i], a.jlim.hi[i], a.jlim.on, p, v, ac);
+        const double dth = tab[2 * i + 1];
+        const float v = (float)rn_mul(sd, dth), ac = (float)rn_mul(sdd, dth);
         if (stage) {
-            stage[i] = p;
             stage[kDynThreads * N + i] = v;
             stage[2 * kDynThreads * N + i] = ac;
         }
-        th = (T)p;
+        th = T(0);  // (the joint rotations were evaluated up front)
         qd = (T)v;
         qdd = (T)ac;
     }
 };
 
+// The same, positions included, everything produced when the recursion reaches the link (the joint
+// rotation is then evaluated there too: MPK_FUSED_LAZY_SINCOS, fewer registers, one range test and
+// one coefficient fetch per link).
+template <int N, typename T>
+struct TrajInLazy {
+    const TimeScale &ts;
+    const double *tab;
+    const Limits &jlim;
+    float *stage;
+    __device__ __forceinline__ void joint(int i, T &th, T &qd, T &qdd) {
+        const double st = tab[2 * i], dth = tab[2 * i + 1];
+        const float pj = clip_f32((float)rn_add(rn_mul(ts.s, dth), st), jlim.lo[i], jlim.hi[i]);
+        const float v = (float)rn_mul(ts.sd, dth), ac = (float)rn_mul(ts.sdd, dth);
+        if (stage) {
+            stage[i] = pj;
+            stage[kDynThreads * N + i] = v;
+            stage[2 * kDynThreads * N + i] = ac;
+        }
+        th = (T)pj;
+        qd = (T)v;
+        qdd = (T)ac;
+    }
+};
+#ifndef MPK_FUSED_LAZY_SINCOS
+#define MPK_FUSED_LAZY_SINCOS 0
+#endif
+
+// Threads that share one shared-memory slice of the fused kernel (link state / output staging / endpoint
+// table) and synchronise among themselves: a warp (32, only __syncwarp) or the whole block (128,
+// __syncthreads).  Measured on B200 (profiles/r2_variants.md): MPK_FUSED_GROUP.
+#ifndef MPK_FUSED_GROUP
+#define MPK_FUSED_GROUP 128
+#endif
+constexpr int kFusedGroup = MPK_FUSED_GROUP;
+static_assert(kFusedGroup == 32 || kFusedGroup == kDynThreads, "a group is a warp or the block");
+
+// shared memory of the endpoint tables: (start, delta) x N joints x the trajectories one group's
+// consecutive points can touch, one table per group
+__host__ __device__ inline int traj_table_rows(int64_t B, int64_t N) {
+    int64_t k = (kFusedGroup - 1) / (N > 0 ? N : 1) + 2;
+    return (int)(k > B ? B : k);
+}
+inline size_t traj_table_bytes(int n, int64_t B, int64_t N) {
+    return (size_t)(kDynThreads / kFusedGroup) * traj_table_rows(B, N) * n * 2 * sizeof(double);
+}
+
 // WRITE: also materialise the trajectory rows (positions, velocities, accelerations).  The
 // kernel is bound by the fp64 pipe with HBM at 6 %, so the extra 12 N bytes per point ride
 // along at a fraction of their stand-alone cost (0.65 ms against 0.17 + 0.57 ms for the two launches).
+__device__ __forceinline__ void fused_group_sync() {
+    if (kFusedGroup == 32) __syncwarp();
+    else __syncthreads();
+}
+
 template <typename T, int N, bool GEN, bool REV, bool TIP, bool WRITE = false, unsigned GEO = 0>
-__global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
+__global__ void __launch_bounds__(kDynThreads, kFusedMinBlocks)
     traj_rnea_kernel(const __grid_constant__ RobotPack<T, N> rb, const TrajRneaArgs a) {
-    // dynamic shared memory: the per-thread link state of the recursion, then (same bytes) the
-    // block's output rows staged for coalesced stores; WRITE: + three trajectory tiles behind it
+    // Dynamic shared memory, one slice per GROUP of kFusedGroup threads:
+    //   the per-thread link state of the recursion (column stride = group size), whose bytes afterwards
+    //   stage the group's output rows for coalesced stores | the group's endpoint table;
+    //   WRITE: + three block-wide trajectory tiles.
     extern __shared__ __align__(16) double wsm_raw[];
-    T *wsm = reinterpret_cast<T *>(wsm_raw);
-    float *sm = reinterpret_cast<float *>(wsm_raw);
-    float *traj_sm = reinterpret_cast<float *>(
-        reinterpret_cast<char *>(wsm_raw) + wrench_smem<T, N, GEN, REV>());
-    const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
-    const bool live = p0 + threadIdx.x < a.P;
-    int64_t b, t;
-    point_coords(a.div, a.N, live ? p0 + threadIdx.x : 0, b, t);
-    const int64_t rem = a.P - p0;
-    const int cnt = (int)(rem < kDynThreads ? rem : kDynThreads) * N;
-    const int64_t off = p0 * N;
-    // (tail threads of the last block recompute point 0: they take part in the barriers and
-    // their staged rows are never stored)
-    TrajIn<N, T> in{a, time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method), b * N,
-                    WRITE ? traj_sm + threadIdx.x * N : nullptr};
+    constexpr int G = kFusedGroup, kGroups = kDynThreads / G;
+#if MPK_FUSED_LAZY_SINCOS
+    using Store = SmemStore<T, N, G, rnea_fast0(GEN, REV, N)>;
+#else
+    using Store = SmemStorePre<T, N, G, rnea_fast0(GEN, REV, N)>;
+#endif
+    constexpr size_t kGroupState = wrench_smem<T, N, GEN, REV>() / kGroups;  // bytes, a multiple of 128
+    const int grp = threadIdx.x / G, gl = threadIdx.x % G;
+    char *smem = reinterpret_cast<char *>(wsm_raw);
+    T *wsm = reinterpret_cast<T *>(smem + grp * kGroupState);
+    float *sm = reinterpret_cast<float *>(smem + grp * kGroupState);
+    float *traj_sm = reinterpret_cast<float *>(smem + wrench_smem<T, N, GEN, REV>());
+    const int table_rows = traj_table_rows(a.B, a.N);
+    double *table = reinterpret_cast<double *>(smem + wrench_smem<T, N, GEN, REV>() +
+                                               (WRITE ? 3 * sizeof(float) * kDynThreads * N : 0)) +
+                    grp * table_rows * (2 * N);
+    const int64_t pw = (int64_t)blockIdx.x * kDynThreads + grp * G;  // the group's first point
+    if (G == 32 && !WRITE && pw >= a.P) return;                        // whole warp past the end
+    const int64_t rem = a.P - pw;
+    const int live_n = rem <= 0 ? 0 : (int)(rem < G ? rem : G);
+    // (threads past the end recompute the group's first point; their staged rows are never stored.  In
+    // the WRITE variant a warp past the end idles through the block barrier on point 0.)
+    const int64_t pf = live_n > 0 ? pw : 0;
+    int64_t b, t, b0, t0, b1, t1;
+    point_coords(a.div, a.N, gl < live_n ? pw + gl : pf, b, t);
+    point_coords(a.div, a.N, pf, b0, t0);
+    point_coords(a.div, a.N, live_n > 0 ? pw + live_n - 1 : pf, b1, t1);
+    {
+        const int entries = (int)(b1 - b0 + 1) * N;
+        for (int e = gl; e < entries; e += G) {
+            double st, dth;
+            endpoint(a.start, a.end, a.inputs_f32, b0 * N + e, st, dth);
+            table[2 * e] = st;
+            table[2 * e + 1] = dth;
+        }
+    }
+    fused_group_sync();
+    const TimeScale ts = time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method);
+    const double *tab = table + (b - b0) * (2 * N);
+    float *stage = WRITE ? traj_sm + threadIdx.x * N : nullptr;
     float out[N];
     {
         T g0[3], ft[6];
@@ -390,27 +482,41 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
         }
         const T *ftp = TIP ? ft : nullptr;
         T tau[N];
-#if MPK_RNEA_REGSTORE
-        RegStore<T, N> st;
+        Store st;
+        st.base = wsm + gl;
+#if MPK_FUSED_LAZY_SINCOS
+        TrajInLazy<N, T> in{ts, tab, a.jlim, stage};
 #else
-        SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
+        {
+            T th[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                // start + s * delta, one rounding to float32, clipped (bounds are infinite without limits)
+                const float pj = clip_f32((float)rn_add(rn_mul(ts.s, tab[2 * j + 1]), tab[2 * j]), a.jlim.lo[j], a.jlim.hi[j]);
+                if (WRITE) stage[j] = pj;
+                th[j] = (T)pj;
+            }
+            st.template precompute<REV>(rb, th);
+        }
+        TrajInPre<N, T> in{ts.sd, ts.sdd, tab, stage};
 #endif
         rnea<T, N, GEN, REV, GEO>(rb, in, g0, ftp, tau, st);
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            out[j] = (float)tau[j];
-            if (a.tlim.on) out[j] = clip_f32(out[j], a.tlim.lo[j], a.tlim.hi[j]);
-        }
+        for (int j = 0; j < N; ++j) out[j] = clip_f32((float)tau[j], a.tlim.lo[j], a.tlim.hi[j]);
     }
-    __syncthreads();  // every thread is done with its link state: the bytes become the staging tile
+    fused_group_sync();  // every thread of the group is done with its link state: the bytes become the staging tile
 #pragma unroll
-    for (int j = 0; j < N; ++j) sm[threadIdx.x * N + j] = out[j];
-    __syncthreads();
-    tile_store(a.tau + off, sm, cnt);
+    for (int j = 0; j < N; ++j) sm[gl * N + j] = out[j];
+    fused_group_sync();
+    if (live_n > 0) group_tile_store<G>(a.tau + pw * N, sm, live_n * N);
     if (WRITE) {
-        if (a.pos) tile_store(a.pos + off, traj_sm, cnt);
-        if (a.vel) tile_store(a.vel + off, traj_sm + kDynThreads * N, cnt);
-        if (a.acc) tile_store(a.acc + off, traj_sm + 2 * kDynThreads * N, cnt);
+        __syncthreads();
+        const int64_t p0 = (int64_t)blockIdx.x * kDynThreads;
+        const int64_t remb = a.P - p0;
+        const int cnt = (int)(remb < kDynThreads ? remb : kDynThreads) * N;
+        if (a.pos) tile_store(a.pos + p0 * N, traj_sm, cnt);
+        if (a.vel) tile_store(a.vel + p0 * N, traj_sm + kDynThreads * N, cnt);
+        if (a.acc) tile_store(a.acc + p0 * N, traj_sm + 2 * kDynThreads * N, cnt);
     }
 }
 
@@ -742,22 +848,23 @@ void launch_rnea_n(const mpk_robot *rb, const RneaArgs &a, unsigned grid, cudaSt
 template <int F, int N, unsigned GEO>
 void launch_traj_rnea_n(const mpk_robot *rb, const TrajRneaArgs &a, unsigned grid, cudaStream_t s) {
     constexpr bool GEN = flavour_gen(F), REV = flavour_rev(F);
+    const size_t tab = traj_table_bytes(N, a.B, a.N);
     if (a.compute_f32 && a.tip.has_ftip) {
         launch_smem(traj_rnea_kernel<float, N, GEN, REV, true, false, GEO>, grid, kDynThreads,
-                    wrench_smem<float, N, GEN, REV>(), s, narrow<N, float>(rb), a);
+                    wrench_smem<float, N, GEN, REV>() + tab, s, narrow<N, float>(rb), a);
     } else if (a.compute_f32) {
         launch_smem(traj_rnea_kernel<float, N, GEN, REV, false, false, GEO>, grid, kDynThreads,
-                    wrench_smem<float, N, GEN, REV>(), s, narrow<N, float>(rb), a);
+                    wrench_smem<float, N, GEN, REV>() + tab, s, narrow<N, float>(rb), a);
     } else if (a.pos || a.vel || a.acc) {
         // (float64, no tip wrench: the launcher only asks for this variant then)
         launch_smem(traj_rnea_kernel<double, N, GEN, REV, false, true, GEO>, grid, kDynThreads,
-                    wrench_smem<double, N, GEN, REV>() + 3 * sizeof(float) * kDynThreads * N, s, narrow<N>(rb), a);
+                    wrench_smem<double, N, GEN, REV>() + 3 * sizeof(float) * kDynThreads * N + tab, s, narrow<N>(rb), a);
     } else if (a.tip.has_ftip) {
         launch_smem(traj_rnea_kernel<double, N, GEN, REV, true, false, GEO>, grid, kDynThreads,
-                    wrench_smem<double, N, GEN, REV>(), s, narrow<N>(rb), a);
+                    wrench_smem<double, N, GEN, REV>() + tab, s, narrow<N>(rb), a);
     } else {
         launch_smem(traj_rnea_kernel<double, N, GEN, REV, false, false, GEO>, grid, kDynThreads,
-                    wrench_smem<double, N, GEN, REV>(), s, narrow<N>(rb), a);
+                    wrench_smem<double, N, GEN, REV>() + tab, s, narrow<N>(rb), a);
     }
 }
 

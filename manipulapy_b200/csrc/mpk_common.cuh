@@ -185,8 +185,9 @@ inline Limits make_limits(const float *lim, int n) {
     Limits L;
     L.on = lim != nullptr;
     for (int j = 0; j < MPK_MAX_DOF; ++j) {
-        L.lo[j] = (lim && j < n) ? lim[2 * j] : 0.f;
-        L.hi[j] = (lim && j < n) ? lim[2 * j + 1] : 0.f;
+        // (without limits the bounds are infinite, so that code which clips unconditionally is a no-op)
+        L.lo[j] = (lim && j < n) ? lim[2 * j] : -INFINITY;
+        L.hi[j] = (lim && j < n) ? lim[2 * j + 1] : INFINITY;
     }
     return L;
 }
@@ -309,6 +310,32 @@ __device__ __forceinline__ void tile_store(float *o, const float *sm, int cnt) {
         for (int i = (n2 << 1) + threadIdx.x; i < cnt; i += blockDim.x) o[i] = sm[i];
     } else {
         for (int i = threadIdx.x; i < cnt; i += blockDim.x) __stcs(o + i, sm[i]);
+    }
+}
+
+// The same for the rows of a group of G threads (a warp or the block; cnt floats from the group's own
+// shared-memory slice, 16-byte aligned); only the calling group takes part.
+template <int G>
+__device__ __forceinline__ void group_tile_store(float *o, const float *sm, int cnt) {
+    const int gl = threadIdx.x % G;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(o);
+    if ((addr & 15u) == 0) {
+        const int n4 = cnt >> 2;
+        const float4 *s4 = reinterpret_cast<const float4 *>(sm);
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+#pragma unroll 2
+        for (int i = gl; i < n4; i += G) __stcs(o4 + i, s4[i]);
+        for (int i = (n4 << 2) + gl; i < cnt; i += G) o[i] = sm[i];
+    } else if ((addr & 7u) == 0) {
+        const int n2 = cnt >> 1;
+        const float2 *s2 = reinterpret_cast<const float2 *>(sm);
+        float2 *o2 = reinterpret_cast<float2 *>(o);
+#pragma unroll 2
+        for (int i = gl; i < n2; i += G) __stcs(o2 + i, s2[i]);
+        for (int i = (n2 << 1) + gl; i < cnt; i += G) o[i] = sm[i];
+    } else {
+#pragma unroll 2
+        for (int i = gl; i < cnt; i += G) __stcs(o + i, sm[i]);
     }
 }
 

@@ -685,6 +685,12 @@ struct RegStore {
         s = q.s[i];
         d = q.d[i];
     }
+    // (the backward pass asks through its own accessor, so that a store may keep the rotations in
+    // registers for the forward pass only)
+    template <bool REV>
+    MPK_HD void get_cs_back(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
+        get_cs<REV>(rb, i, c, s, d);
+    }
 };
 // ... with the joint rotations q already filled in by the caller (joint_cs_all): rnea() reads
 // them instead of evaluating sin / cos link by link.
@@ -708,7 +714,11 @@ struct SmemStore {
         return (FAST0 ? (l == 0 ? (k == 2 ? 0 : k - 5) : 3 + (l - 1) * 8 + k) : l * 8 + k) * THREADS;
     }
     MPK_HD void put(int i, int k, T v) { base[at(i, k)] = v; }
-    MPK_HD T get(int i, int k) const { return base[at(i, k)]; }
+    // (volatile loads: the compiler must not forward the value it stored in the forward pass to the
+    // backward pass in a register -- that keeps 8 (N-1) doubles alive across the whole recursion,
+    // which is exactly what this store exists to avoid: 72 -> 122 registers, or spills to local memory)
+    MPK_HD T ld(int idx) const { return *static_cast<const volatile T *>(base + idx); }
+    MPK_HD T get(int i, int k) const { return ld(at(i, k)); }
     template <bool REV>
     MPK_HD void put_cs(const RobotPack<T, N> &rb, int i, T c, T s, T d) {
         if (i == 0) return;
@@ -717,15 +727,74 @@ struct SmemStore {
     }
     template <bool REV>
     MPK_HD void get_cs(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
-        const T x = base[at(i - 1, 7)];
+        const T x = ld(at(i - 1, 7));
         if (REV || rb.sr[i] != T(0)) {
-            c = base[at(i - 1, 6)];
+            c = ld(at(i - 1, 6));
             s = x;
             d = rb.d[i];
         } else {
             c = rb.cphi[i];
             s = rb.sphi[i];
             d = x;
+        }
+    }
+    template <bool REV>
+    MPK_HD void get_cs_back(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
+        get_cs<REV>(rb, i, c, s, d);
+    }
+};
+
+// ... with the joint rotations evaluated by the caller BEFORE the recursion (all joints behind one
+// range test: N independent dependency chains in one basic block, the coefficients fetched once
+// instead of once per link).  They go straight to the shared-memory column (where the backward pass
+// reads them anyway), so they cost no registers while the recursion runs; only those of the first
+// link (consumed at once) and of the last link (needed where the two passes meet) stay in registers.
+template <typename T, int N, int THREADS, bool FAST0 = false>
+struct SmemStorePre : SmemStore<T, N, THREADS, FAST0> {
+    using Base = SmemStore<T, N, THREADS, FAST0>;
+    static constexpr bool kPrecomputedCS = true;
+    T c0_, s0_, d0_, cl_, sl_, dl_;  // first / last link (d: only touched for chains with a prismatic joint)
+    template <bool REV>
+    MPK_HD void precompute(const RobotPack<T, N> &rb, const T (&th)[N]) {
+        T c[N], s[N];
+        bool near = true;
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if (REV || rb.sr[i] != T(0)) near = near && sincos_is_near(rb.phi[i] + th[i]);
+        if (near) {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (REV || rb.sr[i] != T(0)) sincos_near(rb.trig, rb.phi[i] + th[i], &s[i], &c[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i)
+                if (REV || rb.sr[i] != T(0)) sincos_pack(rb.trig, rb.phi[i] + th[i], &s[i], &c[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T d = rb.d[i];
+            if (!REV && rb.sr[i] == T(0)) {
+                c[i] = rb.cphi[i];
+                s[i] = rb.sphi[i];
+                d = rb.d[i] + rb.st[i] * th[i];
+            }
+            if (i == 0) {
+                c0_ = c[i]; s0_ = s[i]; d0_ = d;
+            }
+            if (i == N - 1) {
+                cl_ = c[i]; sl_ = s[i]; dl_ = d;
+            }
+            if (i > 0 && i < N - 1) Base::template put_cs<REV>(rb, i, c[i], s[i], d);
+        }
+    }
+    template <bool REV>
+    MPK_HD void get_cs(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
+        if (i == 0) {
+            c = c0_; s = s0_; d = REV ? rb.d[0] : d0_;
+        } else if (i == N - 1) {
+            c = cl_; s = sl_; d = REV ? rb.d[N - 1] : dl_;
+        } else {
+            Base::template get_cs<REV>(rb, i, c, s, d);
         }
     }
 };
@@ -940,7 +1009,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
             for (int j = N - 1; j >= 1; --j) {
                 tau[j] = (REV || rb.sr[j] != T(0)) ? an[2] : rb.st[j] * af[2];
                 // the wrench of link j, moved to frame j-1, is added to link j-1's local wrench
-                if (j < N - 1) st_.template get_cs<REV>(rb, j, cj, sj, dj);
+                if (j < N - 1) st_.template get_cs_back<REV>(rb, j, cj, sj, dj);
                 if (FAST0 && j == 1) {
                     an[2] = wrench_to_parent_nz<T, N, !REV, GEO>(rb, 1, cj, sj, dj, an, af, st_.get(0, 2));
                 } else {
