@@ -62,8 +62,10 @@ METRIC, UNIT = "rnea_trajectory_points_per_s", "points/s"
 FLOP_PER_POINT = 2070 + 60            # textbook fp64 Newton-Euler recursion (n = 6) + time scaling
 # what the fused kernel executes per point (scripts/sass_census.py on the main path; ncu agrees):
 # fp64 instructions (DFMA + DMUL + DADD) and the flops they stand for
-FP64_INSTR_PER_POINT = {"fused": 736, "two_kernel": 712}
-FLOP_EXECUTED_PER_POINT = {"fused": 1250, "two_kernel": 1226}
+# (ncu, profiles/r2_traj_rnea_instruction_mix.csv: 439 DFMA + 138 DMUL + 48 DADD per point with the UR
+# family's link-geometry kernels; round 1's general kernel executed 514 + 181 + 41 = 736)
+FP64_INSTR_PER_POINT = {"fused": 625, "two_kernel": 601}
+FLOP_EXECUTED_PER_POINT = {"fused": 1064, "two_kernel": 1034}
 BYTES_FUSED = 6 * 4                   # float32 torque row out; endpoints amortised over 2441 points
 BYTES_RNEA = 3 * 6 * 4 + 6 * 4        # float32 theta, dtheta, ddtheta in; float32 torque out
 BYTES_TRAJ = 3 * 6 * 4                # float32 pos, vel, acc out

@@ -255,6 +255,42 @@ int mpk_fma_peak(int dtype, int blocks, int threads, int64_t iters, double *sink
  * events to get the write-only HBM ceiling the trajectory kernel's roofline is quoted against. */
 int mpk_store_peak(void *dst_dev, int64_t bytes, int mode, int blocks, void *stream);
 
+/* ---- collision / limit post-processing hook of joint_trajectory -------------------
+ * Replaces the per-row host loop of planning/collision_host.py:40-88 -- URDF.link_fk over the link tree
+ * (urdf/core.py:532-633), CollisionChecker.check_collision (potential_field/collision.py:162-221: boxes
+ * of the transformed hull points, pairwise overlap outside the allowed-collision set) and the attractive
+ * potential-field step (potential_field/fields.py:112-170 with no obstacles).
+ *
+ * The collision model is packed once on the host and uploaded by the caller (no hidden allocation):
+ *   link_joint (L) int32      actuated joint each link hangs on, -1 = fixed to the base
+ *   link_home  (L, 4, 4)      link poses at the zero configuration (URDF.link_fk(zeros))
+ *   acm        (L, L) uint8   1 = pair excluded (potential_field/adjacency.py:9-30)
+ *   hull_link  (H) int32, hull_count (H) int32, hull_points (sum counts, 3) float64
+ *                             ConvexHull.points of every link that has geometry, link frame, in the
+ *                             checker's insertion order
+ * mpk_collision_model_bytes gives the size of the packed model, mpk_collision_model_pack fills `out`
+ * (host memory).  Launchers take the packed model twice: `model_host` (only its header is read, for
+ * validation) and `model_dev` (the same bytes in device memory). */
+size_t mpk_collision_model_bytes(int n, int L, int H, int64_t npoints);
+int mpk_collision_model_pack(const mpk_robot *rb, int L, const int32_t *link_joint, const double *link_home,
+                             const uint8_t *acm, int H, const int32_t *hull_link, const int32_t *hull_count,
+                             const double *hull_points, void *out, size_t out_bytes);
+/* URDF.link_fk_batch (urdf/core.py:577-633): T dev (P, L, 4, 4) float64, theta dev (P, n) theta_dtype */
+int mpk_link_fk_batch(const mpk_robot *rb, const void *model_host, const void *model_dev, int64_t P,
+                      const void *theta, int theta_dtype, double *T, void *stream);
+/* CollisionChecker.check_collision per configuration: flags dev (P) uint8 */
+int mpk_self_collision_aabb(const mpk_robot *rb, const void *model_host, const void *model_dev, int64_t P,
+                            const void *theta, int theta_dtype, uint8_t *flags, void *stream);
+/* _apply_collision_avoidance_cpu (collision_host.py:40-88): rows dev (P, n) float32 are nudged IN PLACE,
+ * row p towards goal[p / rows_per_goal] (goal dev (G, n) float32: thetaend of the row's trajectory):
+ * while the row collides and fewer than max_iterations steps were taken,
+ *   row <- row - step * (attractive_gain * (row - goal))       (float32, every operation rounded)
+ * iterations dev (P) int32 (steps taken) and flags dev (P) uint8 (still colliding) may be NULL.
+ * The reference uses step = 0.01, max_iterations = 100, attractive_gain = 1. */
+int mpk_collision_avoidance(const mpk_robot *rb, const void *model_host, const void *model_dev, int64_t P,
+                            float *rows, const float *goal, int64_t rows_per_goal, double attractive_gain,
+                            double step, int max_iterations, int32_t *iterations, uint8_t *flags, void *stream);
+
 /* Result buffers shared by the processes of one box (one process per GPU), SURVEY.md 8e: the
  * rank that collects a sharded result allocates it with mpk_peer_alloc and hands the 64-byte handle
  * to the other ranks (any channel: torch.distributed's object broadcast in the Python host); they

@@ -15,6 +15,7 @@ from .cuda_kernels import KERNEL_REGISTRY, KernelRegistration, KernelRegistry, e
 from .dynamics import ManipulatorDynamics
 from .kinematics import SerialManipulator
 from .path_planning import OptimizedTrajectoryPlanning, TrajectoryPlanning
+from .potential_field import CollisionChecker, PotentialField
 from .robots import RobotBundle, available_robots, load_robot
 from .sharding import gather_rows, shard_range
 from .singularity import Singularity
@@ -27,5 +28,5 @@ __all__ = [
     "KERNEL_REGISTRY", "KernelRegistration", "KernelRegistry", "execute_registered_kernel",
     "ManipulatorDynamics", "SerialManipulator", "OptimizedTrajectoryPlanning", "TrajectoryPlanning",
     "RobotBundle", "available_robots", "load_robot", "gather_rows", "shard_range", "bind_host_to_device",
-    "ik_helpers", "Singularity",
+    "ik_helpers", "Singularity", "CollisionChecker", "PotentialField",
 ]

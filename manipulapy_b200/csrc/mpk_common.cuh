@@ -14,6 +14,7 @@ struct mpk_robot {
     int plain;         // all revolute and every link plain Denavit-Hartenberg (beta = 0): flavour 0
     int first_revolute;  // joint 0 is revolute (required by the rigid kernel flavours)
     int has_dynamics;
+    double F[MPK_MAX_DOF][12];  // home pose of link frame k in space (R row-major 9, p 3): e^{[S_k] th} F_k = F_k Rz(th)
     unsigned geo;      // link geometry classes (mpk_device.cuh kGeo*), 4 bits per link; 0 unless `plain`
     mpk::RobotPack<double, MPK_MAX_DOF> pack;  // host copy, frames 0..n-1 valid
 };

@@ -349,6 +349,75 @@ void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads
           "fma_peak");
 }
 
+// ---- collision hook (csrc/collision.cu) ---------------------------------------------------------
+Tensor collision_model_pack(int64_t h, const Tensor &link_joint, const Tensor &link_home, const Tensor &acm,
+                            const Tensor &hull_link, const Tensor &hull_count, const Tensor &hull_points) {
+    mpk_robot *rb = robot(h);
+    Tensor lj = link_joint.to(at::kCPU, at::kInt).contiguous(), lh = link_home.to(at::kCPU, at::kDouble).contiguous();
+    Tensor ac = acm.to(at::kCPU, at::kByte).contiguous();
+    Tensor hl = hull_link.to(at::kCPU, at::kInt).contiguous(), hc = hull_count.to(at::kCPU, at::kInt).contiguous();
+    Tensor hp = hull_points.to(at::kCPU, at::kDouble).contiguous();
+    const int64_t L = lj.numel(), H = hl.numel();
+    TORCH_CHECK(lh.numel() == L * 16 && ac.numel() == L * L, "mpk: link_home must be (L, 4, 4) and acm (L, L)");
+    TORCH_CHECK(hc.numel() == H && hp.numel() == hc.sum().item<int64_t>() * 3, "mpk: hull tables do not match");
+    const size_t bytes = mpk_collision_model_bytes(mpk_robot_dof(rb), (int)L, (int)H, hp.numel() / 3);
+    Tensor out = at::zeros({(int64_t)bytes}, at::TensorOptions().dtype(at::kByte));
+    check(mpk_collision_model_pack(rb, (int)L, lj.data_ptr<int32_t>(), lh.data_ptr<double>(), ac.data_ptr<uint8_t>(),
+                                   (int)H, H ? hl.data_ptr<int32_t>() : nullptr, H ? hc.data_ptr<int32_t>() : nullptr,
+                                   H ? hp.data_ptr<double>() : nullptr, out.data_ptr<uint8_t>(), bytes),
+          "collision_model_pack");
+    return out;
+}
+
+Tensor link_fk_batch(int64_t h, const Tensor &model_host, const Tensor &model_dev, const Tensor &theta, int64_t L) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th = dev_rows(theta, n, "theta", true);
+    TORCH_CHECK(model_dev.is_cuda() && !model_host.is_cuda(), "mpk: model_host / model_dev");
+    const int64_t P = th.numel() / n;
+    c10::cuda::CUDAGuard guard(th.device());
+    Tensor T = at::empty({P, L, 4, 4}, th.options().dtype(at::kDouble));
+    check(mpk_link_fk_batch(rb, model_host.data_ptr(), model_dev.data_ptr(), P, th.data_ptr(), dtype_of(th),
+                            T.data_ptr<double>(), stream_of(th)),
+          "link_fk_batch");
+    return T;
+}
+
+Tensor self_collision(int64_t h, const Tensor &model_host, const Tensor &model_dev, const Tensor &theta) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    Tensor th = dev_rows(theta, n, "theta", true);
+    TORCH_CHECK(model_dev.is_cuda() && !model_host.is_cuda(), "mpk: model_host / model_dev");
+    const int64_t P = th.numel() / n;
+    c10::cuda::CUDAGuard guard(th.device());
+    Tensor flags = at::empty({P}, th.options().dtype(at::kByte));
+    check(mpk_self_collision_aabb(rb, model_host.data_ptr(), model_dev.data_ptr(), P, th.data_ptr(), dtype_of(th),
+                                  flags.data_ptr<uint8_t>(), stream_of(th)),
+          "self_collision_aabb");
+    return flags;
+}
+
+// rows (P, n) float32 are modified in place; -> (iterations int32 (P), still-colliding flags uint8 (P))
+std::tuple<Tensor, Tensor> collision_avoidance(int64_t h, const Tensor &model_host, const Tensor &model_dev,
+                                               Tensor rows, const Tensor &goal, int64_t rows_per_goal,
+                                               double attractive_gain, double step, int64_t max_iterations) {
+    mpk_robot *rb = robot(h);
+    const int64_t n = mpk_robot_dof(rb);
+    TORCH_CHECK(rows.is_cuda() && rows.scalar_type() == at::kFloat && rows.is_contiguous() && rows.size(-1) == n,
+                "mpk: rows must be a contiguous CUDA float32 (P, n) tensor");
+    Tensor g = goal.to(rows.device(), at::kFloat).contiguous();
+    const int64_t P = rows.numel() / n;
+    TORCH_CHECK(rows_per_goal >= 1 && g.numel() % n == 0 && (P + rows_per_goal - 1) / rows_per_goal <= g.numel() / n,
+                "mpk: goal must hold one row per rows_per_goal rows");
+    c10::cuda::CUDAGuard guard(rows.device());
+    Tensor it = at::empty({P}, rows.options().dtype(at::kInt)), fl = at::empty({P}, rows.options().dtype(at::kByte));
+    check(mpk_collision_avoidance(rb, model_host.data_ptr(), model_dev.data_ptr(), P, rows.data_ptr<float>(),
+                                  g.data_ptr<float>(), rows_per_goal, attractive_gain, step, (int)max_iterations,
+                                  it.data_ptr<int32_t>(), fl.data_ptr<uint8_t>(), stream_of(rows)),
+          "collision_avoidance");
+    return {it, fl};
+}
+
 // ---- peer-shared result buffers (csrc/peer.cu) ----------------------------------------------
 // -> (float32 tensor of `numel` elements on `like`'s device, owning the cudaMalloc'd buffer; 64-byte handle)
 std::tuple<Tensor, Tensor> peer_alloc(int64_t numel, const Tensor &like) {
@@ -431,6 +500,14 @@ TORCH_LIBRARY(mpk, m) {
           &cartesian_trajectory);
     m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
     m.def("store_peak(Tensor dst, int mode, int blocks) -> ()", &store_peak);
+    m.def("collision_model_pack(int robot, Tensor link_joint, Tensor link_home, Tensor acm, Tensor hull_link, "
+          "Tensor hull_count, Tensor hull_points) -> Tensor",
+          &collision_model_pack);
+    m.def("link_fk_batch(int robot, Tensor model_host, Tensor model_dev, Tensor theta, int L) -> Tensor", &link_fk_batch);
+    m.def("self_collision(int robot, Tensor model_host, Tensor model_dev, Tensor theta) -> Tensor", &self_collision);
+    m.def("collision_avoidance(int robot, Tensor model_host, Tensor model_dev, Tensor(a!) rows, Tensor goal, "
+          "int rows_per_goal, float attractive_gain, float step, int max_iterations) -> (Tensor, Tensor)",
+          &collision_avoidance);
     m.def("peer_alloc(int numel, Tensor like) -> (Tensor, Tensor)", &peer_alloc);
     m.def("peer_open(Tensor handle, int numel, Tensor like) -> Tensor", &peer_open);
 }

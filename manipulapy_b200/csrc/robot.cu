@@ -467,6 +467,10 @@ extern "C" int mpk_robot_create(int n, const double *S_list, const double *M, co
             }
         }
     }
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 9; ++k) rb->F[i][k] = frames[i].R[k];
+        for (int k = 0; k < 3; ++k) rb->F[i][9 + k] = frames[i].p[k];
+    }
     const SE3 E = mul(inverse(frames[n - 1]), from_mat4(M));
     for (int k = 0; k < 9; ++k) rb->pack.Ree[k] = E.R[k];
     for (int k = 0; k < 3; ++k) rb->pack.pee[k] = E.p[k];

@@ -16,8 +16,11 @@ float32-rounded joint / torque limits (:218-223), position clip after generation
 row cast to float32 then clipped, semi-implicit Euler with ``intRes`` sub-steps, ``theta``
 clip without velocity reset, row 0 = initial state, ``IndexError`` for an empty ``taumat``.
 There is no CPU routing: every call runs the CUDA kernels (``use_cuda=False`` raises).
-The collision / potential-field post-processing hook (planning/collision_host.py) is outside
-the hot path and not applied.
+The collision / potential-field post-processing hook of ``joint_trajectory``
+(planning/trajectory.py:311-317, planning/collision_host.py:40-88) is applied when a
+``collision_checker`` (``manipulapy_b200.CollisionChecker``) and a ``potential_field`` are attached:
+the reference builds its checker from the URDF's meshes, this package from link data and hull points
+(``planner.attach_collision_checker(hulls)``), since mesh parsing is outside the hot path.
 """
 
 from __future__ import annotations
@@ -65,8 +68,13 @@ class OptimizedTrajectoryPlanning:
         self.enable_profiling = bool(enable_profiling)
         self.cuda_available = True
         self.cpu_threshold = 0  # everything runs on the GPU
+        # the reference builds CollisionChecker(urdf_path) here (trajectory_planning.py:232-238); without its
+        # mesh loader the hook starts detached -- attach_collision_checker() switches it on
         self.collision_checker = None
         self.potential_field = None
+        if urdf_path is not None:
+            logger.warning("urdf_path is given, but manipulapy_b200 does not parse URDF meshes: the collision "
+                           "hook of joint_trajectory stays off until attach_collision_checker(hulls) is called")
         self.device = _host.default_device(device if device is not None
                                            else getattr(dynamics, "_device_arg", None))
         p = torch.cuda.get_device_properties(self.device)
@@ -110,6 +118,19 @@ class OptimizedTrajectoryPlanning:
         KERNEL_REGISTRY.get(f"trajectory.{kt}")  # KeyError for unknown names, like the reference
         return kt
 
+    def attach_collision_checker(self, checker_or_hulls, links=None, potential_field=None) -> None:
+        """Switch on the collision hook of ``joint_trajectory``: a ``CollisionChecker``, or
+        ``{link name: (V, 3) hull points}`` together with the robot's link table."""
+        from .potential_field import CollisionChecker, PotentialField
+
+        if isinstance(checker_or_hulls, CollisionChecker):
+            self.collision_checker = checker_or_hulls
+        else:
+            if links is None:
+                raise ValueError("links (the robot's link table) is required with a hull dictionary")
+            self.collision_checker = CollisionChecker(self.dynamics, links, checker_or_hulls, device=self.device)
+        self.potential_field = potential_field or PotentialField()
+
     # -- trajectory generation ------------------------------------------------------------------------
     def joint_trajectory(self, thetastart, thetaend, Tf, N, method, kernel_type=None,
                          enable_monitoring=None) -> Dict[str, Any]:
@@ -120,6 +141,9 @@ class OptimizedTrajectoryPlanning:
         s = _host.to_device(thetastart, dev).reshape(1, -1)
         e = _host.to_device(thetaend, dev).reshape(1, -1)
         pos, vel, acc = _native.ops().joint_trajectory(s, e, True, float(Tf), int(N), int(method), self._jl)
+        if self.collision_checker and self.potential_field and int(N) > 0:
+            # planning/trajectory.py:316-317: colliding rows are nudged towards thetaend (float32, as cast above)
+            self.collision_checker.avoid(pos[0], e.float(), self.potential_field)
         out = {"positions": pos[0], "velocities": vel[0], "accelerations": acc[0]}
         if not on_dev:
             out = {k: _host.to_host(v) for k, v in out.items()}

@@ -19,7 +19,7 @@ _DIR = Path(__file__).resolve().parent
 
 
 def available_robots() -> list[str]:
-    return sorted(p.stem for p in _DIR.glob("*.npz"))
+    return sorted(p.stem for p in _DIR.glob("*.npz") if not p.stem.endswith("_links"))
 
 
 @dataclass
@@ -52,6 +52,22 @@ class RobotBundle:
     @property
     def serial_manipulator(self):
         return self.dynamics
+
+    @property
+    def links(self) -> dict:
+        """Link table of the robot's URDF (names, the joint each link hangs on, home poses,
+        allowed-collision matrix), extracted by the reference's loader (``<name>_links.npz``)."""
+        path = _DIR / f"{self.name}_links.npz"
+        if not path.exists():
+            raise KeyError(f"no link table bundled for '{self.name}'")
+        with np.load(path) as d:
+            return {k: d[k] for k in d.files}
+
+    def collision_checker(self, hulls):
+        """``CollisionChecker`` over ``hulls = {link name: (V, 3) points in the link frame}``."""
+        from ..potential_field import CollisionChecker
+
+        return CollisionChecker(self.dynamics, self.links, hulls, device=self.device)
 
     def planner(self, torque_limits=None, **kw):
         from ..path_planning import OptimizedTrajectoryPlanning

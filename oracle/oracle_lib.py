@@ -494,3 +494,90 @@ class Oracle:
         if single:
             pos, vel, acc = pos[0], vel[0], acc[0]
         return {"positions": pos, "velocities": vel, "accelerations": acc}
+
+
+class CollisionOracle:
+    """numpy restatement of the collision / limit post-processing hook of ``joint_trajectory``
+    (SURVEY.md 8f-1).  TEST INFRASTRUCTURE ONLY; pinned on tests/golden/collision.npz, which records
+    what the unmodified reference does with injected hulls (oracle/gen_collision_golden.py).
+
+    ``link_joint[l]``   index of the actuated joint link l hangs on (-1: fixed to the base)
+    ``link_home[l]``    pose of link l at the zero configuration
+    ``hulls``           {link index: (V, 3) points in the link frame}, in the checker's insertion order
+    ``acm[a, b]``       1 if the pair is excluded (adjacent / grandparent links,
+                        potential_field/adjacency.py:9-30)
+    """
+
+    def __init__(self, S_list, link_joint, link_home, hulls, acm):
+        self.S = _d(S_list)
+        self.n = self.S.shape[1]
+        self.link_joint = np.asarray(link_joint, np.int64)
+        self.link_home = _d(link_home)
+        self.hulls = {int(k): _d(v) for k, v in hulls.items()}
+        self.acm = np.asarray(acm, bool)
+
+    def link_fk_batch(self, cfgs):
+        """URDF.link_fk_batch (urdf/core.py:577-633): pose of every link for every configuration.  The
+        tree walk ``T_child = T_parent @ origin @ R(axis, q)`` equals, for the serial chain whose space
+        screws the same loader extracted, ``prod_{j <= k} e^{[S_j] q_j} @ T_link(0)``."""
+        q = _d(cfgs).reshape(-1, self.n)
+        L = self.link_home.shape[0]
+        out = np.empty((q.shape[0], L, 4, 4))
+        for p in range(q.shape[0]):
+            P = [np.eye(4)]
+            for j in range(self.n):
+                P.append(P[-1] @ Oracle._exp_twist(self.S[:, j], q[p, j]))
+            for l in range(L):
+                out[p, l] = P[self.link_joint[l] + 1] @ self.link_home[l]
+        return out
+
+    def check_collision(self, cfgs):
+        """CollisionChecker.check_collision (potential_field/collision.py:162-195) per configuration:
+        any pair of hulls, not in the allowed-collision set, whose world axis-aligned boxes overlap
+        (``_points_intersect`` :197-221: max_a >= min_b and max_b >= min_a on every axis)."""
+        q = np.asarray(cfgs)
+        q = q.reshape(-1, self.n)
+        T = self.link_fk_batch(q.astype(np.float64))
+        names = list(self.hulls)
+        flags = np.zeros(q.shape[0], np.uint8)
+        for p in range(q.shape[0]):
+            box = {}
+            for l in names:
+                w = (T[p, l, :3, :3] @ self.hulls[l].T + T[p, l, :3, 3:4]).T
+                box[l] = (w.min(0), w.max(0))
+            hit = False
+            for ia in range(len(names)):
+                for ib in range(ia + 1, len(names)):
+                    a, b = names[ia], names[ib]
+                    if self.acm[a, b]:
+                        continue
+                    if np.all(box[a][1] >= box[b][0]) and np.all(box[b][1] >= box[a][0]):
+                        hit = True
+                        break
+                if hit:
+                    break
+            flags[p] = hit
+        return flags
+
+    def avoid(self, rows, goal, attractive_gain=1.0, step=0.01, max_iterations=100):
+        """_apply_collision_avoidance_cpu (planning/collision_host.py:40-88) on float32 rows with the
+        float32 goal ``thetaend``: a colliding row takes up to ``max_iterations`` steps
+        ``row <- row - 0.01 * gradient`` in float32 arithmetic, where with no obstacles
+        ``PotentialField.compute_gradient`` (potential_field/fields.py:112-170) is
+        ``attractive_gain * (row - goal)``, until ``check_collision(row)`` clears.
+        Returns (rows, iterations taken per row)."""
+        out = np.array(rows, np.float32, copy=True)
+        goal = np.asarray(goal, np.float32)
+        gain, st = np.float32(attractive_gain), np.float32(step)
+        iters = np.zeros(out.shape[0], np.int32)
+        for i in range(out.shape[0]):
+            r = out[i]
+            if self.check_collision(r)[0]:
+                for k in range(max_iterations):
+                    grad = gain * ((r - goal) * np.float32(1.0))
+                    r = np.asarray(r - st * grad, np.float32)
+                    iters[i] = k + 1
+                    if not self.check_collision(r)[0]:
+                        break
+            out[i] = r
+        return out, iters

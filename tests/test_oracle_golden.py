@@ -317,3 +317,41 @@ def test_robot_zoo_vs_reference(robot, analytic):
         o.gravity_forces(th, g, analytic), o.velocity_quadratic_forces(th, dth, analytic),
         o.inverse_dynamics(th, dth, ddth, g, ft, analytic),
         o.forward_dynamics(th, dth, z["taus"], g, ft, analytic))
+
+
+# ---------------------------------------------------------------------------------------------
+# collision / limit post-processing hook of joint_trajectory
+# ---------------------------------------------------------------------------------------------
+def _collision_case(robot):
+    from oracle.oracle_lib import CollisionOracle
+
+    g = load_golden("collision")
+    pack = load_pack(robot)
+    from conftest import ROBOTS as ROBOT_DIR
+
+    with np.load(ROBOT_DIR / f"{robot}_links.npz") as d:
+        links = {k: d[k] for k in d.files}
+    names = [str(x) for x in links["link_names"]]
+    hulls = {names.index(str(nm)): g[f"{robot}_hull_{nm}"] for nm in g[f"{robot}_hull_links"]}
+    return g, links, CollisionOracle(pack["S_list"], links["link_joint"], links["link_home"], hulls, links["link_acm"])
+
+
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_collision_oracle_vs_reference_golden(robot):
+    """Every link pose of URDF.link_fk_batch, the checker's flags and the rows the hook nudged, as
+    recorded from the unmodified reference with injected hulls."""
+    g, links, co = _collision_case(robot)
+    cfgs = g[f"{robot}_cfgs"]
+    np.testing.assert_allclose(co.link_fk_batch(cfgs), g[f"{robot}_link_fk"], rtol=0, atol=1e-12)
+    assert np.array_equal(co.check_collision(cfgs), g[f"{robot}_flags"])
+    assert 0 < g[f"{robot}_flags"].sum() < len(cfgs)
+    for k in (0, 1):
+        t = f"{robot}_traj{k}_"
+        raw, end = g[t + "raw"], g[t + "end"].astype(np.float32)
+        assert np.array_equal(co.check_collision(raw), g[t + "flags_before"])
+        got, iters = co.avoid(raw, end, attractive_gain=g[f"{robot}_gains"][0])
+        assert np.array_equal(got.view(np.uint32), g[t + "positions"].view(np.uint32))  # float32 steps: bit for bit
+        assert np.array_equal(co.check_collision(got), g[t + "flags_after"])
+        assert (iters[g[t + "flags_before"] == 0] == 0).all()
+        if k == 1:  # ends in collision: rows run into the 100-iteration cap
+            assert (iters == 100).any() and g[t + "flags_after"].any()
