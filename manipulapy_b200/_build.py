@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 # (source, object stem, extra defines).  The dynamics kernels exist in three flavours (rigid +
 # all-revolute, rigid, general inertias; csrc/dyn_kernels.cuh), each its own translation unit
 # so that the build uses every core.
-CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", []), ("kin.cu", "kin", []), ("ik.cu", "ik", []),
+CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", os.environ.get("MPK_TRAJ_DEFINES", "").split()), ("kin.cu", "kin", []), ("ik.cu", "ik", []),
             ("dyn.cu", "dyn", []), ("peer.cu", "peer", []), ("collision.cu", "collision", [])]
 # MPK_FD_DEFINES / MPK_DYN_DEFINES (environment, e.g. "-DMPK_FD_MINBLOCKS=16"): extra defines for
 # the forward-dynamics / inverse-dynamics flavour units, for tuning sweeps on the GPU box.

@@ -113,6 +113,7 @@ static int trajectory_inverse_dynamics_impl(const mpk_robot *rb, int64_t B, int6
     a.tau = tau;
     a.pos = a.vel = a.acc = nullptr;
     a.compute_f32 = compute_f32;
+    a.table_rows = traj_table_rows(B, N);
     unsigned grid;
     if (int rc = grid_for(a.P, grid)) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);

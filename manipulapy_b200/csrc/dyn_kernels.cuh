@@ -79,6 +79,7 @@ struct TrajRneaArgs {
     const double *ts_table;
     FastDiv div;
     int compute_f32;
+    int table_rows;  // trajectories one thread group's consecutive points can touch (traj_table_rows)
 };
 
 struct MassArgs {
@@ -183,6 +184,25 @@ static void launch_smem_l1(void (*kern)(KArgs...), unsigned grid, int threads, s
     if (pct > 100) pct = 100;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     kern<<<grid, threads, smem, s>>>(args...);
+}
+
+// Threads that share one shared-memory slice of the fused kernel (link state / output staging / endpoint
+// table) and synchronise among themselves: a warp (32, only __syncwarp) or the whole block (128,
+// __syncthreads).  Measured on B200 (profiles/r2_variants.md): MPK_FUSED_GROUP.
+#ifndef MPK_FUSED_GROUP
+#define MPK_FUSED_GROUP 128
+#endif
+constexpr int kFusedGroup = MPK_FUSED_GROUP;
+static_assert(kFusedGroup == 32 || kFusedGroup == kDynThreads, "a group is a warp or the block");
+
+// shared memory of the endpoint tables: (start, delta) x N joints x the trajectories one group's
+// consecutive points can touch, one table per group
+__host__ __device__ inline int traj_table_rows(int64_t B, int64_t N) {
+    int64_t k = (kFusedGroup - 1) / (N > 0 ? N : 1) + 2;
+    return (int)(k > B ? B : k);
+}
+inline size_t traj_table_bytes(int n, int64_t B, int64_t N) {
+    return (size_t)(kDynThreads / kFusedGroup) * traj_table_rows(B, N) * n * 2 * sizeof(double);
 }
 
 #ifdef MPK_FLAVOUR_KERNELS
@@ -396,25 +416,6 @@ struct TrajInLazy {
 #define MPK_FUSED_LAZY_SINCOS 0
 #endif
 
-// Threads that share one shared-memory slice of the fused kernel (link state / output staging / endpoint
-// table) and synchronise among themselves: a warp (32, only __syncwarp) or the whole block (128,
-// __syncthreads).  Measured on B200 (profiles/r2_variants.md): MPK_FUSED_GROUP.
-#ifndef MPK_FUSED_GROUP
-#define MPK_FUSED_GROUP 128
-#endif
-constexpr int kFusedGroup = MPK_FUSED_GROUP;
-static_assert(kFusedGroup == 32 || kFusedGroup == kDynThreads, "a group is a warp or the block");
-
-// shared memory of the endpoint tables: (start, delta) x N joints x the trajectories one group's
-// consecutive points can touch, one table per group
-__host__ __device__ inline int traj_table_rows(int64_t B, int64_t N) {
-    int64_t k = (kFusedGroup - 1) / (N > 0 ? N : 1) + 2;
-    return (int)(k > B ? B : k);
-}
-inline size_t traj_table_bytes(int n, int64_t B, int64_t N) {
-    return (size_t)(kDynThreads / kFusedGroup) * traj_table_rows(B, N) * n * 2 * sizeof(double);
-}
-
 // WRITE: also materialise the trajectory rows (positions, velocities, accelerations).  The
 // kernel is bound by the fp64 pipe with HBM at 6 %, so the extra 12 N bytes per point ride
 // along at a fraction of their stand-alone cost (0.65 ms against 0.17 + 0.57 ms for the two launches).
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(kDynThreads, kFusedMinBlocks)
     T *wsm = reinterpret_cast<T *>(smem + grp * kGroupState);
     float *sm = reinterpret_cast<float *>(smem + grp * kGroupState);
     float *traj_sm = reinterpret_cast<float *>(smem + wrench_smem<T, N, GEN, REV>());
-    const int table_rows = traj_table_rows(a.B, a.N);
+    const int table_rows = a.table_rows;
     double *table = reinterpret_cast<double *>(smem + wrench_smem<T, N, GEN, REV>() +
                                                (WRITE ? 3 * sizeof(float) * kDynThreads * N : 0)) +
                     grp * table_rows * (2 * N);

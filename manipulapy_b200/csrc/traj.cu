@@ -14,6 +14,17 @@
 namespace mpk {
 
 constexpr int kTrajThreads = 256;
+// Store flavour of the row stream (tuning knob).  In the bare store micro-benchmark plain write-back
+// stores reach 6.6 TB/s and streaming (.cs) stores 6.4-6.5 TB/s (profiles/r2_peaks_store_and_fp64_patterns.json);
+// in this kernel the streaming flavour is the faster one by 1-2 % (0.1486 against 0.1505 ms).
+#ifndef MPK_TRAJ_STREAMING_STORES
+#define MPK_TRAJ_STREAMING_STORES 1
+#endif
+#if MPK_TRAJ_STREAMING_STORES
+#define TRAJ_STORE(p, v) __stcs(p, v)
+#else
+#define TRAJ_STORE(p, v) (*(p) = (v))
+#endif
 
 struct TrajArgs {
     int64_t B, N, P;
@@ -25,6 +36,7 @@ struct TrajArgs {
     Limits lim;
     float *pos, *vel, *acc;
     const double *ts_table;
+    int table_rows;  // trajectories one warp's 32 consecutive points can touch: min(B, 31 / N + 2)
 };
 
 __global__ void time_scaling_table_kernel(int64_t N, double Tf, int method, double *table) {
@@ -45,26 +57,54 @@ const double *prepare_time_scaling(double *scratch, int64_t B, int64_t N, double
 
 // One thread = one (trajectory, step) point, all joints.  Each warp stages its 32 rows of the
 // three outputs in its own shared-memory slice and writes them out with 16-byte-per-lane
-// coalesced streaming stores (a warp's rows are contiguous: 32 N floats, a multiple of 128 B).
+// coalesced stores (a warp's rows are contiguous: 32 N floats, a multiple of 128 B).
 // Only __syncwarp: warps never wait for each other.
+//
+// The kernel is a pure 12 N bytes-per-point write stream, and what stood between it and the write
+// bandwidth of HBM (6.6 TB/s with plain 16-byte stores, profiles/r2_peaks_store_and_fp64_patterns.json)
+// was the conversion unit: 3 N double -> float conversions per point are inherent (one rounding to
+// float32 per output), but another 3 N went into re-deriving the endpoints (float32 rounding of start /
+// end, their difference, back to double) in EVERY thread -- at 16 conversions per clock per SM that is
+// more XU time than the stores take (ncu round 1: XU 58 % busy at 64 % of the copy bandwidth).  A warp's
+// 32 consecutive points belong to at most 31 / N + 2 trajectories, so each warp now derives those
+// endpoints once into a small shared-memory table and its lanes read (start, delta) pairs from there.
+__host__ __device__ inline int traj_warp_table_rows(int64_t B, int64_t N) {
+    int64_t k = 31 / (N > 0 ? N : 1) + 2;
+    return (int)(k > B ? B : k);
+}
+
 template <int N>
 __global__ void __launch_bounds__(kTrajThreads) traj_kernel(const TrajArgs a) {
-    __shared__ __align__(16) float sm[kTrajThreads / 32][3][32 * N];
+    extern __shared__ __align__(16) unsigned char traj_smem[];
+    constexpr int kWarps = kTrajThreads / 32;
+    float(*sm)[3][32 * N] = reinterpret_cast<float(*)[3][32 * N]>(traj_smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *table = reinterpret_cast<double *>(traj_smem + sizeof(float) * kWarps * 3 * 32 * N) + warp * a.table_rows * 2 * N;
     const int64_t pw = (int64_t)blockIdx.x * kTrajThreads + warp * 32;  // warp's first point
     if (pw >= a.P) return;                                               // whole warp out of range
-    const int64_t p = pw + lane;
-    if (p < a.P) {
-        int64_t b, t;
-        point_coords(a.div, a.N, p, b, t);
+    const int64_t rem = a.P - pw;
+    const int live = (int)(rem < 32 ? rem : 32);
+    int64_t b, t;
+    point_coords(a.div, a.N, lane < live ? pw + lane : pw, b, t);
+    // first / last trajectory of the warp's points: lanes 0 and live - 1 already know them
+    const int64_t b0 = __shfl_sync(0xffffffffu, b, 0), b1 = __shfl_sync(0xffffffffu, b, live - 1);
+    {
+        const int entries = (int)(b1 - b0 + 1) * N;
+        for (int e = lane; e < entries; e += 32) {
+            double st, dth;
+            endpoint(a.start, a.end, a.inputs_f32, b0 * N + e, st, dth);
+            table[2 * e] = st;
+            table[2 * e + 1] = dth;
+        }
+    }
+    __syncwarp();
+    if (lane < live) {
         const TimeScale ts = time_scaling_at(a.ts_table, t, a.N, a.Tf, a.method);
+        const double *tab = table + (b - b0) * (2 * N);
         float pr[N], vr[N], ar[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            double st, dth;
-            endpoint(a.start, a.end, a.inputs_f32, b * N + j, st, dth);
-            traj_point(ts, st, dth, a.lim.lo[j], a.lim.hi[j], a.lim.on, pr[j], vr[j], ar[j]);
-        }
+        for (int j = 0; j < N; ++j)
+            traj_point(ts, tab[2 * j], tab[2 * j + 1], a.lim.lo[j], a.lim.hi[j], true, pr[j], vr[j], ar[j]);
         // row stores: 8-byte vectors when N is even (conflict-free at a 4 N byte lane stride)
         float *r0 = &sm[warp][0][lane * N], *r1 = &sm[warp][1][lane * N], *r2 = &sm[warp][2][lane * N];
         if (N % 2 == 0) {
@@ -84,21 +124,39 @@ __global__ void __launch_bounds__(kTrajThreads) traj_kernel(const TrajArgs a) {
         }
     }
     __syncwarp();
-    const int64_t rem = a.P - pw;
-    const int cnt = (int)(rem < 32 ? rem : 32) * N;  // floats of this warp per output
     const int64_t off = pw * N;
-    float *outs[3] = {a.pos, a.vel, a.acc};
+    if (live == 32) {
+        // full warp (all but the batch's last one): 8 N 16-byte vectors per output, trip count known at compile time
+        constexpr int kVec = 8 * N;
+        auto flush = [&](float *out, int k) {
+            if (!out) return;
+            const float4 *s4 = reinterpret_cast<const float4 *>(sm[warp][k]);
+            float4 *o4 = reinterpret_cast<float4 *>(out + off);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float *o = outs[k];
-        if (!o) continue;
-        o += off;
+            for (int i0 = 0; i0 < kVec; i0 += 32) {
+                if (i0 + 32 <= kVec || lane < kVec - i0) TRAJ_STORE(o4 + i0 + lane, s4[i0 + lane]);
+            }
+        };
+        flush(a.pos, 0);
+        flush(a.vel, 1);
+        flush(a.acc, 2);
+        return;
+    }
+    const int cnt = live * N;  // floats of this warp per output
+    auto flush_tail = [&](float *out, int k) {
+        if (!out) return;
+        float *o = out + off;
         const float4 *s4 = reinterpret_cast<const float4 *>(sm[warp][k]);
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const int n4 = cnt >> 2;
-        for (int i = lane; i < n4; i += 32) __stcs(o4 + i, s4[i]);
+#pragma unroll 1
+        for (int i = lane; i < n4; i += 32) TRAJ_STORE(o4 + i, s4[i]);
+#pragma unroll 1
         for (int i = (n4 << 2) + lane; i < cnt; i += 32) o[i] = sm[warp][k][i];
-    }
+    };
+    flush_tail(a.pos, 0);
+    flush_tail(a.vel, 1);
+    flush_tail(a.acc, 2);
 }
 
 int launch_joint_trajectory(int n, int64_t B, int64_t N, const double *start, const double *end,
@@ -121,9 +179,16 @@ int launch_joint_trajectory(int n, int64_t B, int64_t N, const double *start, co
     a.vel = vel;
     a.acc = acc;
     a.ts_table = ts_table;
+    a.table_rows = traj_warp_table_rows(B, N);
     const int64_t blocks = (a.P + kTrajThreads - 1) / kTrajThreads;
     if (blocks > 0x7fffffffLL) return fail(MPK_EINVAL, "B*N exceeds the grid limit (2^39 points)");
-    MPK_DISPATCH_DOF(n, (traj_kernel<N_><<<(unsigned)blocks, kTrajThreads, 0, s>>>(a)));
+    MPK_DISPATCH_DOF(n, {
+        const size_t smem = sizeof(float) * (kTrajThreads / 32) * 3 * 32 * N_ +
+                            sizeof(double) * (kTrajThreads / 32) * traj_warp_table_rows(B, N) * 2 * N_;
+        auto kern = traj_kernel<N_>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<(unsigned)blocks, kTrajThreads, smem, s>>>(a);
+    });
     return check_launch("joint_trajectory");
 }
 
