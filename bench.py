@@ -727,7 +727,7 @@ def run_ours(args) -> None:
                        "taumat": "float32 (B, N, 7) resident in HBM: gravity compensation at theta0 + per-joint uniform "
                                  "noise of amplitude [4, 4, 2, 2, 0.4, 0.2, 0.08] N m (SURVEY 8d's literal U(-20, 20) makes "
                                  "explicit Euler overflow for a few rollouts, in the reference too; that distribution is "
-                                 "covered by test_full_size_cfg4_literal_torques)",
+                                 "covered at full size by test_full_size_cfg4_literal_torques: ~3 % of the rollouts overflow, at the oracle's step)",
                        "outputs": "3 x float32 (B, N, 7)"}}
         line["fd_rollout"] = fd_entry
         configs.append(dict(fd_entry, name="cfg4_iiwa14_forward_dynamics_rollouts_65536x1000", baseline_config=3,

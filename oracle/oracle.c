@@ -475,6 +475,43 @@ int orc_forward_dynamics_analytic(const orc_robot *rb, const double *theta, cons
     return lu_solve(n, Mm, ddtheta);
 }
 
+/* The kernels' solve: LDL^T without pivoting (csrc/mpk_device.cuh ldlt_factor / ldlt_apply, same
+ * operation order; the mass matrix is symmetric positive definite).  With it the oracle differs from a
+ * rollout kernel only by roundings inside one operation (FMA contraction, the reciprocal of a pivot), so
+ * what divergence is left after many chaotic steps is attributable to those, not to LU against LDL^T. */
+static int ldlt_solve(int n, double *A, double *b) {
+    double dinv[ORC_MAX_DOF];
+    for (int j = 0; j < n; ++j) {
+        double dj = A[j * n + j];
+        for (int k = 0; k < j; ++k) dj -= A[j * n + k] * A[j * n + k] * A[k * n + k];
+        if (dj == 0.0) return -1;
+        A[j * n + j] = dj;
+        dinv[j] = 1.0 / dj;
+        for (int i = j + 1; i < n; ++i) {
+            double l = A[i * n + j];
+            for (int k = 0; k < j; ++k) l -= A[i * n + k] * A[j * n + k] * A[k * n + k];
+            A[i * n + j] = l * dinv[j];
+        }
+    }
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < i; ++k) b[i] -= A[i * n + k] * b[k];
+    for (int i = 0; i < n; ++i) b[i] *= dinv[i];
+    for (int i = n - 1; i >= 0; --i)
+        for (int k = i + 1; k < n; ++k) b[i] -= A[k * n + i] * b[k];
+    return 0;
+}
+
+int orc_forward_dynamics_analytic_ldlt(const orc_robot *rb, const double *theta, const double *dtheta,
+                                       const double *tau, const double *g3, const double *Ftip,
+                                       double *ddtheta) {
+    const int n = rb->n;
+    double zero[ORC_MAX_DOF] = {0}, bias[ORC_MAX_DOF], Mm[ORC_MAX_DOF * ORC_MAX_DOF];
+    orc_rnea_analytic(rb, theta, dtheta, zero, g3, Ftip, bias);
+    orc_mass_matrix_analytic(rb, theta, Mm);
+    for (int i = 0; i < n; ++i) ddtheta[i] = tau[i] - bias[i];
+    return ldlt_solve(n, Mm, ddtheta);
+}
+
 /* ------------------------------------------------------------------ trajectory level */
 
 static float clipf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
@@ -527,7 +564,8 @@ void orc_joint_trajectory(int n, const double *start, const double *end, int inp
 
 /* planning/trajectory_dynamics.py:308-380 (_inverse_dynamics_cpu): per point ID in
  * float64, row cast to float32, then clip to float32 torque limits.
- * analytic = 0 -> literal finite-difference path, 1 -> analytic recursion.
+ * analytic = 0 -> literal finite-difference path, 1 -> analytic recursion (2, rollouts: ... with the
+ * kernels' LDL^T solve instead of LU).
  * Ftip is one (6,) wrench for every point. */
 void orc_inverse_dynamics_trajectory(const orc_robot *rb, int64_t P, const double *theta,
                                      const double *dtheta, const double *ddtheta, const double *g3,
@@ -609,8 +647,9 @@ int orc_forward_dynamics_trajectory(const orc_robot *rb, const double *theta0,
         for (int j = 0; j < n; ++j) last[j] = 0.0;
         for (int r = 0; r < intRes; ++r) {
             const double *F = Ftipmat ? Ftipmat + 6 * i : z6;
-            int e = analytic ? orc_forward_dynamics_analytic(rb, th, dth, taumat + i * n, g3, F, dd)
-                             : orc_forward_dynamics(rb, th, dth, taumat + i * n, g3, F, dd);
+            int e = analytic == 2 ? orc_forward_dynamics_analytic_ldlt(rb, th, dth, taumat + i * n, g3, F, dd)
+                    : analytic ? orc_forward_dynamics_analytic(rb, th, dth, taumat + i * n, g3, F, dd)
+                               : orc_forward_dynamics(rb, th, dth, taumat + i * n, g3, F, dd);
             if (e) { rc = -1; continue; }
             for (int j = 0; j < n; ++j) {
                 dth[j] = dth[j] + dd[j] * dts;

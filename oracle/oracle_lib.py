@@ -42,6 +42,7 @@ def load_oracle():
         _lib = C.CDLL(str(_LIB_PATH))
         _lib.orc_forward_dynamics.restype = C.c_int
         _lib.orc_forward_dynamics_analytic.restype = C.c_int
+        _lib.orc_forward_dynamics_analytic_ldlt.restype = C.c_int
         _lib.orc_forward_dynamics_trajectory.restype = C.c_int
         _lib.orc_forward_dynamics_rollout_batch.restype = C.c_int
         _lib.orc_max_dof.restype = C.c_int
@@ -176,7 +177,8 @@ class Oracle:
         g = _d(g)
         F = np.zeros((P, 6)) if Ftip is None else np.broadcast_to(_d(Ftip), (P, 6)).copy()
         out = np.empty((P, self.n))
-        fn = self.lib.orc_forward_dynamics_analytic if analytic else self.lib.orc_forward_dynamics
+        fn = (self.lib.orc_forward_dynamics_analytic_ldlt if analytic == 2 else
+              self.lib.orc_forward_dynamics_analytic if analytic else self.lib.orc_forward_dynamics)
         for p in range(P):
             rc = fn(self._r, _p(th[p]), _p(dth[p]), _p(ta[p]), _p(g), _p(F[p]), _p(out[p]))
             if rc:
@@ -463,7 +465,9 @@ class Oracle:
 
     def forward_dynamics_trajectory(self, theta0, dtheta0, taumat, g, Ftipmat, dt, intRes,
                                     joint_limits=None, analytic=False):
-        """Single ``(n,)`` start or batched ``(B, n)`` starts with ``taumat (B, N, n)``."""
+        """Single ``(n,)`` start or batched ``(B, n)`` starts with ``taumat (B, N, n)``.
+        ``analytic``: False literal reference algorithm, True analytic recursion + LU, 2 analytic
+        recursion + the kernels' LDL^T solve."""
         th0 = _d(theta0)
         single = th0.ndim == 1
         th0 = th0.reshape(-1, self.n)

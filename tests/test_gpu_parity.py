@@ -944,15 +944,55 @@ def test_full_size_cfg4_iiwa_rollouts(robots, oracle_factory, B):
     lo32, hi32 = lo.float(), hi.float()
     ok = torch.isfinite(pos)
     assert bool(((pos >= lo32) | ~ok).all()) and bool(((pos <= hi32) | ~ok).all())
-    sel = [0, 1, 4097, B - 1]
+    sel = [0, 1, 4097, B // 2 + 1, B - 7, B - 1]
+    sel = [b for b in sel if b not in bad]
+    # Against the oracle with the kernels' own LDL^T solve AND with the reference's LU: over all 1000 steps
+    # the float32 rows agree to float32 rounding (measured: bit-identical for these rollouts,
+    # scripts/cfg4_diag.py), so the solver is not a source of divergence at this step count.
+    for solver in (2, True):
+        ref = o.forward_dynamics_trajectory(th0[sel].cpu().numpy(), dth0[sel].cpu().numpy(),
+                                            tau[sel].double().cpu().numpy(), [0, 0, -9.81], None, 1e-3, 1,
+                                            rb.joint_limits, analytic=solver)
+        for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
+            assert _rel_rows(got[sel].cpu().numpy().reshape(-1, n), ref[k].reshape(-1, n)) < 1e-6, (k, solver)
+
+
+def test_full_size_cfg4_literal_torques(robots, oracle_factory):
+    """SURVEY.md 8d cfg 4 to the letter: taumat ~ U(-20, 20) N m on every joint of the iiwa14, 65,536
+    rollouts x 1000 steps.  20 N m on a wrist link of ~1e-3 kg m^2 is 2e4 rad/s^2: explicit Euler at
+    dt = 1 ms leaves the joint range at once, the clip pins the angle, the velocity keeps integrating, and
+    about 3 % of the rollouts overflow float32 before step 1000 -- in the reference's algorithm just the
+    same.  Checked here: a rollout that overflows does so at the oracle's step; the rows before that, and
+    all rows of the rollouts that stay finite, agree with the oracle to float32 rounding."""
+    rb, o = robots["iiwa14"], oracle_factory("iiwa14")
+    B, N, n = 65536, 1000, 7
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    lo = torch.from_numpy(rb.joint_limits[:, 0]).cuda()
+    hi = torch.from_numpy(rb.joint_limits[:, 1]).cuda()
+    th0 = 0.5 * (lo + (hi - lo) * torch.rand(B, n, dtype=torch.float64, device="cuda", generator=gen))
+    dth0 = torch.rand(B, n, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    tau = (torch.rand(B, N, n, dtype=torch.float32, device="cuda", generator=gen) - 0.5) * 40.0
+    r = rb.planner().forward_dynamics_trajectory(th0, dth0, tau, [0, 0, -9.81], None, 1e-3, 1)
+    pos, vel, acc = r["positions"], r["velocities"], r["accelerations"]
+    fin = torch.isfinite(acc).all(dim=2) & torch.isfinite(vel).all(dim=2)
+    bad = torch.nonzero(~fin.all(dim=1)).flatten().tolist()
+    assert 0 < len(bad) < B // 10
+    good = [b for b in (0, 1, 4097, B // 2 + 1, B - 1) if b not in bad][:4]
+    sel = bad[:4] + good
     ref = o.forward_dynamics_trajectory(th0[sel].cpu().numpy(), dth0[sel].cpu().numpy(), tau[sel].double().cpu().numpy(),
-                                        [0, 0, -9.81], None, 1e-3, 1, rb.joint_limits, analytic=True)
-    # 1000 chaotic steps amplify rounding differences between LDL^T and the oracle's LU: 1e-5 per row
-    for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
-        assert _rel_rows(got[sel].cpu().numpy().reshape(-1, n), ref[k].reshape(-1, n)) < 1e-4, k
-    # the first 50 steps agree to float32 rounding
-    for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
-        assert _rel_rows(got[sel, :50].cpu().numpy().reshape(-1, n), ref[k][:, :50].reshape(-1, n)) < 1e-6, k
+                                        [0, 0, -9.81], None, 1e-3, 1, rb.joint_limits, analytic=2)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for i, b in enumerate(sel):
+            fin_ref = np.isfinite(ref["accelerations"][i]).all(1) & np.isfinite(ref["velocities"][i]).all(1)
+            fin_got = fin[b].cpu().numpy()
+            assert np.array_equal(fin_ref, fin_got), f"rollout {b}: overflow at different steps"
+            upto = int(np.argmin(fin_got)) if not fin_got.all() else N
+            assert (b in bad) == (upto < N)
+            for k, got in (("positions", pos), ("velocities", vel), ("accelerations", acc)):
+                assert _rel_rows(got[b, :upto].cpu().numpy(), ref[k][i, :upto]) < 1e-6, (b, k)
+    lo32, hi32 = lo.float(), hi.float()
+    okp = torch.isfinite(pos)
+    assert bool(((pos >= lo32) | ~okp).all()) and bool(((pos <= hi32) | ~okp).all())
 
 
 # ---------------------------------------------------------------------------------------------
