@@ -291,6 +291,19 @@ int mpk_collision_avoidance(const mpk_robot *rb, const void *model_host, const v
                             float *rows, const float *goal, int64_t rows_per_goal, double attractive_gain,
                             double step, int max_iterations, int32_t *iterations, uint8_t *flags, void *stream);
 
+/* The reference's LEGACY dynamics path: a ManipulatorDynamics built without Mlist_per_link
+ * falls back to _mass_matrix_legacy (dynamics/mass_matrix.py:101-132) and _gravity_forces_legacy
+ * (dynamics/forces.py:135-154), with finite-difference Coriolis forces (dynamics/cache.py:23-56), inverse and
+ * forward dynamics (dynamics/id_fd.py:16-83) on top.  Documented by the reference as incorrect physics;
+ * reproduced for parity, not tuned.  S_list (6, n), M (4, 4), Glist (n, 6, 6) host float64;
+ *   mode 0 mass matrix  out (P, n, n)          mode 1 gravity forces  out (P, n)
+ *   mode 2 velocity-quadratic forces (dtheta)   mode 3 inverse dynamics (dtheta, third = ddtheta)
+ *   mode 4 forward dynamics (dtheta, third = tau);   theta / dtheta / third / out dev float64;
+ *   g host (3); Ftip host (6) or NULL; Ftip_rows dev (P, 6) or NULL (overrides Ftip) */
+int mpk_legacy_dynamics(int n, const double *S_list, const double *M, const double *Glist, int mode, int64_t P,
+                        const double *theta, const double *dtheta, const double *third, const double *g,
+                        const double *Ftip, const double *Ftip_rows, double *out, void *stream);
+
 /* Result buffers shared by the processes of one box (one process per GPU), SURVEY.md 8e: the
  * rank that collects a sharded result allocates it with mpk_peer_alloc and hands the 64-byte handle
  * to the other ranks (any channel: torch.distributed's object broadcast in the Python host); they

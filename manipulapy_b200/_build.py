@@ -31,7 +31,7 @@ NVCC_FLAGS = [
 # all-revolute, rigid, general inertias; csrc/dyn_kernels.cuh), each its own translation unit
 # so that the build uses every core.
 CU_UNITS = [("robot.cu", "robot", []), ("traj.cu", "traj", os.environ.get("MPK_TRAJ_DEFINES", "").split()), ("kin.cu", "kin", []), ("ik.cu", "ik", []),
-            ("dyn.cu", "dyn", []), ("peer.cu", "peer", []), ("collision.cu", "collision", [])]
+            ("dyn.cu", "dyn", []), ("peer.cu", "peer", []), ("collision.cu", "collision", []), ("legacy.cu", "legacy", [])]
 # MPK_FD_DEFINES / MPK_DYN_DEFINES (environment, e.g. "-DMPK_FD_MINBLOCKS=16"): extra defines for
 # the forward-dynamics / inverse-dynamics flavour units, for tuning sweeps on the GPU box.
 CU_UNITS += [(f"{base}_flavour.cu", f"{base}_flavour{k}",

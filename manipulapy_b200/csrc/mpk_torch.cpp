@@ -349,6 +349,34 @@ void fma_peak(const Tensor &sink, int64_t dtype, int64_t blocks, int64_t threads
           "fma_peak");
 }
 
+// ---- legacy dynamics path (csrc/legacy.cu) -----------------------------------------------------------
+Tensor legacy_dynamics(const Tensor &S_list, const Tensor &M, const Tensor &Glist, int64_t mode, const Tensor &theta,
+                       const OptT &dtheta, const OptT &third, c10::ArrayRef<double> g,
+                       std::optional<c10::ArrayRef<double>> ftip, const OptT &ftip_rows) {
+    Tensor S = S_list.to(at::kCPU, at::kDouble).contiguous(), Mh = M.to(at::kCPU, at::kDouble).contiguous();
+    Tensor G = Glist.to(at::kCPU, at::kDouble).contiguous();
+    TORCH_CHECK(S.dim() == 2 && S.size(0) == 6 && Mh.numel() == 16, "mpk: S_list must be (6, n) and M (4, 4)");
+    const int64_t n = S.size(1);
+    TORCH_CHECK(G.numel() == n * 36, "mpk: Glist must be (n, 6, 6)");
+    Tensor th = dev_rows(theta, n, "theta", false);
+    const int64_t P = th.numel() / n;
+    Tensor d1, d3, fr;
+    const double *p1 = nullptr, *p3 = nullptr, *pf = nullptr;
+    if (dtheta.has_value()) { d1 = dev_rows(*dtheta, n, "dtheta", false); p1 = d1.data_ptr<double>(); }
+    if (third.has_value()) { d3 = dev_rows(*third, n, "ddtheta / tau", false); p3 = d3.data_ptr<double>(); }
+    if (ftip_rows.has_value()) { fr = dev_rows(*ftip_rows, 6, "Ftip rows", false); pf = fr.data_ptr<double>(); }
+    auto gv = host_vec(g, 3, "g");
+    std::vector<double> fv;
+    if (ftip.has_value()) fv = host_vec(*ftip, 6, "Ftip");
+    c10::cuda::CUDAGuard guard(th.device());
+    Tensor out = mode == 0 ? at::empty({P, n, n}, th.options()) : at::empty({P, n}, th.options());
+    check(mpk_legacy_dynamics((int)n, S.data_ptr<double>(), Mh.data_ptr<double>(), G.data_ptr<double>(), (int)mode, P,
+                              th.data_ptr<double>(), p1, p3, gv.data(), fv.empty() ? nullptr : fv.data(), pf,
+                              out.data_ptr<double>(), stream_of(th)),
+          "legacy_dynamics");
+    return out;
+}
+
 // ---- collision hook (csrc/collision.cu) ---------------------------------------------------------
 Tensor collision_model_pack(int64_t h, const Tensor &link_joint, const Tensor &link_home, const Tensor &acm,
                             const Tensor &hull_link, const Tensor &hull_count, const Tensor &hull_points) {
@@ -500,6 +528,9 @@ TORCH_LIBRARY(mpk, m) {
           &cartesian_trajectory);
     m.def("fma_peak(Tensor sink, int dtype, int blocks, int threads, int iters) -> ()", &fma_peak);
     m.def("store_peak(Tensor dst, int mode, int blocks) -> ()", &store_peak);
+    m.def("legacy_dynamics(Tensor S_list, Tensor M, Tensor Glist, int mode, Tensor theta, Tensor? dtheta, Tensor? third, "
+          "float[] g, float[]? Ftip, Tensor? Ftip_rows) -> Tensor",
+          &legacy_dynamics);
     m.def("collision_model_pack(int robot, Tensor link_joint, Tensor link_home, Tensor acm, Tensor hull_link, "
           "Tensor hull_count, Tensor hull_points) -> Tensor",
           &collision_model_pack);

@@ -585,3 +585,60 @@ class CollisionOracle:
                         break
             out[i] = r
         return out, iters
+
+
+class LegacyOracle:
+    """numpy restatement of the reference's LEGACY dynamics path (no ``Mlist_per_link``; SURVEY.md
+    8f-4).  TEST INFRASTRUCTURE ONLY; pinned on tests/golden/legacy_dynamics.npz.
+
+    With ``T_i = e^{[S_1] th_1} ... e^{[S_i] th_i} M`` (kinematics/fk.py:61-70 on ``theta[:i + 1]`` -- the
+    END-EFFECTOR home pose for every link) and ``J`` the space Jacobian:
+      mass matrix   row i = J[:, i]^T (Ad(T_i)^T G_i Ad(T_i)) J, then 0.5 (M + M^T)   (mass_matrix.py:101-132)
+      gravity       g_i = (R_i^T g) . colsum(G_i[:3, :3])                             (forces.py:135-154)
+      Coriolis      c_i = dth^T Gamma_i dth, Gamma from central differences of M, eps = 1e-6 (forces.py:26-59,
+                    cache.py:23-56)
+      inverse dynamics  M ddth + c + g + J^T Ftip;   forward dynamics  solve(M, tau - c - g - J^T Ftip)
+    """
+
+    def __init__(self, S_list, M, Glist):
+        self.S, self.M, self.G = _d(S_list), _d(M), _d(Glist)
+        self.n = self.S.shape[1]
+
+    def _prefixes(self, th):
+        T, out, J = np.eye(4), [], np.empty((6, self.n))
+        for i in range(self.n):
+            J[:, i] = Oracle._adjoint(T) @ self.S[:, i]
+            T = T @ Oracle._exp_twist(self.S[:, i], th[i])
+            out.append(T @ self.M)
+        return out, J
+
+    def mass_matrix(self, th):
+        Ts, J = self._prefixes(_d(th))
+        Mm = np.empty((self.n, self.n))
+        for i in range(self.n):
+            Ad = Oracle._adjoint(Ts[i])
+            Mm[i] = (J[:, i] @ (Ad.T @ self.G[i] @ Ad)) @ J
+        return 0.5 * (Mm + Mm.T)
+
+    def gravity_forces(self, th, g):
+        Ts, _ = self._prefixes(_d(th))
+        return np.array([(Ts[i][:3, :3].T @ _d(g)) @ self.G[i][:3, :3].sum(0) for i in range(self.n)])
+
+    def velocity_quadratic_forces(self, th, dth, eps=1e-6):
+        th, dth, n = _d(th), _d(dth), self.n
+        dM = np.empty((n, n, n))
+        for k in range(n):
+            e = np.zeros(n)
+            e[k] = 1.0
+            dM[:, :, k] = (self.mass_matrix(th + eps * e) - self.mass_matrix(th - eps * e)) / (2.0 * eps)
+        return np.array([dth @ (0.5 * (dM[i] + dM[i].T - dM[:, :, i])) @ dth for i in range(n)])
+
+    def inverse_dynamics(self, th, dth, ddth, g, Ftip):
+        _, J = self._prefixes(_d(th))
+        return (self.mass_matrix(th) @ _d(ddth) + self.velocity_quadratic_forces(th, dth) + self.gravity_forces(th, g)
+                + J.T @ _d(Ftip))
+
+    def forward_dynamics(self, th, dth, tau, g, Ftip):
+        _, J = self._prefixes(_d(th))
+        rhs = _d(tau) - self.velocity_quadratic_forces(th, dth) - self.gravity_forces(th, g) - J.T @ _d(Ftip)
+        return np.linalg.solve(self.mass_matrix(th), rhs)

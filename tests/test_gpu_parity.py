@@ -1081,3 +1081,50 @@ def test_widened_rows_edge_cases(robots):
     assert sg.workspace_points([(-1, 1)] * n, 0).shape == (0, 3)
     with pytest.raises(NotImplementedError):
         sm.smart_inverse_kinematics(T1[0], strategy="cached", cache=object())
+
+
+# ---------------------------------------------------------------------------------------------
+# legacy dynamics path and its single-sample consumer, the computed-torque law
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_legacy_dynamics_path_vs_reference_golden(robot):
+    """A ManipulatorDynamics built without Mlist_per_link, opted into the reference's legacy formulas:
+    its numbers at the reference's own golden tolerances (finite-difference Coriolis: rtol 1e-7 / atol 1e-8)."""
+    from manipulapy_b200 import ManipulatorDynamics
+
+    g = load_golden("legacy_dynamics")
+    S, M, G = g[f"{robot}_S"], g[f"{robot}_M"], g[f"{robot}_G"]
+    with pytest.raises(NotImplementedError):
+        ManipulatorDynamics(M, None, None, None, S, None, G)
+    with pytest.warns(UserWarning):
+        dyn = ManipulatorDynamics(M, None, None, None, S, None, G, legacy=True)
+    th, dth, ddth, tau, ft, gv = (g[f"{robot}_{k}"] for k in ("th", "dth", "ddth", "tau", "ft", "g"))
+    np.testing.assert_allclose(dyn.mass_matrix(th), g[f"{robot}_mass"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dyn.mass_matrix(th[0]), g[f"{robot}_mass"][0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dyn.gravity_forces(th, gv), g[f"{robot}_grav"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dyn.velocity_quadratic_forces(th, dth), g[f"{robot}_cor"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(dyn.inverse_dynamics(th, dth, ddth, gv, ft), g[f"{robot}_id"], rtol=1e-7, atol=1e-8)
+    assert _rel_rows(dyn.forward_dynamics(th, dth, tau, gv, ft), g[f"{robot}_fd"]) < 1e-6
+    # FK / Jacobian of such an object are the ordinary kinematics
+    T = dyn.forward_kinematics(th)
+    assert T.shape == (th.shape[0], 4, 4) and np.allclose(T[:, 3, 3], 1.0)
+    # computed-torque law = M (Kp e + Ki eint + Kd de) + inverse dynamics at the desired acceleration
+    thd, dthd, eint = th + 0.1, dth - 0.05, 0.01 * np.ones_like(th)
+    Kp, Ki, Kd = 30.0, 0.5, 2.0
+    got = dyn.computed_torque(thd, dthd, ddth, th, dth, gv, Kp, Ki, Kd, eint)
+    want = (np.einsum("pij,pj->pi", g[f"{robot}_mass"], Kp * (thd - th) + Ki * eint + Kd * (dthd - dth))
+            + dyn.inverse_dynamics(th, dth, ddth, gv, None))
+    assert _rel_rows(got, want) < 1e-9
+
+
+def test_computed_torque_on_the_per_link_model(robots, oracle_factory):
+    rb, o = robots["ur5"], oracle_factory("ur5")
+    rng = np.random.default_rng(17)
+    th, dth, ddthd = rng.uniform(-2, 2, (50, 6)), rng.uniform(-1, 1, (50, 6)), rng.uniform(-2, 2, (50, 6))
+    thd, dthd = th + rng.uniform(-0.1, 0.1, (50, 6)), dth + rng.uniform(-0.1, 0.1, (50, 6))
+    Kp, Kd = np.full(6, 40.0), np.linspace(1, 3, 6)
+    got = rb.dynamics.computed_torque(thd, dthd, ddthd, th, dth, [0, 0, -9.81], Kp, 0.0, Kd)
+    M = o.mass_matrix(th, analytic=True)
+    want = (np.einsum("pij,pj->pi", M, Kp * (thd - th) + Kd * (dthd - dth))
+            + o.inverse_dynamics(th, dth, ddthd, analytic=True))
+    assert _rel_rows(got, want) < 1e-9

@@ -355,3 +355,24 @@ def test_collision_oracle_vs_reference_golden(robot):
         assert (iters[g[t + "flags_before"] == 0] == 0).all()
         if k == 1:  # ends in collision: rows run into the 100-iteration cap
             assert (iters == 100).any() and g[t + "flags_after"].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# legacy dynamics path: objects built without Mlist_per_link
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
+def test_legacy_oracle_vs_reference_golden(robot):
+    from oracle.oracle_lib import LegacyOracle
+
+    g = load_golden("legacy_dynamics")
+    lo = LegacyOracle(g[f"{robot}_S"], g[f"{robot}_M"], g[f"{robot}_G"])
+    for p in range(g[f"{robot}_th"].shape[0]):
+        th, dth, ddth = g[f"{robot}_th"][p], g[f"{robot}_dth"][p], g[f"{robot}_ddth"][p]
+        np.testing.assert_allclose(lo.mass_matrix(th), g[f"{robot}_mass"][p], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(lo.gravity_forces(th, g[f"{robot}_g"]), g[f"{robot}_grav"][p], rtol=0, atol=1e-12)
+        # finite differences of eps = 1e-6: the reference's own noise floor is ~1e-9
+        np.testing.assert_allclose(lo.velocity_quadratic_forces(th, dth), g[f"{robot}_cor"][p], rtol=1e-7, atol=1e-8)
+        np.testing.assert_allclose(lo.inverse_dynamics(th, dth, ddth, g[f"{robot}_g"], g[f"{robot}_ft"][p]),
+                                   g[f"{robot}_id"][p], rtol=1e-7, atol=1e-8)
+        fd = lo.forward_dynamics(th, dth, g[f"{robot}_tau"][p], g[f"{robot}_g"], g[f"{robot}_ft"][p])
+        assert np.abs(fd - g[f"{robot}_fd"][p]).max() <= 1e-6 * max(1.0, np.abs(g[f"{robot}_fd"][p]).max())
