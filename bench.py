@@ -565,7 +565,9 @@ def run_ours(args) -> None:
             if Ptot > args.sweep_max:
                 continue
             Bt = -(-Ptot // N_STEPS)
-            blo, bhi = shard_range(Bt, world, rank)
+            # (even shard boundaries: 2441 x 6 x 4 bytes per trajectory is 8 mod 16, and a shard of the shared
+            # result buffer that starts on a 16-byte boundary is written with full-width vector stores)
+            blo, bhi = shard_range(Bt, world, rank, align=2)
             Bl = bhi - blo
             gen5 = torch.Generator(device=dev).manual_seed(5)
             # (every rank draws the same global endpoint table and keeps its rows: cheap, 48 B per 58 KB of output)
@@ -646,7 +648,10 @@ def run_ours(args) -> None:
                 entry["nccl_pipelined_ms"], entry["nccl_transfer_only_ms"] = t_n * 1e3, t_g * 1e3
                 entry["nccl_gathered_points_per_s"] = Bt * N_STEPS / t_n
                 entry["nccl_overlap_fraction"] = max(0.0, min(1.0, (t_c + t_g - t_n) / max(1e-12, min(t_c, t_g))))
-                entry["nvlink_ingest_gbs_rank0"] = (Bt - (shard_bounds(Bt, world)[1])) * N_STEPS * 24 / t_g / 1e9
+                entry["nvlink_ingest_gbs_rank0"] = (Bt - (shard_bounds(Bt, world, None, 2)[1])) * N_STEPS * 24 / t_g / 1e9
+                if "peer_store_ms" in entry:
+                    entry["nvlink_ingest_gbs_rank0_peer_store"] = ((Bt - shard_bounds(Bt, world, None, 2)[1]) * N_STEPS * 24
+                                                                   / (entry["peer_store_ms"] / 1e3) / 1e9)
                 if "gathered_points_per_s" not in entry:
                     entry["gathered_points_per_s"] = entry["nccl_gathered_points_per_s"]
                     entry["gather"] = "NCCL isend / irecv, 8 chunks, second stream"

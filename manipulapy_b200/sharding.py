@@ -25,15 +25,18 @@ import torch
 import torch.distributed as dist
 
 
-def shard_bounds(units: int, world_size: int, weights: Optional[Sequence[float]] = None) -> list:
+def shard_bounds(units: int, world_size: int, weights: Optional[Sequence[float]] = None, align: int = 1) -> list:
     """``world_size + 1`` row offsets of the contiguous shards.  ``weights=None``:
     ``ceil(units / world)`` rows per rank.  With weights (e.g. each rank's measured device->host
-    rate when the results are host-destined) rank r gets a share proportional to ``weights[r]``."""
-    units, world_size = int(units), int(world_size)
+    rate when the results are host-destined) rank r gets a share proportional to ``weights[r]``.
+    ``align``: interior boundaries are multiples of ``align`` units (so that every shard of a shared
+    result buffer starts on a 16-byte boundary and is written with full-width vector stores)."""
+    units, world_size, align = int(units), int(world_size), max(1, int(align))
     if world_size < 1:
         raise ValueError("bad world_size")
     if weights is None:
         per = -(-units // world_size)
+        per = -(-per // align) * align
         return [min(units, r * per) for r in range(world_size)] + [units]
     w = [float(x) for x in weights]
     if len(w) != world_size or any(not (x > 0) for x in w):
@@ -41,16 +44,17 @@ def shard_bounds(units: int, world_size: int, weights: Optional[Sequence[float]]
     total, acc, out = sum(w), 0.0, [0]
     for r in range(world_size - 1):
         acc += w[r]
-        out.append(min(units, max(out[-1], int(round(units * acc / total)))))
+        b = int(round(units * acc / total / align)) * align
+        out.append(min(units, max(out[-1], b)))
     return out + [units]
 
 
 def shard_range(units: int, world_size: int, rank: int,
-                weights: Optional[Sequence[float]] = None) -> Tuple[int, int]:
+                weights: Optional[Sequence[float]] = None, align: int = 1) -> Tuple[int, int]:
     """Contiguous ``[lo, hi)`` of ``units`` owned by ``rank`` (see ``shard_bounds``)."""
     if world_size < 1 or not (0 <= rank < world_size):
         raise ValueError("bad world_size / rank")
-    b = shard_bounds(units, world_size, weights)
+    b = shard_bounds(units, world_size, weights, align)
     return b[rank], b[rank + 1]
 
 
@@ -181,7 +185,14 @@ class PeerRows:
         self.world, self.rank = _world(group)
         self.group, self.dst, self.units, self.tail = group, dst, int(units), tuple(int(x) for x in tail)
         self.device = torch.device(device)
-        self.bounds = shard_bounds(units, self.world, weights)
+        # every rank's slice starts on a 16-byte boundary: full-width vector stores over the link
+        row_bytes = 4
+        for x in self.tail:
+            row_bytes *= x
+        import math
+
+        self.align = 16 // math.gcd(16, row_bytes)
+        self.bounds = shard_bounds(units, self.world, weights, self.align)
         self.lo, self.hi = self.bounds[self.rank], self.bounds[self.rank + 1]
         shape = (self.units, *self.tail)
         numel = 1
