@@ -755,11 +755,15 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
             dth[j] = a.dth0[b * N + j];
             last[j] = 0.0;
         }
-        if (live) {
-            store_state<N>(a.pos, base, th);
-            store_state<N>(a.vel, base, dth);
-            store_state<N>(a.acc, base, last);
-        }
+        // The chain that bounds a step is  (c, s) [A] -> mass matrix, factorisation, solve [B] -> Euler
+        // update [A] -> (c, s) of the next step; everything else has to stay OFF it:
+        //  * the row of the step just finished is stored after (c, s) of the next step has been handed
+        //    over (th, dth, last are unchanged until the next update), not before;
+        //  * the bias recursion takes (c, s) from the shared-memory copy, re-read AFTER bar.arrive: fed
+        //    from the registers, ptxas schedules most of the recursion's arithmetic ahead of the barrier
+        //    (a bar.arrive orders memory, not register arithmetic) and warp B waits for (c, s) through most
+        //    of the recursion -- 47 % of B's stall samples in profiles/r2_ncu_fd_rollout_pair_source.md.
+        int64_t pending = base;  // row that th / dth / last still have to be stored to
         for (int64_t i = 1; i < a.N; ++i) {
             for (int r = 0; r < a.intRes; ++r) {
                 RegStorePre<double, N> st_;
@@ -770,6 +774,19 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
                     cs[32 * (N + j)] = st_.q.s[j];
                 }
                 pair_arrive(1);
+                if (pending >= 0) {
+                    if (live) {
+                        store_state<N>(a.pos, pending, th);
+                        store_state<N>(a.vel, pending, dth);
+                        store_state<N>(a.acc, pending, last);
+                    }
+                    pending = -1;
+                }
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    st_.q.c[j] = *(volatile double *)(cs + 32 * j);
+                    st_.q.s[j] = *(volatile double *)(cs + 32 * (N + j));
+                }
                 double bias[N];
                 ArrayInNoAcc<double, N> in{th, dth};
                 rnea<double, N, false, true, GEO>(rb, in, a.g0, nullptr, bias, st_);
@@ -789,12 +806,13 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
                     th[j] = x;
                     last[j] = dd;
                 }
+                if (r + 1 == a.intRes) pending = base + i;
             }
-            if (live) {
-                store_state<N>(a.pos, base + i, th);
-                store_state<N>(a.vel, base + i, dth);
-                store_state<N>(a.acc, base + i, last);
-            }
+        }
+        if (live && pending >= 0) {
+            store_state<N>(a.pos, pending, th);
+            store_state<N>(a.vel, pending, dth);
+            store_state<N>(a.acc, pending, last);
         }
     } else {
         // ---- warp B: torque rows, mass matrix, factorisation, solve ----
