@@ -16,6 +16,8 @@
 //      (the reference's 8-DOF Panda)
 //   2  general symmetric 6x6 link inertias (and the rare rigid chain whose first joint is prismatic)
 #pragma once
+#include <cstdlib>
+
 #include "mpk_common.cuh"
 
 namespace mpk {
@@ -714,7 +716,9 @@ __global__ void __launch_bounds__(kRolloutThreads, MPK_FD_MINBLOCKS)
 // so the bias forces and the mass matrix -- the two halves of the chain -- run side by side, and
 // each warp holds about half of the state.  Hand-over by named barriers (bar.arrive on the
 // producer, bar.sync on the consumer, 64 threads each): 1 = (c, s) ready, 2 = bias ready,
-// 3 = ddtheta ready.  Same arithmetic as fd_rollout_kernel (the same bits: test_rollout_kernels_agree).
+// 3 = ddtheta ready.  Same arithmetic as fd_rollout_kernel (the same bits over short horizons:
+// test_rollout_kernels_agree; to the last float32 bit of a few entries in 1e7 over 1000 steps:
+// test_rollout_kernels_long_horizon -- ptxas contracts the same expressions differently per kernel).
 // Plain revolute chains with
 // rigid links and no tip wrench; everything else takes fd_rollout_kernel.
 // (no fence: st.shared; bar.arrive | bar.sync; ld.shared is the PTX ISA's own producer / consumer
@@ -845,6 +849,196 @@ __global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
     }
 }
 
+// ---- ... and across THREE warps -------------------------------------------------------------
+// After the pair kernel's hand-over fix the step's longest path runs through warp A: Euler update,
+// seven sin / cos, the row stores, the bias recursion, then B's solve.  A third warp S takes what does
+// not have to be there: it keeps its own copy of the state (the same Euler update on the same inputs:
+// the same bits), stores the three output rows, and evaluates sin / cos of the OUTER joints -- the ones
+// the mass-matrix recursion (which starts at the tip) needs first -- while A evaluates the inner ones,
+// which its own recursion (which starts at the base) needs first.
+//   A: Euler | sin / cos of joints [0, NA) -> shared | ... (c, s) of S | bias forces -> shared | ... ddtheta
+//   S: Euler | sin / cos of joints [NA, N) -> shared | row stores | ... ddtheta
+//   B: torque row | ... (c, s) | CRBA + LDL^T | ... bias | solve -> ddtheta to shared
+// Barriers: 1 = A's (c, s) (A arrives, B waits: 64), 4 = S's (c, s) (S arrives, A and B wait: 96),
+// 2 = bias (A arrives, B waits: 64), 3 = ddtheta (B arrives, A and S wait: 96).
+// The pair kernel takes the batches between 2 x 32 x SMs and 4 x 32 x SMs rollouts.
+template <int N, int LO, int HI>
+__device__ __forceinline__ void joint_cs_part(const RobotPack<double, N> &rb, const double (&th)[N], JointCS<double, N> &q) {
+    bool near = true;
+#pragma unroll
+    for (int i = LO; i < HI; ++i) near = near && sincos_is_near(rb.phi[i] + th[i]);
+    if (near) {
+        // (one basic block: the independent dependency chains interleave)
+#pragma unroll
+        for (int i = LO; i < HI; ++i) sincos_near(rb.trig, rb.phi[i] + th[i], &q.s[i], &q.c[i]);
+    } else {
+#pragma unroll
+        for (int i = LO; i < HI; ++i) sincos_pack(rb.trig, rb.phi[i] + th[i], &q.s[i], &q.c[i]);
+    }
+#pragma unroll
+    for (int i = LO; i < HI; ++i) q.d[i] = rb.d[i];
+}
+
+template <int N>
+__device__ __forceinline__ void euler_update(const RolloutArgs &a, const double *dd_s, double (&th)[N], double (&dth)[N],
+                                             double (&last)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double dd = *(volatile const double *)(dd_s + 32 * j);
+        dth[j] = rn_add(dth[j], rn_mul(dd, a.dts));
+        double x = rn_add(th[j], rn_mul(dth[j], a.dts));
+        if (a.lim.on) {
+            const double lo = (double)a.lim.lo[j], hi = (double)a.lim.hi[j];
+            x = x < lo ? lo : (x > hi ? hi : x);
+        }
+        th[j] = x;
+        last[j] = dd;
+    }
+}
+
+// Block layout: 8 warp slots, two groups of 32 rollouts, one block per SM.  Warps are dealt to the SM's
+// four schedulers round robin, so the slot order decides who shares one.  B0 B1 A0 A1 - - S1 S0 (layout 1):
+// the two B warps get a scheduler each, A of one group shares with S of the other, two slots stay empty
+// (their warps exit at once).  Measured alternatives (iiwa14, 1000 steps, profiles/r2_variants.md):
+// three-warp blocks, two per SM (A B S | A B S: B of the second block lands on A's scheduler): 8,192
+// rollouts 2.53 ms; six-warp block B0 B1 A0 A1 S0 S1 (layout 0, S on its own group's B's scheduler):
+// 2.36 ms; layout 1: 2.02 ms.  Batches up to 64 x SMs rollouts; `groups` = 1 leaves the second group's
+// warps out (batches up to 32 x SMs: one group per SM).
+#ifndef MPK_FD_TRIO_LAYOUT
+#define MPK_FD_TRIO_LAYOUT 1
+#endif
+constexpr int kTrioThreads = MPK_FD_TRIO_LAYOUT == 1 ? 256 : 192;
+template <int N, unsigned GEO = 0>
+__global__ void __launch_bounds__(kTrioThreads, 1)
+    fd_rollout_trio_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a, const int groups) {
+    constexpr int NA = (N + 1) / 2;  // joints [0, NA): warp A; [NA, N): warp S
+    extern __shared__ __align__(16) double psm[];
+    const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+    // slot -> (role, group): 0 = A, 1 = B, 2 = S, 3 = none
+#if MPK_FD_TRIO_LAYOUT == 1
+    const int role = slot < 2 ? 1 : (slot < 4 ? 0 : (slot < 6 ? 3 : 2));
+    const int grp = slot < 4 ? (slot & 1) : (slot == 6 ? 1 : 0);
+#else
+    const int role = slot < 2 ? 1 : (slot < 4 ? 0 : 2);
+    const int grp = slot & 1;
+#endif
+    if (role == 3 || grp >= groups) return;
+    double *cs = psm + grp * (32 * 6 * N) + lane;  // [2 N][32]
+    double *bias_s = cs + 32 * 2 * N;      // [N][32]
+    double *dd_s = bias_s + 32 * N;        // [N][32]
+    double *stage = dd_s + 32 * N;         // [2][N][32]
+    const int64_t b_ = ((int64_t)blockIdx.x * groups + grp) * 32 + lane;
+    const bool live = b_ < a.B;            // surplus lanes shadow the last rollout
+    const int64_t b = live ? b_ : a.B - 1;
+    const int64_t base = b * a.N;
+    const int bar0 = 4 * grp;              // named barriers 1..4 (group 0), 5..8 (group 1)
+    const auto pair_arrive = [bar0](int id) { asm volatile("bar.arrive %0, 64;" ::"r"(bar0 + id) : "memory"); };
+    const auto pair_wait = [bar0](int id) { asm volatile("bar.sync %0, 64;" ::"r"(bar0 + id) : "memory"); };
+    const auto arrive96 = [bar0](int id) { asm volatile("bar.arrive %0, 96;" ::"r"(bar0 + id) : "memory"); };
+    const auto wait96 = [bar0](int id) { asm volatile("bar.sync %0, 96;" ::"r"(bar0 + id) : "memory"); };
+    if (role == 1) {
+        // ---- warp B: torque rows, mass matrix, factorisation, solve ----
+        if (a.N > 1) tau_row_async<N>(stage + 32 * N, a.taumat, a.tau_dtype, base + 1);
+        for (int64_t i = 1; i < a.N; ++i) {
+            double tau[N];
+            tau_row_take<N>(stage + (i & 1) * 32 * N, a.tau_dtype, tau);
+            if (i + 1 < a.N) tau_row_async<N>(stage + ((i + 1) & 1) * 32 * N, a.taumat, a.tau_dtype, base + i + 1);
+            for (int r = 0; r < a.intRes; ++r) {
+                JointCS<double, N> q;
+                wait96(4);
+                pair_wait(1);
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    q.c[j] = *(volatile double *)(cs + 32 * j);
+                    q.s[j] = *(volatile double *)(cs + 32 * (N + j));
+                    q.d[j] = rb.d[j];
+                }
+                double Mm[N][N], dinv[N], dd[N];
+                crba<double, N, true, GEO>(rb, q, Mm);
+                ldlt_factor<double, N, true>(Mm, dinv);
+                pair_wait(2);
+#pragma unroll
+                for (int j = 0; j < N; ++j) dd[j] = tau[j] - *(volatile double *)(bias_s + 32 * j);
+                ldlt_apply<double, N>(Mm, dinv, dd);
+#pragma unroll
+                for (int j = 0; j < N; ++j) dd_s[32 * j] = dd[j];
+                arrive96(3);
+            }
+        }
+        return;
+    }
+    double th[N], dth[N], last[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        th[j] = a.th0[b * N + j];
+        dth[j] = a.dth0[b * N + j];
+        last[j] = 0.0;
+    }
+    if (role == 0) {
+        // ---- warp A: inner joints' sin / cos, bias forces ----
+        for (int64_t i = 1; i < a.N; ++i) {
+            for (int r = 0; r < a.intRes; ++r) {
+                RegStorePre<double, N> st_;
+                joint_cs_part<N, 0, NA>(rb, th, st_.q);
+#pragma unroll
+                for (int j = 0; j < NA; ++j) {
+                    cs[32 * j] = st_.q.c[j];
+                    cs[32 * (N + j)] = st_.q.s[j];
+                }
+                pair_arrive(1);
+                wait96(4);
+                // (all of (c, s) re-read behind the barriers: fed from registers, ptxas schedules the
+                // recursion's arithmetic ahead of bar.arrive and B waits for it)
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    st_.q.c[j] = *(volatile double *)(cs + 32 * j);
+                    st_.q.s[j] = *(volatile double *)(cs + 32 * (N + j));
+                    st_.q.d[j] = rb.d[j];
+                }
+                double bias[N];
+                ArrayInNoAcc<double, N> in{th, dth};
+                rnea<double, N, false, true, GEO>(rb, in, a.g0, nullptr, bias, st_);
+#pragma unroll
+                for (int j = 0; j < N; ++j) bias_s[32 * j] = bias[j];
+                pair_arrive(2);
+                wait96(3);
+                euler_update<N>(a, dd_s, th, dth, last);
+            }
+        }
+    } else {
+        // ---- warp S: outer joints' sin / cos, output rows ----
+        int64_t pending = base;  // row that th / dth / last still have to be stored to
+        for (int64_t i = 1; i < a.N; ++i) {
+            for (int r = 0; r < a.intRes; ++r) {
+                JointCS<double, N> q;
+                joint_cs_part<N, NA, N>(rb, th, q);
+#pragma unroll
+                for (int j = NA; j < N; ++j) {
+                    cs[32 * j] = q.c[j];
+                    cs[32 * (N + j)] = q.s[j];
+                }
+                arrive96(4);
+                if (pending >= 0) {
+                    if (live) {
+                        store_state<N>(a.pos, pending, th);
+                        store_state<N>(a.vel, pending, dth);
+                        store_state<N>(a.acc, pending, last);
+                    }
+                    pending = -1;
+                }
+                wait96(3);
+                euler_update<N>(a, dd_s, th, dth, last);
+                if (r + 1 == a.intRes) pending = base + i;
+            }
+        }
+        if (live && pending >= 0) {
+            store_state<N>(a.pos, pending, th);
+            store_state<N>(a.vel, pending, dth);
+            store_state<N>(a.acc, pending, last);
+        }
+    }
+}
+
 // ======================================================================================
 // launchers per (flavour, joint count, geometry signature)
 // ======================================================================================
@@ -922,16 +1116,28 @@ void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s)
     constexpr int threads = kRolloutThreads;
     const unsigned grid = (unsigned)((a.B + threads - 1) / threads);
 #if MPK_FD_PAIR
-    // A batch that fits the GPU in one wave of warp pairs (4 blocks x 32 rollouts per SM) runs each
-    // step split across two warps: a lone warp is bound by its own instruction issue (~1950 fp64
-    // instructions at one per two cycles on ONE scheduler's fp64 unit), the pair uses two schedulers.
-    // Measured (iiwa14, 1000 steps): 2,048 rollouts 3.30 -> 2.76 ms, 8,192: 3.95 -> 3.25, 18,944:
-    // 4.71 -> 4.00; beyond one wave the single-warp kernel wins (28,416: 5.60 against 7.13 ms).
+    // A batch that fits the GPU in one wave runs each step split across warps: a lone warp is bound by its
+    // own instruction issue (~2000 instructions per step, one fp64 instruction per 2.6 - 3 cycles:
+    // scripts/lone_warp_probe.py), and with less than one warp per scheduler the other schedulers idle.
+    // Up to 2 x 32 rollouts per SM: three warps per 32 rollouts (fd_rollout_trio_kernel); up to 4 x 32 per
+    // SM: two (fd_rollout_pair_kernel).  Beyond one wave the single-warp kernel wins (28,416: 5.60 against
+    // 7.13 ms).  MPK_FD_SPLIT (tuning knob): 2 = two warps whatever the batch.
     if constexpr (!GEN && REV && N >= 2) {
-        if (!a.ftipmat && a.B <= (int64_t)kRolloutPairBlocksPerSm * 32 * sm_count()) {
+        static const int knob = [] {
+            const char *e = std::getenv("MPK_FD_SPLIT");
+            return e ? std::atoi(e) : 3;
+        }();
+        const int64_t wave = 32 * (int64_t)sm_count();
+        if (!a.ftipmat && a.B <= 4 * wave) {
             // plain revolute chain, rigid links, no tip wrench
-            launch_smem(fd_rollout_pair_kernel<N, GEO>, (unsigned)((a.B + 31) / 32), 64, rollout_pair_smem<N>(), s,
-                        narrow<N>(rb), a);
+            const unsigned blocks = (unsigned)((a.B + 31) / 32);
+            if (knob == 3 && a.B <= 2 * wave) {
+                const int groups = a.B <= wave ? 1 : 2;
+                launch_smem(fd_rollout_trio_kernel<N, GEO>, (unsigned)((a.B + 32 * groups - 1) / (32 * groups)), kTrioThreads,
+                            2 * rollout_pair_smem<N>(), s, narrow<N>(rb), a, groups);
+            }
+            else
+                launch_smem(fd_rollout_pair_kernel<N, GEO>, blocks, 64, rollout_pair_smem<N>(), s, narrow<N>(rb), a);
             return;
         }
     }
