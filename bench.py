@@ -400,20 +400,37 @@ def run_ours(args) -> None:
     # end to end through the public host API: NumPy endpoints in, NumPy float32 torques out.  The
     # results are host-destined, so at N > 1 the global batch is split in proportion to each rank's
     # measured share of the PCIe uplinks (equal shards pin the step to the slowest link).
-    e2e_bounds = shard_bounds(world * B_TRAJ, world, d2h_rates if world > 1 else None)
-    elo, ehi = e2e_bounds[rank], e2e_bounds[rank + 1]
-    se_host, ee_host = start_all[elo:ehi].copy(), end_all[elo:ehi].copy()
-
-    def e2e_step():
-        return planner.trajectory_inverse_dynamics(se_host, ee_host, TF, N_STEPS, METHOD)
-
-    # warm-up in the steady-state pattern of the timed loop (the caller holds the previous result
-    # while the next one is produced, so two pinned result buffers are in rotation; the first
-    # use of each is a ~100 ms cudaHostAlloc that torch's host allocator then caches; a caller that
-    # keeps its results passes out= instead, see OptimizedTrajectoryPlanning.trajectory_inverse_dynamics)
+    # The copy-rate probe is the starting point; the split is then re-balanced twice from each rank's own
+    # measured end-to-end rate (its step time with every other rank running: the uplink shares shift with
+    # who is copying when), all outside the timed region.
+    e2e_weights = list(d2h_rates)
+    e2e_rebalance = []
     out = None
-    for _ in range(max(3, args.warmup)):
-        out = e2e_step()
+    for balance_round in range(3 if world > 1 else 1):
+        e2e_bounds = shard_bounds(world * B_TRAJ, world, e2e_weights if world > 1 else None)
+        elo, ehi = e2e_bounds[rank], e2e_bounds[rank + 1]
+        se_host, ee_host = start_all[elo:ehi].copy(), end_all[elo:ehi].copy()
+
+        def e2e_step():
+            return planner.trajectory_inverse_dynamics(se_host, ee_host, TF, N_STEPS, METHOD)
+
+        # warm-up in the steady-state pattern of the timed loop (the caller holds the previous result
+        # while the next one is produced, so two pinned result buffers are in rotation; the first
+        # use of each is a ~100 ms cudaHostAlloc that torch's host allocator then caches; a caller that
+        # keeps its results passes out= instead, see OptimizedTrajectoryPlanning.trajectory_inverse_dynamics)
+        out = None
+        for _ in range(max(3, args.warmup)):
+            out = e2e_step()
+        if world > 1 and balance_round < 2:
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(6):
+                out = e2e_step()
+            mine = torch.zeros(world, dtype=torch.float64, device=dev)
+            mine[rank] = (ehi - elo) / (time.perf_counter() - t0)
+            dist.all_reduce(mine)
+            e2e_weights = [float(x) for x in mine.cpu()]
+            e2e_rebalance.append([b_ - a_ for a_, b_ in zip(e2e_bounds, e2e_bounds[1:])])
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -640,7 +657,7 @@ def run_ours(args) -> None:
                         if compute:
                             launch_into(dest, a_ - blo, b_ - blo)
                     return gather_rows_pipelined(lf, Bt, (N_STEPS, 6), torch.float32, dev, dst=0, chunks=chunks,
-                                                 out=full, side=side)
+                                                 out=full, side=side, align=2)
 
                 t_n = timed(lambda: nccl_pipe(8), steps5, 2) / steps5
                 t_g = timed(lambda: nccl_pipe(1, False), steps5, 1) / steps5  # the transfer alone
@@ -691,8 +708,10 @@ def run_ours(args) -> None:
                 "pcie_d2h_gbs_measured": d2h_gbs, "pcie_d2h_gbs_all_ranks_together": d2h_rates,
                 "pcie_d2h_gbs_all_ranks_together_min": d2h_min, "pcie_d2h_gbs_all_ranks_together_sum": d2h_sum,
                 "host_cpus_bound_to": numa_cpus,
-                "sharding": ("trajectories split in proportion to each rank's measured device->host rate: "
+                "sharding": ("trajectories split in proportion to each rank's measured end-to-end rate (start: the "
+                             "concurrent device->host copy rates; re-balanced twice outside the timed region): "
                              + str([b_ - a_ for a_, b_ in zip(e2e_bounds, e2e_bounds[1:])])) if world > 1 else "one rank",
+                "sharding_rebalance_history": e2e_rebalance,
                 # ceilings of the e2e number: every result byte crosses PCIe; with weighted shards the
                 # aggregate rate counts, with equal shards the slowest rank's
                 "pcie_bound_points_per_s": d2h_sum * 1e9 / (6 * 4),

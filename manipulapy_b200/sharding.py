@@ -96,16 +96,17 @@ def gather_rows(local: torch.Tensor, units: int, group: Optional[dist.ProcessGro
 def gather_rows_pipelined(launch: Callable[[int, int, torch.Tensor], None], units: int, tail: Sequence[int],
                           dtype: torch.dtype, device: torch.device, dst: int = 0, chunks: int = 8,
                           group: Optional[dist.ProcessGroup] = None, out: Optional[torch.Tensor] = None,
-                          side: Optional[torch.cuda.Stream] = None) -> Optional[torch.Tensor]:
+                          side: Optional[torch.cuda.Stream] = None, align: int = 1) -> Optional[torch.Tensor]:
     """Compute this rank's shard of ``units`` rows in ``chunks`` pieces and gather them on ``dst``
     while computing: ``launch(lo, hi, dest)`` enqueues the kernel for global rows ``[lo, hi)`` writing
     into ``dest`` (``(hi - lo, *tail)``) on the current stream; every finished chunk is handed to NCCL
     (``isend`` on the producers, ``irecv`` straight into the final buffer on ``dst``) on a second
     stream, so the transfer of chunk k overlaps the kernel of chunk k + 1.  Returns the full
-    ``(units, *tail)`` tensor on ``dst`` (``out`` if given), ``None`` elsewhere.  Works with any
-    backend (the CPU tests run it over gloo)."""
+    ``(units, *tail)`` tensor on ``dst`` (``out`` if given), ``None`` elsewhere.  ``align``: shard
+    boundaries as ``shard_bounds(..., align=align)`` gives them.  Works with any backend (the CPU
+    tests run it over gloo)."""
     world, rank = _world(group)
-    bounds = shard_bounds(units, world)
+    bounds = shard_bounds(units, world, None, align)
     lo, hi = bounds[rank], bounds[rank + 1]
     cuda = torch.device(device).type == "cuda"
     if rank == dst:

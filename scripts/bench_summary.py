@@ -6,7 +6,7 @@ for path in sys.argv[1:]:
     print(f"== {path}: n_gpus {d['n_gpus']}  value {d['value']:.4e} {d['unit']}  {d['ms_per_step']:.4f} ms/step  "
           f"e2e {d['e2e']['value']:.4e}  clocks {d['clocks']['sm_mhz']} MHz {d['clocks']['reasons']}")
     e = d["e2e"]
-    print(f"   e2e sharding: {e.get('sharding')}  d2h together {[round(x, 1) for x in e['pcie_d2h_gbs_all_ranks_together']]} "
+    print(f"   e2e sharding: {str(e.get("sharding"))[-80:]}  d2h together {[round(x, 1) for x in e['pcie_d2h_gbs_all_ranks_together']]} "
           f"bound {e['pcie_bound_points_per_s']:.3e} (equal shards {e['pcie_bound_points_per_s_equal_shards']:.3e})")
     r = d["roofline"]
     print(f"   roofline hbm {r['frac']:.3f}  fp64 flop frac {r['fp64']['frac']:.3f}  issue frac {r['fp64']['pipe_issue_frac']:.3f}")
