@@ -400,13 +400,14 @@ def run_ours(args) -> None:
     # end to end through the public host API: NumPy endpoints in, NumPy float32 torques out.  The
     # results are host-destined, so at N > 1 the global batch is split in proportion to each rank's
     # measured share of the PCIe uplinks (equal shards pin the step to the slowest link).
-    # The copy-rate probe is the starting point; the split is then re-balanced twice from each rank's own
+    # The copy-rate probe is the starting point; the split is then re-balanced five times from each rank's own
     # measured end-to-end rate (its step time with every other rank running: the uplink shares shift with
     # who is copying when), all outside the timed region.
     e2e_weights = list(d2h_rates)
     e2e_rebalance = []
     out = None
-    for balance_round in range(3 if world > 1 else 1):
+    E2E_BALANCE_ROUNDS = 5
+    for balance_round in range(E2E_BALANCE_ROUNDS + 1 if world > 1 else 1):
         e2e_bounds = shard_bounds(world * B_TRAJ, world, e2e_weights if world > 1 else None)
         elo, ehi = e2e_bounds[rank], e2e_bounds[rank + 1]
         se_host, ee_host = start_all[elo:ehi].copy(), end_all[elo:ehi].copy()
@@ -421,7 +422,7 @@ def run_ours(args) -> None:
         out = None
         for _ in range(max(3, args.warmup)):
             out = e2e_step()
-        if world > 1 and balance_round < 2:
+        if world > 1 and balance_round < E2E_BALANCE_ROUNDS:
             barrier()
             t0 = time.perf_counter()
             for _ in range(6):
@@ -709,7 +710,7 @@ def run_ours(args) -> None:
                 "pcie_d2h_gbs_all_ranks_together_min": d2h_min, "pcie_d2h_gbs_all_ranks_together_sum": d2h_sum,
                 "host_cpus_bound_to": numa_cpus,
                 "sharding": ("trajectories split in proportion to each rank's measured end-to-end rate (start: the "
-                             "concurrent device->host copy rates; re-balanced twice outside the timed region): "
+                             "concurrent device->host copy rates; re-balanced five times outside the timed region): "
                              + str([b_ - a_ for a_, b_ in zip(e2e_bounds, e2e_bounds[1:])])) if world > 1 else "one rank",
                 "sharding_rebalance_history": e2e_rebalance,
                 # ceilings of the e2e number: every result byte crosses PCIe; with weighted shards the
