@@ -221,6 +221,19 @@ __global__ void __launch_bounds__(kTrajThreads) cartesian_kernel(const CartArgs 
     float *buf = sm[warp];
     const float *src3[3] = {pos, vel, acc};
     float *dst3[3] = {a.pos, a.vel, a.acc};
+    // A full warp's rows are 384 B (1152 B of orientations) starting on a multiple of that: 16-byte vector
+    // stores when the array itself is 16-byte aligned, scalar stores for the ragged last warp.
+    const auto flush = [&](float *dst, int per_row) {
+        float *o = dst + pw * per_row;
+        const int cnt = rows * per_row;
+        if (rows == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(buf);
+            float4 *o4 = reinterpret_cast<float4 *>(o);
+            for (int e = lane; e < cnt / 4; e += 32) __stcs(o4 + e, s4[e]);
+        } else {
+            for (int e = lane; e < cnt; e += 32) __stcs(o + e, buf[e]);
+        }
+    };
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         if (!dst3[k]) continue;
@@ -229,7 +242,7 @@ __global__ void __launch_bounds__(kTrajThreads) cartesian_kernel(const CartArgs 
             for (int j = 0; j < 3; ++j) buf[lane * 3 + j] = src3[k][j];
         }
         __syncwarp();
-        for (int e = lane; e < rows * 3; e += 32) __stcs(dst3[k] + pw * 3 + e, buf[e]);
+        flush(dst3[k], 3);
         __syncwarp();
     }
     if (a.orient) {
@@ -238,7 +251,7 @@ __global__ void __launch_bounds__(kTrajThreads) cartesian_kernel(const CartArgs 
             for (int j = 0; j < 9; ++j) buf[lane * 9 + j] = R[j];
         }
         __syncwarp();
-        for (int e = lane; e < rows * 9; e += 32) __stcs(a.orient + pw * 9 + e, buf[e]);
+        flush(a.orient, 9);
     }
 }
 
