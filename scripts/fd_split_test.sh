@@ -1,2 +1,7 @@
-python -m pytest tests -m gpu -x -q -k "rollout" 2>&1 | tail -2
-for K in 3; do for B in 2048 4736 8192 9472; do echo "knob $K B $B: $(MPK_FD_SPLIT=$K python scripts/fd_probe.py $B 1000 3 | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(d["ms_min"], d["checksum"])')"; done; done
+for L in manipulapy_b200/_lib manipulapy_b200/_lib_nofmad; do
+echo "== $L"
+MPK_LIB_DIR=$L python scripts/fd_bits2.py 1000 | python -c "
+import json,sys; d=json.load(sys.stdin)
+for k,v in d.items(): print(k, {a:(b['differing'], b.get('max_ulps')) for a,b in v.items()})"
+for B in 8192 65536; do echo "B $B: $(MPK_LIB_DIR=$L python scripts/fd_probe.py $B 1000 3 | python -c 'import json,sys; d=json.loads(sys.stdin.read()); print(d["ms_min"])')"; done
+done
