@@ -230,6 +230,9 @@ class SerialManipulator:
         would; batched and device-resident calls use a counter-based generator keyed by ``seed``."""
         if plot_residuals:
             raise NotImplementedError("plot_residuals is outside the B200 hot path (no plotting)")
+        if int(max_iterations) < 1:
+            # the reference's loop never runs and its epilogue touches the unset loop counter (kinematics/ik.py:271-273)
+            raise UnboundLocalError("max_iterations must be at least 1 (the reference fails on its unset loop counter 'k')")
         flags = (1 if adaptive_tuning else 0) | (2 if backtracking else 0)
         on_dev = _host.any_device(T_desired, thetalist0)
         dev = (thetalist0.device if _host.is_device_tensor(thetalist0)

@@ -283,7 +283,13 @@ class OptimizedTrajectoryPlanning:
 
     def forward_dynamics_trajectory(self, thetalist, dthetalist, taumat, g, Ftipmat, dt, intRes) -> Dict[str, Any]:
         """Single rollout (reference call: ``thetalist (n,)``, ``taumat (N, n)``, ``Ftipmat (N, 6)``)
-        or ``B`` independent rollouts (``(B, n)``, ``(B, N, n)``, ``(B, N, 6)`` or ``None``)."""
+        or ``B`` independent rollouts (``(B, n)``, ``(B, N, n)``, ``(B, N, 6)`` or ``None``).
+
+        The state is integrated in float64 whatever the dtype of ``thetalist`` / ``dthetalist``.  (Deviation: the
+        reference keeps the state in the INPUT dtype -- trajectory_dynamics.py:619-678 casts back after every
+        sub-step -- so a float32 initial state, e.g. ``traj["positions"][0]``, makes it integrate, and evaluate its
+        trigonometry, in float32; here such a state is upcast exactly and the rollout equals the reference's on
+        the float64 copy of the same state.)"""
         t0 = time.perf_counter()
         on_dev = _host.any_device(thetalist, dthetalist, taumat)
         dyn = self.dynamics
