@@ -575,6 +575,56 @@ def run_ours(args) -> None:
                         "value": P / sec, "unit": "points/s", "launches_timed": n, "roofline": rt, "clocks": ck,
                         "outputs": "3 x float32 (B, N, 6)"})
 
+        # the collision / limit hook of joint_trajectory (>= 99 % of cfg 1's wall time in the
+        # reference: a host loop of link_fk + AABB tests per row).  Synthetic per-link point sets (the reference's
+        # hulls come from meshes, which nothing here loads): link FK of the whole link tree and the self-collision
+        # flags over 1 M random UR5 configurations, and cfg 1's trajectory with the hook applied.
+        hr = np.random.default_rng(11)
+        link_names = [str(x) for x in rb.links["link_names"]]
+        hulls = {nm: hr.uniform(-0.03, 0.03, 3) + hr.uniform(-1, 1, (16, 3)) * hr.uniform(0.05, 0.10, 3)
+                 for nm in link_names[3:9]}  # the six moving links
+        checker = rb.collision_checker(hulls)
+        Pk, L = 1_000_000, len(link_names)
+        lo_ = torch.from_numpy(rb.joint_limits[:, 0]).to(dev)
+        hi_ = torch.from_numpy(rb.joint_limits[:, 1]).to(dev)
+        th = lo_ + (hi_ - lo_) * torch.rand(Pk, 6, dtype=torch.float64, device=dev, generator=gen)
+        sec, n, ck = measure(lambda: ops.link_fk_batch(handle, checker._model_host, checker._model_dev, th, L))
+        configs.append({"name": "link_fk_batch_1M_ur5", "survey_row": "8f-1", "links": L, "ms": sec * 1e3,
+                        "value": Pk / sec, "unit": "configs/s", "launches_timed": n,
+                        "roofline": roof(48 + 128 * L, Pk, sec, "hbm"), "clocks": ck,
+                        "outputs": "float64 (P, L, 4, 4) poses of every link"})
+        sec, n, ck = measure(lambda: ops.self_collision(handle, checker._model_host, checker._model_dev, th))
+        flags = ops.self_collision(handle, checker._model_host, checker._model_dev, th)
+        configs.append({"name": "self_collision_aabb_1M_ur5", "survey_row": "8f-1", "hulls": len(hulls),
+                        "points_per_hull": 16, "ms": sec * 1e3, "value": Pk / sec, "unit": "configs/s",
+                        "launches_timed": n, "colliding_fraction": float(flags.float().mean()),
+                        "roofline": roof(48 + 1, Pk, sec, "fp64 pipe (6 hulls x 16 points x 9 FMA + 15 pair tests per row)",
+                                         6 * 16 * 18 + 170 * 6, fp64_peak_tf), "clocks": ck,
+                        "outputs": "uint8 (P,) flags"})
+        # cfg 1's call with the hook on, from a COLLIDING start configuration (so that rows are actually nudged)
+        hit = torch.nonzero(flags)
+        s1c = th[int(hit[0])].cpu().numpy() if hit.numel() else s1
+        del th, flags
+        hook_planner = rb.planner()
+        hook_planner.attach_collision_checker(checker)
+        for _ in range(5):
+            hook_planner.joint_trajectory(s1c, e1, TF, 1000, METHOD)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            tr_hook = hook_planner.joint_trajectory(s1c, e1, TF, 1000, METHOD)
+        hook_s = (time.perf_counter() - t0) / 50
+        t0 = time.perf_counter()
+        for _ in range(50):
+            planner.joint_trajectory(s1c, e1, TF, 1000, METHOD)
+        plain_s = (time.perf_counter() - t0) / 50
+        configs.append({"name": "cfg1_joint_trajectory_with_collision_hook_N1000", "survey_row": "8f-1", "baseline_config": 0,
+                        "ms": hook_s * 1e3, "value": 1000 / hook_s, "unit": "points/s",
+                        "ms_without_hook": plain_s * 1e3,
+                        "api": "planner.joint_trajectory with a CollisionChecker attached, NumPy in / NumPy out (host time)",
+                        "rows_nudged": int((tr_hook["positions"] != planner.joint_trajectory(s1c, e1, TF, 1000, METHOD)["positions"])
+                                           .any(axis=1).sum()),
+                        "reference_cpu_s": "the host hook is >= 99 % of the reference's joint_trajectory wall time (SURVEY 8a1)"})
+
     # ---- cfg 5: 1e6 .. 1e9 points, strong scaling, gathered on rank 0 inside the timed region ----
     sweep = []
     if not args.no_sweep:
