@@ -157,6 +157,12 @@ def main():
         dth, tau = rand(Pk, n), rand(Pk, n, lo=-20, hi=20)
         rec(f"forward_dynamics_{name}", Pk, timeit(lambda: ops.forward_dynamics(h, th, dth, tau, g, None, None)), 32 * n, 5300, "points")
 
+    # Cartesian straight-line trajectories: 4096 pose pairs x 2441 steps, 72 B of float32 out per step
+    Xs, _ = ops.fk_jacobian(h6, rand(B, 6, lo=-np.pi, hi=np.pi), True, False)
+    Xe, _ = ops.fk_jacobian(h6, rand(B, 6, lo=-np.pi, hi=np.pi), True, False)
+    rec("cartesian_trajectory", P, timeit(lambda: ops.cartesian_trajectory(Xs, Xe, 2.0, N, 5)), 72, 150, "points")
+    del Xs, Xe
+
     iiwa = load_robot("iiwa14", device=dev)
     h7 = iiwa.dynamics.robot.handle
     lo = torch.from_numpy(iiwa.joint_limits[:, 0]).to(dev)
