@@ -381,15 +381,28 @@ def run_ours(args) -> None:
     torch.cuda.synchronize()
     d2h_gbs = pin.numel() / (a.elapsed_time(b) / 1e3) / 1e9
     # ... and with every rank copying at the same time: the GPUs of one box share PCIe uplinks, so
-    # the per-GPU rate drops (8 GPUs: 57 -> 12-18 GB/s, profiles/r1_d2h_n8.json) and differs between GPUs
+    # the per-GPU rate drops (8 GPUs: 57 -> 8-18 GB/s) and differs between GPUs.  Measured over a fixed
+    # WINDOW in which every rank copies continuously (64 MiB pieces, 0.3 s): with a fixed amount per rank
+    # instead, the ranks on the faster uplink finish first and the others then see less contention than a
+    # sustained load gives them (round 2 until now: 11.8 GB/s reported for GPUs 0-3 where the sustained
+    # share is ~8.4 GB/s, and a ceiling 12 % too high).
+    piece = 64 << 20
     barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(4):
-        pin.copy_(src, non_blocking=True)
-    b.record()
+    t0 = time.perf_counter()
+    done_bytes, t_last, k = 0, t0, 0
+    while True:
+        lo_ = (k % 4) * piece
+        pin[lo_:lo_ + piece].copy_(src[lo_:lo_ + piece], non_blocking=True)
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if now - t0 > 0.3:
+            break
+        done_bytes, t_last, k = done_bytes + piece, now, k + 1
+    my_rate = done_bytes / max(1e-9, t_last - t0) / 1e9
+    # (keep copying until every rank has left its window, so that nobody's last pieces run uncontended)
+    for _ in range(2):
+        pin[:piece].copy_(src[:piece], non_blocking=True)
     torch.cuda.synchronize()
-    my_rate = 4 * pin.numel() / (a.elapsed_time(b) / 1e3) / 1e9
     rates = torch.zeros(world, dtype=torch.float64, device=dev)
     rates[rank] = my_rate
     if world > 1:
