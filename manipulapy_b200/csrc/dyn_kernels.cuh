@@ -737,8 +737,11 @@ constexpr size_t rollout_pair_smem() {
     return sizeof(double) * 32 * (6 * N);
 }
 
-template <int N, unsigned GEO = 0>
-__global__ void __launch_bounds__(64, MPK_FD_PAIR_MINBLOCKS)
+// MINB: resident blocks per SM the kernel is compiled for (4: up to 255 registers, batches of one wave; 6: a
+// 168-register cap, 12 warps per SM, for batches of several waves -- 65,536 rollouts 11.2 ms against 12.0 ms
+// for the single-warp kernel and 12.3 ms at MINB = 4, profiles/r2_variants.md C).
+template <int N, unsigned GEO = 0, int MINB = MPK_FD_PAIR_MINBLOCKS>
+__global__ void __launch_bounds__(64, MINB)
     fd_rollout_pair_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a) {
     extern __shared__ __align__(16) double psm[];
     const int lane = threadIdx.x & 31;
@@ -1120,17 +1123,20 @@ void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s)
     // own instruction issue (~2000 instructions per step, one fp64 instruction per 2.6 - 3 cycles:
     // scripts/lone_warp_probe.py), and with less than one warp per scheduler the other schedulers idle.
     // Up to 2 x 32 rollouts per SM: three warps per 32 rollouts (fd_rollout_trio_kernel); up to 4 x 32 per
-    // SM: two (fd_rollout_pair_kernel).  Beyond one wave the single-warp kernel wins (28,416: 5.60 against
-    // 7.13 ms).  MPK_FD_SPLIT (tuning knob): 2 = two warps whatever the batch.
+    // SM: two (fd_rollout_pair_kernel).  Up to 8 x 32 per SM -- one wave of the single-warp kernel -- that
+    // kernel wins (28,416: 5.09 against 5.12 - 6.24 ms); beyond, the pair kernel compiled for 6 blocks per SM
+    // does (12 warps per SM hide more latency than 8: 65,536 rollouts 11.2 against 12.0 ms).
+    // MPK_FD_SPLIT (tuning knob): 1 = single-warp kernel only, 2 = no three-warp kernel, 4 = pair kernel (4
+    // blocks per SM) whatever the batch.
     if constexpr (!GEN && REV && N >= 2) {
         static const int knob = [] {
             const char *e = std::getenv("MPK_FD_SPLIT");
             return e ? std::atoi(e) : 3;
         }();
         const int64_t wave = 32 * (int64_t)sm_count();
-        if (!a.ftipmat && a.B <= 4 * wave) {
+        const unsigned blocks = (unsigned)((a.B + 31) / 32);
+        if (!a.ftipmat && knob != 1 && (a.B <= 4 * wave || knob == 4)) {
             // plain revolute chain, rigid links, no tip wrench
-            const unsigned blocks = (unsigned)((a.B + 31) / 32);
             if (knob == 3 && a.B <= 2 * wave) {
                 const int groups = a.B <= wave ? 1 : 2;
                 launch_smem(fd_rollout_trio_kernel<N, GEO>, (unsigned)((a.B + 32 * groups - 1) / (32 * groups)), kTrioThreads,
@@ -1138,6 +1144,10 @@ void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s)
             }
             else
                 launch_smem(fd_rollout_pair_kernel<N, GEO>, blocks, 64, rollout_pair_smem<N>(), s, narrow<N>(rb), a);
+            return;
+        }
+        if (!a.ftipmat && knob != 1 && a.B > 8 * wave) {
+            launch_smem(fd_rollout_pair_kernel<N, GEO, 6>, blocks, 64, rollout_pair_smem<N>(), s, narrow<N>(rb), a);
             return;
         }
     }

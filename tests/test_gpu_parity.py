@@ -296,7 +296,8 @@ def test_batched_rollouts_vs_oracle(robots, oracle_factory, robot, B, N, intres)
 def test_rollout_kernels_agree(robots, oracle_factory, robot):
     """A batch that fits the GPU in one wave runs each Euler step split across warps -- three per 32
     rollouts up to 64 x SMs rollouts (fd_rollout_trio_kernel, one or two groups per block), two up to
-    128 x SMs (fd_rollout_pair_kernel); larger batches run one warp per 32 rollouts (fd_rollout_kernel).
+    128 x SMs (fd_rollout_pair_kernel); up to 256 x SMs one warp per 32 rollouts (fd_rollout_kernel), beyond the pair
+    kernel again (compiled for 6 blocks per SM).
     The same rollouts through all of them -- one call of 24,000 against calls of 4,000, 6,000 and 14,000 --
     give the same bits (so a batch sharded over GPUs equals the batch on one GPU whichever kernel each
     shard takes), ragged last block, intRes = 2, and all agree with the oracle on sampled rollouts."""
@@ -318,6 +319,14 @@ def test_rollout_kernels_agree(robots, oracle_factory, robot):
     for k in big:
         small = np.concatenate([p[k] for p in parts])
         assert _bits_equal(small, big[k]), k
+    # beyond one wave of the single-warp kernel (256 x SMs rollouts) the pair kernel compiled for 6 blocks per SM runs:
+    # 40,000 rollouts (two copies of the first 20,000) against the 20,000 through the single-warp kernel
+    assert 2 * 20000 > 8 * 32 * sms >= 20000 > 4 * 32 * sms
+    half = planner.forward_dynamics_trajectory(th0[:20000], dth0[:20000], tau[:20000, :12], [0, 0, -9.81], None, 1e-3, 2)
+    twice = planner.forward_dynamics_trajectory(np.tile(th0[:20000], (2, 1)), np.tile(dth0[:20000], (2, 1)),
+                                                np.tile(tau[:20000, :12], (2, 1, 1)), [0, 0, -9.81], None, 1e-3, 2)
+    for k in half:
+        assert _bits_equal(twice[k][:20000], half[k]) and _bits_equal(twice[k][20000:], half[k]), k
     odd = planner.forward_dynamics_trajectory(th0[:1001], dth0[:1001], tau[:1001], [0, 0, -9.81], None, 1e-3, 2)
     idx = np.array([0, 31, 32, 999, 1000])
     ref = o.forward_dynamics_trajectory(th0[idx], dth0[idx], tau[idx].astype(np.float64), [0, 0, -9.81], None, 1e-3, 2,
