@@ -1413,8 +1413,9 @@ MPK_HD void cartesian_point(const double *Xs, const double *Xe, int64_t idx, int
     double s;
     if (method == 3) s = 3.0 * (tq * tq) - 2.0 * (tq * tq * tq);
     else s = 10.0 * (tq * tq * tq) - 15.0 * (tq * tq * tq * tq) + 6.0 * (tq * tq * tq * tq * tq);
-    // ... and of the linear velocity / acceleration (trajectory.py:703-717)
-    const double tau = rn_div(rn_mul((double)idx, rn_div(Tf, (double)(N - 1))), Tf);
+    // ... and of the linear velocity / acceleration (trajectory.py:703-717): idx * (Tf / (N - 1)) / Tf there, the same
+    // double as tq (a product does not depend on the order of its factors, and (double)N - 1 == (double)(N - 1))
+    const double tau = tq;
     double sd = 0.0, sdd = 0.0;
     if (method == 3) {
         sd = 6.0 * tau * (1.0 - tau) / Tf;
@@ -1433,8 +1434,10 @@ MPK_HD void cartesian_point(const double *Xs, const double *Xe, int64_t idx, int
         B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
     } else {
         const double th = sqrt(th2 > 1e-12 ? th2 : 1e-12);
-        A = sin(th) / th;
-        B = (1.0 - cos(th)) / (th * th);
+        double sn, cs;
+        sincos_t(th, &sn, &cs);  // (one argument reduction for both)
+        A = sn / th;
+        B = (1.0 - cs) / (th * th);
     }
     // exp = 1 + A K + B K^2,  K = [k]x,  K^2 = k k^T - |k|^2 1
     const double X[9] = {1.0 + B * (kx * kx - th2), -A * kz + B * kx * ky, A * ky + B * kx * kz,
