@@ -1062,6 +1062,41 @@ def test_robot_zoo_vs_reference(robot):
     assert np.array_equal(dyn.mass_matrix(big)[: th.shape[0]], dyn.mass_matrix(th))
 
 
+@pytest.mark.parametrize("robot,joints", [("ur10e", 2), ("abb_irb2400", 3), ("gen3", 4), ("xarm6", 5), ("crx10ia", 6),
+                                          ("fanuc_lrmate", 6), ("abb_irb2400", 6), ("xarm6", 6), ("kinova_gen3", 7)])
+def test_split_rollout_kernels_over_joint_counts(robot, joints):
+    """The rollout kernels that split a step across warps, for every joint count they are compiled for (2 .. 7: chains
+    cut from the robot database, general link geometry) and for the arm families with their own link-geometry
+    kernels: 100 rollouts (three warps per 32 rollouts, ragged last block) against the oracle, and against the same
+    rollouts inside batches that take the two-warp and the single-warp kernel (bit for bit)."""
+    from manipulapy_b200 import ManipulatorDynamics, OptimizedTrajectoryPlanning
+    from oracle import Oracle
+
+    z = load_zoo()[robot]
+    k = joints
+    S, G, Mc, lim = z["S_list"][:, :k], z["Glist"][:k], z["Mlist_per_link"][:k], z["joint_limits"][:k]
+    M = z["M"] if k == z["S_list"].shape[1] else Mc[-1]
+    dyn = ManipulatorDynamics(M, None, None, None, S, None, G, Mc)
+    planner = OptimizedTrajectoryPlanning(dyn, None, dyn, lim)
+    o = Oracle(S, M, G, Mc)
+    rng = np.random.default_rng(31 + k)
+    B, N = 100, 30
+    lo, hi = np.maximum(lim[:, 0], -3.0), np.minimum(lim[:, 1], 3.0)
+    th0 = rng.uniform(0.5 * lo, 0.5 * hi, (B, k))
+    dth0 = rng.uniform(-0.5, 0.5, (B, k))
+    tau = rng.uniform(-3, 3, (B, N, k)).astype(np.float32)
+    r = planner.forward_dynamics_trajectory(th0, dth0, tau, [0, 0, -9.81], None, 1e-3, 1)
+    ref = o.forward_dynamics_trajectory(th0, dth0, tau.astype(np.float64), [0, 0, -9.81], None, 1e-3, 1, lim, analytic=True)
+    for key in ref:
+        assert _rel_rows(r[key].reshape(-1, k), ref[key].reshape(-1, k)) <= 1e-6, key
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for reps in (2 * 32 * sms // B + 1, 4 * 32 * sms // B + 1):  # two warps, one warp per 32 rollouts
+        big = planner.forward_dynamics_trajectory(np.tile(th0, (reps, 1)), np.tile(dth0, (reps, 1)), np.tile(tau, (reps, 1, 1)),
+                                                  [0, 0, -9.81], None, 1e-3, 1)
+        for key in r:
+            assert _bits_equal(big[key][:B], r[key]) and _bits_equal(big[key][-B:], r[key]), (key, reps)
+
+
 @pytest.mark.parametrize("robot", ["ur5", "iiwa14"])
 def test_singularity_callers(robot):
     """Singularity.condition_number / singularity_analysis / near_singularity_detection
