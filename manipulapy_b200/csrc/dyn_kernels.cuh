@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(kDynThreads, kRneaMinBlocks)
     const T *ftt = tip_to<T>(a.tip, ftp, tt);
     RowIn<N, T, REST> in{a.th, a.dth, a.ddth, a.in_dtype, p * N, {T(0), T(0), T(0)}, {}};
     in.begin(a.vec_in != 0);
-    SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + threadIdx.x};
+    SmemStore<T, N, kDynThreads, rnea_fast0(GEN, REV, N)> st{wsm + 2 * threadIdx.x};
     T tau[N];
     rnea<T, N, GEN, REV, GEO>(rb, in, tt.g0, ftt, tau, st);
     store_tau<N, T>(a.out, a.out_dtype, a.vec_out, p, tau, a.lim);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kDynThreads, kFusedMinBlocks)
         const T *ftp = TIP ? ft : nullptr;
         T tau[N];
         Store st;
-        st.base = wsm + gl;
+        st.base = wsm + 2 * gl;
 #if MPK_FUSED_LAZY_SINCOS
         TrajInLazy<N, T> in{ts, tab, a.jlim, stage};
 #else

@@ -673,6 +673,20 @@ struct RegStore {
     JointCS<T, N> q;
     MPK_HD void put(int i, int k, T v) { x[i][k] = v; }
     MPK_HD T get(int i, int k) const { return x[i][k]; }
+    MPK_HD void put_wrench(int i, const T (&n)[3], const T (&f)[3]) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x[i][k] = n[k];
+            x[i][3 + k] = f[k];
+        }
+    }
+    MPK_HD void get_wrench(int i, T (&n)[3], T (&f)[3]) const {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            n[k] = x[i][k];
+            f[k] = x[i][3 + k];
+        }
+    }
     template <bool REV>
     MPK_HD void put_cs(const RobotPack<T, N> &, int i, T c, T s, T d) {
         q.c[i] = c;
@@ -703,39 +717,79 @@ struct RegStorePre : RegStore<T, N> {
 // (the rigid kernel flavours are only used for chains whose FIRST joint is revolute)
 constexpr bool rnea_fast0(bool GEN, bool REV, int N) { return (void)REV, !GEN && N >= 2; }
 
+// Two values of T side by side: the unit of the link-state column (one 16-byte shared-memory access for doubles).
+template <typename T>
+struct alignas(2 * sizeof(T)) Pair {
+    T a, b;
+};
+// Volatile pair load: the compiler must not forward the value it stored in the forward pass to the
+// backward pass in a register -- that keeps 8 (N-1) doubles alive across the whole recursion,
+// which is exactly what this store exists to avoid: 72 -> 122 registers, or spills to local memory.
+template <typename T>
+MPK_HD Pair<T> ld_pair(const Pair<T> *p) {
+#ifdef __CUDA_ARCH__
+    Pair<T> r;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+    if constexpr (sizeof(T) == 8) {
+        asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.a), "=d"(r.b) : "r"(addr) : "memory");
+    } else {
+        asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.a), "=f"(r.b) : "r"(addr) : "memory");
+    }
+    return r;
+#else
+    return *p;
+#endif
+}
+
 template <typename T, int N, int THREADS, bool FAST0 = false>
 struct SmemStore {
     static constexpr bool kPrecomputedCS = false;
-    T *base;  // shared memory + threadIdx.x; slot l = wrench of link l, (c, s) of link l + 1
-    // values per thread: 8 per link 0..N-2; with FAST0 link 0 keeps 3 (its z moment and (c, s) of link 1)
-    static constexpr int kValues = N > 1 ? (FAST0 ? 3 + (N - 2) * 8 : (N - 1) * 8) : 0;
+    // shared memory + 2 threadIdx.x (in units of T): a column of PAIRS per thread, pair q of thread t at
+    // ((q THREADS + t) pairs: consecutive threads 16 bytes apart, so a warp's access is 512 contiguous bytes.
+    // Link l (l >= 1, or every link without FAST0) owns four pairs: (n0, n1) (n2, f0) (f1, f2) of its wrench
+    // and (c, s) of link l + 1; with FAST0 link 0 owns two: (its z moment, -) and (c, s) of link 1.
+    T *base;
+    static constexpr int kPairs = N > 1 ? (FAST0 ? 2 + (N - 2) * 4 : (N - 1) * 4) : 0;
+    static constexpr int kValues = 2 * kPairs;
     static constexpr size_t kBytes = (size_t)kValues * THREADS * sizeof(T);
-    static constexpr MPK_HD int at(int l, int k) {
-        return (FAST0 ? (l == 0 ? (k == 2 ? 0 : k - 5) : 3 + (l - 1) * 8 + k) : l * 8 + k) * THREADS;
+    static constexpr MPK_HD int pair_of(int l, int q) { return FAST0 ? (l == 0 ? q : 2 + (l - 1) * 4 + q) : l * 4 + q; }
+    MPK_HD Pair<T> *pp(int l, int q) const { return reinterpret_cast<Pair<T> *>(base) + (size_t)pair_of(l, q) * THREADS; }
+    // single values: (i, 2) of link 0 under FAST0 (its z moment) lives in the first half of pair 0
+    MPK_HD void put(int i, int k, T v) {
+        if (FAST0 && i == 0) pp(0, 0)->a = v;
+        else (&pp(i, k >> 1)->a)[k & 1] = v;
     }
-    MPK_HD void put(int i, int k, T v) { base[at(i, k)] = v; }
-    // (volatile loads: the compiler must not forward the value it stored in the forward pass to the
-    // backward pass in a register -- that keeps 8 (N-1) doubles alive across the whole recursion,
-    // which is exactly what this store exists to avoid: 72 -> 122 registers, or spills to local memory)
-    MPK_HD T ld(int idx) const { return *static_cast<const volatile T *>(base + idx); }
-    MPK_HD T get(int i, int k) const { return ld(at(i, k)); }
+    MPK_HD T get(int i, int k) const {
+        if (FAST0 && i == 0) return *static_cast<const volatile T *>(&pp(0, 0)->a);
+        return *static_cast<const volatile T *>(&pp(i, k >> 1)->a + (k & 1));
+    }
+    MPK_HD void put_wrench(int i, const T (&n)[3], const T (&f)[3]) {
+        *pp(i, 0) = Pair<T>{n[0], n[1]};
+        *pp(i, 1) = Pair<T>{n[2], f[0]};
+        *pp(i, 2) = Pair<T>{f[1], f[2]};
+    }
+    MPK_HD void get_wrench(int i, T (&n)[3], T (&f)[3]) const {
+        const Pair<T> p0 = ld_pair(pp(i, 0)), p1 = ld_pair(pp(i, 1)), p2 = ld_pair(pp(i, 2));
+        n[0] = p0.a; n[1] = p0.b; n[2] = p1.a;
+        f[0] = p1.b; f[1] = p2.a; f[2] = p2.b;
+    }
+    MPK_HD Pair<T> *cs_pair(int i) const { return pp(i - 1, (FAST0 && i == 1) ? 1 : 3); }
     template <bool REV>
     MPK_HD void put_cs(const RobotPack<T, N> &rb, int i, T c, T s, T d) {
         if (i == 0) return;
-        base[at(i - 1, 6)] = c;
-        base[at(i - 1, 7)] = (REV || rb.sr[i] != T(0)) ? s : d;
+        *cs_pair(i) = Pair<T>{c, (REV || rb.sr[i] != T(0)) ? s : d};
     }
     template <bool REV>
     MPK_HD void get_cs(const RobotPack<T, N> &rb, int i, T &c, T &s, T &d) const {
-        const T x = ld(at(i - 1, 7));
+        const Pair<T> p = ld_pair(cs_pair(i));
         if (REV || rb.sr[i] != T(0)) {
-            c = ld(at(i - 1, 6));
-            s = x;
+            c = p.a;
+            s = p.b;
             d = rb.d[i];
         } else {
             c = rb.cphi[i];
             s = rb.sphi[i];
-            d = x;
+            d = p.b;
         }
     }
     template <bool REV>
@@ -989,11 +1043,7 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
             Fn[2] = Fn[2] + cg[0] * fy - cg[1] * fx;
         }
         if (i < N - 1) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                st_.put(i, k, Fn[k]);
-                st_.put(i, 3 + k, Ff[k]);
-            }
+            st_.put_wrench(i, Fn, Ff);
         } else {
             // last link: the backward pass starts straight from registers
             T an[3] = {Fn[0], Fn[1], Fn[2]}, af[3] = {Ff[0], Ff[1], Ff[2]};
@@ -1013,8 +1063,8 @@ MPK_HD void rnea(const RobotPack<T, N> &rb, In &in, const T (&g0)[3], const T *f
                 if (FAST0 && j == 1) {
                     an[2] = wrench_to_parent_nz<T, N, !REV, GEO>(rb, 1, cj, sj, dj, an, af, st_.get(0, 2));
                 } else {
-                    T bn[3] = {st_.get(j - 1, 0), st_.get(j - 1, 1), st_.get(j - 1, 2)};
-                    T bf[3] = {st_.get(j - 1, 3), st_.get(j - 1, 4), st_.get(j - 1, 5)};
+                    T bn[3], bf[3];
+                    st_.get_wrench(j - 1, bn, bf);
                     wrench_to_parent_acc<T, N, !REV, GEO>(rb, j, cj, sj, dj, an, af, bn, bf);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
