@@ -194,11 +194,12 @@ extern "C" int mpk_inverse_kinematics_dls_modes(const mpk_robot *rb, int64_t P, 
     // Re-packing ladder when the caller supplies a large enough workspace and there is a tail to cut.
     // First rung: 16 iterations (measured best for the plain solver, mean 36 iterations on random 7-DOF
     // targets, and with the line search, mean 16); then doubling.
-    int rung = 16;
-    if (const char *e = std::getenv("MPK_IK_SPLIT")) {  // tuning knob
-        const int v = std::atoi(e);
-        if (v > 0) rung = v;
-    }
+    static const int first_rung = [] {  // MPK_IK_SPLIT: tuning knob, read once
+        const char *e = std::getenv("MPK_IK_SPLIT");
+        const int v = e ? std::atoi(e) : 0;
+        return v > 0 ? v : 16;
+    }();
+    int rung = first_rung;
     const bool ladder = workspace && workspace_bytes >= mpk_inverse_kinematics_workspace_bytes(rb->n, P) &&
                         P >= 1024 && max_iterations > 2 * rung;
     char *queue[2] = {static_cast<char *>(workspace),
