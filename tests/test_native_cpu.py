@@ -550,6 +550,17 @@ def test_shard_bounds_weighted():
     for bad in ([1.0] * 7, [1.0] * 7 + [0.0], [1.0] * 7 + [float("nan")]):
         with pytest.raises(ValueError):
             shard_bounds(10, 8, bad)
+    # aligned interior boundaries (a shard of a shared float32 result buffer whose rows are 8 mod 16 bytes long must
+    # start on an even row to be 16-byte aligned): still a partition, every interior boundary a multiple of `align`
+    for units, world, wts in ((4097, 8, None), (410, 8, None), (37, 2, None), (37, 2, [1.0, 3.0]), (1, 4, None), (0, 3, None),
+                              (32768, 8, w)):
+        for align in (1, 2, 4):
+            bb = shard_bounds(units, world, wts, align)
+            assert bb[0] == 0 and bb[-1] == units and len(bb) == world + 1
+            assert all(y >= x for x, y in zip(bb, bb[1:]))
+            assert all(x % align == 0 or x == units for x in bb[1:-1])
+            assert shard_range(units, world, world - 1, wts, align) == (bb[-2], bb[-1])
+    assert shard_bounds(4097, 8, None, 2) == [0, 514, 1028, 1542, 2056, 2570, 3084, 3598, 4097]
 
 
 def test_gather_rows_gloo_world2(tmp_path):
