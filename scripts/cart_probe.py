@@ -1,3 +1,4 @@
+"""Device time of the Cartesian straight-line trajectory kernel (4096 pose pairs x 2441 steps):  python scripts/cart_probe.py"""
 import sys, json, torch, numpy as np
 sys.path.insert(0, '.')
 from manipulapy_b200 import _native, load_robot
