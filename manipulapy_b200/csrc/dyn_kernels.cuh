@@ -911,10 +911,13 @@ __device__ __forceinline__ void euler_update(const RolloutArgs &a, const double 
 #define MPK_FD_TRIO_LAYOUT 1
 #endif
 constexpr int kTrioThreads = MPK_FD_TRIO_LAYOUT == 1 ? 256 : 192;
-template <int N, unsigned GEO = 0>
+// NA: sin / cos of joints [0, NA) on warp A, of [NA, N) on warp S.  With two groups per SM S shares a scheduler
+// with the other group's A and takes the smaller half (NA = (N + 1) / 2); with one group per SM it has a
+// scheduler to itself and takes the larger one (NA = N / 2: 2,048 rollouts 1.79 -> 1.62 ms; with two groups that
+// split costs 7 %, profiles/r2_variants.md C).
+template <int N, unsigned GEO = 0, int NA = (N + 1) / 2>
 __global__ void __launch_bounds__(kTrioThreads, 1)
     fd_rollout_trio_kernel(const __grid_constant__ RobotPack<double, N> rb, const RolloutArgs a, const int groups) {
-    constexpr int NA = (N + 1) / 2;  // joints [0, NA): warp A; [NA, N): warp S
     extern __shared__ __align__(16) double psm[];
     const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
     // slot -> (role, group): 0 = A, 1 = B, 2 = S, 3 = none
@@ -1138,9 +1141,12 @@ void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s)
         if (!a.ftipmat && knob != 1 && (a.B <= 4 * wave || knob == 4)) {
             // plain revolute chain, rigid links, no tip wrench
             if (knob == 3 && a.B <= 2 * wave) {
-                const int groups = a.B <= wave ? 1 : 2;
-                launch_smem(fd_rollout_trio_kernel<N, GEO>, (unsigned)((a.B + 32 * groups - 1) / (32 * groups)), kTrioThreads,
-                            2 * rollout_pair_smem<N>(), s, narrow<N>(rb), a, groups);
+                if (a.B <= wave)
+                    launch_smem(fd_rollout_trio_kernel<N, GEO, N / 2>, blocks, kTrioThreads, 2 * rollout_pair_smem<N>(), s,
+                                narrow<N>(rb), a, 1);
+                else
+                    launch_smem(fd_rollout_trio_kernel<N, GEO>, (unsigned)((a.B + 63) / 64), kTrioThreads,
+                                2 * rollout_pair_smem<N>(), s, narrow<N>(rb), a, 2);
             }
             else
                 launch_smem(fd_rollout_pair_kernel<N, GEO>, blocks, 64, rollout_pair_smem<N>(), s, narrow<N>(rb), a);
