@@ -729,6 +729,13 @@ __device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 6
 #ifndef MPK_FD_PAIR_MINBLOCKS
 #define MPK_FD_PAIR_MINBLOCKS 4
 #endif
+// MPK_FD_PAIR_REREAD_MAX (tuning knob): instantiations compiled for more resident blocks than this skip A's re-read of (c, s)
+// from shared memory (the re-read keeps ptxas from scheduling the bias recursion ahead of the hand-over, which matters when
+// B has nothing else to run -- one wave; with 12 warps per SM the schedulers always have another warp, and without the
+// re-read 40,000 rollouts take 7.25 instead of 7.94 ms, 65,536 the same 11.2 ms)
+#ifndef MPK_FD_PAIR_REREAD_MAX
+#define MPK_FD_PAIR_REREAD_MAX 4
+#endif
 constexpr int kRolloutPairBlocksPerSm = MPK_FD_PAIR_MINBLOCKS;
 
 // doubles of shared memory per block: (c, s) 2 N, bias N, ddtheta N, two torque-row stages 2 N
@@ -789,10 +796,12 @@ __global__ void __launch_bounds__(64, MINB)
                     }
                     pending = -1;
                 }
+                if (MINB <= MPK_FD_PAIR_REREAD_MAX) {
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                    st_.q.c[j] = *(volatile double *)(cs + 32 * j);
-                    st_.q.s[j] = *(volatile double *)(cs + 32 * (N + j));
+                    for (int j = 0; j < N; ++j) {
+                        st_.q.c[j] = *(volatile double *)(cs + 32 * j);
+                        st_.q.s[j] = *(volatile double *)(cs + 32 * (N + j));
+                    }
                 }
                 double bias[N];
                 ArrayInNoAcc<double, N> in{th, dth};
