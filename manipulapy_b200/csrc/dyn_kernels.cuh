@@ -733,6 +733,10 @@ __device__ __forceinline__ void pair_wait(int id) { asm volatile("bar.sync %0, 6
 // from shared memory (the re-read keeps ptxas from scheduling the bias recursion ahead of the hand-over, which matters when
 // B has nothing else to run -- one wave; with 12 warps per SM the schedulers always have another warp, and without the
 // re-read 40,000 rollouts take 7.25 instead of 7.94 ms, 65,536 the same 11.2 ms)
+// MPK_FD_PAIR_WAVES_MINBLOCKS: resident blocks per SM of the instantiation that takes batches of several waves
+#ifndef MPK_FD_PAIR_WAVES_MINBLOCKS
+#define MPK_FD_PAIR_WAVES_MINBLOCKS 6
+#endif
 #ifndef MPK_FD_PAIR_REREAD_MAX
 #define MPK_FD_PAIR_REREAD_MAX 4
 #endif
@@ -1162,7 +1166,8 @@ void launch_rollout_n(const mpk_robot *rb, const RolloutArgs &a, cudaStream_t s)
             return;
         }
         if (!a.ftipmat && knob != 1 && a.B > 8 * wave) {
-            launch_smem(fd_rollout_pair_kernel<N, GEO, 6>, blocks, 64, rollout_pair_smem<N>(), s, narrow<N>(rb), a);
+            launch_smem(fd_rollout_pair_kernel<N, GEO, MPK_FD_PAIR_WAVES_MINBLOCKS>, blocks, 64, rollout_pair_smem<N>(), s,
+                        narrow<N>(rb), a);
             return;
         }
     }
