@@ -416,7 +416,7 @@ def run_ours(args) -> None:
     # The copy-rate probe is the starting point; the split is then re-balanced five times from each rank's own
     # measured end-to-end rate (its step time with every other rank running: the uplink shares shift with
     # who is copying when), all outside the timed region.
-    e2e_weights = list(d2h_rates)
+    e2e_weights = [max(x, 0.02 * max(d2h_rates)) for x in d2h_rates]
     e2e_rebalance = []
     out = None
     E2E_BALANCE_ROUNDS = 5
@@ -444,6 +444,7 @@ def run_ours(args) -> None:
             mine[rank] = (ehi - elo) / (time.perf_counter() - t0)
             dist.all_reduce(mine)
             e2e_weights = [float(x) for x in mine.cpu()]
+            e2e_weights = [max(x, 0.02 * max(e2e_weights)) for x in e2e_weights]  # (never starve a rank completely)
             e2e_rebalance.append([b_ - a_ for a_, b_ in zip(e2e_bounds, e2e_bounds[1:])])
     barrier()
     t0 = time.perf_counter()
